@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""Benchmark of the qbot state path on B200 -- the metric of BASELINE.json:
+gates/sec and achieved HBM GB/s of random-circuit gate application on a complex128 ket
+(30 qubits on one GPU; 34 qubits sharded over 2/4/8 GPUs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one application of the whole synthetic circuit rc(n, depth, seed)
+(qbot_b200/circuits.py) to the device-resident ket.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+                                          '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baselines (oracle = port of the reference's algorithm)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_algorithm(n_ref: int, budget_s: float, seed: int):
+    """The reference's own way of applying a gate: materialise the 2^n x 2^n unitary and do
+    U rho U^dagger with two dense matmuls (qbot/qgates.py:161-182, 228-275, 278-279), on the
+    same generator's circuit at the largest size that representation allows."""
+    from oracle import qbot_oracle as orc
+    from qbot_b200.circuits import rc
+    gates = rc(n_ref, 4, seed)
+    rho = np.zeros((1 << n_ref, 1 << n_ref), dtype=complex)
+    rho[0, 0] = 1
+    rho = orc.reference_style_gate(rho, n_ref, gates[0].target, gates[0].matrix(), gates[0].controls)   # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    for g in gates[1:]:
+        rho = orc.reference_style_gate(rho, n_ref, g.target, g.matrix(), g.controls)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def cpu_ket_port(n: int, budget_s: float, seed: int):
+    """Not a reference code path (the reference has no ket path): the oracle's
+    strided ket update in numpy, for scale."""
+    from oracle import qbot_oracle as orc
+    from qbot_b200.circuits import rc
+    gates = rc(n, 2, seed)
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[0] = 1
+    psi = orc.ket_apply(psi, n, gates[0].target, gates[0].matrix(), gates[0].controls)
+    t0 = time.perf_counter()
+    done = 0
+    for g in gates[1:]:
+        psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference is Python and
+    does not travel to the GPU box) timed on the host cores.  The reference cannot represent
+    the 30/34-qubit workload at all (16*4^n bytes per matrix), so each step is a bounded sample
+    of the same generator at n = 12, the largest size its dense 2^n x 2^n form allows."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import qbot_oracle as orc
+    from qbot_b200.circuits import rc
+    n_ref = args.ref_qubits
+    total_steps = args.steps + args.warmup
+    budget = 150.0 / max(total_steps, 1)
+    gates = rc(n_ref, 50, 12)
+    rho = np.zeros((1 << n_ref, 1 << n_ref), dtype=complex)
+    rho[0, 0] = 1
+    # calibrate: one gate
+    t0 = time.perf_counter()
+    rho = orc.reference_style_gate(rho, n_ref, gates[0].target, gates[0].matrix(), gates[0].controls)
+    one = time.perf_counter() - t0
+    per_step = max(1, int(budget / max(one, 1e-6)))
+    per_step = min(per_step, 64)
+    gi = 1
+    times = []
+    for s in range(total_steps):
+        t0 = time.perf_counter()
+        for _ in range(per_step):
+            g = gates[gi % len(gates)]
+            gi += 1
+            rho = orc.reference_style_gate(rho, n_ref, g.target, g.matrix(), g.controls)
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = per_step * len(times) / total
+    cores = os.cpu_count()
+    sample = (f"rc({n_ref}, 50, 12): {per_step} gates/step on a {1 << n_ref}x{1 << n_ref} complex128 density matrix "
+              f"(reference algorithm: full-space unitary + U rho U^dagger; it cannot represent n >= 14)")
+    line = {"impl": "reference", "metric": "gates/sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
+            "config": {"workload": sample, "qubits": n_ref},
+            "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def apply_circuit(st, gates, mats):
+    for g, m in zip(gates, mats):
+        st.apply_gate(m, g.target, g.controls)
+
+
+def run_single_gpu(args):
+    import torch
+    from qbot_b200 import DeviceState, circuits
+    from qbot_b200 import _lib
+
+    n = args.qubits or 30
+    depth = args.depth or 20
+    seed = args.seed if args.seed is not None else n
+    gates = circuits.rc(n, depth, seed)
+    mats = [np.ascontiguousarray(g.matrix()) for g in gates]
+    ngates = len(gates)
+    alg_bytes = circuits.total_algorithmic_bytes(gates, n)
+    peak, peak_src = measured_peaks()
+
+    torch.cuda.init()
+    st = DeviceState.zero_state(n)
+    st.set_fusion(not args.no_fusion)
+    for _ in range(args.warmup):
+        apply_circuit(st, gates, mats)
+    st.sync()
+    st.reset_stats()
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    st.timer_start()
+    for _ in range(args.steps):
+        apply_circuit(st, gates, mats)
+    ms = st.timer_stop()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    stats = st.stats()
+    secs = ms / 1e3
+    value = ngates * args.steps / secs
+    norm = float(st.norm2()[0])
+
+    launches = stats['kernel_launches']
+    passes = stats['state_passes']
+    pass_bytes = 32 * (1 << n)
+    if stats['fused_passes'] > 0:
+        # dominant kernel = fused tile sweep: one read + one write of the whole ket per launch
+        dom_launches = stats['fused_passes']
+        dom_bytes = pass_bytes
+        dom_kernel = 'k_tile_pass (fused multi-gate sweep)'
+        dom_unit = "one sweep = 32*2^n B (read + write of the ket)"
+    else:
+        dom_launches = launches
+        dom_bytes = alg_bytes * args.steps / max(launches, 1)
+        dom_kernel = 'k_dense<1> / k_diag (one gate per sweep)'
+        dom_unit = "per gate 32*2^(n-controls) B (SURVEY 8(d))"
+    avg_launch_s = secs / max(dom_launches, 1)
+    achieved = dom_bytes / avg_launch_s / 1e9
+    unfused_equiv = alg_bytes * args.steps / secs / 1e9
+
+    out = {
+        "metric": "gates/sec", "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "complex128 (f64)", "data": "synthetic",
+        "config": {"workload": f"rc({n}, {depth}, seed={seed}) random circuit (H .35 / RZ .35 / CNOT .20 / Toffoli .10) on a "
+                               f"{n}-qubit complex128 ket", "qubits": n, "depth": depth, "gates_per_step": ngates,
+                   "state_bytes": 16 * (1 << n), "l2": "state (16*2^n B) larger than L2; no flush needed",
+                   "fusion": not args.no_fusion},
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": dom_kernel, "per_launch": dom_unit, "launches": dom_launches,
+                     "avg_launch_ms": 1e3 * avg_launch_s, "peak_source": peak_src,
+                     "unfused_equivalent_gbs": unfused_equiv, "unfused_equivalent_frac": unfused_equiv / peak,
+                     "sweeps_per_step": passes / args.steps, "gates_per_sweep": ngates * args.steps / max(passes, 1)},
+        "amp_updates_per_s": value * (1 << n),
+        "norm_check": norm,
+    }
+
+    # end to end through the C ABI with HOST buffers: upload the ket from pinned host memory,
+    # run the circuit, read the outcome weights of 4 qubits back
+    if not args.no_e2e:
+        try:
+            host = torch.zeros(1 << n, dtype=torch.complex128, pin_memory=True)
+            host[0] = 1
+            hnp = host.numpy()
+            import ctypes as C
+            outp = np.empty(16, dtype=np.float64)
+            qs = [0, n // 3, (2 * n) // 3, n - 1]
+
+            def e2e_step():
+                _lib.call('qb_upload', st._h, C.c_void_p(hnp.ctypes.data), hnp.nbytes)
+                apply_circuit(st, gates, mats)
+                return st.probs(qs)
+
+            e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                pr = e2e_step()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            mat_bytes = sum(m.nbytes for m in mats)
+            out["e2e"] = {"value": ngates * args.steps / dt, "unit": "gates/s", "h2d_bytes_per_step": int(hnp.nbytes + mat_bytes),
+                          "d2h_bytes_per_step": int(pr.nbytes), "ms_per_step": 1e3 * dt / args.steps,
+                          "what": "qb_upload(pinned host ket) + circuit via qb_apply_gate (host matrices) + qb_probs -> host"}
+            del host
+        except Exception as e:  # keep the headline even if pinned allocation fails
+            out["e2e"] = {"value": None, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(e)[:200]}
+
+    if not args.no_cpu_baseline:
+        v, done, dt = cpu_reference_algorithm(args.ref_qubits_default, 12.0, 12)
+        kv, kdone, kdt = cpu_ket_port(24, 6.0, 24)
+        out["cpu_baseline"] = {
+            "value": v, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{done} gates of rc({args.ref_qubits_default}, 4, 12) in {dt:.1f}s with the reference's algorithm (full 2^n x 2^n unitary, "
+                      f"U rho U^dagger) on a {args.ref_qubits_default}-qubit density matrix; the reference cannot represent n={n}",
+            "ket_port": {"value": kv, "unit": "gates/s", "qubits": 24,
+                         "sample": f"{kdone} gates of rc(24, 2, 24) in {kdt:.1f}s, numpy strided ket update (not a reference code path)"}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--qubits', type=int, default=None)
+    ap.add_argument('--depth', type=int, default=None)
+    ap.add_argument('--seed', type=int, default=None)
+    ap.add_argument('--no-fusion', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-qubits', type=int, default=12)
+    ap.add_argument('--ref-qubits-default', type=int, default=11)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.gpus > 1 or world > 1:
+        from qbot_b200.dist_bench import run_multi_gpu
+        run_multi_gpu(args)
+    else:
+        run_single_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,142 @@
+/*
+ * qbot_b200 C ABI -- the drop-in boundary of the B200 state-path backend.
+ *
+ * The reference (PrinceOfPuppers/qbot) has no FFI layer: its state path is Python calling
+ * numpy.  The nearest thing to a plugin interface is the `operations` table
+ * (qbot/operators.py:477-506); the six state ops in it (`qset`, `gate`, `disc`, `swap`, `meas`,
+ * `peek`) do all their arithmetic through the functions named next to each entry point below.
+ * A maintainer binds this library with ctypes and re-registers those six
+ * ops; nothing else in the reference changes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative qb_status otherwise, and never throws;
+ *     qb_last_error() returns the message of the last failure on the calling thread.
+ *   - all matrices / vectors crossing the boundary are HOST pointers to row-major
+ *     complex128 (interleaved re, im doubles) unless the name says `_dev`.
+ *   - a state is an opaque handle owning `nbranch << nbits` complex128 amplitudes in HBM,
+ *     nbits = nqubits (ket) or 2*nqubits (density matrix stored row-major, row index in the
+ *     high nqubits bits).  "bit" arguments are positions in the basis-state index of ONE
+ *     branch, bit 0 = stride-1.  Reference qubit q of an n-qubit register is bit n-1-q
+ *     (qbot/qgates.py:161-182: qubit 0 is the most significant index bit).
+ *   - calls are asynchronous on the handle's stream except those that return host data.
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails with
+ *     QB_ERR_CUDA.
+ */
+#ifndef QBOT_B200_H
+#define QBOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qb_state qb_state;
+
+typedef enum {
+    QB_OK = 0,
+    QB_ERR_ARG = -1,      /* bad argument (message says which) */
+    QB_ERR_CUDA = -2,     /* CUDA runtime error (message = cudaGetErrorString) */
+    QB_ERR_ALLOC = -3,    /* out of device memory */
+    QB_ERR_STATE = -4     /* operation not valid for this kind of state */
+} qb_status;
+
+enum { QB_KET = 0, QB_DM = 1 };
+
+/* counters a caller can read back (bench.py: gpu_launches, passes, bytes) */
+typedef struct {
+    uint64_t kernel_launches;   /* CUDA kernels launched on behalf of this handle */
+    uint64_t gates_applied;     /* ket-level gate operations executed */
+    uint64_t state_passes;      /* full read+write sweeps over the state */
+    uint64_t fused_passes;      /* sweeps done by the fused tile kernel */
+    uint64_t fused_gates;       /* gates executed inside fused sweeps */
+    uint64_t bytes_moved;       /* bytes the launched kernels were asked to read + write */
+} qb_stats;
+
+/* ---- library ------------------------------------------------------------------------ */
+const char* qb_version(void);
+const char* qb_last_error(void);
+int qb_device_count(int* count);
+int qb_device_info(int device, char* name, int name_len, int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor);
+
+/* ---- lifetime ------------------------------------------------------------------------
+ * The register the reference keeps in localNameSpace['state'] (qbot/interpreter.py:218-224). */
+int qb_create(qb_state** out, int kind, int nqubits, int64_t nbranch, int device);
+/* adopt memory owned by someone else (e.g. a torch tensor); stream may be NULL */
+int qb_create_external(qb_state** out, int kind, int nqubits, int64_t nbranch, int device,
+                       void* amplitudes_dev, void* cuda_stream);
+int qb_destroy(qb_state* s);
+int qb_clone(const qb_state* s, qb_state** out);
+int qb_info(const qb_state* s, int* kind, int* nqubits, int64_t* nbranch, int* device);
+int qb_device_ptr(qb_state* s, void** amplitudes_dev);
+int qb_set_stream(qb_state* s, void* cuda_stream);
+
+/* ---- state constructors: density.tensorProd / tensorExp / Basis.__getitem__ results
+ *      (qbot/density.py:7-29, qbot/basis.py:27-28) without a host 2^n array ---------------- */
+int qb_init_basis(qb_state* s, uint64_t index);                       /* |index><index| or |index> in every branch */
+/* per-qubit 2-vectors, qubit 0 first: vecs[(b*nq + q)*2 + {0,1}] complex; per_branch=0 shares one set */
+int qb_init_product(qb_state* s, const double* vecs, int per_branch);
+int qb_upload(qb_state* s, const void* host, size_t bytes);            /* qset with a host array (operators.py:143-153) */
+int qb_download(qb_state* s, void* host, size_t bytes);                /* what a user expression reading `state` sees */
+int qb_download_range(qb_state* s, uint64_t first_amp, uint64_t count, void* host);
+
+/* ---- gate application ------------------------------------------------------------------
+ * replaces qgates.genGateForFullHilbertSpace (qgates.py:161-182), genMultiControlledGate
+ * (228-275) and applyGate (278-279) as used by operators._gate / gate (operators.py:255-329):
+ * ket: psi <- U_c psi ; density matrix: rho <- U_c rho U_c^dagger, where U_c applies `matrix`
+ * to target_bits when every bit of control_mask is 1.  target_bits[0] carries the matrix's
+ * most significant index bit.  Gates are queued and fused; qb_flush drains the queue. */
+int qb_apply_gate(qb_state* s, const double* matrix, int k, const int* target_bits, uint64_t control_mask);
+/* replaces genSwapGate (qgates.py:77-133) + applyGate as used by operators._swap / swap (364-393) */
+int qb_apply_swap(qb_state* s, int bit_a, int bit_b);
+/* piece (5): one launch over all branches, each with its own gate (probVal.funcWrapper loop,
+ * probVal.py:347-390 + operators.py:313-316).  matrices[b*4^k..], target_bits[b*k..],
+ * control_masks[b], enable[b] (0 = leave branch b untouched; NULL = all enabled). */
+int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int* target_bits,
+                          const uint64_t* control_masks, const uint8_t* enable);
+int qb_flush(qb_state* s);
+int qb_sync(qb_state* s);
+int qb_set_fusion(qb_state* s, int enabled);
+
+/* ---- measurement ----------------------------------------------------------------------
+ * computational-basis outcome weights of `m` listed bits (bits[0] = most significant outcome
+ * bit): ket  out[b*2^m + j] = sum |psi|^2 ; density matrix  out = |sum of diagonal entries|.
+ * This is the abs(trace(rho_A P_j)) loop of measurement.measureArbitraryMultiState
+ * (measurement.py:147-155) for the computational basis; other bases rotate first. */
+int qb_probs(qb_state* s, const int* bits, int m, double* out);
+int qb_norm2(qb_state* s, double* out);                                /* per branch: <psi|psi> or tr rho */
+/* ket only: project the listed bits on `outcome` and renormalise (textbook collapse) */
+int qb_project_renorm(qb_state* s, const int* bits, int m, uint64_t outcome);
+
+/* ---- density-matrix structure ops -----------------------------------------------------
+ * density.partialTraceArbitrary (density.py:122-148): keep the listed qubit-bits (keep_bits[0]
+ * = most significant bit of the result), trace the others.  Returns a new DM handle. */
+int qb_ptrace(qb_state* s, const int* keep_bits, int nkeep, qb_state** out);
+/* density.interweaveDensities / replaceArbitrary (density.py:150-227): out = A (x) B with A's
+ * i-th qubit-bit (most significant first) placed at bit a_bits[i] of the result and B's at
+ * b_bits[i].  b may be NULL (nb = 0). `scale` multiplies the result (the 1x1 [[tr rho]]
+ * factor the reference carries when nothing is left, density.py:203-204). */
+int qb_scatter_product(qb_state* a, qb_state* b, const int* a_bits, const int* b_bits,
+                       const double* scale, qb_state** out);
+/* density.densityEnsambleToDensity (density.py:49-58): out = sum_i probs[i] * states[i],
+ * accumulated in list order without FMA contraction (bit-identical to the numpy loop). */
+int qb_mix(qb_state* const* states, const double* probs, int count, qb_state** out);
+/* same over the branch axis of one batched state -> single-branch state */
+int qb_mix_branches(qb_state* s, const double* probs, qb_state** out);
+/* ket -> density matrix: conj=0 gives psi psi^T as density.ketToDensity does (density.py:31-32),
+ * conj=1 gives psi psi^dagger */
+int qb_outer(qb_state* ket, int conj, qb_state** out);
+/* copy one state into every branch of a batched state (fan-out before a batched gate) */
+int qb_broadcast(qb_state* src, qb_state* dst_batched);
+
+/* ---- instrumentation ------------------------------------------------------------------- */
+int qb_get_stats(const qb_state* s, qb_stats* out);
+int qb_reset_stats(qb_state* s);
+int qb_timer_start(qb_state* s);                 /* CUDA event on the handle's stream */
+int qb_timer_stop(qb_state* s, float* ms);       /* records, synchronises, returns elapsed ms */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QBOT_B200_H */

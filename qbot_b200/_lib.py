@@ -1,0 +1,111 @@
+"""ctypes binding of the C ABI declared in ``include/qbot_b200.h``.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a) as
+``qbot_b200/lib/libqbot_b200.so``.  There is no fallback: if the library is missing, or no
+CUDA device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libqbot_b200.so')
+
+c_state_p = C.c_void_p
+
+
+class QbStats(C.Structure):
+    _fields_ = [('kernel_launches', C.c_uint64), ('gates_applied', C.c_uint64), ('state_passes', C.c_uint64),
+                ('fused_passes', C.c_uint64), ('fused_gates', C.c_uint64), ('bytes_moved', C.c_uint64)]
+
+
+class QbotB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"qbot_b200 [{code}]: {msg}")
+        self.code = code
+
+
+# name -> (restype, argtypes); every entry must exist in include/qbot_b200.h (tests check both ways)
+PROTOTYPES = {
+    'qb_version': (C.c_char_p, []),
+    'qb_last_error': (C.c_char_p, []),
+    'qb_device_count': (C.c_int, [C.POINTER(C.c_int)]),
+    'qb_device_info': (C.c_int, [C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'qb_create': (C.c_int, [C.POINTER(c_state_p), C.c_int, C.c_int, C.c_int64, C.c_int]),
+    'qb_create_external': (C.c_int, [C.POINTER(c_state_p), C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    'qb_destroy': (C.c_int, [c_state_p]),
+    'qb_clone': (C.c_int, [c_state_p, C.POINTER(c_state_p)]),
+    'qb_info': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    'qb_device_ptr': (C.c_int, [c_state_p, C.POINTER(C.c_void_p)]),
+    'qb_set_stream': (C.c_int, [c_state_p, C.c_void_p]),
+    'qb_init_basis': (C.c_int, [c_state_p, C.c_uint64]),
+    'qb_init_product': (C.c_int, [c_state_p, C.c_void_p, C.c_int]),
+    'qb_upload': (C.c_int, [c_state_p, C.c_void_p, C.c_size_t]),
+    'qb_download': (C.c_int, [c_state_p, C.c_void_p, C.c_size_t]),
+    'qb_download_range': (C.c_int, [c_state_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    'qb_apply_gate': (C.c_int, [c_state_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_uint64]),
+    'qb_apply_swap': (C.c_int, [c_state_p, C.c_int, C.c_int]),
+    'qb_apply_gate_batched': (C.c_int, [c_state_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.c_void_p]),
+    'qb_flush': (C.c_int, [c_state_p]),
+    'qb_sync': (C.c_int, [c_state_p]),
+    'qb_set_fusion': (C.c_int, [c_state_p, C.c_int]),
+    'qb_probs': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
+    'qb_norm2': (C.c_int, [c_state_p, C.c_void_p]),
+    'qb_project_renorm': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_uint64]),
+    'qb_ptrace': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.POINTER(c_state_p)]),
+    'qb_scatter_product': (C.c_int, [c_state_p, c_state_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.POINTER(c_state_p)]),
+    'qb_mix': (C.c_int, [C.POINTER(c_state_p), C.POINTER(C.c_double), C.c_int, C.POINTER(c_state_p)]),
+    'qb_mix_branches': (C.c_int, [c_state_p, C.POINTER(C.c_double), C.POINTER(c_state_p)]),
+    'qb_outer': (C.c_int, [c_state_p, C.c_int, C.POINTER(c_state_p)]),
+    'qb_broadcast': (C.c_int, [c_state_p, c_state_p]),
+    'qb_get_stats': (C.c_int, [c_state_p, C.POINTER(QbStats)]),
+    'qb_reset_stats': (C.c_int, [c_state_p]),
+    'qb_timer_start': (C.c_int, [c_state_p]),
+    'qb_timer_stop': (C.c_int, [c_state_p, C.POINTER(C.c_float)]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise QbotB200Error(-2, f"{LIB_PATH} not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
+                                    "there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)        # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code: int):
+    if code != 0:
+        raise QbotB200Error(code, load().qb_last_error().decode(errors='replace'))
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    call('qb_device_count', C.byref(n))
+    return n.value
+
+
+def int_array(vals):
+    vals = [int(v) for v in vals]
+    return (C.c_int * max(len(vals), 1))(*vals)

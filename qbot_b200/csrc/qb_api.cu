@@ -1,0 +1,799 @@
+// qbot_b200 -- C ABI (include/qbot_b200.h): state handles, gate queue, dispatch to kernels.
+#include "../../include/qbot_b200.h"
+#include "qb_common.cuh"
+#include "qb_engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+static thread_local std::string g_err;
+
+#define QB_API_BEGIN try {
+#define QB_API_END                                                                             \
+    return QB_OK;                                                                              \
+    } catch (const qb_error& e) { g_err = e.what(); return e.code; }                           \
+    catch (const std::bad_alloc&) { g_err = "host allocation failed"; return QB_ERR_ALLOC; }   \
+    catch (const std::exception& e) { g_err = e.what(); return QB_ERR_ARG; }                   \
+    catch (...) { g_err = "unknown error"; return QB_ERR_ARG; }
+
+static inline cplx C(double re, double im) { return make_double2(re, im); }
+
+// ---------------------------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------------------------
+struct DevGuard {
+    int prev;
+    explicit DevGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) QB_CUDA(cudaSetDevice(dev)); else prev = -1; }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int sm_count_of(int dev) {
+    int v = 0;
+    QB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    return v;
+}
+
+qb_state::~qb_state() {
+    if (d && owns) cudaFree(d);
+    if (scratch) cudaFree(scratch);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream && owns_stream) cudaStreamDestroy(stream);
+}
+
+static qb_state* new_state(int kind, int nq, int64_t nbranch, int device, void* ext, void* ext_stream) {
+    QB_REQUIRE(kind == QB_KET || kind == QB_DM, "kind must be QB_KET or QB_DM");
+    QB_REQUIRE(nq >= 0 && nq <= 40, "nqubits out of range");
+    QB_REQUIRE(nbranch >= 1, "nbranch must be >= 1");
+    int nbits = kind == QB_KET ? nq : 2 * nq;
+    QB_REQUIRE(nbits <= 40, "state too large (index bits > 40)");
+    int ndev = 0;
+    QB_CUDA(cudaGetDeviceCount(&ndev));
+    QB_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+    std::unique_ptr<qb_state> s(new qb_state());
+    s->kind = kind; s->nq = nq; s->nbits = nbits; s->nbranch = nbranch; s->device = device;
+    DevGuard g(device);
+    s->sms = sm_count_of(device);
+    if (ext_stream) { s->stream = (cudaStream_t)ext_stream; s->owns_stream = false; }
+    else { QB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->owns_stream = true; }
+    if (ext) { s->d = (cplx*)ext; s->owns = false; }
+    else { QB_CUDA(cudaMalloc((void**)&s->d, s->bytes())); s->owns = true; }
+    return s.release();
+}
+
+LaunchCtx qb_state::ctx() { return LaunchCtx{stream, sms, &stats.kernel_launches}; }
+
+cplx* qb_state::get_scratch() {
+    if (!scratch) QB_CUDA(cudaMalloc((void**)&scratch, bytes()));
+    return scratch;
+}
+
+// ---------------------------------------------------------------------------------------------
+// gate classification + queue
+// ---------------------------------------------------------------------------------------------
+static QGate classify(const cplx* m, int k, const int* tb, uint64_t cmask) {
+    QGate g;
+    g.k = k; g.cmask = cmask;
+    for (int i = 0; i < k; i++) g.tb[i] = tb[i];
+    const int D = 1 << k;
+    bool diag = true, mono = true;
+    std::vector<int> src(D, -1);
+    std::vector<int> colcnt(D, 0);
+    for (int i = 0; i < D; i++) {
+        int nz = 0;
+        for (int j = 0; j < D; j++) {
+            const cplx v = m[i * D + j];
+            if (v.x != 0.0 || v.y != 0.0) {
+                nz++;
+                src[i] = j;
+                colcnt[j]++;
+                if (i != j) diag = false;
+            }
+        }
+        if (nz != 1) mono = false;
+    }
+    for (int j = 0; j < D && mono; j++) if (colcnt[j] != 1) mono = false;
+    // a zero on the diagonal of a "diagonal" matrix is still diagonal; nz==0 rows are handled by DENSE
+    if (diag) {
+        g.type = QB_G_DIAG;
+        g.m.resize(D);
+        for (int i = 0; i < D; i++) g.m[i] = m[i * D + i];
+    } else if (mono) {
+        g.type = QB_G_MONO;
+        g.m.resize(D);
+        g.src = src;
+        for (int i = 0; i < D; i++) g.m[i] = m[i * D + src[i]];
+    } else {
+        g.type = QB_G_DENSE;
+        g.m.assign(m, m + (size_t)D * D);
+    }
+    return g;
+}
+
+static bool is_identity(const QGate& g) {
+    if (g.type != QB_G_DIAG) return false;
+    for (const cplx& v : g.m) if (v.x != 1.0 || v.y != 0.0) return false;
+    return true;
+}
+
+static std::vector<cplx> dense_of(const QGate& g) {
+    const int D = 1 << g.k;
+    if (g.type == QB_G_DENSE) return g.m;
+    std::vector<cplx> m((size_t)D * D, C(0, 0));
+    if (g.type == QB_G_DIAG) for (int i = 0; i < D; i++) m[i * D + i] = g.m[i];
+    else for (int i = 0; i < D; i++) m[i * D + g.src[i]] = g.m[i];
+    return m;
+}
+
+static void fill_ins(uint64_t mask, int nbits_total, int* ins, int& nins) {
+    nins = 0;
+    for (int p = 0; p < nbits_total; p++) if ((mask >> p) & 1ull) ins[nins++] = p;
+}
+
+cplx* qb_state::upload_small(const void* host, size_t bytes) {
+    // staging ring for gate matrices: consecutive launches must not overwrite each other
+    if (!stage) { QB_CUDA(cudaMalloc((void**)&stage, STAGE_BYTES)); stage_off = 0; }
+    size_t need = (bytes + 255) & ~size_t(255);
+    QB_REQUIRE(need <= STAGE_BYTES, "matrix too large for the staging buffer");
+    if (stage_off + need > STAGE_BYTES) { QB_CUDA(cudaStreamSynchronize(stream)); stage_off = 0; }
+    char* dst = (char*)stage + stage_off;
+    stage_off += need;
+    QB_CUDA(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, stream));
+    // pageable source: the copy is staged by the runtime before returning, so `host` may die
+    return (cplx*)dst;
+}
+
+// one ket-level gate, one sweep (no fusion)
+void qb_state::run_gate_unfused(const QGate& g) {
+    const int K = g.k;
+    const uint64_t total_bits_mask_ok = (nbits >= 64) ? ~0ull : ((1ull << nbits) - 1ull);
+    QB_REQUIRE((g.tmask() & ~total_bits_mask_ok) == 0 && (g.cmask & ~total_bits_mask_ok) == 0, "gate bit out of range");
+    QB_REQUIRE((g.tmask() & g.cmask) == 0, "control overlaps target");
+    LaunchCtx c = ctx();
+    const int ncontrols = __builtin_popcountll(g.cmask);
+    const uint64_t touched = ((uint64_t)nbranch << nbits) >> ncontrols;
+    if (g.type == QB_G_DIAG && K <= QB_DIAG_MAXK) {
+        DiagArgs a;
+        memset(&a, 0, sizeof(a));
+        a.psi = d; a.cmask = g.cmask; a.k = K;
+        for (int i = 0; i < K; i++) a.tb[i] = g.tb[i];
+        fill_ins(g.cmask, nbits, a.ins, a.nins);
+        a.nwork = touched;
+        if (K <= 2) for (int i = 0; i < (1 << K); i++) a.inl[i] = g.m[i];
+        else a.diag = upload_small(g.m.data(), sizeof(cplx) << K);
+        qb_launch_diag(c, a);
+        stats.bytes_moved += touched * 32;
+    } else if (K <= QB_REG_MAXK) {
+        std::vector<cplx> m = dense_of(g);
+        DenseArgs a;
+        memset(&a, 0, sizeof(a));
+        a.psi = d; a.cmask = g.cmask;
+        for (int i = 0; i < K; i++) a.tb[i] = g.tb[i];
+        fill_ins(g.cmask | g.tmask(), nbits, a.ins, a.nins);
+        a.nwork = touched >> K;
+        if (K <= 2) for (int i = 0; i < (1 << (2 * K)); i++) a.inl[i] = m[i];
+        else a.mat = upload_small(m.data(), sizeof(cplx) << (2 * K));
+        qb_launch_dense(c, K, a);
+        stats.bytes_moved += touched * 32;
+    } else {
+        QB_REQUIRE(K <= QB_BIG_MAXK, "gate acts on too many qubits");
+        std::vector<cplx> m = dense_of(g);
+        const int D = 1 << K;
+        std::vector<uint64_t> offs(D);
+        for (int j = 0; j < D; j++) {
+            uint64_t o = 0;
+            for (int b = 0; b < K; b++) if ((j >> (K - 1 - b)) & 1) o |= 1ull << g.tb[b];
+            offs[j] = o;
+        }
+        // the matrix can exceed the staging ring: give it its own allocation
+        cplx* dm = nullptr; uint64_t* doffs = nullptr;
+        QB_CUDA(cudaMalloc((void**)&dm, sizeof(cplx) * (size_t)D * D));
+        QB_CUDA(cudaMalloc((void**)&doffs, sizeof(uint64_t) * D));
+        QB_CUDA(cudaMemcpyAsync(dm, m.data(), sizeof(cplx) * (size_t)D * D, cudaMemcpyHostToDevice, stream));
+        QB_CUDA(cudaMemcpyAsync(doffs, offs.data(), sizeof(uint64_t) * D, cudaMemcpyHostToDevice, stream));
+        BigArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = d; a.out = get_scratch(); a.mat = dm; a.offs = doffs;
+        a.total = (uint64_t)nbranch << nbits; a.cmask = g.cmask; a.tmask = g.tmask(); a.k = K;
+        for (int i = 0; i < K; i++) a.tb[i] = g.tb[i];
+        qb_launch_big(c, a);
+        if (owns) std::swap(d, scratch);
+        else QB_CUDA(cudaMemcpyAsync(d, scratch, bytes(), cudaMemcpyDeviceToDevice, stream));
+        QB_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(dm); cudaFree(doffs);
+        stats.bytes_moved += a.total * 32;
+    }
+    stats.gates_applied++;
+    stats.state_passes++;
+}
+
+void qb_state::enqueue(QGate&& g) {
+    if (is_identity(g)) return;
+    queue.push_back(std::move(g));
+    if (!fusion || queue.size() >= 4096) flush();
+}
+
+void qb_state::flush() {
+    if (queue.empty()) return;
+    DevGuard gd(device);
+    std::vector<QGate> q;
+    q.swap(queue);
+    if (fusion && qb_engine_available()) {
+        qb_engine_run(this, q);
+    } else {
+        for (const QGate& g : q) run_gate_unfused(g);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* qb_version(void) { return "qbot_b200 0.1.0 (sm_100a)"; }
+const char* qb_last_error(void) { return g_err.c_str(); }
+
+int qb_device_count(int* count) {
+    QB_API_BEGIN
+    QB_REQUIRE(count, "count is NULL");
+    *count = 0;
+    QB_CUDA(cudaGetDeviceCount(count));
+    QB_API_END
+}
+
+int qb_device_info(int device, char* name, int name_len, int* sm_count, size_t* total_mem, int* cc_major, int* cc_minor) {
+    QB_API_BEGIN
+    cudaDeviceProp p;
+    QB_CUDA(cudaGetDeviceProperties(&p, device));
+    if (name && name_len > 0) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    QB_API_END
+}
+
+int qb_create(qb_state** out, int kind, int nqubits, int64_t nbranch, int device) {
+    QB_API_BEGIN
+    QB_REQUIRE(out, "out is NULL");
+    *out = new_state(kind, nqubits, nbranch, device, nullptr, nullptr);
+    QB_API_END
+}
+
+int qb_create_external(qb_state** out, int kind, int nqubits, int64_t nbranch, int device, void* amplitudes_dev, void* cuda_stream) {
+    QB_API_BEGIN
+    QB_REQUIRE(out && amplitudes_dev, "NULL argument");
+    *out = new_state(kind, nqubits, nbranch, device, amplitudes_dev, cuda_stream);
+    QB_API_END
+}
+
+int qb_destroy(qb_state* s) {
+    QB_API_BEGIN
+    if (s) {
+        DevGuard g(s->device);
+        cudaStreamSynchronize(s->stream);
+        if (s->stage) cudaFree(s->stage);
+        delete s;
+    }
+    QB_API_END
+}
+
+int qb_clone(const qb_state* cs, qb_state** out) {
+    QB_API_BEGIN
+    qb_state* s = const_cast<qb_state*>(cs);
+    QB_REQUIRE(s && out, "NULL argument");
+    s->flush();
+    DevGuard g(s->device);
+    qb_state* n = new_state(s->kind, s->nq, s->nbranch, s->device, nullptr, s->owns_stream ? nullptr : (void*)s->stream);
+    n->fusion = s->fusion;
+    QB_CUDA(cudaMemcpyAsync(n->d, s->d, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    *out = n;
+    QB_API_END
+}
+
+int qb_info(const qb_state* s, int* kind, int* nqubits, int64_t* nbranch, int* device) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    if (kind) *kind = s->kind;
+    if (nqubits) *nqubits = s->nq;
+    if (nbranch) *nbranch = s->nbranch;
+    if (device) *device = s->device;
+    QB_API_END
+}
+
+int qb_device_ptr(qb_state* s, void** p) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && p, "NULL argument");
+    s->flush();
+    *p = s->d;
+    QB_API_END
+}
+
+int qb_set_stream(qb_state* s, void* cuda_stream) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    s->flush();
+    DevGuard g(s->device);
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->owns_stream && s->stream) cudaStreamDestroy(s->stream);
+    if (cuda_stream) { s->stream = (cudaStream_t)cuda_stream; s->owns_stream = false; }
+    else { QB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->owns_stream = true; }
+    QB_API_END
+}
+
+int qb_init_basis(qb_state* s, uint64_t index) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    s->queue.clear();
+    DevGuard g(s->device);
+    uint64_t per = s->per_branch();
+    uint64_t flat = index;
+    if (s->kind == QB_DM) {
+        QB_REQUIRE(index < (1ull << s->nq), "basis index out of range");
+        flat = (index << s->nq) | index;
+    } else QB_REQUIRE(index < per, "basis index out of range");
+    qb_launch_fill_basis(s->ctx(), s->d, per, s->nbranch, flat);
+    s->stats.bytes_moved += s->bytes();
+    QB_API_END
+}
+
+int qb_init_product(qb_state* s, const double* vecs, int per_branch) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && vecs, "NULL argument");
+    s->queue.clear();
+    DevGuard g(s->device);
+    size_t per = (s->kind == QB_KET ? 2 : 4) * (size_t)s->nq;
+    size_t count = per * (per_branch ? (size_t)s->nbranch : 1);
+    cplx* dv = nullptr;
+    QB_CUDA(cudaMalloc((void**)&dv, sizeof(cplx) * std::max<size_t>(count, 1)));
+    QB_CUDA(cudaMemcpyAsync(dv, vecs, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));
+    qb_launch_init_product(s->ctx(), s->d, s->kind, s->nq, s->nbranch, dv, per_branch);
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(dv);
+    s->stats.bytes_moved += s->bytes();
+    QB_API_END
+}
+
+int qb_upload(qb_state* s, const void* host, size_t bytes) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && host, "NULL argument");
+    QB_REQUIRE(bytes == s->bytes(), "upload: byte count does not match the state size");
+    s->queue.clear();
+    DevGuard g(s->device);
+    QB_CUDA(cudaMemcpyAsync(s->d, host, bytes, cudaMemcpyHostToDevice, s->stream));
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    QB_API_END
+}
+
+int qb_download(qb_state* s, void* host, size_t bytes) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && host, "NULL argument");
+    QB_REQUIRE(bytes == s->bytes(), "download: byte count does not match the state size");
+    s->flush();
+    DevGuard g(s->device);
+    QB_CUDA(cudaMemcpyAsync(host, s->d, bytes, cudaMemcpyDeviceToHost, s->stream));
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    QB_API_END
+}
+
+int qb_download_range(qb_state* s, uint64_t first, uint64_t count, void* host) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && host, "NULL argument");
+    QB_REQUIRE(first + count <= s->total(), "download_range: out of bounds");
+    s->flush();
+    DevGuard g(s->device);
+    QB_CUDA(cudaMemcpyAsync(host, s->d + first, count * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    QB_API_END
+}
+
+int qb_apply_gate(qb_state* s, const double* matrix, int k, const int* target_bits, uint64_t control_mask) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && matrix && target_bits, "NULL argument");
+    QB_REQUIRE(k >= 1 && k <= QB_BIG_MAXK, "gate size out of range");
+    QB_REQUIRE(k <= s->nq, "gate has more qubits than the register");
+    const cplx* m = (const cplx*)matrix;
+    uint64_t tmask = 0;
+    for (int i = 0; i < k; i++) {
+        QB_REQUIRE(target_bits[i] >= 0 && target_bits[i] < s->nq, "target bit out of range");
+        QB_REQUIRE(!((tmask >> target_bits[i]) & 1ull), "duplicate target bit");
+        tmask |= 1ull << target_bits[i];
+    }
+    QB_REQUIRE(s->nq >= 64 || (control_mask >> s->nq) == 0, "control bit out of range");
+    QB_REQUIRE((tmask & control_mask) == 0, "control overlaps target");
+    if (s->kind == QB_KET) {
+        s->enqueue(classify(m, k, target_bits, control_mask));
+    } else {
+        // rho <- U rho U^dagger on vec(rho): U on the row bits, conj(U) on the column bits
+        int tb_row[QB_BIG_MAXK];
+        for (int i = 0; i < k; i++) tb_row[i] = target_bits[i] + s->nq;
+        s->enqueue(classify(m, k, tb_row, control_mask << s->nq));
+        const size_t D2 = (size_t)1 << (2 * k);
+        std::vector<cplx> mc(D2);
+        for (size_t i = 0; i < D2; i++) mc[i] = C(m[i].x, -m[i].y);
+        s->enqueue(classify(mc.data(), k, target_bits, control_mask));
+    }
+    QB_API_END
+}
+
+int qb_apply_swap(qb_state* s, int bit_a, int bit_b) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    QB_REQUIRE(bit_a >= 0 && bit_a < s->nq && bit_b >= 0 && bit_b < s->nq, "swap bit out of range");
+    if (bit_a == bit_b) return QB_OK;
+    s->flush();
+    DevGuard g(s->device);
+    int lo = std::min(bit_a, bit_b), hi = std::max(bit_a, bit_b);
+    qb_launch_swap(s->ctx(), s->d, s->total(), lo, hi);
+    s->stats.bytes_moved += s->bytes();
+    s->stats.state_passes++;
+    if (s->kind == QB_DM) {
+        qb_launch_swap(s->ctx(), s->d, s->total(), lo + s->nq, hi + s->nq);
+        s->stats.bytes_moved += s->bytes();
+        s->stats.state_passes++;
+    }
+    s->stats.gates_applied++;
+    QB_API_END
+}
+
+int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int* target_bits,
+                          const uint64_t* control_masks, const uint8_t* enable) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && matrices && target_bits, "NULL argument");
+    QB_REQUIRE(k >= 1 && k <= QB_REG_MAXK, "batched gate: k must be 1..5");
+    QB_REQUIRE(k <= s->nq, "gate has more qubits than the register");
+    s->flush();
+    DevGuard g(s->device);
+    const int64_t B = s->nbranch;
+    const size_t D2 = (size_t)1 << (2 * k);
+    for (int64_t b = 0; b < B; b++) {
+        uint64_t tmask = 0;
+        for (int i = 0; i < k; i++) {
+            int t = target_bits[b * k + i];
+            QB_REQUIRE(t >= 0 && t < s->nq, "batched gate: target bit out of range");
+            QB_REQUIRE(!((tmask >> t) & 1ull), "batched gate: duplicate target bit");
+            tmask |= 1ull << t;
+        }
+        uint64_t cm = control_masks ? control_masks[b] : 0;
+        QB_REQUIRE((cm >> s->nq) == 0 && (cm & tmask) == 0, "batched gate: bad control mask");
+    }
+    const int passes = s->kind == QB_KET ? 1 : 2;
+    // device descriptor tables
+    size_t mat_bytes = sizeof(cplx) * D2 * B, tb_bytes = sizeof(int) * k * B, cm_bytes = sizeof(uint64_t) * B;
+    char* buf = nullptr;
+    size_t off_tb = (mat_bytes + 255) & ~size_t(255), off_cm = (off_tb + tb_bytes + 255) & ~size_t(255),
+           off_en = (off_cm + cm_bytes + 255) & ~size_t(255), tot = off_en + B + 256;
+    QB_CUDA(cudaMalloc((void**)&buf, tot));
+    std::vector<cplx> hm((const cplx*)matrices, (const cplx*)matrices + D2 * B);
+    std::vector<int> htb(target_bits, target_bits + (size_t)k * B);
+    std::vector<uint64_t> hcm(B, 0);
+    if (control_masks) hcm.assign(control_masks, control_masks + B);
+    for (int pass = 0; pass < passes; pass++) {
+        if (s->kind == QB_DM && pass == 0) {
+            for (auto& t : htb) t += s->nq;
+            for (auto& c : hcm) c <<= s->nq;
+        } else if (s->kind == QB_DM && pass == 1) {
+            htb.assign(target_bits, target_bits + (size_t)k * B);
+            if (control_masks) hcm.assign(control_masks, control_masks + B); else std::fill(hcm.begin(), hcm.end(), 0);
+            for (auto& v : hm) v.y = -v.y;
+        }
+        QB_CUDA(cudaMemcpyAsync(buf, hm.data(), mat_bytes, cudaMemcpyHostToDevice, s->stream));
+        QB_CUDA(cudaMemcpyAsync(buf + off_tb, htb.data(), tb_bytes, cudaMemcpyHostToDevice, s->stream));
+        QB_CUDA(cudaMemcpyAsync(buf + off_cm, hcm.data(), cm_bytes, cudaMemcpyHostToDevice, s->stream));
+        if (enable) QB_CUDA(cudaMemcpyAsync(buf + off_en, enable, B, cudaMemcpyHostToDevice, s->stream));
+        qb_launch_dense_batched(s->ctx(), k, s->d, s->nbits, B, (const cplx*)buf, (const int*)(buf + off_tb),
+                                (const uint64_t*)(buf + off_cm), enable ? (const uint8_t*)(buf + off_en) : nullptr);
+        QB_CUDA(cudaStreamSynchronize(s->stream));
+        s->stats.bytes_moved += s->bytes() * 2;
+        s->stats.state_passes++;
+    }
+    cudaFree(buf);
+    s->stats.gates_applied += B;
+    QB_API_END
+}
+
+int qb_flush(qb_state* s) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    s->flush();
+    QB_API_END
+}
+
+int qb_sync(qb_state* s) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    s->flush();
+    DevGuard g(s->device);
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    QB_API_END
+}
+
+int qb_set_fusion(qb_state* s, int enabled) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    s->flush();
+    s->fusion = enabled != 0;
+    QB_API_END
+}
+
+// outcome weights ---------------------------------------------------------------------------
+static void run_bins(qb_state* s, const int* bits, int m, std::vector<cplx>& host_out) {
+    const int nb = s->nq;     // binned index: ket -> amplitude index, dm -> diagonal index
+    QB_REQUIRE(m >= 0 && m <= nb, "probs: bad number of target bits");
+    QB_REQUIRE(m <= 26, "probs: too many outcome bits");
+    uint64_t seen = 0;
+    for (int t = 0; t < m; t++) {
+        QB_REQUIRE(bits[t] >= 0 && bits[t] < nb, "probs: bit out of range");
+        QB_REQUIRE(!((seen >> bits[t]) & 1ull), "probs: duplicate bit");
+        seen |= 1ull << bits[t];
+    }
+    s->flush();
+    DevGuard g(s->device);
+    BinArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = s->d;
+    a.mode = s->kind == QB_KET ? 0 : 1;
+    a.nb = nb;
+    a.elem_stride = s->kind == QB_KET ? 1 : ((1ull << s->nq) + 1ull);
+    a.branch_stride = s->per_branch();
+    a.c = std::min(nb, 11);
+    a.nchunks = 1ull << (nb - a.c);
+    a.nfold = 0; a.ml = 0;
+    for (int p = 0; p < a.c; p++) {
+        if ((seen >> p) & 1ull) a.lowt[a.ml++] = p;
+        else a.foldbits[a.nfold++] = p;
+    }
+    BinFinalArgs f;
+    memset(&f, 0, sizeof(f));
+    f.m = m; f.c = a.c; f.nb = nb; f.nchunks = a.nchunks; f.ml = a.ml;
+    for (int t = 0; t < m; t++) {
+        f.tbits[t] = bits[t];
+        f.lowrank[t] = -1;
+        if (bits[t] < a.c) for (int r = 0; r < a.ml; r++) if (a.lowt[r] == bits[t]) f.lowrank[t] = r;
+    }
+    size_t npartial = (size_t)s->nbranch * a.nchunks << a.ml;
+    size_t nout = (size_t)s->nbranch << m;
+    cplx *dpart = nullptr, *dout = nullptr;
+    QB_CUDA(cudaMalloc((void**)&dpart, sizeof(cplx) * npartial));
+    QB_CUDA(cudaMalloc((void**)&dout, sizeof(cplx) * nout));
+    a.partial = dpart; f.partial = dpart; f.out = dout;
+    qb_launch_bins(s->ctx(), a, s->nbranch);
+    qb_launch_bins_final(s->ctx(), f, s->nbranch);
+    host_out.resize(nout);
+    QB_CUDA(cudaMemcpyAsync(host_out.data(), dout, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, s->stream));
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(dpart); cudaFree(dout);
+    s->stats.bytes_moved += (s->kind == QB_KET ? s->bytes() : (sizeof(cplx) * (size_t)s->nbranch << s->nq));
+}
+
+int qb_probs(qb_state* s, const int* bits, int m, double* out) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && out && (bits || m == 0), "NULL argument");
+    std::vector<cplx> h;
+    run_bins(s, bits, m, h);
+    for (size_t i = 0; i < h.size(); i++) out[i] = s->kind == QB_KET ? h[i].x : std::hypot(h[i].x, h[i].y);
+    QB_API_END
+}
+
+int qb_norm2(qb_state* s, double* out) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && out, "NULL argument");
+    std::vector<cplx> h;
+    run_bins(s, nullptr, 0, h);
+    for (size_t i = 0; i < h.size(); i++) out[i] = h[i].x;
+    QB_API_END
+}
+
+int qb_project_renorm(qb_state* s, const int* bits, int m, uint64_t outcome) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && bits, "NULL argument");
+    QB_REQUIRE(s->kind == QB_KET, "project_renorm is defined for kets only");
+    QB_REQUIRE(s->nbranch == 1, "project_renorm: single-branch states only");
+    QB_REQUIRE(m >= 1 && m <= s->nq && outcome < (1ull << m), "project_renorm: bad outcome");
+    std::vector<cplx> h;
+    run_bins(s, bits, m, h);
+    double p = h[outcome].x;
+    QB_REQUIRE(p > 0.0, "project_renorm: outcome has zero probability");
+    uint64_t mask = 0, want = 0;
+    for (int t = 0; t < m; t++) {
+        mask |= 1ull << bits[t];
+        if ((outcome >> (m - 1 - t)) & 1ull) want |= 1ull << bits[t];
+    }
+    DevGuard g(s->device);
+    qb_launch_project(s->ctx(), s->d, s->total(), mask, want, 1.0 / std::sqrt(p));
+    s->stats.bytes_moved += s->bytes() * 2;
+    s->stats.state_passes++;
+    QB_API_END
+}
+
+// density-matrix structure ops ------------------------------------------------------------------
+int qb_ptrace(qb_state* s, const int* keep_bits, int nkeep, qb_state** out) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && out && (keep_bits || nkeep == 0), "NULL argument");
+    QB_REQUIRE(s->kind == QB_DM && s->nbranch == 1, "ptrace needs a single-branch density matrix");
+    QB_REQUIRE(nkeep >= 0 && nkeep <= s->nq, "ptrace: bad keep count");
+    s->flush();
+    DevGuard g(s->device);
+    PtraceArgs a;
+    memset(&a, 0, sizeof(a));
+    uint64_t seen = 0;
+    for (int i = 0; i < nkeep; i++) {
+        QB_REQUIRE(keep_bits[i] >= 0 && keep_bits[i] < s->nq, "ptrace: bit out of range");
+        QB_REQUIRE(!((seen >> keep_bits[i]) & 1ull), "ptrace: duplicate bit");
+        seen |= 1ull << keep_bits[i];
+        a.keepb[i] = keep_bits[i];
+    }
+    a.nq = s->nq; a.nkeep = nkeep; a.ntr = 0;
+    for (int p = 0; p < s->nq; p++) if (!((seen >> p) & 1ull)) a.trb[a.ntr++] = p;
+    qb_state* o = new_state(QB_DM, nkeep, 1, s->device, nullptr, s->owns_stream ? nullptr : (void*)s->stream);
+    o->fusion = s->fusion;
+    a.rho = s->d; a.out = o->d;
+    // order the new handle's stream after ours
+    qb_launch_ptrace(s->ctx(), a);
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    s->stats.bytes_moved += (sizeof(cplx) << (s->nq + nkeep)) + o->bytes();
+    *out = o;
+    QB_API_END
+}
+
+int qb_scatter_product(qb_state* a, qb_state* b, const int* a_bits, const int* b_bits, const double* scale, qb_state** out) {
+    QB_API_BEGIN
+    QB_REQUIRE(a && out && a_bits, "NULL argument");
+    QB_REQUIRE(a->kind == QB_DM && a->nbranch == 1, "scatter_product: A must be a single-branch density matrix");
+    if (b) QB_REQUIRE(b->kind == QB_DM && b->nbranch == 1 && b->device == a->device && b_bits, "scatter_product: bad B");
+    a->flush();
+    if (b) b->flush();
+    DevGuard g(a->device);
+    const int na = a->nq, nb = b ? b->nq : 0, n = na + nb;
+    ScatterArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    uint64_t seen = 0;
+    for (int i = 0; i < na; i++) {
+        QB_REQUIRE(a_bits[i] >= 0 && a_bits[i] < n && !((seen >> a_bits[i]) & 1ull), "scatter_product: bad A position");
+        seen |= 1ull << a_bits[i]; sa.abits[i] = a_bits[i];
+    }
+    for (int i = 0; i < nb; i++) {
+        QB_REQUIRE(b_bits[i] >= 0 && b_bits[i] < n && !((seen >> b_bits[i]) & 1ull), "scatter_product: bad B position");
+        seen |= 1ull << b_bits[i]; sa.bbits[i] = b_bits[i];
+    }
+    qb_state* o = new_state(QB_DM, n, 1, a->device, nullptr, a->owns_stream ? nullptr : (void*)a->stream);
+    o->fusion = a->fusion;
+    sa.a = a->d; sa.b = (b && nb > 0) ? b->d : nullptr; sa.out = o->d; sa.n = n; sa.na = na; sa.nb = nb;
+    cplx extra = C(1, 0);
+    bool has = false;
+    if (b && nb == 0) {   // 1x1 factor
+        cplx h;
+        QB_CUDA(cudaStreamSynchronize(b->stream));
+        QB_CUDA(cudaMemcpy(&h, b->d, sizeof(cplx), cudaMemcpyDeviceToHost));
+        extra = h; has = true;
+    }
+    if (scale) {
+        cplx sc = C(scale[0], scale[1]);
+        extra = has ? C(extra.x * sc.x - extra.y * sc.y, extra.x * sc.y + extra.y * sc.x) : sc;
+        has = true;
+    }
+    sa.has_scale = has ? 1 : 0; sa.scale = extra;
+    if (b) QB_CUDA(cudaStreamSynchronize(b->stream));
+    qb_launch_scatter(a->ctx(), sa);
+    QB_CUDA(cudaStreamSynchronize(a->stream));
+    a->stats.bytes_moved += o->bytes();
+    *out = o;
+    QB_API_END
+}
+
+int qb_mix(qb_state* const* states, const double* probs, int count, qb_state** out) {
+    QB_API_BEGIN
+    QB_REQUIRE(states && probs && out && count >= 1, "bad argument");
+    qb_state* s0 = states[0];
+    QB_REQUIRE(s0, "NULL state");
+    for (int i = 0; i < count; i++) {
+        QB_REQUIRE(states[i] && states[i]->kind == s0->kind && states[i]->nq == s0->nq &&
+                   states[i]->nbranch == s0->nbranch && states[i]->device == s0->device, "mix: states differ in shape");
+        states[i]->flush();
+    }
+    DevGuard g(s0->device);
+    for (int i = 1; i < count; i++) QB_CUDA(cudaStreamSynchronize(states[i]->stream));
+    qb_state* o = new_state(s0->kind, s0->nq, s0->nbranch, s0->device, nullptr, s0->owns_stream ? nullptr : (void*)s0->stream);
+    o->fusion = s0->fusion;
+    for (int first = 0; first < count; first += QB_MIX_MAX) {
+        MixArgs a;
+        memset(&a, 0, sizeof(a));
+        a.count = std::min(QB_MIX_MAX, count - first);
+        for (int i = 0; i < a.count; i++) { a.src[i] = states[first + i]->d; a.p[i] = probs[first + i]; }
+        a.accumulate = first > 0; a.out = o->d; a.total = s0->total();
+        qb_launch_mix(s0->ctx(), a);
+    }
+    QB_CUDA(cudaStreamSynchronize(s0->stream));
+    s0->stats.bytes_moved += s0->bytes() * (count + 1);
+    *out = o;
+    QB_API_END
+}
+
+int qb_mix_branches(qb_state* s, const double* probs, qb_state** out) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && probs && out, "NULL argument");
+    s->flush();
+    DevGuard g(s->device);
+    qb_state* o = new_state(s->kind, s->nq, 1, s->device, nullptr, s->owns_stream ? nullptr : (void*)s->stream);
+    o->fusion = s->fusion;
+    double* dp = nullptr;
+    QB_CUDA(cudaMalloc((void**)&dp, sizeof(double) * s->nbranch));
+    QB_CUDA(cudaMemcpyAsync(dp, probs, sizeof(double) * s->nbranch, cudaMemcpyHostToDevice, s->stream));
+    qb_launch_mix_branches(s->ctx(), s->d, dp, s->nbranch, s->per_branch(), o->d);
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(dp);
+    s->stats.bytes_moved += s->bytes() + o->bytes();
+    *out = o;
+    QB_API_END
+}
+
+int qb_outer(qb_state* ket, int conj, qb_state** out) {
+    QB_API_BEGIN
+    QB_REQUIRE(ket && out, "NULL argument");
+    QB_REQUIRE(ket->kind == QB_KET && ket->nbranch == 1, "outer: needs a single-branch ket");
+    QB_REQUIRE(2 * ket->nq <= 40, "outer: density matrix would be too large");
+    ket->flush();
+    DevGuard g(ket->device);
+    qb_state* o = new_state(QB_DM, ket->nq, 1, ket->device, nullptr, ket->owns_stream ? nullptr : (void*)ket->stream);
+    o->fusion = ket->fusion;
+    qb_launch_outer(ket->ctx(), ket->d, o->d, ket->nq, conj);
+    QB_CUDA(cudaStreamSynchronize(ket->stream));
+    ket->stats.bytes_moved += o->bytes();
+    *out = o;
+    QB_API_END
+}
+
+int qb_broadcast(qb_state* src, qb_state* dst) {
+    QB_API_BEGIN
+    QB_REQUIRE(src && dst, "NULL argument");
+    QB_REQUIRE(src->nbranch == 1 && src->kind == dst->kind && src->nq == dst->nq && src->device == dst->device,
+               "broadcast: shapes differ");
+    src->flush();
+    dst->queue.clear();
+    DevGuard g(src->device);
+    QB_CUDA(cudaStreamSynchronize(src->stream));
+    for (int64_t b = 0; b < dst->nbranch; b++)
+        QB_CUDA(cudaMemcpyAsync(dst->d + (uint64_t)b * dst->per_branch(), src->d, src->bytes(), cudaMemcpyDeviceToDevice, dst->stream));
+    dst->stats.bytes_moved += dst->bytes() * 2;
+    QB_API_END
+}
+
+int qb_get_stats(const qb_state* s, qb_stats* out) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && out, "NULL argument");
+    *out = s->stats;
+    QB_API_END
+}
+
+int qb_reset_stats(qb_state* s) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    memset(&s->stats, 0, sizeof(s->stats));
+    QB_API_END
+}
+
+int qb_timer_start(qb_state* s) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    s->flush();
+    DevGuard g(s->device);
+    if (!s->ev0) { QB_CUDA(cudaEventCreate(&s->ev0)); QB_CUDA(cudaEventCreate(&s->ev1)); }
+    QB_CUDA(cudaEventRecord(s->ev0, s->stream));
+    QB_API_END
+}
+
+int qb_timer_stop(qb_state* s, float* ms) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && ms && s->ev0, "timer not started");
+    s->flush();
+    DevGuard g(s->device);
+    QB_CUDA(cudaEventRecord(s->ev1, s->stream));
+    QB_CUDA(cudaEventSynchronize(s->ev1));
+    QB_CUDA(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    QB_API_END
+}
+
+}  // extern "C"

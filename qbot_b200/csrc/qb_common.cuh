@@ -1,0 +1,175 @@
+// qbot_b200 -- shared definitions for the CUDA state-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+typedef double2 cplx;   // x = re, y = im : one amplitude == one 128-bit word
+
+#define QB_MAX_BITS   48      // index bits of one branch (ket: nq, dm: 2*nq)
+#define QB_MAX_INS    48      // zero-insert positions (targets + controls)
+#define QB_REG_MAXK   5       // dense gates up to 5 target bits run out of registers
+#define QB_BIG_MAXK   14      // larger dense gates use the out-of-place fallback
+#define QB_DIAG_MAXK  12
+
+struct qb_error : public std::runtime_error {
+    int code;
+    qb_error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define QB_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            throw qb_error(e__ == cudaErrorMemoryAllocation ? -3 : -2,                         \
+                           std::string(#call) + ": " + cudaGetErrorString(e__));               \
+    } while (0)
+
+#define QB_REQUIRE(cond, msg)                                                                  \
+    do {                                                                                       \
+        if (!(cond)) throw qb_error(-1, std::string(msg));                                     \
+    } while (0)
+
+__host__ __device__ __forceinline__ uint64_t qb_insert_zero(uint64_t w, int p) {
+    return ((w >> p) << (p + 1)) | (w & ((1ull << p) - 1ull));
+}
+
+__device__ __forceinline__ cplx qb_cmul(cplx a, cplx b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ cplx qb_cfma(cplx a, cplx b, cplx c) {   // a*b + c
+    return make_double2(c.x + a.x * b.x - a.y * b.y, c.y + a.x * b.y + a.y * b.x);
+}
+
+// ---- ket-level gate as queued by the API --------------------------------------------------
+enum QbGateType { QB_G_DENSE = 0, QB_G_DIAG = 1, QB_G_MONO = 2 };
+
+struct QGate {
+    int type;
+    int k;
+    int tb[QB_BIG_MAXK];          // target bits, tb[0] = most significant matrix index bit
+    uint64_t cmask;
+    std::vector<cplx> m;          // DENSE: 4^k row-major | DIAG: 2^k | MONO: 2^k coefficients
+    std::vector<int> src;         // MONO: y[i] = m[i] * x[src[i]]
+    uint64_t tmask() const { uint64_t t = 0; for (int i = 0; i < k; i++) t |= 1ull << tb[i]; return t; }
+};
+
+// ---- kernel argument blocks (passed by value) ------------------------------------------------
+struct DenseArgs {
+    cplx* psi;
+    const cplx* mat;              // device matrix for K >= 3
+    uint64_t nwork;
+    uint64_t cmask;
+    int nins;
+    int ins[QB_MAX_INS];
+    int tb[QB_REG_MAXK];
+    cplx inl[16];                 // inline matrix for K <= 2
+};
+
+struct DiagArgs {
+    cplx* psi;
+    const cplx* diag;             // device diagonal for k >= 3
+    uint64_t nwork;
+    uint64_t cmask;
+    int nins;
+    int ins[QB_MAX_INS];
+    int k;
+    int tb[QB_DIAG_MAXK];
+    cplx inl[4];
+};
+
+struct BigArgs {
+    const cplx* in;
+    cplx* out;
+    const cplx* mat;
+    const uint64_t* offs;
+    uint64_t total;
+    uint64_t cmask;
+    uint64_t tmask;
+    int k;
+    int tb[QB_BIG_MAXK];
+};
+
+struct BinArgs {
+    const cplx* src;
+    cplx* partial;
+    int mode;                     // 0: |psi_i|^2   1: rho_ii
+    int nb;                       // bits of the binned index i
+    uint64_t elem_stride;         // ket 1, dm 2^nq + 1
+    uint64_t branch_stride;       // amplitudes per branch
+    int c;                        // chunk bits
+    uint64_t nchunks;             // per branch
+    int nfold;
+    int foldbits[16];
+    int ml;
+    int lowt[16];                 // low target bit positions, ascending
+};
+
+struct BinFinalArgs {
+    const cplx* partial;
+    cplx* out;                    // [nbranch][2^m]
+    int m;
+    int c;
+    int nb;
+    uint64_t nchunks;
+    int ml;
+    int tbits[QB_MAX_BITS];       // target bits, MSB-first as listed
+    int lowrank[QB_MAX_BITS];     // for target t with bit < c: its rank among low targets, else -1
+};
+
+struct PtraceArgs {
+    const cplx* rho;
+    cplx* out;
+    int nq;
+    int nkeep;
+    int ntr;
+    int keepb[QB_MAX_BITS];       // MSB-first
+    int trb[QB_MAX_BITS];         // ascending
+};
+
+struct ScatterArgs {
+    const cplx* a;
+    const cplx* b;                // may be null
+    cplx* out;
+    int n, na, nb;
+    int abits[QB_MAX_BITS];       // MSB-first positions in the n-bit index
+    int bbits[QB_MAX_BITS];
+    int has_scale;
+    cplx scale;
+};
+
+#define QB_MIX_MAX 16
+struct MixArgs {
+    const cplx* src[QB_MIX_MAX];
+    double p[QB_MIX_MAX];
+    int count;
+    int accumulate;               // 1: out already holds a partial sum
+    cplx* out;
+    uint64_t total;
+};
+
+// launch wrappers implemented in qb_kernels.cu ------------------------------------------------
+struct LaunchCtx {
+    cudaStream_t stream;
+    int sms;
+    uint64_t* launches;
+};
+
+void qb_launch_fill_basis(const LaunchCtx&, cplx* d, uint64_t per_branch, int64_t nbranch, uint64_t index);
+void qb_launch_init_product(const LaunchCtx&, cplx* d, int kind, int nq, int64_t nbranch, const cplx* vecs_dev, int per_branch);
+void qb_launch_dense(const LaunchCtx&, int K, const DenseArgs& a);
+void qb_launch_diag(const LaunchCtx&, const DiagArgs& a);
+void qb_launch_swap(const LaunchCtx&, cplx* d, uint64_t total, int lo, int hi);
+void qb_launch_big(const LaunchCtx&, const BigArgs& a);
+void qb_launch_dense_batched(const LaunchCtx&, int K, cplx* psi, int nbits, int64_t nbranch, const cplx* mats,
+                             const int* tb, const uint64_t* cmasks, const uint8_t* enable);
+void qb_launch_bins(const LaunchCtx&, const BinArgs& a, int64_t nbranch);
+void qb_launch_bins_final(const LaunchCtx&, const BinFinalArgs& a, int64_t nbranch);
+void qb_launch_ptrace(const LaunchCtx&, const PtraceArgs& a);
+void qb_launch_scatter(const LaunchCtx&, const ScatterArgs& a);
+void qb_launch_mix(const LaunchCtx&, const MixArgs& a);
+void qb_launch_mix_branches(const LaunchCtx&, const cplx* src, const double* probs_dev, int64_t nbranch, uint64_t per_branch, cplx* out);
+void qb_launch_outer(const LaunchCtx&, const cplx* ket, cplx* out, int nq, int conj);
+void qb_launch_project(const LaunchCtx&, cplx* psi, uint64_t total, uint64_t mask, uint64_t want, double scale);

@@ -1,0 +1,44 @@
+// qbot_b200 -- state handle layout and the fused-engine entry points.
+#pragma once
+#include "../../include/qbot_b200.h"
+#include "qb_common.cuh"
+
+struct qb_state {
+    int kind = 0;
+    int nq = 0;
+    int nbits = 0;                 // index bits per branch
+    int64_t nbranch = 1;
+    int device = 0;
+    int sms = 148;
+    cplx* d = nullptr;
+    cplx* scratch = nullptr;
+    bool owns = true;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = true;
+    bool fusion = true;
+    std::vector<QGate> queue;
+    qb_stats stats = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // staging ring for small per-gate tables
+    static constexpr size_t STAGE_BYTES = 4u << 20;
+    void* stage = nullptr;
+    size_t stage_off = 0;
+    // fused engine scratch (plan tables on the device)
+    void* plan_dev = nullptr;
+    size_t plan_dev_bytes = 0;
+
+    ~qb_state();
+    uint64_t per_branch() const { return 1ull << nbits; }
+    uint64_t total() const { return (uint64_t)nbranch << nbits; }
+    size_t bytes() const { return (size_t)total() * sizeof(cplx); }
+    LaunchCtx ctx();
+    cplx* get_scratch();
+    cplx* upload_small(const void* host, size_t bytes);
+    void enqueue(QGate&& g);
+    void flush();
+    void run_gate_unfused(const QGate& g);
+};
+
+// fused tile engine (qb_tile.cu)
+bool qb_engine_available();
+void qb_engine_run(qb_state* s, const std::vector<QGate>& gates);

@@ -1,0 +1,507 @@
+// qbot_b200 -- per-operation CUDA kernels for the state path (sm_100a).
+//
+// Every kernel here is HBM-bound strided complex128 work: one amplitude is exactly one
+// 128-bit word, so all loads/stores are 128-bit; work items are enumerated so that a warp's
+// footprint is contiguous (zero-insertion addressing keeps the low index bits in the lane
+// id), grids are sized in multiples of the SM count with 64-bit grid-stride loops.
+// The fused multi-gate tile kernel lives in qb_tile.cu; these are the general-case and
+// structure (trace / scatter / mix / reduce) kernels.
+#include "qb_common.cuh"
+
+static inline int grid_for(const LaunchCtx& c, uint64_t work, int threads, int per_sm = 8) {
+    uint64_t blocks = (work + threads - 1) / threads;
+    uint64_t cap = (uint64_t)c.sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+#define COUNT_LAUNCH(c) do { if ((c).launches) ++*(c).launches; } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// initialisation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fill_basis(cplx* d, uint64_t per_branch, uint64_t total, uint64_t index) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        uint64_t l = i % per_branch;
+        d[i] = make_double2(l == index ? 1.0 : 0.0, 0.0);
+    }
+}
+
+void qb_launch_fill_basis(const LaunchCtx& c, cplx* d, uint64_t per_branch, int64_t nbranch, uint64_t index) {
+    uint64_t total = per_branch * (uint64_t)nbranch;
+    k_fill_basis<<<grid_for(c, total, 256), 256, 0, c.stream>>>(d, per_branch, total, index);
+    COUNT_LAUNCH(c);
+}
+
+// ket: psi[i] = prod_q v_q[bit_q(i)]   dm: rho[r][c] = prod_q D_q[r_q][c_q]   (qubit 0 first,
+// multiplied left to right like the reference's kron chain, density.py:7-24)
+__global__ void __launch_bounds__(256) k_init_product(cplx* d, int kind, int nq, uint64_t per_branch, uint64_t total,
+                                                      const cplx* __restrict__ vecs, int per_branch_vecs) {
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    int per = kind == 0 ? 2 : 4;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        uint64_t b = i / per_branch, l = i % per_branch;
+        const cplx* v = vecs + (per_branch_vecs ? b * (uint64_t)nq * per : 0);
+        cplx acc = make_double2(1.0, 0.0);
+        for (int q = 0; q < nq; q++) {
+            int sel;
+            if (kind == 0) sel = (int)((l >> (nq - 1 - q)) & 1);
+            else sel = (int)((((l >> (2 * nq - 1 - q)) & 1) << 1) | ((l >> (nq - 1 - q)) & 1));
+            cplx f = v[q * per + sel];
+            acc = q == 0 ? f : qb_cmul(acc, f);
+        }
+        d[i] = acc;
+    }
+}
+
+void qb_launch_init_product(const LaunchCtx& c, cplx* d, int kind, int nq, int64_t nbranch, const cplx* vecs_dev, int per_branch) {
+    uint64_t per = 1ull << (kind == 0 ? nq : 2 * nq);
+    uint64_t total = per * (uint64_t)nbranch;
+    k_init_product<<<grid_for(c, total, 256), 256, 0, c.stream>>>(d, kind, nq, per, total, vecs_dev, per_branch);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense k-qubit gate, in place, registers (K <= 5), optional control mask
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ uint64_t sub_offset(int j, const uint64_t (&tbm)[K]) {
+    uint64_t o = 0;
+#pragma unroll
+    for (int b = 0; b < K; b++)
+        if ((j >> (K - 1 - b)) & 1) o |= tbm[b];
+    return o;
+}
+
+template <int K>
+__global__ void __launch_bounds__(K >= 5 ? 128 : 256) k_dense(DenseArgs a) {
+    constexpr int D = 1 << K;
+    __shared__ cplx sm[D * D];
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) sm[i] = (K <= 2) ? a.inl[i] : a.mat[i];
+    __syncthreads();
+    uint64_t tbm[K];
+#pragma unroll
+    for (int b = 0; b < K; b++) tbm[b] = 1ull << a.tb[b];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < a.nwork; w += stride) {
+        uint64_t base = w;
+        for (int i = 0; i < a.nins; i++) base = qb_insert_zero(base, a.ins[i]);
+        base |= a.cmask;
+        cplx x[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) x[j] = a.psi[base | sub_offset<K>(j, tbm)];
+#pragma unroll(K <= 2 ? D : 1)
+        for (int i = 0; i < D; i++) {
+            cplx acc = qb_cmul(sm[i * D], x[0]);
+#pragma unroll
+            for (int j = 1; j < D; j++) acc = qb_cfma(sm[i * D + j], x[j], acc);
+            a.psi[base | sub_offset<K>(i, tbm)] = acc;
+        }
+    }
+}
+
+void qb_launch_dense(const LaunchCtx& c, int K, const DenseArgs& a) {
+    int threads = K >= 5 ? 128 : 256;
+    int grid = grid_for(c, a.nwork, threads);
+    switch (K) {
+        case 1: k_dense<1><<<grid, threads, 0, c.stream>>>(a); break;
+        case 2: k_dense<2><<<grid, threads, 0, c.stream>>>(a); break;
+        case 3: k_dense<3><<<grid, threads, 0, c.stream>>>(a); break;
+        case 4: k_dense<4><<<grid, threads, 0, c.stream>>>(a); break;
+        case 5: k_dense<5><<<grid, threads, 0, c.stream>>>(a); break;
+        default: throw qb_error(-1, "qb_launch_dense: K out of range");
+    }
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagonal gate: psi[idx] *= d[bits(idx)] on the control-satisfying subspace
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_diag(DiagArgs a) {
+    extern __shared__ cplx sd[];
+    int D = 1 << a.k;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sd[i] = (a.k <= 2) ? a.inl[i] : a.diag[i];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < a.nwork; w += stride) {
+        uint64_t idx = w;
+        for (int i = 0; i < a.nins; i++) idx = qb_insert_zero(idx, a.ins[i]);
+        idx |= a.cmask;
+        int j = 0;
+        for (int b = 0; b < a.k; b++) j |= (int)((idx >> a.tb[b]) & 1) << (a.k - 1 - b);
+        a.psi[idx] = qb_cmul(sd[j], a.psi[idx]);
+    }
+}
+
+void qb_launch_diag(const LaunchCtx& c, const DiagArgs& a) {
+    size_t smem = sizeof(cplx) << a.k;
+    k_diag<<<grid_for(c, a.nwork, 256), 256, smem, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// qubit transposition: exchange amplitudes whose bits (lo, hi) are (1,0) <-> (0,1)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_swap(cplx* d, uint64_t nwork, int lo, int hi) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += stride) {
+        uint64_t base = qb_insert_zero(qb_insert_zero(w, lo), hi);
+        uint64_t i1 = base | (1ull << lo), i2 = base | (1ull << hi);
+        cplx t = d[i1];
+        d[i1] = d[i2];
+        d[i2] = t;
+    }
+}
+
+void qb_launch_swap(const LaunchCtx& c, cplx* d, uint64_t total, int lo, int hi) {
+    uint64_t nwork = total >> 2;
+    k_swap<<<grid_for(c, nwork, 256), 256, 0, c.stream>>>(d, nwork, lo, hi);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// large dense gate (K > 5): out-of-place, one output amplitude per thread
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_big(BigArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int D = 1 << a.k;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < a.total; idx += stride) {
+        if ((idx & a.cmask) != a.cmask) { a.out[idx] = a.in[idx]; continue; }
+        int row = 0;
+        for (int b = 0; b < a.k; b++) row |= (int)((idx >> a.tb[b]) & 1) << (a.k - 1 - b);
+        uint64_t base = idx & ~a.tmask;
+        const cplx* mrow = a.mat + (size_t)row * D;
+        cplx acc = qb_cmul(mrow[0], a.in[base | a.offs[0]]);
+        for (int j = 1; j < D; j++) acc = qb_cfma(mrow[j], a.in[base | a.offs[j]], acc);
+        a.out[idx] = acc;
+    }
+}
+
+void qb_launch_big(const LaunchCtx& c, const BigArgs& a) {
+    k_big<<<grid_for(c, a.total, 256), 256, 0, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched dense gate: branch b applies its own matrix / targets / controls (piece 5)
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(K >= 5 ? 128 : 256)
+k_dense_batched(cplx* psi, int nbits, const cplx* __restrict__ mats, const int* __restrict__ tb,
+                const uint64_t* __restrict__ cmasks, const uint8_t* __restrict__ enable) {
+    constexpr int D = 1 << K;
+    const uint64_t b = blockIdx.y;
+    if (enable && !enable[b]) return;
+    __shared__ cplx sm[D * D];
+    __shared__ int s_ins[QB_MAX_INS];
+    __shared__ int s_nins;
+    for (int i = threadIdx.x; i < D * D; i += blockDim.x) sm[i] = mats[b * (D * D) + i];
+    uint64_t tbm[K];
+    uint64_t tmask = 0;
+#pragma unroll
+    for (int q = 0; q < K; q++) { tbm[q] = 1ull << tb[b * K + q]; tmask |= tbm[q]; }
+    const uint64_t cmask = cmasks ? cmasks[b] : 0ull;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        uint64_t m = tmask | cmask;
+        for (int p = 0; p < nbits; p++) if ((m >> p) & 1) s_ins[n++] = p;
+        s_nins = n;
+    }
+    __syncthreads();
+    const int nins = s_nins;
+    const uint64_t nwork = 1ull << (nbits - nins);
+    cplx* base_ptr = psi + (b << nbits);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += stride) {
+        uint64_t base = w;
+        for (int i = 0; i < nins; i++) base = qb_insert_zero(base, s_ins[i]);
+        base |= cmask;
+        cplx x[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) x[j] = base_ptr[base | sub_offset<K>(j, tbm)];
+#pragma unroll(K <= 2 ? D : 1)
+        for (int i = 0; i < D; i++) {
+            cplx acc = qb_cmul(sm[i * D], x[0]);
+#pragma unroll
+            for (int j = 1; j < D; j++) acc = qb_cfma(sm[i * D + j], x[j], acc);
+            base_ptr[base | sub_offset<K>(i, tbm)] = acc;
+        }
+    }
+}
+
+void qb_launch_dense_batched(const LaunchCtx& c, int K, cplx* psi, int nbits, int64_t nbranch, const cplx* mats,
+                             const int* tb, const uint64_t* cmasks, const uint8_t* enable) {
+    int threads = K >= 5 ? 128 : 256;
+    uint64_t work = 1ull << (nbits - K);
+    uint64_t gx = (work + threads - 1) / threads;
+    uint64_t cap = (uint64_t)c.sms * 8 / (uint64_t)(nbranch < 1 ? 1 : nbranch) + 1;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    QB_REQUIRE(nbranch <= 65535, "batched gate: more than 65535 branches per launch");
+    dim3 grid((unsigned)gx, (unsigned)nbranch);
+    switch (K) {
+        case 1: k_dense_batched<1><<<grid, threads, 0, c.stream>>>(psi, nbits, mats, tb, cmasks, enable); break;
+        case 2: k_dense_batched<2><<<grid, threads, 0, c.stream>>>(psi, nbits, mats, tb, cmasks, enable); break;
+        case 3: k_dense_batched<3><<<grid, threads, 0, c.stream>>>(psi, nbits, mats, tb, cmasks, enable); break;
+        case 4: k_dense_batched<4><<<grid, threads, 0, c.stream>>>(psi, nbits, mats, tb, cmasks, enable); break;
+        case 5: k_dense_batched<5><<<grid, threads, 0, c.stream>>>(psi, nbits, mats, tb, cmasks, enable); break;
+        default: throw qb_error(-1, "batched gate: k must be 1..5");
+    }
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// outcome weights: deterministic two-stage binned reduction (no atomics)
+//   stage 1: one block folds a chunk of 2^c consecutive values over its non-target bits in smem
+//   stage 2: one block per (branch, outcome) sums the matching chunks with a fixed tree
+// ---------------------------------------------------------------------------------------------
+#define BIN_C 11
+__global__ void __launch_bounds__(256) k_bins(BinArgs a) {
+    __shared__ double sre[1 << BIN_C];
+    __shared__ double sim[1 << BIN_C];
+    const uint64_t blk = blockIdx.x;                 // = branch * nchunks + chunk
+    const uint64_t branch = blk / a.nchunks, q = blk % a.nchunks;
+    const int C = 1 << a.c;
+    const cplx* src = a.src + branch * a.branch_stride;
+    for (int l = threadIdx.x; l < C; l += blockDim.x) {
+        uint64_t i = (q << a.c) | (uint64_t)l;
+        cplx v = src[i * a.elem_stride];
+        if (a.mode == 0) { sre[l] = v.x * v.x + v.y * v.y; sim[l] = 0.0; }
+        else { sre[l] = v.x; sim[l] = v.y; }
+    }
+    __syncthreads();
+    unsigned folded = 0;
+    for (int f = 0; f < a.nfold; f++) {
+        unsigned bit = 1u << a.foldbits[f];
+        unsigned dead = folded | bit;
+        for (int l = threadIdx.x; l < C; l += blockDim.x) {
+            if ((l & dead) == 0) { sre[l] += sre[l | bit]; sim[l] += sim[l | bit]; }
+        }
+        folded |= bit;
+        __syncthreads();
+    }
+    const int ML = 1 << a.ml;
+    for (int jl = threadIdx.x; jl < ML; jl += blockDim.x) {
+        unsigned l = 0;
+        for (int r = 0; r < a.ml; r++) l |= ((jl >> r) & 1u) << a.lowt[r];
+        a.partial[blk * ML + jl] = make_double2(sre[l], sim[l]);
+    }
+}
+
+void qb_launch_bins(const LaunchCtx& c, const BinArgs& a, int64_t nbranch) {
+    uint64_t blocks = a.nchunks * (uint64_t)nbranch;
+    QB_REQUIRE(blocks < (1ull << 31), "probs: too many chunks");
+    k_bins<<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}
+
+__global__ void __launch_bounds__(256) k_bins_final(BinFinalArgs a) {
+    __shared__ double sre[256];
+    __shared__ double sim[256];
+    const uint64_t M = 1ull << a.m;
+    const uint64_t branch = blockIdx.x / M, j = blockIdx.x % M;
+    // split outcome j into (low part -> slot inside a chunk's partial, high part -> fixed chunk bits)
+    uint64_t jl = 0, hfix = 0, hmask = 0;
+    for (int t = 0; t < a.m; t++) {
+        uint64_t v = (j >> (a.m - 1 - t)) & 1ull;
+        if (a.tbits[t] < a.c) jl |= v << a.lowrank[t];
+        else { hfix |= v << (a.tbits[t] - a.c); hmask |= 1ull << (a.tbits[t] - a.c); }
+    }
+    const int qbits = a.nb - a.c > 0 ? a.nb - a.c : 0;
+    int nfix = __popcll(hmask);
+    const uint64_t nfree = 1ull << (qbits - nfix);
+    const uint64_t ML = 1ull << a.ml;
+    double re = 0.0, im = 0.0;
+    for (uint64_t r = threadIdx.x; r < nfree; r += blockDim.x) {
+        uint64_t q = r;
+        for (int p = 0; p < qbits; p++) if ((hmask >> p) & 1ull) q = qb_insert_zero(q, p);
+        q |= hfix;
+        cplx v = a.partial[(branch * a.nchunks + q) * ML + jl];
+        re += v.x; im += v.y;
+    }
+    sre[threadIdx.x] = re; sim[threadIdx.x] = im;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sre[threadIdx.x] += sre[threadIdx.x + s]; sim[threadIdx.x] += sim[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.out[blockIdx.x] = make_double2(sre[0], sim[0]);
+}
+
+void qb_launch_bins_final(const LaunchCtx& c, const BinFinalArgs& a, int64_t nbranch) {
+    uint64_t blocks = ((uint64_t)nbranch) << a.m;
+    QB_REQUIRE(blocks < (1ull << 31), "probs: too many outcomes");
+    k_bins_final<<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// partial trace: out[i][j] = sum_t rho[dep(i)|sp(t)][dep(j)|sp(t)]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pt_spread(uint64_t v, const int* pos, int n, bool msb_first) {
+    uint64_t o = 0;
+    for (int x = 0; x < n; x++) {
+        uint64_t bit = msb_first ? (v >> (n - 1 - x)) & 1ull : (v >> x) & 1ull;
+        o |= bit << pos[x];
+    }
+    return o;
+}
+
+// small traced space: one thread per output entry, terms added in ascending t (np.trace order)
+__global__ void __launch_bounds__(256) k_ptrace_seq(PtraceArgs a) {
+    const uint64_t A = 1ull << a.nkeep, total = A * A, T = 1ull << a.ntr;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        uint64_t rb = pt_spread(e >> a.nkeep, a.keepb, a.nkeep, true);
+        uint64_t cb = pt_spread(e & (A - 1), a.keepb, a.nkeep, true);
+        double re = 0.0, im = 0.0;
+        for (uint64_t t = 0; t < T; t++) {
+            uint64_t sp = pt_spread(t, a.trb, a.ntr, false);
+            cplx v = a.rho[((rb | sp) << a.nq) | (cb | sp)];
+            re += v.x; im += v.y;
+        }
+        a.out[e] = make_double2(re, im);
+    }
+}
+
+// large traced space: one block per output entry, fixed-shape tree
+__global__ void __launch_bounds__(256) k_ptrace_blk(PtraceArgs a) {
+    __shared__ double sre[256];
+    __shared__ double sim[256];
+    const uint64_t A = 1ull << a.nkeep, total = A * A, T = 1ull << a.ntr;
+    for (uint64_t e = blockIdx.x; e < total; e += gridDim.x) {
+        uint64_t rb = pt_spread(e >> a.nkeep, a.keepb, a.nkeep, true);
+        uint64_t cb = pt_spread(e & (A - 1), a.keepb, a.nkeep, true);
+        double re = 0.0, im = 0.0;
+        for (uint64_t t = threadIdx.x; t < T; t += blockDim.x) {
+            uint64_t sp = pt_spread(t, a.trb, a.ntr, false);
+            cplx v = a.rho[((rb | sp) << a.nq) | (cb | sp)];
+            re += v.x; im += v.y;
+        }
+        sre[threadIdx.x] = re; sim[threadIdx.x] = im;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) { sre[threadIdx.x] += sre[threadIdx.x + s]; sim[threadIdx.x] += sim[threadIdx.x + s]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) a.out[e] = make_double2(sre[0], sim[0]);
+        __syncthreads();
+    }
+}
+
+void qb_launch_ptrace(const LaunchCtx& c, const PtraceArgs& a) {
+    uint64_t total = 1ull << (2 * a.nkeep);
+    if (a.ntr <= 6) {
+        k_ptrace_seq<<<grid_for(c, total, 256), 256, 0, c.stream>>>(a);
+    } else {
+        uint64_t blocks = total < (uint64_t)c.sms * 16 ? total : (uint64_t)c.sms * 16;
+        k_ptrace_blk<<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+    }
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter product: out[r][c] = A[ga(r)][ga(c)] * B[gb(r)][gb(c)]   (interweave / replace)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t sc_gather(uint64_t v, const int* pos, int n) {
+    uint64_t o = 0;
+    for (int x = 0; x < n; x++) o |= ((v >> pos[x]) & 1ull) << (n - 1 - x);
+    return o;
+}
+
+__global__ void __launch_bounds__(256) k_scatter(ScatterArgs a) {
+    const uint64_t N = 1ull << a.n, total = N * N;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        uint64_t r = e >> a.n, cidx = e & (N - 1);
+        cplx v = a.a[(sc_gather(r, a.abits, a.na) << a.na) | sc_gather(cidx, a.abits, a.na)];
+        if (a.b) v = qb_cmul(v, a.b[(sc_gather(r, a.bbits, a.nb) << a.nb) | sc_gather(cidx, a.bbits, a.nb)]);
+        if (a.has_scale) v = qb_cmul(v, a.scale);
+        a.out[e] = v;
+    }
+}
+
+void qb_launch_scatter(const LaunchCtx& c, const ScatterArgs& a) {
+    uint64_t total = 1ull << (2 * a.n);
+    k_scatter<<<grid_for(c, total, 256), 256, 0, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ensemble mix: out = sum_i p_i * src_i, list order, round-to-nearest mul then add (no FMA),
+// so it is bit-identical to the reference's `result += probs[i] * density` loop
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mix(MixArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.total; e += stride) {
+        double re = 0.0, im = 0.0;
+        if (a.accumulate) { cplx o = a.out[e]; re = o.x; im = o.y; }
+        for (int i = 0; i < a.count; i++) {
+            cplx v = a.src[i][e];
+            re = __dadd_rn(re, __dmul_rn(a.p[i], v.x));
+            im = __dadd_rn(im, __dmul_rn(a.p[i], v.y));
+        }
+        a.out[e] = make_double2(re, im);
+    }
+}
+
+void qb_launch_mix(const LaunchCtx& c, const MixArgs& a) {
+    k_mix<<<grid_for(c, a.total, 256), 256, 0, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}
+
+__global__ void __launch_bounds__(256) k_mix_branches(const cplx* __restrict__ src, const double* __restrict__ p,
+                                                      int64_t nbranch, uint64_t per, cplx* out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += stride) {
+        double re = 0.0, im = 0.0;
+        for (int64_t b = 0; b < nbranch; b++) {
+            cplx v = src[(uint64_t)b * per + e];
+            re = __dadd_rn(re, __dmul_rn(p[b], v.x));
+            im = __dadd_rn(im, __dmul_rn(p[b], v.y));
+        }
+        out[e] = make_double2(re, im);
+    }
+}
+
+void qb_launch_mix_branches(const LaunchCtx& c, const cplx* src, const double* probs_dev, int64_t nbranch, uint64_t per, cplx* out) {
+    k_mix_branches<<<grid_for(c, per, 256), 256, 0, c.stream>>>(src, probs_dev, nbranch, per, out);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// rank-1 density from a ket
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_outer(const cplx* __restrict__ ket, cplx* out, int nq, int conj) {
+    const uint64_t N = 1ull << nq, total = N * N;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        cplx r = ket[e >> nq], cc = ket[e & (N - 1)];
+        if (conj) cc.y = -cc.y;
+        out[e] = qb_cmul(r, cc);
+    }
+}
+
+void qb_launch_outer(const LaunchCtx& c, const cplx* ket, cplx* out, int nq, int conj) {
+    uint64_t total = 1ull << (2 * nq);
+    k_outer<<<grid_for(c, total, 256), 256, 0, c.stream>>>(ket, out, nq, conj);
+    COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ket projection + renormalisation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_project(cplx* psi, uint64_t total, uint64_t mask, uint64_t want, double scale) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        cplx v = psi[i];
+        if ((i & mask) == want) psi[i] = make_double2(v.x * scale, v.y * scale);
+        else psi[i] = make_double2(0.0, 0.0);
+    }
+}
+
+void qb_launch_project(const LaunchCtx& c, cplx* psi, uint64_t total, uint64_t mask, uint64_t want, double scale) {
+    k_project<<<grid_for(c, total, 256), 256, 0, c.stream>>>(psi, total, mask, want, scale);
+    COUNT_LAUNCH(c);
+}

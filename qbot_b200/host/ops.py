@@ -1,0 +1,569 @@
+"""The six state operations of the DSL on the device backend.
+
+Signature and behaviour follow the reference's operator interface
+(``qbot/operators.py:121-130``: ``op(localNameSpace, lines, lineNum, tokens)``; state ops return
+None and rebind ``localNameSpace['state']``):
+
+    qset  operators.py:133-166      gate  operators.py:255-329      swap  operators.py:364-393
+    disc  operators.py:169-188      meas  operators.py:396-425      peek  operators.py:427-428
+
+Validation, argument defaults, error text and ProbVal fan-out order are the reference's; the
+arithmetic below them (full-space unitaries, U rho U^dagger, partial traces, interweave,
+ensemble sums) is replaced by calls into the CUDA library through ``DeviceState``.
+
+The module is written against a *binding* (``Host``) so that the same functions serve
+  * the in-repo mirror interpreter (``qbot_b200.host.interp``), and
+  * a real qbot checkout (``qbot_b200.install()`` re-registers them in ``qbot.operators.operations``).
+"""
+from __future__ import annotations
+
+import sys
+from typing import List, Sequence
+
+import numpy as np
+
+from . import hostmath as hm
+
+
+class Host:
+    """What the ops need from the hosting interpreter."""
+
+    def __init__(self, ProbVal, funcWrapper, evaluateWrapper, err, Basis, state_cls, MeasurementResult=None):
+        self.MeasurementResult = MeasurementResult
+        self.ProbVal = ProbVal
+        self.funcWrapper = funcWrapper
+        self.evaluateWrapper = evaluateWrapper
+        self.err = err
+        self.Basis = Basis
+        self.State = state_cls            # DeviceState (or a test double with the same methods)
+
+
+class MeasurementIndexError(Exception):
+    pass
+
+
+PROB_ROUNDING = 15
+
+
+class MeasurementResult:
+    """Same slots, rounding and text as the reference's MeasurementResult
+    (qbot/measurement.py:10-39)."""
+    __slots__ = ('unMeasuredDensity', 'probs', 'basisDensity', 'basisSymbols', 'newState')
+
+    def __init__(self, unMeasuredDensity, probs, basisDensity, basisSymbols, newState=None):
+        self.unMeasuredDensity = unMeasuredDensity
+        self.probs = probs
+        s = sum(self.probs)
+        for i in range(len(self.probs)):
+            self.probs[i] /= s
+            self.probs[i] = round(self.probs[i], PROB_ROUNDING)
+        self.basisDensity = basisDensity
+        self.basisSymbols = basisSymbols
+        self.newState = newState
+
+    def __repr__(self):
+        return ''.join(f'{self.basisSymbols[i]}- {p} ({p * 100}%)\n' for i, p in enumerate(self.probs))
+
+    def toDensity(self):
+        acc = np.zeros(np.asarray(self.basisDensity[0]).shape, dtype=complex)
+        for p, d in zip(self.probs, self.basisDensity):
+            acc += p * d
+        return acc
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers shared by the ops
+# ---------------------------------------------------------------------------------------------
+def is_state(x) -> bool:
+    return getattr(x, '_qb_device_state', False)
+
+
+def hilbertSpaceNumQubits(state) -> int:
+    if len(state.shape) == 0 or state.size == 0:
+        return 0
+    return int(np.log2(state.shape[0]))
+
+
+def _unaliased(ns, key) -> bool:
+    """True when the namespace holds the only reference to ns[key], so an op may update the
+    device buffer in place instead of cloning it (the reference's ops never mutate the
+    register, they rebind it, so an aliased register must stay untouched)."""
+    return sys.getrefcount(ns[key]) <= 2        # the dict slot + the call argument
+
+
+class GateDesc:
+    """What ``_gate`` returns instead of a 2^n x 2^n unitary: the small matrix and where it
+    acts.  Equality is equality of the full-space unitaries the reference would have built
+    (needed because ProbVal.normalize de-duplicates the branch unitaries, operators.py:308 +
+    probVal.py:37-44): both sides are reduced to a canonical (support, operator) pair."""
+    __slots__ = ('matrix', 'k', 'target', 'controls', '_canon')
+
+    def __init__(self, matrix, target, controls):
+        self.matrix = np.asarray(matrix, dtype=complex)
+        self.k = hm.ilog2(self.matrix.shape[0])
+        self.target = int(target)
+        self.controls = [int(c) for c in controls]
+        self._canon = None
+
+    def canonical(self):
+        if self._canon is None:
+            self._canon = _canonical_operator(self.matrix, self.target, self.controls)
+        return self._canon
+
+    def __eq__(self, other):
+        if not isinstance(other, GateDesc):
+            return False
+        (sa, ma), (sb, mb) = self.canonical(), other.canonical()
+        return sa == sb and ma.shape == mb.shape and bool((ma == mb).all())
+
+    __hash__ = None
+
+
+def _canonical_operator(matrix, target, controls):
+    """Operator on its support qubits (ascending), with qubits it acts trivially on removed."""
+    k = hm.ilog2(matrix.shape[0])
+    qubits = sorted(set(controls)) + list(range(target, target + k))
+    order = sorted(qubits)
+    m = len(order)
+    dim = 1 << m
+    # build the controlled operator on `order` by its action on basis states
+    op = np.zeros((dim, dim), dtype=complex)
+    pos = {q: m - 1 - order.index(q) for q in order}          # qubit -> bit in the local index
+    cmask = 0
+    for c in controls:
+        cmask |= 1 << pos[c]
+    tbits = [pos[target + j] for j in range(k)]
+    tmask = 0
+    for b in tbits:
+        tmask |= 1 << b
+    for col in range(dim):
+        if (col & cmask) != cmask:
+            op[col, col] = 1
+            continue
+        jin = 0
+        for j, b in enumerate(tbits):
+            jin |= ((col >> b) & 1) << (k - 1 - j)
+        rest = col & ~tmask
+        for jout in range(1 << k):
+            v = matrix[jout, jin]
+            if v != 0:
+                row = rest
+                for j, b in enumerate(tbits):
+                    row |= ((jout >> (k - 1 - j)) & 1) << b
+                op[row, col] = v
+    # strip qubits on which the operator is the identity tensor factor
+    support = list(order)
+    i = 0
+    while i < len(support):
+        mm = len(support)
+        t = op.reshape((2,) * (2 * mm))
+        a00 = np.take(np.take(t, 0, axis=i), 0, axis=mm + i - 1)
+        a11 = np.take(np.take(t, 1, axis=i), 1, axis=mm + i - 1)
+        a01 = np.take(np.take(t, 0, axis=i), 1, axis=mm + i - 1)
+        a10 = np.take(np.take(t, 1, axis=i), 0, axis=mm + i - 1)
+        if not a01.any() and not a10.any() and (a00 == a11).all():
+            op = a00.reshape(1 << (mm - 1), 1 << (mm - 1))
+            del support[i]
+        else:
+            i += 1
+    return tuple(support), op
+
+
+class SwapDesc(GateDesc):
+    __slots__ = ('a', 'b')
+
+    def __init__(self, a, b):
+        self.a, self.b = int(a), int(b)
+        self._canon = None
+
+    def canonical(self):
+        if self._canon is None:
+            if self.a == self.b:
+                self._canon = ((), np.ones((1, 1), dtype=complex))
+            else:
+                sw = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
+                self._canon = (tuple(sorted((self.a, self.b))), sw)
+        return self._canon
+
+
+def make_ops(host: Host) -> dict:
+    ProbVal, funcWrapper, evaluateWrapper, err, State = host.ProbVal, host.funcWrapper, host.evaluateWrapper, host.err, host.State
+    Result = host.MeasurementResult or MeasurementResult
+
+    # ---- type plumbing (operators.py:50-116) -------------------------------------------------
+    def assertProbValType(lines, lineNum, pv, t):
+        if isinstance(pv, t):
+            return
+        if isinstance(pv, ProbVal):
+            if not isinstance(pv.instance(), t):
+                err.raiseFormattedError(err.customTypeError(lines, lineNum, [t.__name__, f"ProbVal<{t.__name__}>"], pv.typeString()))
+            return
+        err.raiseFormattedError(err.customTypeError(lines, lineNum, [t.__name__, f"ProbVal<{t.__name__}>"], type(pv).__name__))
+
+    def _containerErr(lines, lineNum, val, requiredType):
+        a = [f'{x}<{str(requiredType)}>' for x in ('list', 'set', 'tuple')]
+        a.append(requiredType)
+        b = [f'ProbVal<{x}>' for x in a]
+        a.extend(b)
+        err.raiseFormattedError(err.customTypeError(lines, lineNum, b, type(val).__name__))
+
+    def ensureContainer(lines, lineNum, val, requiredType=int):
+        if isinstance(val, (list, set, tuple)):
+            for item in val:
+                if not isinstance(item, requiredType):
+                    _containerErr(lines, lineNum, val, requiredType)
+            return val
+        if isinstance(val, ProbVal):
+            for i, item in enumerate(val.values):
+                if isinstance(item, (list, set, tuple)):
+                    for sub in item:
+                        if not isinstance(sub, requiredType):
+                            _containerErr(lines, lineNum, val, requiredType)
+                    continue
+                if not isinstance(item, requiredType):
+                    _containerErr(lines, lineNum, val, requiredType)
+                val.values[i] = [item]
+            return val
+        if not isinstance(val, requiredType):
+            _containerErr(lines, lineNum, val, requiredType)
+        return [val]
+
+    def to_device(val):
+        """ndarray / DeviceState -> DeviceState.  A 2-D array is a density matrix; a 1-D array
+        of 2^n amplitudes becomes a ket-mode register (the reference has no working ket path,
+        SURVEY.md F1 -- this is the new representation); empty values stay as they are."""
+        if is_state(val):
+            return val
+        if val.size == 0 or val.ndim not in (1, 2):
+            return val
+        return State.from_host(val)
+
+    def convertToDensity(lines, lineNum, val):
+        if isinstance(val, ProbVal):
+            try:
+                return val.toDensityMatrix()
+            except Exception:
+                err.raiseFormattedError(err.customTypeError(lines, lineNum, ['np.ndarray', 'ProbVal<np.ndarray>'], val.typeString()))
+        if not isinstance(val, np.ndarray) and not is_state(val):
+            err.raiseFormattedError(err.customTypeError(lines, lineNum, ['np.ndarray', 'ProbVal<np.ndarray>'], type(val).__name__))
+        return val
+
+    def setState(ns, lines, lineNum, value):
+        ns['state'] = to_device(convertToDensity(lines, lineNum, value))
+        ns['__is_q_state'] = True
+        ns['__updated_state'] = True
+
+    def current(ns):
+        """The register as a DeviceState (uploads it if a foreign op left a host array there)."""
+        st = ns['state']
+        if not is_state(st) and isinstance(st, np.ndarray) and st.ndim in (1, 2) and st.size:
+            ns['state'] = State.from_host(st)
+        return ns['state']
+
+    def current_dm(ns):
+        return current(ns).as_density()
+
+    def writable(ns):
+        """A DeviceState the op may update in place: the register itself when nothing else
+        references it, otherwise a device-side copy."""
+        current(ns)
+        own = _unaliased(ns, 'state')
+        st = ns['state']
+        return st if own else st.clone()
+
+    # ---- gate (operators.py:255-329) ------------------------------------------------------------
+    def _gate(lines, lineNum, numQubits, controls, firstTarget, gate):
+        gateSize = hilbertSpaceNumQubits(gate)
+        lastTarget = firstTarget + gateSize - 1
+        if firstTarget < 0 or lastTarget > numQubits - 1:
+            err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', firstTarget, numQubits - gateSize))
+        for control in controls:
+            if control < 0 or control > numQubits - 1:
+                err.raiseFormattedError(err.customIndexError(lines, lineNum, 'control', control, numQubits - 1))
+            if firstTarget <= control <= lastTarget:
+                err.raiseFormattedError(err.customControlTargetOverlapError(lines, lineNum, control, firstTarget, lastTarget))
+        size = hm.ensure_square(np.asarray(gate))
+        if size & (size - 1):
+            raise Exception("gate size must be power of 2")
+        return GateDesc(gate, firstTarget, list(controls))
+
+    def apply_descs(ns, g):
+        """Apply one descriptor in place, or a ProbVal of descriptors as ONE batched launch
+        followed by the weighted branch reduction (piece 5)."""
+        if isinstance(g, ProbVal):
+            base = current(ns)
+            descs: List[GateDesc] = g.values
+            batch = base.broadcast(len(descs))
+            if all(isinstance(d, SwapDesc) for d in descs):
+                sw = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
+                _apply_batched_generic(batch, [(sw, (d.a, d.b), []) if d.a != d.b else None for d in descs])
+            else:
+                _apply_batched_generic(batch, [(d.matrix, tuple(range(d.target, d.target + d.k)), d.controls) for d in descs])
+            return batch.mix_branches(g.probs)
+        st = writable(ns)
+        if isinstance(g, SwapDesc):
+            st.apply_swap(g.a, g.b)
+        elif isinstance(g, GateDesc):
+            st.apply_gate(g.matrix, g.target, g.controls)
+        else:
+            raise Exception("gate is not array or ProbVal")
+        return st
+
+    def _apply_batched_generic(batch, items):
+        """items[b] = (matrix, target qubits, controls) or None (identity)."""
+        ks = {hm.ilog2(np.asarray(it[0]).shape[0]) for it in items if it is not None}
+        if len(ks) == 1 and next(iter(ks)) <= 5:
+            k = next(iter(ks))
+            eye = np.eye(1 << k, dtype=complex)
+            mats = np.stack([np.asarray(it[0], dtype=complex) if it is not None else eye for it in items])
+            qubits = [list(it[1]) if it is not None else list(range(k)) for it in items]
+            controls = [it[2] if it is not None else [] for it in items]
+            enable = [it is not None for it in items]
+            batch.apply_gate_batched_qubits(mats, qubits, controls, enable)
+            return
+        # mixed sizes / non-contiguous targets: per-branch descriptors through the bit-level entry
+        batch.apply_branch_gates(items)
+
+    def gate(ns, lines, lineNum, tokens):
+        numQubits = hilbertSpaceNumQubits(ns['state'])
+        g = evaluateWrapper(lines, lineNum, tokens[1], ns)
+        if len(tokens) < 3:
+            firstTarget = 0
+        else:
+            firstTarget = evaluateWrapper(lines, lineNum, tokens[2], ns)
+            assertProbValType(lines, lineNum, firstTarget, int)
+        if len(tokens) < 4:
+            controls = []
+        else:
+            controls = ensureContainer(lines, lineNum, evaluateWrapper(lines, lineNum, tokens[3], ns))
+        if len(tokens) < 5:
+            cond = True
+        else:
+            cond = evaluateWrapper(lines, lineNum, tokens[4], ns)
+            assertProbValType(lines, lineNum, cond, bool)
+        if not isinstance(cond, ProbVal) and not cond:
+            return
+        try:
+            desc = funcWrapper(_gate, lines, lineNum, numQubits, controls, firstTarget, g)
+        except Exception as e:
+            err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+        if not isinstance(desc, (ProbVal, GateDesc)):
+            raise Exception("gate is not array or ProbVal")
+        if isinstance(cond, ProbVal):
+            before = current(ns).clone()
+            val = apply_descs(ns, desc)
+            pair = [val, before] if cond.values[0] else [before, val]
+            val = State.mix(cond.probs, pair)
+        else:
+            val = apply_descs(ns, desc)
+        setState(ns, lines, lineNum, val)
+
+    # ---- swap (operators.py:364-393) -------------------------------------------------------------
+    def _swap(lines, lineNum, numQubits, qubitA, qubitB):
+        if qubitA < 0 or qubitA >= numQubits:
+            err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', qubitA, numQubits - 1))
+        if qubitB < 0 or qubitB >= numQubits:
+            err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', qubitB, numQubits - 1))
+        return SwapDesc(qubitA, qubitB)
+
+    def swap(ns, lines, lineNum, tokens):
+        numQubits = hilbertSpaceNumQubits(ns['state'])
+        a = evaluateWrapper(lines, lineNum, tokens[1], ns)
+        b = evaluateWrapper(lines, lineNum, tokens[2], ns)
+        assertProbValType(lines, lineNum, a, int)
+        assertProbValType(lines, lineNum, b, int)
+        try:
+            desc = funcWrapper(_swap, lines, lineNum, numQubits, a, b)
+        except Exception as e:
+            err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+        setState(ns, lines, lineNum, apply_descs(ns, desc))
+
+    # ---- qset (operators.py:133-166) / density.replaceArbitrary (density.py:195-227) -----------
+    def replace_arbitrary(st, new_dm, targets):
+        """Trace `targets` out of st and put new_dm's qubits there (ascending target order)."""
+        n = st.nq
+        k = hilbertSpaceNumQubits(new_dm)
+        if len(targets) != k:
+            raise ValueError(f'number of target qubits {len(targets)} does not equal number of provided qubits {k}')
+        tset = sorted(set(int(t) for t in targets))
+        if tset[0] < 0 or tset[-1] > n - 1:
+            raise IndexError()
+        rest = [q for q in range(n) if q not in tset]
+        new_dev = to_device(new_dm)
+        b = st.ptrace_keep(rest)                  # (for n == k this is the 1x1 [[tr rho]] factor)
+        return State.scatter_product(new_dev, b, tset, rest)
+
+    def _qset(val, ns, lines, lineNum, numQubits, targets):
+        for target in targets:
+            if target < 0 or target > numQubits - 1:
+                err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', target, numQubits - 1))
+        try:
+            return replace_arbitrary(current_dm(ns), val, list(targets))
+        except ValueError as e:
+            err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+
+    def qset(ns, lines, lineNum, tokens):
+        numQubits = hilbertSpaceNumQubits(ns['state'])
+        x = evaluateWrapper(lines, lineNum, tokens[1], ns)
+        val = convertToDensity(lines, lineNum, x)
+        if len(tokens) == 2:
+            if is_state(val) and val is ns.get('state'):
+                val = val.clone()
+            setState(ns, lines, lineNum, val)
+            return
+        targets = ensureContainer(lines, lineNum, evaluateWrapper(lines, lineNum, tokens[2], ns))
+        if isinstance(targets, ProbVal):
+            dens = funcWrapper(_qset, val, ns, lines, lineNum, numQubits, targets)
+            if isinstance(dens, ProbVal):
+                dens = dens.toDensityMatrix()
+            setState(ns, lines, lineNum, dens)
+            return
+        setState(ns, lines, lineNum, _qset(val, ns, lines, lineNum, numQubits, targets))
+
+    # ---- disc (operators.py:169-188) / density.partialTraceArbitrary (density.py:122-148) ------
+    def _disc(ns, lines, lineNum, numQubits, targets):
+        for target in targets:
+            if target < 0 or target > numQubits - 1:
+                err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', target, numQubits - 1))
+        st = current_dm(ns)
+        drop = set(int(t) for t in targets)
+        return st.ptrace_keep([q for q in range(st.nq) if q not in drop])
+
+    def disc(ns, lines, lineNum, tokens):
+        numQubits = hilbertSpaceNumQubits(ns['state'])
+        targets = ensureContainer(lines, lineNum, evaluateWrapper(lines, lineNum, tokens[1], ns))
+        if isinstance(targets, ProbVal):
+            val = funcWrapper(_disc, ns, lines, lineNum, numQubits, targets)
+        else:
+            val = _disc(ns, lines, lineNum, numQubits, targets)
+        setState(ns, lines, lineNum, convertToDensity(lines, lineNum, val))
+
+    # ---- meas / peek (operators.py:396-428; measurement.py:107-165) ---------------------------
+    HOST_MEAS_QUBITS = 7       # rho_A up to 128x128 is handled with the reference's host arithmetic
+
+    def measure(st, basis, toMeasure=None, returnState=True):
+        numQubits = st.nq
+        if toMeasure is None:
+            numTargets = numQubits
+        else:
+            toMeasure = list(toMeasure) if isinstance(toMeasure, set) else list(set(toMeasure))
+            for target in toMeasure:
+                if target < 0 or target > numQubits - 1:
+                    raise MeasurementIndexError(f"measurement target {target} outside of valid range [{0}, {numQubits - 1}]",
+                                                target, 0, numQubits - 1)
+            numTargets = len(toMeasure)
+        basisQubitSize = hm.ilog2(hm.ensure_square(basis.density[0]))
+        if numTargets == 0:
+            raise ValueError("measurement must have targets")
+        if numTargets % basisQubitSize != 0:
+            raise ValueError(f"number of qubits to measure {numTargets} must be divisable by the number of qubits in the basis states {basisQubitSize}")
+        full = toMeasure is None or len(toMeasure) == numQubits
+        targets_sorted = list(range(numQubits)) if full else sorted(toMeasure)
+        rest = [q for q in range(numQubits) if q not in targets_sorted]
+        sysA_dev = st if full else st.ptrace_keep(targets_sorted)
+        sysB_dev = None if full else st.ptrace_keep(rest)
+        numTensProd = numTargets // basisQubitSize
+        nOutcomes = len(basis.density) ** numTensProd
+
+        if numTargets <= HOST_MEAS_QUBITS:
+            # small rho_A: the outcome loop of the reference, on the host copy of rho_A
+            sysA = np.asarray(sysA_dev)
+            probs, basisStates, basisSymbols = [], [], []
+            s = 0
+            for i in range(nOutcomes):
+                proj, sym = hm.permute_basis(numTensProd, i, basis)
+                probs.append(abs(np.trace(np.matmul(sysA, proj))))
+                basisStates.append(proj)
+                basisSymbols.append(sym)
+                s += probs[-1]
+            for i in range(len(probs)):
+                probs[i] /= s
+            measured = None
+            if returnState:
+                acc = np.zeros(basisStates[0].shape, dtype=complex)
+                for p, d in zip(probs, basisStates):
+                    acc += p * d
+                measured = State.from_host(acc)
+            unmeasured = sysA
+        else:
+            if basis.numQubits != 1 or not _is_computational(basis):
+                raise NotImplementedError(f"measuring {numTargets} qubits at once is only supported in the computational basis")
+            w = sysA_dev.probs(list(range(numTargets)))
+            s = 0
+            probs = []
+            for x in w:
+                probs.append(float(x))
+                s += probs[-1]
+            probs = [p / s for p in probs]
+            basisStates = _LazyProjectors(numTensProd, basis)
+            basisSymbols = _LazySymbols(numTensProd, basis)
+            measured = State.from_host(np.diag(np.array(probs, dtype=complex))) if returnState else None
+            unmeasured = sysA_dev
+
+        newState = None
+        if returnState:
+            if full:
+                newState = measured
+            else:
+                newState = State.scatter_product(measured, sysB_dev, targets_sorted, rest)
+        return Result(unmeasured, probs, basisStates, basisSymbols, newState)
+
+    def meas(ns, lines, lineNum, tokens, changeState=True):
+        varName = tokens[1]
+        if not varName.isidentifier():
+            err.raiseFormattedError(err.customInvalidVariableName(lines, lineNum, varName))
+        measBasis = evaluateWrapper(lines, lineNum, tokens[2], ns)
+        if not isinstance(measBasis, host.Basis):
+            err.raiseFormattedError(err.customTypeError(lines, lineNum, ['Basis'], type(measBasis).__name__))
+        try:
+            st = current_dm(ns)
+            if len(tokens) < 4:
+                result = measure(st, measBasis, None, changeState)
+            else:
+                targets = ensureContainer(lines, lineNum, evaluateWrapper(lines, lineNum, tokens[3], ns))
+                if isinstance(targets, ProbVal):
+                    # the reference crashes here (MeasurementResult.fromProbVal)
+                    raise AttributeError("type object 'ProbVal' has no attribute 'probs'")
+                result = measure(st, measBasis, targets, changeState)
+        except MeasurementIndexError as e:
+            err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', e.args[1], e.args[3]))
+        except Exception as e:
+            err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+        ns[varName] = result
+        if changeState:
+            setState(ns, lines, lineNum, result.newState)
+
+    def peek(ns, lines, lineNum, tokens):
+        return meas(ns, lines, lineNum, tokens, changeState=False)
+
+    return dict(qset=qset, gate=gate, disc=disc, swap=swap, meas=meas, peek=peek,
+                # exposed for direct (non-DSL) use and for tests
+                measure=measure, replace_arbitrary=replace_arbitrary, convertToDensity=convertToDensity,
+                ensureContainer=ensureContainer, assertProbValType=assertProbValType, to_device=to_device)
+
+
+def _is_computational(basis) -> bool:
+    k = basis.kets
+    return len(k) == 2 and k[0].shape == (2,) and k[0][0] == 1 and k[0][1] == 0 and k[1][0] == 0 and k[1][1] == 1
+
+
+class _LazyProjectors:
+    """basisDensity for many outcomes: projector i is built when asked for."""
+
+    def __init__(self, factors, basis):
+        self.factors, self.basis = factors, basis
+
+    def __len__(self):
+        return len(self.basis.density) ** self.factors
+
+    def __getitem__(self, i):
+        if i < 0 or i >= len(self):
+            raise IndexError(i)
+        return hm.permute_basis(self.factors, i, self.basis)[0]
+
+
+class _LazySymbols(_LazyProjectors):
+    def __getitem__(self, i):
+        if i < 0 or i >= len(self):
+            raise IndexError(i)
+        return hm.permute_basis(self.factors, i, self.basis)[1]

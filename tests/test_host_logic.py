@@ -1,0 +1,113 @@
+"""Host logic (interpreter mirror, ops, ProbVal) against programs run through the REAL
+reference (tests/golden/scripts.json), with the numpy test double standing in for the device.
+CPU only; the same programs run against the CUDA backend in test_gpu_scripts.py."""
+import io
+import json
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+import qbot_b200
+from qbot_b200.host.probval import ProbVal, funcWrapper
+from qbot_b200.host import hostmath as hm
+from qbot_b200.host.ops import GateDesc, SwapDesc
+from fake_backend import FakeState
+from conftest import close
+
+
+def run_script(text, state_cls):
+    buf = io.StringIO()
+    exited = False
+    ns = {}
+    try:
+        with redirect_stdout(buf):
+            ns = qbot_b200.executeTxt(text, state_cls=state_cls)
+    except SystemExit:
+        exited = True
+    return ns, buf.getvalue(), exited
+
+
+def check_script(rec, arrays, state_cls, rtol=1e-12):
+    ns, out, exited = run_script(rec['text'], state_cls)
+    assert exited == rec['exited'], rec['name']
+    assert out == rec['stdout'], rec['name']
+    if 'state' in rec:
+        assert close(np.asarray(ns['state']), arrays[rec['state']], rtol), rec['name']
+    for name, exp in rec['vars'].items():
+        got = ns[name]
+        if exp['type'] == 'meas':
+            assert got.probs == exp['probs'], (rec['name'], got.probs)
+            assert list(got.basisSymbols) == exp['symbols']
+            assert close(np.asarray(got.unMeasuredDensity), arrays[f"{rec['state']}_{name}_un"], rtol)
+        elif exp['type'] == 'array':
+            assert close(np.asarray(got), arrays[exp['key']], rtol)
+        elif exp['type'] == 'py':
+            assert json.loads(json.dumps(got, default=str)) == exp['value'], rec['name']
+
+
+def test_all_golden_scripts(golden):
+    assert len(golden.scripts) >= 60
+    for rec in golden.scripts:
+        check_script(rec, golden.scripts_arr, FakeState)
+
+
+def test_probval_rules(golden):
+    for c in golden.probval:
+        if c['kind'] == 'normalize':
+            vals = [tuple(v) for v in c['values']] if c['tuple_values'] else c['values']
+            pv = ProbVal(c['probs'], vals)
+            assert pv.probs == c['out_probs']
+            assert [list(v) if isinstance(v, tuple) else v for v in pv.values] == c['out_values']
+        elif c['kind'] == 'nested':
+            pv = ProbVal([.25, .75], [ProbVal([.5, .5], [10, 20]), 30])
+            assert pv.probs == c['out_probs'] and pv.values == c['out_values']
+        elif c['kind'] == 'unwrap':
+            assert ProbVal.fromUnzipped([.5, .5], [7, 7]) == c['result']
+    a = ProbVal([.5, .5], [0, 1])
+    b = ProbVal([.2, .3, .5], [10, 20, 30])
+    by_kind = {(c['kind'], c.get('expr')): c for c in golden.probval}
+    r = funcWrapper(lambda x, c, y: (x, c, y), a, 'k', b)
+    assert [list(v) for v in r.values] == by_kind[('fanout', None)]['out_values'] and r.probs == by_kind[('fanout', None)]['out_probs']
+    r2 = funcWrapper(lambda x, y: x + y, a, b)
+    assert r2.values == by_kind[('fanout_sum', None)]['out_values'] and r2.probs == by_kind[('fanout_sum', None)]['out_probs']
+    for expr, val in (('a*2+1', a * 2 + 1), ('a+b', a + b), ('a==0', a == 0), ('-b', -b), ('a-b', a - b), ('3-a', 3 - a)):
+        exp = by_kind.get(('arith', expr))
+        if exp is not None:
+            assert val.probs == exp['out_probs'] and val.values == exp['out_values'], expr
+
+
+def test_gate_descriptor_equality_matches_full_unitaries():
+    """GateDesc.__eq__ must agree with elementwise equality of the unitaries the reference
+    would have built (it is what ProbVal.normalize de-duplicates on)."""
+    from oracle import qbot_oracle as orc
+    H = hm.tensor_prod(np.eye(2), np.array([[1, 1], [1, -1]]) / np.sqrt(2))
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    Z = np.diag([1, -1]).astype(complex)
+    I = np.eye(2, dtype=complex)
+    n = 4
+    descs = [GateDesc(X, 1, []), GateDesc(np.kron(I, X), 0, []), GateDesc(np.kron(X, I), 1, []), GateDesc(X, 1, [0]),
+             GateDesc(X, 1, [0, 3]), GateDesc(X, 1, [3, 0]), GateDesc(Z, 1, [2]), GateDesc(Z, 2, [1]), GateDesc(I, 0, [1]),
+             GateDesc(np.eye(4), 2, []), GateDesc(X, 2, []), GateDesc(np.kron(I, np.kron(X, I)), 0, [])]
+    full = [orc.controlled_unitary(n, d.controls, d.target, d.matrix) for d in descs]
+    for i, a in enumerate(descs):
+        for j, b in enumerate(descs):
+            assert (a == b) == bool((full[i] == full[j]).all()), (i, j)
+    assert SwapDesc(1, 2) == SwapDesc(2, 1) and SwapDesc(0, 0) == SwapDesc(3, 3) and not (SwapDesc(0, 1) == SwapDesc(0, 2))
+
+
+def test_inplace_only_when_unaliased():
+    # `cdef old ; state` aliases the register: the next gate must not change `old`
+    ns, _, _ = run_script("qset comp[0]\ncdef old ; state\ngate pauliXGate ; 0\n", FakeState)
+    assert np.asarray(ns['old'])[0, 0] == 1 and np.asarray(ns['state'])[1, 1] == 1
+    ns, _, _ = run_script("qset tensorExp(comp[0], 2)\nmeas x ; comp ; 0\ngate pauliXGate ; 1\n", FakeState)
+    assert np.asarray(ns['x'].newState)[0, 0] == 1 and np.asarray(ns['state'])[1, 1] == 1
+
+
+def test_ket_register_new_representation():
+    # a 1-D qset starts a ket-mode register (the reference has no working ket path)
+    ns, _, _ = run_script("qset np_array([1, 0, 0, 0]) * (1+0j)\ngate hadamardGate ; 0\ngate pauliXGate ; 1 ; [0]\n", FakeState)
+    psi = np.asarray(ns['state'])
+    assert psi.shape == (4,) and close(psi, np.array([1, 0, 0, 1]) / np.sqrt(2))
+    ns, _, _ = run_script("qset np_array([1, 0, 0, 0]) * (1+0j)\ngate hadamardGate ; 0\ngate pauliXGate ; 1 ; [0]\nmeas x ; bell\n", FakeState)
+    assert ns['x'].probs == [1.0, 0.0, 0.0, 0.0]
