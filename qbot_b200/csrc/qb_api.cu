@@ -19,6 +19,7 @@ static thread_local std::string g_err;
     catch (...) { g_err = "unknown error"; return QB_ERR_ARG; }
 
 static inline cplx C(double re, double im) { return make_double2(re, im); }
+#include "qb_plan.h"
 
 // ---------------------------------------------------------------------------------------------
 // state
@@ -36,6 +37,7 @@ static int sm_count_of(int dev) {
 }
 
 qb_state::~qb_state() {
+    qb_engine_free(this);
     if (d && owns) cudaFree(d);
     if (scratch) cudaFree(scratch);
     if (ev0) cudaEventDestroy(ev0);
@@ -73,60 +75,6 @@ cplx* qb_state::get_scratch() {
 // ---------------------------------------------------------------------------------------------
 // gate classification + queue
 // ---------------------------------------------------------------------------------------------
-static QGate classify(const cplx* m, int k, const int* tb, uint64_t cmask) {
-    QGate g;
-    g.k = k; g.cmask = cmask;
-    for (int i = 0; i < k; i++) g.tb[i] = tb[i];
-    const int D = 1 << k;
-    bool diag = true, mono = true;
-    std::vector<int> src(D, -1);
-    std::vector<int> colcnt(D, 0);
-    for (int i = 0; i < D; i++) {
-        int nz = 0;
-        for (int j = 0; j < D; j++) {
-            const cplx v = m[i * D + j];
-            if (v.x != 0.0 || v.y != 0.0) {
-                nz++;
-                src[i] = j;
-                colcnt[j]++;
-                if (i != j) diag = false;
-            }
-        }
-        if (nz != 1) mono = false;
-    }
-    for (int j = 0; j < D && mono; j++) if (colcnt[j] != 1) mono = false;
-    // a zero on the diagonal of a "diagonal" matrix is still diagonal; nz==0 rows are handled by DENSE
-    if (diag) {
-        g.type = QB_G_DIAG;
-        g.m.resize(D);
-        for (int i = 0; i < D; i++) g.m[i] = m[i * D + i];
-    } else if (mono) {
-        g.type = QB_G_MONO;
-        g.m.resize(D);
-        g.src = src;
-        for (int i = 0; i < D; i++) g.m[i] = m[i * D + src[i]];
-    } else {
-        g.type = QB_G_DENSE;
-        g.m.assign(m, m + (size_t)D * D);
-    }
-    return g;
-}
-
-static bool is_identity(const QGate& g) {
-    if (g.type != QB_G_DIAG) return false;
-    for (const cplx& v : g.m) if (v.x != 1.0 || v.y != 0.0) return false;
-    return true;
-}
-
-static std::vector<cplx> dense_of(const QGate& g) {
-    const int D = 1 << g.k;
-    if (g.type == QB_G_DENSE) return g.m;
-    std::vector<cplx> m((size_t)D * D, C(0, 0));
-    if (g.type == QB_G_DIAG) for (int i = 0; i < D; i++) m[i * D + i] = g.m[i];
-    else for (int i = 0; i < D; i++) m[i * D + g.src[i]] = g.m[i];
-    return m;
-}
-
 static void fill_ins(uint64_t mask, int nbits_total, int* ins, int& nins) {
     nins = 0;
     for (int p = 0; p < nbits_total; p++) if ((mask >> p) & 1ull) ins[nins++] = p;
@@ -166,7 +114,7 @@ void qb_state::run_gate_unfused(const QGate& g) {
         qb_launch_diag(c, a);
         stats.bytes_moved += touched * 32;
     } else if (K <= QB_REG_MAXK) {
-        std::vector<cplx> m = dense_of(g);
+        std::vector<cplx> m = qb_dense_of(g);
         DenseArgs a;
         memset(&a, 0, sizeof(a));
         a.psi = d; a.cmask = g.cmask;
@@ -179,7 +127,7 @@ void qb_state::run_gate_unfused(const QGate& g) {
         stats.bytes_moved += touched * 32;
     } else {
         QB_REQUIRE(K <= QB_BIG_MAXK, "gate acts on too many qubits");
-        std::vector<cplx> m = dense_of(g);
+        std::vector<cplx> m = qb_dense_of(g);
         const int D = 1 << K;
         std::vector<uint64_t> offs(D);
         for (int j = 0; j < D; j++) {
@@ -210,7 +158,7 @@ void qb_state::run_gate_unfused(const QGate& g) {
 }
 
 void qb_state::enqueue(QGate&& g) {
-    if (is_identity(g)) return;
+    if (qb_is_identity(g)) return;
     queue.push_back(std::move(g));
     if (!fusion || queue.size() >= 4096) flush();
 }
@@ -405,16 +353,16 @@ int qb_apply_gate(qb_state* s, const double* matrix, int k, const int* target_bi
     QB_REQUIRE(s->nq >= 64 || (control_mask >> s->nq) == 0, "control bit out of range");
     QB_REQUIRE((tmask & control_mask) == 0, "control overlaps target");
     if (s->kind == QB_KET) {
-        s->enqueue(classify(m, k, target_bits, control_mask));
+        s->enqueue(qb_classify(m, k, target_bits, control_mask));
     } else {
         // rho <- U rho U^dagger on vec(rho): U on the row bits, conj(U) on the column bits
         int tb_row[QB_BIG_MAXK];
         for (int i = 0; i < k; i++) tb_row[i] = target_bits[i] + s->nq;
-        s->enqueue(classify(m, k, tb_row, control_mask << s->nq));
+        s->enqueue(qb_classify(m, k, tb_row, control_mask << s->nq));
         const size_t D2 = (size_t)1 << (2 * k);
         std::vector<cplx> mc(D2);
         for (size_t i = 0; i < D2; i++) mc[i] = C(m[i].x, -m[i].y);
-        s->enqueue(classify(mc.data(), k, target_bits, control_mask));
+        s->enqueue(qb_classify(mc.data(), k, target_bits, control_mask));
     }
     QB_API_END
 }

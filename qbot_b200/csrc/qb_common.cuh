@@ -6,12 +6,11 @@
 #include <vector>
 #include <stdexcept>
 
-typedef double2 cplx;   // x = re, y = im : one amplitude == one 128-bit word
+#include "qb_gate.h"
 
 #define QB_MAX_BITS   48      // index bits of one branch (ket: nq, dm: 2*nq)
 #define QB_MAX_INS    48      // zero-insert positions (targets + controls)
 #define QB_REG_MAXK   5       // dense gates up to 5 target bits run out of registers
-#define QB_BIG_MAXK   14      // larger dense gates use the out-of-place fallback
 #define QB_DIAG_MAXK  12
 
 struct qb_error : public std::runtime_error {
@@ -42,19 +41,6 @@ __device__ __forceinline__ cplx qb_cmul(cplx a, cplx b) {
 __device__ __forceinline__ cplx qb_cfma(cplx a, cplx b, cplx c) {   // a*b + c
     return make_double2(c.x + a.x * b.x - a.y * b.y, c.y + a.x * b.y + a.y * b.x);
 }
-
-// ---- ket-level gate as queued by the API --------------------------------------------------
-enum QbGateType { QB_G_DENSE = 0, QB_G_DIAG = 1, QB_G_MONO = 2 };
-
-struct QGate {
-    int type;
-    int k;
-    int tb[QB_BIG_MAXK];          // target bits, tb[0] = most significant matrix index bit
-    uint64_t cmask;
-    std::vector<cplx> m;          // DENSE: 4^k row-major | DIAG: 2^k | MONO: 2^k coefficients
-    std::vector<int> src;         // MONO: y[i] = m[i] * x[src[i]]
-    uint64_t tmask() const { uint64_t t = 0; for (int i = 0; i < k; i++) t |= 1ull << tb[i]; return t; }
-};
 
 // ---- kernel argument blocks (passed by value) ------------------------------------------------
 struct DenseArgs {

@@ -23,9 +23,8 @@ struct qb_state {
     static constexpr size_t STAGE_BYTES = 4u << 20;
     void* stage = nullptr;
     size_t stage_off = 0;
-    // fused engine scratch (plan tables on the device)
-    void* plan_dev = nullptr;
-    size_t plan_dev_bytes = 0;
+    // fused engine state (plan cache, device copies of the sweep programs)
+    void* engine = nullptr;
 
     ~qb_state();
     uint64_t per_branch() const { return 1ull << nbits; }
@@ -42,3 +41,4 @@ struct qb_state {
 // fused tile engine (qb_tile.cu)
 bool qb_engine_available();
 void qb_engine_run(qb_state* s, const std::vector<QGate>& gates);
+void qb_engine_free(qb_state* s);

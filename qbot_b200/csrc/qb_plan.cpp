@@ -1,0 +1,493 @@
+// qbot_b200 -- fusion planner: groups the queued gates into sweeps, picks each sweep's tile
+// bits, splits the sweep into register stages and serialises the program the tile kernel runs.
+// Pure host code (compiled into the CUDA library and into the CPU plan emulator of the tests).
+#include "qb_gate.h"
+#include "qb_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+QGate qb_classify(const cplx* m, int k, const int* tb, uint64_t cmask) {
+    QGate g;
+    g.k = k; g.cmask = cmask;
+    for (int i = 0; i < k; i++) g.tb[i] = tb[i];
+    const int D = 1 << k;
+    bool diag = true, mono = true;
+    std::vector<int> src(D, -1), colcnt(D, 0);
+    for (int i = 0; i < D; i++) {
+        int nz = 0;
+        for (int j = 0; j < D; j++) {
+            const cplx v = m[i * D + j];
+            if (v.x != 0.0 || v.y != 0.0) {
+                nz++;
+                src[i] = j;
+                colcnt[j]++;
+                if (i != j) diag = false;
+            }
+        }
+        if (nz != 1) mono = false;
+    }
+    for (int j = 0; j < D && mono; j++) if (colcnt[j] != 1) mono = false;
+    if (diag) {
+        g.type = QB_G_DIAG;
+        g.m.resize(D);
+        for (int i = 0; i < D; i++) g.m[i] = m[i * D + i];
+    } else if (mono) {
+        g.type = QB_G_MONO;
+        g.m.resize(D);
+        g.src = src;
+        for (int i = 0; i < D; i++) g.m[i] = m[i * D + src[i]];
+    } else {
+        g.type = QB_G_DENSE;
+        g.m.assign(m, m + (size_t)D * D);
+    }
+    return g;
+}
+
+bool qb_is_identity(const QGate& g) {
+    if (g.type != QB_G_DIAG) return false;
+    for (const cplx& v : g.m) if (v.x != 1.0 || v.y != 0.0) return false;
+    return true;
+}
+
+std::vector<cplx> qb_dense_of(const QGate& g) {
+    const int D = 1 << g.k;
+    if (g.type == QB_G_DENSE) return g.m;
+    std::vector<cplx> m((size_t)D * D, cplx{0.0, 0.0});
+    if (g.type == QB_G_DIAG) for (int i = 0; i < D; i++) m[i * D + i] = g.m[i];
+    else for (int i = 0; i < D; i++) m[i * D + g.src[i]] = g.m[i];
+    return m;
+}
+
+namespace {
+
+struct GInfo {
+    uint64_t wmask = 0;     // bits the gate acts on non-diagonally ("writes")
+    uint64_t rmask = 0;     // bits it only reads (controls, diagonal targets)
+    bool tileable = false;  // can run inside a fused sweep
+};
+
+GInfo analyse(const QGate& g) {
+    GInfo gi;
+    if (g.type == QB_G_DIAG) {
+        gi.rmask = g.tmask() | g.cmask;
+        gi.tileable = g.k <= 3;
+    } else {
+        gi.wmask = g.tmask();
+        gi.rmask = g.cmask;
+        gi.tileable = g.k <= 2;
+    }
+    return gi;
+}
+
+// One order-preserving pass: which of `rem` (gate indices, circuit order) can run now, given
+// that a gate needs all its write bits inside `allowed` and must not overtake an earlier
+// non-commuting gate that stays behind.
+void select_pass(const std::vector<int>& rem, const std::vector<GInfo>& info, uint64_t allowed,
+                 size_t window, std::vector<int>* picked, int* count) {
+    uint64_t blocked_w = 0, blocked_r = 0;   // bits written / read by a gate left behind
+    int c = 0;
+    size_t n = std::min(rem.size(), window);
+    for (size_t x = 0; x < n; x++) {
+        const GInfo& gi = info[rem[x]];
+        bool ok = gi.tileable && (gi.wmask & ~allowed) == 0 &&
+                  ((gi.wmask | gi.rmask) & blocked_w) == 0 && (gi.wmask & blocked_r) == 0;
+        if (ok) {
+            c++;
+            if (picked) picked->push_back(rem[x]);
+        } else {
+            blocked_w |= gi.wmask;
+            blocked_r |= gi.rmask;
+            if (blocked_w == ~0ull) break;
+        }
+    }
+    if (count) *count = c;
+}
+
+bool is_hadamard_like(const QGate& g, double* s) {
+    if (g.type != QB_G_DENSE || g.k != 1) return false;
+    const cplx* m = g.m.data();
+    if (m[0].y != 0 || m[1].y != 0 || m[2].y != 0 || m[3].y != 0) return false;
+    if (!(m[0].x > 0) || m[1].x != m[0].x || m[2].x != m[0].x || m[3].x != -m[0].x) return false;
+    *s = m[0].x;
+    return true;
+}
+
+bool is_pauli_x(const QGate& g) {
+    return g.type == QB_G_MONO && g.k == 1 && g.src[0] == 1 && g.src[1] == 0 && g.m[0].x == 1 && g.m[0].y == 0 &&
+           g.m[1].x == 1 && g.m[1].y == 0;
+}
+
+std::vector<cplx> dense_matrix(const QGate& g) { return qb_dense_of(g); }
+
+int bank_class(int p) {          // contribution of tile-local bit p to (slot mod 8), see qt_slot
+    if (p < 3) return 1 << p;
+    if (p < QT_L) return 0;
+    return 1 << ((p - QT_L) % 3);
+}
+
+struct StageBuild {
+    QtStage st;
+    std::vector<QtOp> ops;
+    std::vector<uint64_t> op_w;                  // write mask (index bits) of each op, for phase merging
+    std::vector<std::vector<double>> payload;    // pool data of each op (placed at serialisation)
+    void push(const QtOp& op, uint64_t w, const double* v, size_t n) {
+        ops.push_back(op);
+        op_w.push_back(w);
+        payload.emplace_back(v, v + n);
+    }
+};
+
+struct SweepBuild {
+    std::vector<int> hb;                 // free tile bits (index positions), ascending
+    int local_of[64];                    // index bit -> tile-local position, -1 if outside the tile
+    std::vector<StageBuild> stages;
+    int ngates = 0;
+};
+
+// predicate of a gate's controls (and value-controls) split by where each bit lives in this stage
+struct Pred {
+    uint16_t regsel, lmask, lval;
+    uint64_t gmask, gval;
+};
+
+Pred make_pred(const SweepBuild& sw, const QtStage& st, int R, uint64_t ones_mask, uint64_t zeros_mask) {
+    Pred p{0, 0, 0, 0, 0};
+    uint32_t reg_need1 = 0, reg_need0 = 0;
+    for (int b = 0; b < 64; b++) {
+        bool one = (ones_mask >> b) & 1ull, zero = (zeros_mask >> b) & 1ull;
+        if (!one && !zero) continue;
+        int lp = sw.local_of[b];
+        if (lp < 0) {
+            p.gmask |= 1ull << b;
+            if (one) p.gval |= 1ull << b;
+            continue;
+        }
+        int ri = -1;
+        for (int q = 0; q < R; q++) if (st.rb[q] == lp) ri = q;
+        if (ri >= 0) { if (one) reg_need1 |= 1u << ri; else reg_need0 |= 1u << ri; }
+        else { p.lmask |= (uint16_t)(1u << lp); if (one) p.lval |= (uint16_t)(1u << lp); }
+    }
+    for (int i = 0; i < (1 << R); i++)
+        if ((i & reg_need1) == reg_need1 && (i & reg_need0) == 0) p.regsel |= (uint16_t)(1u << i);
+    return p;
+}
+
+int reg_index(const QtStage& st, int R, int lp) {
+    for (int q = 0; q < R; q++) if (st.rb[q] == lp) return q;
+    return -1;
+}
+
+void set_pred(QtOp& op, const Pred& p) {
+    op.regsel = p.regsel; op.lmask = p.lmask; op.lval = p.lval; op.gmask = p.gmask; op.gval = p.gval;
+}
+
+// append one gate to a stage as one or more ops
+void emit_gate(SweepBuild& sw, StageBuild& sb, int R, const QGate& g, bool merge_phases) {
+    QtOp op;
+    memset(&op, 0, sizeof(op));
+    const QtStage& st = sb.st;
+    if (g.type == QB_G_DIAG) {
+        if (g.k == 1 && g.cmask == 0) {
+            // uncontrolled 1-qubit diagonal: entry of a PHASE op (merged backwards when it commutes)
+            const int bit = g.tb[0];
+            const int lp = sw.local_of[bit];
+            int loc, pos;
+            if (lp < 0) { loc = QT_LOC_GLOBAL; pos = bit; }
+            else {
+                int ri = reg_index(st, R, lp);
+                if (ri >= 0) { loc = QT_LOC_REG; pos = ri; } else { loc = QT_LOC_LOCAL; pos = lp; }
+            }
+            double ent[5] = {(double)(loc | (pos << 8)), g.m[0].x, g.m[0].y, g.m[1].x, g.m[1].y};
+            if (merge_phases) {
+                for (int x = (int)sb.ops.size() - 1; x >= 0; x--) {
+                    if (sb.ops[x].type == QT_OP_PHASE && sb.ops[x].nent < 200) {
+                        sb.payload[x].insert(sb.payload[x].end(), ent, ent + 5);
+                        sb.ops[x].nent++;
+                        return;
+                    }
+                    if (sb.op_w[x] & (1ull << bit)) break;       // cannot move before a write of this bit
+                }
+            }
+            op.type = QT_OP_PHASE;
+            op.nent = 1;
+            op.regsel = 0xffff;
+            sb.push(op, 0, ent, 5);
+            return;
+        }
+        // (controlled / multi-qubit) diagonal: one CDIAG per assignment of the leading target bits
+        const int k = g.k;
+        const int last = g.tb[k - 1];
+        for (int v = 0; v < (1 << (k - 1)); v++) {
+            cplx d0 = g.m[2 * v], d1 = g.m[2 * v + 1];
+            if (d0.x == 1 && d0.y == 0 && d1.x == 1 && d1.y == 0) continue;
+            uint64_t ones = g.cmask, zeros = 0;
+            for (int j = 0; j < k - 1; j++) {
+                if ((v >> (k - 2 - j)) & 1) ones |= 1ull << g.tb[j]; else zeros |= 1ull << g.tb[j];
+            }
+            QtOp o;
+            memset(&o, 0, sizeof(o));
+            o.type = QT_OP_CDIAG;
+            set_pred(o, make_pred(sw, st, R, ones, zeros));
+            const int lp = sw.local_of[last];
+            if (lp < 0) { o.t1 = QT_LOC_GLOBAL; o.t0 = (uint8_t)last; }
+            else {
+                int ri = reg_index(st, R, lp);
+                if (ri >= 0) { o.t1 = QT_LOC_REG; o.t0 = (uint8_t)ri; } else { o.t1 = QT_LOC_LOCAL; o.t0 = (uint8_t)lp; }
+            }
+            double d[4] = {d0.x, d0.y, d1.x, d1.y};
+            sb.push(o, 0, d, 4);
+        }
+        return;
+    }
+    set_pred(op, make_pred(sw, st, R, g.cmask, 0));
+    if (g.k == 1) {
+        op.t0 = (uint8_t)reg_index(st, R, sw.local_of[g.tb[0]]);
+        double s;
+        if (is_hadamard_like(g, &s)) { op.type = QT_OP_H; sb.push(op, g.tmask(), &s, 1); }
+        else if (is_pauli_x(g)) { op.type = QT_OP_X; sb.push(op, g.tmask(), nullptr, 0); }
+        else {
+            std::vector<cplx> m = dense_matrix(g);
+            op.type = QT_OP_U2;
+            sb.push(op, g.tmask(), (const double*)m.data(), 8);
+        }
+    } else {
+        std::vector<cplx> m = dense_matrix(g);
+        op.type = QT_OP_U4;
+        op.t0 = (uint8_t)reg_index(st, R, sw.local_of[g.tb[0]]);
+        op.t1 = (uint8_t)reg_index(st, R, sw.local_of[g.tb[1]]);
+        sb.push(op, g.tmask(), (const double*)m.data(), 32);
+    }
+}
+
+void choose_thread_bits(QtStage& st, int R) {
+    bool is_reg[QT_M] = {false};
+    for (int q = 0; q < R; q++) is_reg[st.rb[q]] = true;
+    std::vector<int> freep;
+    for (int p = 0; p < QT_M; p++) if (!is_reg[p]) freep.push_back(p);
+    // the three lowest thread bits select the 16-byte bank group of an LDS.128 phase: give them
+    // tile bits of three different bank classes when available
+    std::vector<int> order;
+    for (int cls : {1, 2, 4}) {
+        for (size_t x = 0; x < freep.size(); x++) {
+            if (bank_class(freep[x]) == cls) { order.push_back(freep[x]); freep.erase(freep.begin() + x); break; }
+        }
+    }
+    for (int p : freep) order.push_back(p);
+    for (int q = 0; q < QT_M - R; q++) st.tpos[q] = (uint8_t)order[q];
+}
+
+std::vector<uint8_t> serialise(const SweepBuild& sw, int R) {
+    QtHeader h;
+    memset(&h, 0, sizeof(h));
+    size_t nops = 0, npool = 0;
+    for (const auto& s : sw.stages) {
+        nops += s.ops.size();
+        for (const auto& pl : s.payload) npool += pl.size();
+    }
+    h.nstages = (uint16_t)sw.stages.size();
+    h.nops = (uint16_t)nops;
+    h.R = (uint16_t)R;
+    h.ngates = (uint16_t)sw.ngates;
+    h.stages_off = (uint32_t)((sizeof(QtHeader) + 15) & ~size_t(15));
+    h.ops_off = (uint32_t)((h.stages_off + sizeof(QtStage) * sw.stages.size() + 15) & ~size_t(15));
+    h.pool_off = (uint32_t)((h.ops_off + sizeof(QtOp) * nops + 15) & ~size_t(15));
+    h.total_bytes = (uint32_t)((h.pool_off + sizeof(double) * npool + 15) & ~size_t(15));
+    for (int i = 0; i < QT_H; i++) h.hb[i] = (uint8_t)sw.hb[i];
+    std::vector<uint8_t> out(h.total_bytes, 0);
+    memcpy(out.data(), &h, sizeof(h));
+    size_t first = 0, pool_at = 0;
+    double* pool = (double*)(out.data() + h.pool_off);
+    for (size_t s = 0; s < sw.stages.size(); s++) {
+        QtStage st = sw.stages[s].st;
+        st.first_op = (uint16_t)first;
+        st.nops = (uint16_t)sw.stages[s].ops.size();
+        memcpy(out.data() + h.stages_off + s * sizeof(QtStage), &st, sizeof(st));
+        for (size_t x = 0; x < sw.stages[s].ops.size(); x++) {
+            QtOp op = sw.stages[s].ops[x];
+            const std::vector<double>& pl = sw.stages[s].payload[x];
+            op.pool = (uint32_t)pool_at;
+            if (!pl.empty()) memcpy(pool + pool_at, pl.data(), sizeof(double) * pl.size());
+            pool_at += pl.size();
+            memcpy(out.data() + h.ops_off + (first + x) * sizeof(QtOp), &op, sizeof(op));
+        }
+        first += sw.stages[s].ops.size();
+    }
+    return out;
+}
+
+// split one sweep's gates into register stages and serialise; returns false if too large
+bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& info, const std::vector<int>& sweep_gates,
+                   const std::vector<int>& hb, int R, bool merge_phases, std::vector<uint8_t>* program) {
+    SweepBuild sw;
+    sw.hb = hb;
+    for (int b = 0; b < 64; b++) sw.local_of[b] = -1;
+    for (int b = 0; b < QT_L; b++) sw.local_of[b] = b;
+    for (int i = 0; i < QT_H; i++) sw.local_of[hb[i]] = QT_L + i;
+    sw.ngates = (int)sweep_gates.size();
+    uint64_t tile_mask = 0;
+    for (int b = 0; b < 64; b++) if (sw.local_of[b] >= 0) tile_mask |= 1ull << b;
+    uint64_t index_of_local[QT_M];
+    for (int b = 0; b < 64; b++) if (sw.local_of[b] >= 0) index_of_local[sw.local_of[b]] = (uint64_t)b;
+
+    std::vector<int> rem = sweep_gates;
+    while (!rem.empty()) {
+        // greedy choice of the stage's register bits (as index-bit mask)
+        uint64_t regmask = 0;
+        int cur = 0;
+        select_pass(rem, info, regmask, rem.size(), nullptr, &cur);
+        for (int pick = 0; pick < R; pick++) {
+            int best = -1, best_count = -1;
+            for (int lp = 0; lp < QT_M; lp++) {
+                uint64_t bit = 1ull << index_of_local[lp];
+                if (regmask & bit) continue;
+                int c;
+                select_pass(rem, info, regmask | bit, rem.size(), nullptr, &c);
+                // tie-break: prefer bits that some remaining gate writes, then higher tile bits
+                if (c > best_count) { best_count = c; best = lp; }
+            }
+            if (best_count <= cur) {
+                // no single bit helps (e.g. a two-target gate needs both): try pairs for the head write set
+                int best_pair_a = -1, best_pair_b = -1, bc = cur;
+                if (pick + 1 < R) {
+                    for (int a = 0; a < QT_M; a++) for (int b2 = a + 1; b2 < QT_M; b2++) {
+                        uint64_t bits = (1ull << index_of_local[a]) | (1ull << index_of_local[b2]);
+                        if (regmask & bits) continue;
+                        int c;
+                        select_pass(rem, info, regmask | bits, rem.size(), nullptr, &c);
+                        if (c > bc) { bc = c; best_pair_a = a; best_pair_b = b2; }
+                    }
+                }
+                if (best_pair_a >= 0) {
+                    regmask |= (1ull << index_of_local[best_pair_a]) | (1ull << index_of_local[best_pair_b]);
+                    cur = bc;
+                    pick++;
+                    continue;
+                }
+            }
+            regmask |= 1ull << index_of_local[best];
+            cur = std::max(cur, best_count);
+        }
+        StageBuild sb;
+        memset(&sb.st, 0, sizeof(sb.st));
+        int q = 0;
+        for (int lp = 0; lp < QT_M; lp++) if (regmask & (1ull << index_of_local[lp])) sb.st.rb[q++] = (uint8_t)lp;
+        choose_thread_bits(sb.st, R);
+        std::vector<int> picked;
+        select_pass(rem, info, regmask, rem.size(), &picked, nullptr);
+        if (picked.empty()) return false;   // cannot happen: the head gate always fits
+        for (int gi : picked) emit_gate(sw, sb, R, gates[gi], merge_phases);
+        std::vector<int> next;
+        size_t pi = 0;
+        for (int gi : rem) {
+            if (pi < picked.size() && picked[pi] == gi) pi++; else next.push_back(gi);
+        }
+        rem.swap(next);
+        sw.stages.push_back(std::move(sb));
+        if (sw.stages.size() > 64) return false;
+    }
+    std::vector<uint8_t> prog = serialise(sw, R);
+    if (prog.size() > QT_MAX_PROGRAM_BYTES) return false;
+    program->swap(prog);
+    return true;
+}
+
+}  // namespace
+
+std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt) {
+    std::vector<QtPlanStep> steps;
+    const int R = opt.R;
+    std::vector<GInfo> info(gates.size());
+    for (size_t i = 0; i < gates.size(); i++) info[i] = analyse(gates[i]);
+    std::vector<int> rem(gates.size());
+    for (size_t i = 0; i < gates.size(); i++) rem[i] = (int)i;
+    const bool can_tile = nbits >= QT_M;
+    const size_t WINDOW = 512;
+
+    while (!rem.empty()) {
+        if (!can_tile || !info[rem[0]].tileable) {
+            QtPlanStep st;
+            st.fused = false;
+            st.gate_index = rem[0];
+            st.ngates = 1;
+            steps.push_back(std::move(st));
+            rem.erase(rem.begin());
+            continue;
+        }
+        // ---- choose the sweep's free tile bits greedily ---------------------------------------
+        uint64_t low = (1ull << QT_L) - 1ull;
+        uint64_t allowed = low;
+        int cur;
+        select_pass(rem, info, allowed, WINDOW, nullptr, &cur);
+        std::vector<int> hb;
+        while ((int)hb.size() < QT_H) {
+            int best = -1, best_count = cur;
+            for (int b = QT_L; b < nbits; b++) {
+                if (allowed & (1ull << b)) continue;
+                int c;
+                select_pass(rem, info, allowed | (1ull << b), WINDOW, nullptr, &c);
+                if (c > best_count) { best_count = c; best = b; }
+            }
+            if (best < 0 && (int)hb.size() + 2 <= QT_H) {
+                // two-target gates need both bits at once
+                int ba = -1, bb = -1;
+                for (int a = QT_L; a < nbits; a++) for (int b = a + 1; b < nbits; b++) {
+                    uint64_t bits = (1ull << a) | (1ull << b);
+                    if (allowed & bits) continue;
+                    int c;
+                    select_pass(rem, info, allowed | bits, WINDOW, nullptr, &c);
+                    if (c > best_count) { best_count = c; ba = a; bb = b; }
+                }
+                if (ba >= 0) {
+                    allowed |= (1ull << ba) | (1ull << bb);
+                    hb.push_back(ba); hb.push_back(bb);
+                    cur = best_count;
+                    continue;
+                }
+            }
+            if (best < 0) break;
+            allowed |= 1ull << best;
+            hb.push_back(best);
+            cur = best_count;
+        }
+        // fill up with the lowest unused bits (longer contiguous runs in HBM)
+        for (int b = QT_L; b < nbits && (int)hb.size() < QT_H; b++) {
+            if (!(allowed & (1ull << b))) { allowed |= 1ull << b; hb.push_back(b); }
+        }
+        std::sort(hb.begin(), hb.end());
+        std::vector<int> picked;
+        select_pass(rem, info, allowed, WINDOW, &picked, nullptr);
+        if (picked.empty()) {
+            // the head gate is tileable and unblocked, so this only happens if it needs more
+            // high bits than the tile has; run it unfused
+            QtPlanStep st;
+            st.fused = false;
+            st.gate_index = rem[0];
+            st.ngates = 1;
+            steps.push_back(std::move(st));
+            rem.erase(rem.begin());
+            continue;
+        }
+        // ---- stages + program (shrink the sweep if the program does not fit) -------------------
+        std::vector<uint8_t> program;
+        while (!build_program(gates, info, picked, hb, R, opt.merge_phases, &program)) {
+            if (picked.size() <= 1) throw std::runtime_error("planner: cannot build a program for one gate");
+            picked.resize(picked.size() / 2);
+        }
+        QtPlanStep st;
+        st.fused = true;
+        st.gate_index = -1;
+        st.ngates = (int)picked.size();
+        st.program.swap(program);
+        steps.push_back(std::move(st));
+        std::vector<int> next;
+        size_t pi = 0;
+        for (int gi : rem) {
+            if (pi < picked.size() && picked[pi] == gi) pi++; else next.push_back(gi);
+        }
+        rem.swap(next);
+    }
+    return steps;
+}

@@ -1,0 +1,125 @@
+// TEST INFRASTRUCTURE: CPU emulator of the fused-sweep plan.
+// Runs the planner (qbot_b200/csrc/qb_plan.cpp) on a circuit and executes the resulting
+// programs on a host ket exactly as the tile kernel does -- same tile addressing (qt_tile_base /
+// qt_run_offset / qt_slot), same thread / register mapping, same op semantics
+// (qb_tile_ops.h is shared with the kernel).  Built with g++ by tests/test_planner.py; never
+// part of the product library.
+#include "../../qbot_b200/csrc/qb_gate.h"
+#include "../../qbot_b200/csrc/qb_plan.h"
+#include "../../qbot_b200/csrc/qb_tile_ops.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+static std::string g_err;
+
+template <int R>
+static void run_program(const uint8_t* prog, qt_c* psi, int nbits) {
+    const QtHeader* h = (const QtHeader*)prog;
+    const QtStage* stages = (const QtStage*)(prog + h->stages_off);
+    const QtOp* ops = (const QtOp*)(prog + h->ops_off);
+    const double* pool = (const double*)(prog + h->pool_off);
+    const uint64_t ntiles = 1ull << (nbits - QT_M);
+    const int T = 1 << (QT_M - R);
+    std::vector<qt_c> buf(QT_TILE_UNITS);
+    for (uint64_t t = 0; t < ntiles; t++) {
+        const uint64_t tbase = qt_tile_base(t, h->hb);
+        for (uint32_t k = 0; k < QT_RUNS; k++) {
+            const qt_c* src = psi + tbase + qt_run_offset(k, h->hb);
+            for (uint32_t w = 0; w < (1u << QT_L); w++) buf[qt_slot((k << QT_L) | w)] = src[w];
+        }
+        for (int s = 0; s < h->nstages; s++) {
+            const QtStage& st = stages[s];
+            for (int tid = 0; tid < T; tid++) {
+                const uint32_t lbase = qt_thread_lbase<R>(st, (uint32_t)tid);
+                qt_c a[1 << R];
+                uint32_t slot[1 << R];
+                for (int i = 0; i < (1 << R); i++) {
+                    slot[i] = qt_slot(lbase | qt_reg_offset<R>(st, i));
+                    a[i] = buf[slot[i]];
+                }
+                for (int o = 0; o < st.nops; o++) qt_apply_op<R>(a, ops[st.first_op + o], pool, lbase, tbase);
+                for (int i = 0; i < (1 << R); i++) buf[slot[i]] = a[i];
+            }
+        }
+        for (uint32_t k = 0; k < QT_RUNS; k++) {
+            qt_c* dst = psi + tbase + qt_run_offset(k, h->hb);
+            for (uint32_t w = 0; w < (1u << QT_L); w++) dst[w] = buf[qt_slot((k << QT_L) | w)];
+        }
+    }
+}
+
+static void run_unfused(const QGate& g, qt_c* psi, int nbits) {
+    std::vector<cplx> m = qb_dense_of(g);
+    const int D = 1 << g.k;
+    const uint64_t total = 1ull << nbits, tmask = g.tmask();
+    std::vector<uint64_t> off(D);
+    for (int j = 0; j < D; j++) {
+        uint64_t o = 0;
+        for (int b = 0; b < g.k; b++) if ((j >> (g.k - 1 - b)) & 1) o |= 1ull << g.tb[b];
+        off[j] = o;
+    }
+    std::vector<qt_c> x(D);
+    for (uint64_t base = 0; base < total; base++) {
+        if (base & tmask) continue;
+        if ((base & g.cmask) != g.cmask) continue;
+        for (int j = 0; j < D; j++) x[j] = psi[base | off[j]];
+        for (int i = 0; i < D; i++) {
+            qt_c acc = qt_mk(0, 0);
+            for (int j = 0; j < D; j++) acc = qt_fma(qt_mk(m[i * D + j].x, m[i * D + j].y), x[j], acc);
+            psi[base | off[i]] = acc;
+        }
+    }
+}
+
+extern "C" {
+
+const char* qbt_last_error() { return g_err.c_str(); }
+
+// gates: ks[g], target bits tbs[g*14..], cmasks[g], dense matrices concatenated (4^k complex each)
+// stats out: [steps, fused sweeps, unfused steps, stages, ops, program bytes max, gates in fused sweeps]
+int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t* cmasks, const double* mats,
+            double* psi, int R, int merge, int execute, long long* stats) {
+    try {
+        std::vector<QGate> gates;
+        size_t moff = 0;
+        for (int g = 0; g < ngates; g++) {
+            QGate q = qb_classify((const cplx*)(mats + moff), ks[g], tbs + (size_t)g * QB_BIG_MAXK, cmasks[g]);
+            moff += 2 * ((size_t)1 << (2 * ks[g]));
+            if (!qb_is_identity(q)) gates.push_back(q);
+        }
+        QtPlanOptions opt;
+        opt.R = R;
+        opt.merge_phases = merge != 0;
+        std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
+        long long st[7] = {0, 0, 0, 0, 0, 0, 0};
+        int covered = 0;
+        for (const QtPlanStep& s : steps) {
+            st[0]++;
+            covered += s.ngates;
+            if (s.fused) {
+                const QtHeader* h = (const QtHeader*)s.program.data();
+                st[1]++;
+                st[3] += h->nstages;
+                st[4] += h->nops;
+                if ((long long)s.program.size() > st[5]) st[5] = (long long)s.program.size();
+                st[6] += s.ngates;
+                if (execute) {
+                    if (R == 3) run_program<3>(s.program.data(), (qt_c*)psi, nbits);
+                    else run_program<4>(s.program.data(), (qt_c*)psi, nbits);
+                }
+            } else {
+                st[2]++;
+                if (execute) run_unfused(gates[s.gate_index], (qt_c*)psi, nbits);
+            }
+        }
+        if (covered != (int)gates.size()) { g_err = "plan does not cover every gate exactly once"; return -1; }
+        if (stats) memcpy(stats, st, sizeof(st));
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+}

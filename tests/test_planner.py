@@ -1,0 +1,152 @@
+"""CPU: the fusion planner (qbot_b200/csrc/qb_plan.cpp) checked by executing its sweep programs
+with the CPU plan emulator (same addressing and op semantics as the tile kernel) against the
+oracle.  Covers gate reordering legality, stage / register-bit assignment, predicates on
+register / thread / out-of-tile bits, phase merging and the unfused fallbacks."""
+import numpy as np
+import pytest
+
+import plan_emu
+from oracle import qbot_oracle as orc
+from qbot_b200.circuits import rc
+from conftest import close
+
+
+def rand_ket(rng, n):
+    v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    return v / np.linalg.norm(v)
+
+
+def rand_u(rng, k):
+    a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+    q, r = np.linalg.qr(a)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def oracle_apply_bits(psi, n, m, tb, cmask):
+    """Gate on arbitrary index bits through the oracle (reference qubit = n-1-bit)."""
+    k = len(tb)
+    qs = [n - 1 - b for b in tb]
+    controls = [n - 1 - b for b in range(n) if (cmask >> b) & 1]
+    if qs == list(range(qs[0], qs[0] + k)):
+        return orc.ket_apply(psi, n, qs[0], m, controls)
+    # non-contiguous / unordered targets: permute axes
+    t = np.array(psi, dtype=complex).reshape((2,) * n)
+    sl = [slice(None)] * n
+    for c in controls:
+        sl[c] = 1
+    sub = t[tuple(sl)]
+    ctl = sorted(controls)
+    axes = [q - sum(1 for c in ctl if c < q) for q in qs]
+    g = np.asarray(m, dtype=complex).reshape((2,) * (2 * k))
+    res = np.tensordot(g, sub, axes=(list(range(k, 2 * k)), axes))
+    res = np.moveaxis(res, list(range(k)), axes)
+    t[tuple(sl)] = res
+    return t.reshape(-1)
+
+
+def random_gate_list(rng, n, count):
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    H = np.array([[1, 1], [1, -1]], dtype=complex) * 2 ** -0.5
+    out = []
+    for _ in range(count):
+        kind = int(rng.integers(0, 9))
+        bits = [int(b) for b in rng.permutation(n)]
+        nc = int(rng.integers(0, 3))
+        if kind == 0:
+            m, tb = H, bits[:1]
+        elif kind == 1:
+            m, tb = X, bits[:1]
+        elif kind == 2:
+            m, tb = np.diag(np.exp(1j * rng.uniform(0, 6.28, 2))), bits[:1]
+        elif kind == 3:
+            m, tb = rand_u(rng, 1), bits[:1]
+        elif kind == 4:
+            m, tb = rand_u(rng, 2), bits[:2]
+        elif kind == 5:
+            m, tb = np.diag(np.exp(1j * rng.uniform(0, 6.28, 4))), bits[:2]
+        elif kind == 6:
+            m, tb = np.diag(np.exp(1j * rng.uniform(0, 6.28, 8))), bits[:3]
+        elif kind == 7:
+            p = rng.permutation(4)
+            m = np.zeros((4, 4), dtype=complex)
+            m[np.arange(4), p] = np.exp(1j * rng.uniform(0, 6.28, 4))
+            tb = bits[:2]
+        else:
+            m, tb, nc = rand_u(rng, 3), bits[:3], 0          # not tileable: unfused step
+        cm = 0
+        for c in bits[len(tb):len(tb) + nc]:
+            cm |= 1 << c
+        if kind == 2 and nc == 0 and rng.random() < 0.5:
+            cm = 0
+        out.append((m, tb, cm))
+    return out
+
+
+@pytest.mark.parametrize('R', [3, 4])
+@pytest.mark.parametrize('merge', [True, False])
+def test_random_mixed_circuits(R, merge):
+    rng = np.random.default_rng(100 + R)
+    for n in (12, 13, 15):
+        gl = random_gate_list(rng, n, 60)
+        psi = rand_ket(rng, n)
+        out, st = plan_emu.run(n, gl, psi, R=R, merge=merge)
+        ref = psi
+        for m, tb, cm in gl:
+            ref = oracle_apply_bits(ref, n, m, tb, cm)
+        assert close(out, ref, 1e-12), (n, st)
+        assert st['fused_gates'] + st['unfused_steps'] == len(gl)
+
+
+@pytest.mark.parametrize('R', [3, 4])
+def test_rc_circuits(R):
+    for n, depth, seed in ((12, 10, 1), (14, 12, 2), (16, 6, 3)):
+        gates = rc(n, depth, seed)
+        rng = np.random.default_rng(seed)
+        psi = rand_ket(rng, n)
+        out, st = plan_emu.run(n, plan_emu.circuit_to_bits(n, gates), psi, R=R)
+        ref = psi
+        for g in gates:
+            ref = orc.ket_apply(ref, n, g.target, g.matrix(), g.controls)
+        assert close(out, ref, 1e-12), (n, st)
+        assert st['unfused_steps'] == 0
+
+
+def test_density_matrix_gate_pairs():
+    """DM mode queues U on the row bits and conj(U) on the column bits."""
+    rng = np.random.default_rng(7)
+    n = 6
+    dim = 1 << n
+    v = rand_ket(rng, n)
+    w = rand_ket(rng, n)
+    rho = 0.6 * np.outer(v, v.conj()) + 0.4 * np.outer(w, w.conj())
+    gl, ref = [], rho
+    for _ in range(20):
+        k = int(rng.integers(1, 3))
+        t = int(rng.integers(0, n - k + 1))
+        free = [q for q in range(n) if q < t or q >= t + k]
+        cs = [int(c) for c in rng.choice(free, size=int(rng.integers(0, 3)), replace=False)]
+        g = rand_u(rng, k)
+        tb = [n - 1 - (t + j) for j in range(k)]
+        cm = sum(1 << (n - 1 - c) for c in cs)
+        gl.append((g, [b + n for b in tb], cm << n))
+        gl.append((g.conj(), tb, cm))
+        ref = orc.conjugate(orc.controlled_unitary(n, cs, t, g), ref)
+    out, st = plan_emu.run(2 * n, gl, rho.reshape(-1))
+    assert close(out.reshape(dim, dim), ref, 1e-12)
+
+
+def test_headline_plans_are_compact():
+    """Planning only (no execution) at the benchmark sizes: the whole circuit must fuse and the
+    sweep count must stay far below the gate count."""
+    for n, depth, seed, max_sweeps in ((30, 20, 30, 20), (20, 200, 20, 90), (34, 10, 34, 14)):
+        gates = rc(n, depth, seed)
+        _, st = plan_emu.run(n, plan_emu.circuit_to_bits(n, gates), None, execute=False)
+        assert st['unfused_steps'] == 0 and st['fused_gates'] == len(gates)
+        assert st['fused_sweeps'] <= max_sweeps, st
+        assert st['max_program_bytes'] <= 12288
+
+
+def test_small_states_are_not_tiled():
+    gl = [(np.array([[0, 1], [1, 0]], dtype=complex), [3], 0)]
+    _, st = plan_emu.run(8, gl, np.ones(256, dtype=complex), R=4)
+    assert st['fused_sweeps'] == 0 and st['unfused_steps'] == 1
