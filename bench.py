@@ -310,6 +310,8 @@ def main():
     ap.add_argument('--no-fusion', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
+                    help="multi-GPU global-qubit swap: pack kernel storing into peer memory over NVLink, or pack + NCCL all-to-all")
     ap.add_argument('--ref-qubits', type=int, default=12)
     ap.add_argument('--ref-qubits-default', type=int, default=11)
     args = ap.parse_args()

@@ -130,6 +130,29 @@ int qb_outer(qb_state* ket, int conj, qb_state** out);
 /* copy one state into every branch of a batched state (fan-out before a batched gate) */
 int qb_broadcast(qb_state* src, qb_state* dst_batched);
 
+/* ---- sharded kets (one process per GPU) ----------------------------------
+ * The reference has no distributed path; these are the device-side pieces of the global-qubit
+ * swap that replaces genSwapGate + applyGate (qgates.py:77-133, 278-279) when the exchanged
+ * qubit is one of the index bits that select the GPU.  The host side (qbot_b200/sharded.py)
+ * owns the qubit map and the rendezvous (torch.distributed); this library owns the memory,
+ * the pack kernel and the peer mappings.
+ *
+ * raw device buffers (cudaMalloc, so that they can be exported over CUDA IPC) */
+int qb_buffer_alloc(int device, size_t bytes, void** out_dev);
+int qb_buffer_free(int device, void* dev);
+/* re-point a handle made by qb_create_external at another buffer of the same size */
+int qb_rebind(qb_state* s, void* amplitudes_dev);
+/* 64-byte CUDA IPC handle of a qb_buffer_alloc buffer / mapping of a peer's buffer */
+int qb_ipc_export(int device, void* dev, void* handle64);
+int qb_ipc_open(int device, const void* handle64, void** out_dev);
+int qb_ipc_close(int device, void* dev);
+/* One pass over a single-branch ket: dst index j takes the amplitude at source index
+ * sum_d bit_d(j) << src_bit_of_dst_bit[d]  (a permutation of the index bits), and is written to
+ * chunk_dst[j >> (nbits - chunk_bits)][j & (2^(nbits-chunk_bits) - 1)].  The chunk pointers
+ * may be local (the second shard buffer, followed by an NCCL all-to-all) or IPC mappings of
+ * peer buffers (the exchange then happens inside this kernel, as stores over NVLink). */
+int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst);
+
 /* ---- instrumentation ------------------------------------------------------------------- */
 int qb_get_stats(const qb_state* s, qb_stats* out);
 int qb_reset_stats(qb_state* s);

@@ -61,6 +61,13 @@ PROTOTYPES = {
     'qb_mix_branches': (C.c_int, [c_state_p, C.POINTER(C.c_double), C.POINTER(c_state_p)]),
     'qb_outer': (C.c_int, [c_state_p, C.c_int, C.POINTER(c_state_p)]),
     'qb_broadcast': (C.c_int, [c_state_p, c_state_p]),
+    'qb_buffer_alloc': (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    'qb_buffer_free': (C.c_int, [C.c_int, C.c_void_p]),
+    'qb_rebind': (C.c_int, [c_state_p, C.c_void_p]),
+    'qb_ipc_export': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    'qb_ipc_open': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    'qb_ipc_close': (C.c_int, [C.c_int, C.c_void_p]),
+    'qb_permute_scatter': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     'qb_get_stats': (C.c_int, [c_state_p, C.POINTER(QbStats)]),
     'qb_reset_stats': (C.c_int, [c_state_p]),
     'qb_timer_start': (C.c_int, [c_state_p]),

@@ -709,6 +709,99 @@ int qb_broadcast(qb_state* src, qb_state* dst) {
     QB_API_END
 }
 
+// sharded kets ------------------------------------------------------------------------------
+int qb_buffer_alloc(int device, size_t bytes, void** out_dev) {
+    QB_API_BEGIN
+    QB_REQUIRE(out_dev && bytes > 0, "bad argument");
+    DevGuard g(device);
+    QB_CUDA(cudaMalloc(out_dev, bytes));
+    QB_API_END
+}
+
+int qb_buffer_free(int device, void* dev) {
+    QB_API_BEGIN
+    if (dev) {
+        DevGuard g(device);
+        QB_CUDA(cudaDeviceSynchronize());
+        QB_CUDA(cudaFree(dev));
+    }
+    QB_API_END
+}
+
+int qb_rebind(qb_state* s, void* amplitudes_dev) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && amplitudes_dev, "NULL argument");
+    QB_REQUIRE(!s->owns, "rebind: the handle owns its memory (use qb_create_external)");
+    s->flush();
+    s->d = (cplx*)amplitudes_dev;
+    QB_API_END
+}
+
+int qb_ipc_export(int device, void* dev, void* handle64) {
+    QB_API_BEGIN
+    QB_REQUIRE(dev && handle64, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DevGuard g(device);
+    cudaIpcMemHandle_t h;
+    QB_CUDA(cudaIpcGetMemHandle(&h, dev));
+    memcpy(handle64, &h, 64);
+    QB_API_END
+}
+
+int qb_ipc_open(int device, const void* handle64, void** out_dev) {
+    QB_API_BEGIN
+    QB_REQUIRE(handle64 && out_dev, "NULL argument");
+    DevGuard g(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    QB_CUDA(cudaIpcOpenMemHandle(out_dev, h, cudaIpcMemLazyEnablePeerAccess));
+    QB_API_END
+}
+
+int qb_ipc_close(int device, void* dev) {
+    QB_API_BEGIN
+    if (dev) {
+        DevGuard g(device);
+        QB_CUDA(cudaIpcCloseMemHandle(dev));
+    }
+    QB_API_END
+}
+
+int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && src_bit_of_dst_bit && chunk_dst, "NULL argument");
+    QB_REQUIRE(s->kind == QB_KET && s->nbranch == 1, "permute_scatter: single-branch kets only");
+    QB_REQUIRE(chunk_bits >= 0 && chunk_bits <= 4 && chunk_bits <= s->nbits, "permute_scatter: chunk_bits must be 0..4");
+    s->flush();
+    DevGuard g(s->device);
+    PermArgs a;
+    memset(&a, 0, sizeof(a));
+    uint64_t seen = 0;
+    for (int d = 0; d < s->nbits; d++) {
+        const int f = src_bit_of_dst_bit[d];
+        QB_REQUIRE(f >= 0 && f < s->nbits && !((seen >> f) & 1ull), "permute_scatter: not a permutation of the index bits");
+        seen |= 1ull << f;
+        if (f == d) a.fixed_mask |= 1ull << d;
+        else {
+            QB_REQUIRE(a.nmoved < QB_PERM_MAXMOVED, "permute_scatter: too many moved bits");
+            a.from[a.nmoved] = (uint8_t)f; a.to[a.nmoved] = (uint8_t)d; a.nmoved++;
+        }
+    }
+    a.in = s->d;
+    a.total = s->per_branch();
+    a.chunk_shift = s->nbits - chunk_bits;
+    for (int c = 0; c < (1 << chunk_bits); c++) {
+        QB_REQUIRE(chunk_dst[c], "permute_scatter: NULL chunk destination");
+        QB_REQUIRE(chunk_dst[c] != (void*)s->d, "permute_scatter: destination aliases the source");
+        a.dst[c] = (cplx*)chunk_dst[c];
+    }
+    qb_launch_permute_scatter(s->ctx(), a);
+    QB_CUDA(cudaGetLastError());
+    s->stats.bytes_moved += s->bytes() * 2;
+    s->stats.state_passes++;
+    QB_API_END
+}
+
 int qb_get_stats(const qb_state* s, qb_stats* out) {
     QB_API_BEGIN
     QB_REQUIRE(s && out, "NULL argument");

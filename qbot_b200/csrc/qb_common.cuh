@@ -136,6 +136,19 @@ struct MixArgs {
     uint64_t total;
 };
 
+#define QB_PERM_MAXMOVED 40
+#define QB_PERM_MAXCHUNK 16
+struct PermArgs {
+    const cplx* in;
+    cplx* dst[QB_PERM_MAXCHUNK];  // destination of chunk c (local buffer or a peer mapping)
+    uint64_t total;               // amplitudes of the shard
+    uint64_t fixed_mask;          // index bits that keep their position
+    int chunk_shift;              // nbits - chunk_bits
+    int nmoved;
+    uint8_t from[QB_PERM_MAXMOVED];   // source bit of moved destination bit to[i]
+    uint8_t to[QB_PERM_MAXMOVED];
+};
+
 // launch wrappers implemented in qb_kernels.cu ------------------------------------------------
 struct LaunchCtx {
     cudaStream_t stream;
@@ -158,4 +171,5 @@ void qb_launch_scatter(const LaunchCtx&, const ScatterArgs& a);
 void qb_launch_mix(const LaunchCtx&, const MixArgs& a);
 void qb_launch_mix_branches(const LaunchCtx&, const cplx* src, const double* probs_dev, int64_t nbranch, uint64_t per_branch, cplx* out);
 void qb_launch_outer(const LaunchCtx&, const cplx* ket, cplx* out, int nq, int conj);
+void qb_launch_permute_scatter(const LaunchCtx&, const PermArgs& a);
 void qb_launch_project(const LaunchCtx&, cplx* psi, uint64_t total, uint64_t mask, uint64_t want, double scale);

@@ -505,3 +505,26 @@ void qb_launch_project(const LaunchCtx& c, cplx* psi, uint64_t total, uint64_t m
     k_project<<<grid_for(c, total, 256), 256, 0, c.stream>>>(psi, total, mask, want, scale);
     COUNT_LAUNCH(c);
 }
+
+// ---------------------------------------------------------------------------------------------
+// index-bit permutation with per-chunk destinations (pack step of the global-qubit swap; the
+// destinations may be peer GPUs' buffers mapped over CUDA IPC, in which case the stores travel
+// over NVLink and this kernel *is* the exchange).  One 16-byte amplitude per thread per
+// iteration; the planner keeps the low 5 bits in place so that warps read and write whole
+// 512-byte runs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_permute_scatter(PermArgs a) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t cmask = (1ull << a.chunk_shift) - 1ull;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.total; j += stride) {
+        uint64_t src = j & a.fixed_mask;
+        for (int i = 0; i < a.nmoved; i++) src |= ((j >> a.to[i]) & 1ull) << a.from[i];
+        const cplx v = __ldcs(&a.in[src]);
+        __stcs(&a.dst[j >> a.chunk_shift][j & cmask], v);
+    }
+}
+
+void qb_launch_permute_scatter(const LaunchCtx& c, const PermArgs& a) {
+    k_permute_scatter<<<grid_for(c, a.total, 256), 256, 0, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}

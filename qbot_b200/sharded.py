@@ -1,0 +1,586 @@
+"""Kets sharded over the GPUs of one box (BASELINE config 5).
+
+One process per GPU.  A ket of n qubits lives as P = 2^g contiguous slices: the top g index
+bits select the rank (physical positions nl .. n-1, nl = n - g), the low nl bits address the
+amplitude inside the rank's shard.  Which *logical* index bit sits at which physical position
+is a permutation owned by ``QubitMap`` and is the same on every rank.
+
+  - gates whose non-diagonal targets are all local run on the shard through the C ABI (fused
+    tile engine); a control on a rank bit is a rank predicate, a diagonal factor on a rank bit
+    is a per-rank scalar -- no communication;
+  - when a gate needs a non-diagonal target that currently selects the rank, ``ShardedKet``
+    exchanges qubits: it picks the logical bits whose next non-diagonal use is farthest away
+    to become the new rank bits, packs the shard so that the outgoing bits are the top local
+    bits (one index-bit permutation pass) and swaps chunks with the 2^k - 1 peers.  With
+    ``exchange='p2p'`` the pack kernel stores straight into the peers' buffers over NVLink
+    (CUDA IPC mappings; pack and exchange are ONE kernel); with ``exchange='nccl'`` the pack
+    goes to the local second buffer and a grouped all-to-all (torch.distributed / NCCL) moves
+    the chunks.  No swap-back ever happens: the map just changes.
+
+The reference has no counterpart (it is single-process numpy); the operation replaced is the
+``gate`` op's state path (qbot/operators.py:255-329 -> qgates.py:161-182, 228-279) at sizes the
+reference cannot represent.  Everything in this file is host logic; device work goes through
+``include/qbot_b200.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+INF = 1 << 60
+LOW_KEEP = 5          # local positions 0..4 stay in place during a pack (512-byte runs)
+
+
+# ---------------------------------------------------------------------------------------------
+# gate records on logical index bits
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class LGate:
+    """A gate on logical index bits: ``tb[0]`` carries the matrix's most significant bit."""
+    m: np.ndarray
+    tb: Tuple[int, ...]
+    controls: Tuple[int, ...] = ()
+    wmask: int = 0        # logical bits the gate acts on non-diagonally
+    rmask: int = 0        # logical bits it only reads (controls, block-diagonal target axes)
+
+
+def _axis_is_diagonal(m: np.ndarray, k: int, axis: int) -> bool:
+    """True if m never couples basis states that differ in target `axis` (0 = most significant)."""
+    d = 1 << k
+    bit = 1 << (k - 1 - axis)
+    idx = np.arange(d)
+    off = (idx[:, None] & bit) != (idx[None, :] & bit)
+    return not np.any(m[off] != 0)
+
+
+def make_lgate(matrix, target_bits: Sequence[int], control_bits: Iterable[int] = ()) -> LGate:
+    m = np.ascontiguousarray(np.asarray(matrix), dtype=np.complex128)
+    k = len(target_bits)
+    if m.shape != (1 << k, 1 << k):
+        raise ValueError("matrix does not match the number of target bits")
+    controls = tuple(int(c) for c in control_bits)
+    if set(controls) & set(target_bits):
+        raise ValueError("control overlaps target")
+    w = r = 0
+    for ax, b in enumerate(target_bits):
+        if _axis_is_diagonal(m, k, ax):
+            r |= 1 << b
+        else:
+            w |= 1 << b
+    for c in controls:
+        r |= 1 << c
+    return LGate(m, tuple(int(b) for b in target_bits), controls, w, r)
+
+
+def select_pass(rem: Sequence[LGate], allowed: int) -> List[int]:
+    """Indices of the gates of `rem` (circuit order) that can run now when only the bits of
+    `allowed` may be written: a gate may overtake an earlier gate left behind only if neither
+    writes a bit the other touches (same rule as the fusion planner, qb_plan.cpp)."""
+    picked = []
+    blocked_w = blocked_r = 0
+    for i, g in enumerate(rem):
+        ok = (g.wmask & ~allowed) == 0 and ((g.wmask | g.rmask) & blocked_w) == 0 and (g.wmask & blocked_r) == 0
+        if ok:
+            picked.append(i)
+        else:
+            blocked_w |= g.wmask
+            blocked_r |= g.rmask
+    return picked
+
+
+# ---------------------------------------------------------------------------------------------
+# qubit map + exchange planning (pure host logic, identical on every rank)
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Exchange:
+    """One global-qubit swap.  `src_bit_of_dst_bit` is the local pack permutation; `rank_bits`
+    the rank-bit numbers (ascending) whose qubits come in; chunk-index bit i pairs with
+    rank_bits[i]."""
+    src_bit_of_dst_bit: List[int]
+    rank_bits: List[int]
+
+    @property
+    def k(self) -> int:
+        return len(self.rank_bits)
+
+
+class QubitMap:
+    def __init__(self, n: int, g: int):
+        if g < 0 or g > n:
+            raise ValueError("bad number of rank bits")
+        self.n, self.g, self.nl = n, g, n - g
+        self.pos = list(range(n))        # logical bit -> physical position
+        self.at = list(range(n))         # physical position -> logical bit
+
+    def is_local(self, b: int) -> bool:
+        return self.pos[b] < self.nl
+
+    def local_mask(self) -> int:
+        m = 0
+        for b in range(self.n):
+            if self.pos[b] < self.nl:
+                m |= 1 << b
+        return m
+
+    def plan_exchange(self, rem: Sequence[LGate]) -> Exchange:
+        """Choose the new rank bits (farthest next non-diagonal use) and update the map."""
+        n, nl, g = self.n, self.nl, self.g
+        nxt = [INF] * n
+        for i, gt in enumerate(rem):
+            w = gt.wmask
+            while w:
+                b = (w & -w).bit_length() - 1
+                if nxt[b] == INF:
+                    nxt[b] = i
+                w &= w - 1
+        # a local bit in the low LOW_KEEP positions is a last resort (keeps the pack coalesced)
+        order = sorted(range(n), key=lambda b: (0 if not (self.pos[b] < min(LOW_KEEP, max(nl - g, 0))) else 1,
+                                                -nxt[b], 0 if self.pos[b] >= nl else 1, -self.pos[b]))
+        head_w = rem[0].wmask if rem else 0
+        new_global = []
+        for b in order:
+            if (head_w >> b) & 1:
+                continue
+            new_global.append(b)
+            if len(new_global) == g:
+                break
+        if len(new_global) < g:
+            raise RuntimeError("cannot make the head gate local: it writes more bits than a shard holds")
+        cur_global = [self.at[nl + r] for r in range(g)]
+        victims = sorted((b for b in new_global if b not in cur_global), key=lambda b: self.pos[b])
+        rank_bits = sorted(r for r in range(g) if self.at[nl + r] not in new_global)
+        k = len(victims)
+        assert k == len(rank_bits)
+        perm = list(range(nl))
+        if k:
+            top = list(range(nl - k, nl))
+            vpos = [self.pos[b] for b in victims]
+            displaced = [p for p in top if p not in vpos]          # non-victims sitting in the top-k slots
+            vacated = [p for p in vpos if p not in top]            # victim slots outside the top-k
+            for i, p in enumerate(vpos):
+                perm[nl - k + i] = p
+            for d, s in zip(vacated, displaced):
+                perm[d] = s
+            # new map: pack first ...
+            new_at = list(self.at)
+            for d in range(nl):
+                new_at[d] = self.at[perm[d]]
+            # ... then the exchange swaps top-k local position i with rank bit rank_bits[i]
+            for i, r in enumerate(rank_bits):
+                new_at[nl - k + i], new_at[nl + r] = new_at[nl + r], new_at[nl - k + i]
+            self.at = new_at
+            for p, b in enumerate(self.at):
+                self.pos[b] = p
+        return Exchange(perm, rank_bits)
+
+    def localise(self, g: LGate, rank: int):
+        """The gate as this rank sees it: (matrix, local target positions, local control mask),
+        or None when a rank-bit control is 0 here.  Block-diagonal target axes that sit on rank
+        bits are sliced by the rank's bit value."""
+        nl = self.nl
+        cmask = 0
+        for c in g.controls:
+            p = self.pos[c]
+            if p >= nl:
+                if not (rank >> (p - nl)) & 1:
+                    return None
+            else:
+                cmask |= 1 << p
+        k = len(g.tb)
+        m = g.m
+        glob = [(ax, self.pos[b]) for ax, b in enumerate(g.tb) if self.pos[b] >= nl]
+        if glob:
+            t = m.reshape([2] * (2 * k))
+            keep_axes = [ax for ax in range(k) if self.pos[g.tb[ax]] < nl]
+            sl = [slice(None)] * (2 * k)
+            for ax, p in glob:
+                if (g.wmask >> g.tb[ax]) & 1:
+                    raise RuntimeError("localise: non-diagonal target on a rank bit (exchange missing)")
+                v = (rank >> (p - nl)) & 1
+                sl[ax] = v
+                sl[k + ax] = v
+            t = t[tuple(sl)]
+            kk = len(keep_axes)
+            if kk == 0:
+                s = complex(t)
+                # a per-rank scalar: diag(s, s) on a local bit outside the control mask
+                free = next(p for p in range(nl) if not (cmask >> p) & 1)
+                return np.array([[s, 0], [0, s]], dtype=np.complex128), [free], cmask
+            m = np.ascontiguousarray(t.reshape(1 << kk, 1 << kk))
+            tbits = [self.pos[g.tb[ax]] for ax in keep_axes]
+            return m, tbits, cmask
+        return m, [self.pos[b] for b in g.tb], cmask
+
+
+# ---------------------------------------------------------------------------------------------
+# communicators
+# ---------------------------------------------------------------------------------------------
+class TorchComm:
+    """torch.distributed plumbing (NCCL on the GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+    def allreduce_sum(self, arr: np.ndarray, device=None) -> np.ndarray:
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+        if device is not None:
+            t = t.to(device)
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def allgather_bytes(self, payload: bytes) -> List[bytes]:
+        out = [None] * self.world
+        self.dist.all_gather_object(out, payload, group=self.group)
+        return out
+
+    def all_to_all(self, out_t, in_t, out_splits, in_splits):
+        self.dist.all_to_all_single(out_t, in_t, out_splits, in_splits, group=self.group)
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so that torch can wrap a raw device pointer."""
+
+    def __init__(self, ptr: int, nfloat64: int):
+        self.__cuda_array_interface__ = {'shape': (nfloat64,), 'typestr': '<f8', 'data': (ptr, False), 'version': 2}
+
+
+# ---------------------------------------------------------------------------------------------
+# the shard on a GPU
+# ---------------------------------------------------------------------------------------------
+class CudaShard:
+    """2^nl amplitudes in HBM (two buffers: the live shard and the exchange target)."""
+
+    def __init__(self, nl: int, comm, device: int, exchange: str = 'p2p'):
+        from . import _lib
+        from .state import DeviceState, KET
+        self._lib = _lib
+        self.nl, self.comm, self.device = nl, comm, device
+        self.bytes = 16 << nl
+        self.buf = [C.c_void_p(), C.c_void_p()]
+        for b in self.buf:
+            _lib.call('qb_buffer_alloc', device, self.bytes, C.byref(b))
+        self.cur = 0
+        h = C.c_void_p()
+        _lib.call('qb_create_external', C.byref(h), KET, nl, 1, device, self.buf[0], None)
+        self.state = DeviceState(h, KET, nl, 1)
+        self.exchange_mode = exchange
+        self.peer = None                      # peer[r][i] = mapping of rank r's buffer i
+        self.exchanged_bytes = 0
+        self.exchanges = 0
+        self.exchange_seconds = 0.0           # pack + transfer, measured between the two barriers
+        if exchange == 'p2p' and comm.world > 1:
+            self._open_peers()
+        elif exchange not in ('p2p', 'nccl'):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+
+    def _open_peers(self):
+        lib = self._lib
+        handles = b''
+        for b in self.buf:
+            hb = C.create_string_buffer(64)
+            lib.call('qb_ipc_export', self.device, b, hb)
+            handles += hb.raw
+        allh = self.comm.allgather_bytes(handles)
+        self.peer = []
+        for r, hs in enumerate(allh):
+            if r == self.comm.rank:
+                self.peer.append([self.buf[0].value, self.buf[1].value])
+                continue
+            ptrs = []
+            for i in range(2):
+                p = C.c_void_p()
+                lib.call('qb_ipc_open', self.device, C.create_string_buffer(hs[64 * i:64 * i + 64], 64), C.byref(p))
+                ptrs.append(p.value)
+            self.peer.append(ptrs)
+
+    def init_basis(self, has_one: bool, local_index: int = 0):
+        import torch
+        if has_one:
+            self._lib.call('qb_init_basis', self.state._h, local_index)
+        else:
+            t = torch.as_tensor(_CudaArray(self.buf[self.cur].value, 2 << self.nl), device=f'cuda:{self.device}')
+            t.zero_()
+            torch.cuda.synchronize(self.device)
+        self.state.sync()
+
+    def apply(self, m: np.ndarray, target_positions: Sequence[int], cmask: int):
+        self.state.apply_gate_bits(m, list(target_positions), cmask)
+
+    def flush(self):
+        self.state.flush()
+
+    def sync(self):
+        self.state.sync()
+
+    def do_exchange(self, ex: Exchange):
+        import torch
+        lib, comm = self._lib, self.comm
+        k, nl = ex.k, self.nl
+        if k == 0:
+            return
+        rank = comm.rank
+        my_s = 0
+        for i, r in enumerate(ex.rank_bits):
+            my_s |= ((rank >> r) & 1) << i
+        chunk_bytes = self.bytes >> k
+        other = 1 - self.cur
+
+        def peer_rank(c):
+            pr = rank
+            for i, r in enumerate(ex.rank_bits):
+                pr = (pr & ~(1 << r)) | (((c >> i) & 1) << r)
+            return pr
+
+        perm = lib.int_array(ex.src_bit_of_dst_bit)
+        dst = (C.c_void_p * (1 << k))()
+        if self.exchange_mode == 'p2p':
+            # everyone must be done with the buffer we are about to overwrite remotely
+            self.state.sync()
+            comm.barrier()
+            t0 = time.perf_counter()
+            for c in range(1 << k):
+                dst[c] = self.peer[peer_rank(c)][other] + my_s * chunk_bytes
+            lib.call('qb_permute_scatter', self.state._h, perm, k, dst)
+            self.state.sync()
+            self.exchange_seconds += time.perf_counter() - t0
+            comm.barrier()
+            lib.call('qb_rebind', self.state._h, self.buf[other])
+            self.cur = other
+        else:
+            self.state.sync()
+            t0 = time.perf_counter()
+            for c in range(1 << k):
+                dst[c] = self.buf[other].value + c * chunk_bytes
+            lib.call('qb_permute_scatter', self.state._h, perm, k, dst)
+            self.state.sync()
+            dev = f'cuda:{self.device}'
+            nf = 2 << nl
+            t_in = torch.as_tensor(_CudaArray(self.buf[other].value, nf), device=dev)
+            t_out = torch.as_tensor(_CudaArray(self.buf[self.cur].value, nf), device=dev)
+            splits = [0] * comm.world
+            for c in range(1 << k):
+                splits[peer_rank(c)] = nf >> k
+            comm.all_to_all(t_out, t_in, splits, splits)
+            torch.cuda.synchronize(self.device)
+            self.exchange_seconds += time.perf_counter() - t0
+            # the live shard is again buf[cur]
+        self.exchanged_bytes += chunk_bytes * ((1 << k) - 1)
+        self.exchanges += 1
+
+    def probs_local(self, positions: Sequence[int]) -> np.ndarray:
+        out = np.empty(1 << len(positions), dtype=np.float64)
+        self._lib.call('qb_probs', self.state._h, self._lib.int_array(positions), len(positions),
+                       out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def download_range(self, first: int, count: int) -> np.ndarray:
+        return self.state.download_range(first, count)
+
+    def download(self) -> np.ndarray:
+        out = np.empty(1 << self.nl, dtype=np.complex128)
+        self._lib.call('qb_download', self.state._h, out.ctypes.data_as(C.c_void_p), out.nbytes)
+        return out
+
+    def reduce_device(self):
+        return f'cuda:{self.device}' if getattr(self.comm, 'dist', None) is not None and \
+            self.comm.dist.get_backend(self.comm.group) == 'nccl' else None
+
+    def close(self):
+        lib = self._lib
+        self.state.sync()
+        if self.peer:
+            self.comm.barrier()
+            for r, ptrs in enumerate(self.peer):
+                if r != self.comm.rank:
+                    for p in ptrs:
+                        lib.call('qb_ipc_close', self.device, C.c_void_p(p))
+            self.peer = None
+            self.comm.barrier()
+        self.state = None
+        for b in self.buf:
+            if b.value:
+                lib.call('qb_buffer_free', self.device, b)
+                b.value = None
+
+
+# ---------------------------------------------------------------------------------------------
+# the sharded register
+# ---------------------------------------------------------------------------------------------
+class ShardedKet:
+    """n-qubit ket over comm.world = 2^g ranks.  Qubit arguments use the reference's numbering
+    (qubit 0 = most significant index bit, qbot/qgates.py:161-182)."""
+
+    def __init__(self, nq: int, comm, shard_factory=None, device: Optional[int] = None, exchange: str = 'p2p'):
+        world = comm.world
+        g = world.bit_length() - 1
+        if 1 << g != world:
+            raise ValueError("the number of ranks must be a power of two")
+        if nq - g < 1:
+            raise ValueError("too few qubits for this many ranks")
+        self.nq, self.comm, self.rank = nq, comm, comm.rank
+        self.map = QubitMap(nq, g)
+        if shard_factory is None:
+            if device is None:
+                raise ValueError("device is required for the CUDA shard")
+            shard_factory = lambda nl, cm: CudaShard(nl, cm, device, exchange)     # noqa: E731
+        self.shard = shard_factory(nq - g, comm)
+        self.queue: List[LGate] = []
+        self.gates_applied = 0
+        self.shard.init_basis(self.rank == 0, 0)
+
+    # -- gates ---------------------------------------------------------------------------------
+    def _bit(self, q: int) -> int:
+        return self.nq - 1 - int(q)
+
+    def apply_gate(self, matrix, first_target: int = 0, controls: Iterable[int] = ()):
+        m = np.asarray(matrix)
+        k = int(m.shape[0]).bit_length() - 1
+        if first_target < 0 or first_target + k - 1 >= self.nq:
+            raise IndexError(f"{k} qubit gate does not fit the {self.nq} qubit hilbertspace when started on qubit {first_target}")
+        tb = [self._bit(first_target + j) for j in range(k)]
+        self.queue.append(make_lgate(m, tb, [self._bit(c) for c in controls]))
+        return self
+
+    def flush(self):
+        rem = self.queue
+        self.queue = []
+        mp = self.map
+        while rem:
+            picked = select_pass(rem, mp.local_mask())
+            if picked:
+                ps = set(picked)
+                for i in picked:
+                    loc = mp.localise(rem[i], self.rank)
+                    if loc is not None:
+                        self.shard.apply(*loc)
+                self.gates_applied += len(picked)
+                rem = [g for i, g in enumerate(rem) if i not in ps]
+                if not rem:
+                    break
+            ex = mp.plan_exchange(rem)
+            if ex.k == 0 and not picked:
+                raise RuntimeError("sharded planner made no progress")
+            self.shard.flush()
+            self.shard.do_exchange(ex)
+        self.shard.flush()
+
+    def sync(self):
+        self.flush()
+        self.shard.sync()
+
+    # -- read-outs -----------------------------------------------------------------------------
+    def probs(self, qubits: Sequence[int]) -> np.ndarray:
+        """Outcome weights of the listed qubits (first listed = most significant outcome bit);
+        local binning + one all-reduce of 2^m doubles."""
+        self.flush()
+        mp, nl = self.map, self.map.nl
+        m = len(qubits)
+        loc = [(i, mp.pos[self._bit(q)]) for i, q in enumerate(qubits) if mp.pos[self._bit(q)] < nl]
+        glob = [(i, mp.pos[self._bit(q)] - nl) for i, q in enumerate(qubits) if mp.pos[self._bit(q)] >= nl]
+        pl = self.shard.probs_local([p for _, p in loc])
+        out = np.zeros(1 << m, dtype=np.float64)
+        base = 0
+        for i, r in glob:
+            base |= ((self.rank >> r) & 1) << (m - 1 - i)
+        ml = len(loc)
+        for j in range(1 << ml):
+            idx = base
+            for x, (i, _) in enumerate(loc):
+                idx |= ((j >> (ml - 1 - x)) & 1) << (m - 1 - i)
+            out[idx] = pl[j]
+        return self.comm.allreduce_sum(out, self.shard.reduce_device())
+
+    def norm2(self) -> float:
+        return float(self.probs([])[0])
+
+    def amplitudes(self, indices: Sequence[int]) -> np.ndarray:
+        """Amplitudes at the given basis-state indices (reference index convention)."""
+        self.flush()
+        mp, nl = self.map, self.map.nl
+        out = np.zeros(2 * len(indices), dtype=np.float64)
+        for x, idx in enumerate(indices):
+            phys = 0
+            for b in range(self.nq):
+                phys |= ((idx >> b) & 1) << mp.pos[b]
+            if (phys >> nl) == self.rank:
+                v = self.shard.download_range(phys & ((1 << nl) - 1), 1)[0]
+                out[2 * x], out[2 * x + 1] = v.real, v.imag
+        r = self.comm.allreduce_sum(out, self.shard.reduce_device())
+        return r[0::2] + 1j * r[1::2]
+
+    def gather(self) -> np.ndarray:
+        """The full ket on every rank in the reference's index order (tests / small n only)."""
+        self.flush()
+        mp, n, nl = self.map, self.nq, self.map.nl
+        local = self.shard.download()
+        parts = self.comm.allgather_bytes(local.tobytes())
+        phys = np.concatenate([np.frombuffer(p, dtype=np.complex128) for p in parts])
+        # phys index bit p holds logical bit at[p]
+        t = phys.reshape([2] * n)                      # axis a <-> physical bit n-1-a
+        axes = [n - 1 - mp.pos[n - 1 - a] for a in range(n)]    # logical axis a takes physical axis
+        return np.ascontiguousarray(t.transpose(axes)).reshape(-1)
+
+    def close(self):
+        self.shard.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# ProbVal branch batches sharded over ranks (BASELINE config 4)
+# ---------------------------------------------------------------------------------------------
+class ShardedBranchBatch:
+    """B independent branch kets of n qubits, contiguous blocks of B/P branches per rank (keeps
+    the funcWrapper ordering, qbot/probVal.py:365-375).  No data-path communication; the only
+    collective is the final gather of the outcome weights."""
+
+    def __init__(self, nq: int, nbranch: int, comm, device: int, factors: np.ndarray = None):
+        from .state import DeviceState, KET
+        if nbranch % comm.world:
+            raise ValueError("the number of branches must be a multiple of the number of ranks")
+        self.nq, self.nbranch, self.comm = nq, nbranch, comm
+        self.per = nbranch // comm.world
+        self.first = comm.rank * self.per
+        self.device = device
+        if factors is not None:
+            self.state = DeviceState.product_batch(np.asarray(factors)[self.first:self.first + self.per], device)
+        else:
+            self.state = DeviceState.zero_state(nq, KET, self.per, device)
+
+    def apply_gate(self, matrix, first_target: int = 0, controls: Iterable[int] = ()):
+        """The same gate on every branch (fused engine, all branches in one sweep)."""
+        self.state.apply_gate(matrix, first_target, controls)
+        return self
+
+    def apply_gate_per_branch(self, matrices, first_targets, controls=None, enable=None):
+        """Branch b applies matrices[b] at first_targets[b] (global branch numbering)."""
+        sl = slice(self.first, self.first + self.per)
+        self.state.apply_gate_batched(np.asarray(matrices)[sl], list(first_targets)[sl],
+                                      None if controls is None else list(controls)[sl],
+                                      None if enable is None else list(enable)[sl])
+        return self
+
+    def probs(self, qubits: Sequence[int]) -> np.ndarray:
+        """[nbranch, 2^m] on every rank: local outcome weights + one all-gather."""
+        import torch
+        local = np.ascontiguousarray(self.state.probs(qubits)).reshape(self.per, -1)
+        dist = self.comm.dist
+        backend = dist.get_backend(self.comm.group)
+        dev = f'cuda:{self.device}' if backend == 'nccl' else 'cpu'
+        t = torch.from_numpy(local).to(dev)
+        out = torch.empty((self.nbranch, local.shape[1]), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t, group=self.comm.group)
+        return out.cpu().numpy()
+
+    def sync(self):
+        self.state.sync()

@@ -1,0 +1,113 @@
+"""GPU: the sharded-ket device pieces through the C ABI.  The pack kernel is checked against a
+numpy bit permutation; the peer-memory exchange is exercised with TWO processes sharing
+cuda:0 (CUDA IPC mappings work between processes on one device, gloo does the rendezvous), so
+this runs on a single-GPU box; with >= 2 GPUs the NCCL and P2P exchanges are also run one rank
+per GPU under torchrun."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import qbot_oracle as orc
+from qbot_b200 import circuits
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_permute_scatter_matches_numpy():
+    from qbot_b200 import DeviceState, _lib
+    rng = np.random.default_rng(5)
+    for nl, k in [(8, 0), (9, 1), (12, 2), (14, 3)]:
+        psi = rng.normal(size=1 << nl) + 1j * rng.normal(size=1 << nl)
+        st = DeviceState.from_host(psi)
+        perm = list(range(nl))
+        moved = rng.permutation(np.arange(3, nl))[:5]
+        sh = list(moved)
+        rng.shuffle(sh)
+        for a, b in zip(moved, sh):
+            perm[a] = int(b)
+        buf = C.c_void_p()
+        _lib.call('qb_buffer_alloc', 0, 16 << nl, C.byref(buf))
+        chunk = (16 << nl) >> k
+        # chunks deliberately placed in reverse order
+        dst = (C.c_void_p * (1 << k))(*[buf.value + ((1 << k) - 1 - c) * chunk for c in range(1 << k)])
+        _lib.call('qb_permute_scatter', st._h, _lib.int_array(perm), k, dst)
+        st.sync()
+        h = C.c_void_p()
+        _lib.call('qb_create_external', C.byref(h), 0, nl, 1, 0, buf, None)
+        got = DeviceState(h, 0, nl, 1).to_host().copy()
+        j = np.arange(1 << nl)
+        src = np.zeros_like(j)
+        for d, f in enumerate(perm):
+            src |= ((j >> d) & 1) << f
+        want = psi[src].reshape(1 << k, -1)[::-1].reshape(-1)
+        assert np.array_equal(got, want)
+        _lib.call('qb_buffer_free', 0, buf)
+
+
+WORKER = r'''
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+from qbot_b200.sharded import ShardedKet, TorchComm
+from test_sharded_host import circuit_ops, expected_ket
+from oracle import qbot_oracle as orc
+rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE'])
+mode, backend, n = sys.argv[1], sys.argv[2], int(sys.argv[3])
+dev = int(os.environ.get('LOCAL_RANK', '0')) if backend == 'nccl' else 0
+torch.cuda.set_device(dev)
+dist.init_process_group(backend)
+ops = circuit_ops(n, 6, 11)
+sk = ShardedKet(n, TorchComm(), device=dev, exchange=mode)
+for m, t, cs in ops:
+    sk.apply_gate(m, t, cs)
+ket = sk.gather()
+want = expected_ket(n, ops)
+pr = sk.probs([1, n - 1, 0])
+err = float(np.max(np.abs(ket - want)))
+perr = float(np.max(np.abs(pr - orc.ket_probs(want, n, [1, n - 1, 0]))))
+amp = sk.amplitudes([3, (1 << n) - 2])
+aerr = float(np.max(np.abs(amp - want[[3, (1 << n) - 2]])))
+print(json.dumps(dict(rank=rank, err=err, perr=perr, aerr=aerr, exchanges=sk.shard.exchanges,
+                      launches=sk.shard.state.stats()['kernel_launches'])))
+sk.close()
+dist.barrier()
+dist.destroy_process_group()
+assert err < 1e-12 and perr < 1e-12 and aerr < 1e-12 and sk.shard.exchanges >= 1
+'''
+
+
+def _run_ranks(nproc, mode, backend, n, tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER.format(root=ROOT))
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={nproc}',
+           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script), mode, backend, str(n)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_p2p_exchange_two_processes_one_gpu(tmp_path):
+    out = _run_ranks(2, 'p2p', 'gloo', 14, tmp_path)
+    assert out.count('"err"') == 2
+
+
+def test_p2p_exchange_four_processes_one_gpu(tmp_path):
+    out = _run_ranks(4, 'p2p', 'gloo', 15, tmp_path)
+    assert out.count('"err"') == 4
+
+
+@pytest.mark.parametrize('mode', ['p2p', 'nccl'])
+def test_exchange_one_rank_per_gpu(tmp_path, mode):
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nproc = 1 << (ng.bit_length() - 1)
+    out = _run_ranks(nproc, mode, 'nccl', 16, tmp_path)
+    assert out.count('"err"') == nproc

@@ -1,0 +1,182 @@
+"""CPU: host logic of the sharded ket (qubit map, exchange planning, gate localisation, probability
+gather) on numpy shards -- P virtual ranks in threads, and world_size 2 over torch.distributed gloo.
+The expected ket comes from the oracle's strided update on the full register."""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import qbot_oracle as orc
+from qbot_b200 import circuits
+from qbot_b200.sharded import ShardedKet, QubitMap, make_lgate, select_pass
+from np_shard import NumpyShard, VirtualComm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def extra_gates(n, rng):
+    """2-qubit dense / diagonal / swap-like blocks so that multi-target localisation is covered."""
+    out = []
+    for _ in range(6):
+        t = int(rng.integers(0, n - 1))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+            m, _ = np.linalg.qr(a)
+        elif kind == 1:
+            m = np.diag(np.exp(1j * rng.uniform(0, 6.28, 4)))
+        else:
+            m = np.eye(4, dtype=complex)[[0, 2, 1, 3]]
+        free = [q for q in range(n) if q not in (t, t + 1)]
+        cs = [int(c) for c in rng.choice(free, size=int(rng.integers(0, 3)), replace=False)]
+        out.append((m, t, cs))
+    return out
+
+
+def expected_ket(n, ops):
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[0] = 1
+    for m, t, cs in ops:
+        psi = orc.ket_apply(psi, n, t, m, cs)
+    return psi
+
+
+def circuit_ops(n, depth, seed):
+    ops = [(g.matrix(), g.target, list(g.controls)) for g in circuits.rc(n, depth, seed)]
+    rng = np.random.default_rng(seed + 1)
+    ex = extra_gates(n, rng)
+    # interleave
+    out = []
+    step = max(1, len(ops) // (len(ex) + 1))
+    for i, o in enumerate(ops):
+        out.append(o)
+        if i % step == step - 1 and ex:
+            out.append(ex.pop())
+    return out + ex
+
+
+def run_virtual(n, world, ops, probe):
+    shared = VirtualComm.Shared(world)
+    results = [None] * world
+    errors = []
+
+    def work(rank):
+        try:
+            comm = VirtualComm(shared, rank)
+            sk = ShardedKet(n, comm, shard_factory=NumpyShard)
+            half = len(ops) // 2
+            for m, t, cs in ops[:half]:
+                sk.apply_gate(m, t, cs)
+            sk.flush()
+            for m, t, cs in ops[half:]:
+                sk.apply_gate(m, t, cs)
+            results[rank] = dict(ket=sk.gather(), probs=sk.probs(probe), norm=sk.norm2(),
+                                 amps=sk.amplitudes([0, 5, (1 << n) - 1]), exchanges=sk.shard.exchanges,
+                                 at=list(sk.map.at))
+        except Exception as e:     # pragma: no cover
+            errors.append(e)
+            shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+@pytest.mark.parametrize('n,world', [(6, 2), (7, 4), (9, 8), (10, 4)])
+def test_virtual_ranks_match_oracle(n, world):
+    ops = circuit_ops(n, 6, 100 + n)
+    want = expected_ket(n, ops)
+    probe = [n - 1, 0, 2]
+    res = run_virtual(n, world, ops, probe)
+    for r in res:
+        assert np.max(np.abs(r['ket'] - want)) < 1e-12
+        assert np.max(np.abs(r['probs'] - orc.ket_probs(want, n, probe))) < 1e-12
+        assert abs(r['norm'] - 1.0) < 1e-12
+        assert np.max(np.abs(r['amps'] - want[[0, 5, (1 << n) - 1]])) < 1e-12
+        assert r['at'] == res[0]['at']
+    assert res[0]['exchanges'] >= 1          # the circuit does need global qubits
+
+
+def test_exchange_count_is_small():
+    # rc(12, 10): every layer writes ~2/3 of the qubits; farthest-next-use eviction keeps the
+    # number of exchanges well below one per layer-and-rank-bit
+    n, world = 12, 8
+    ops = [(g.matrix(), g.target, list(g.controls)) for g in circuits.rc(n, 10, 34)]
+    res = run_virtual(n, world, ops, [0])
+    assert np.max(np.abs(res[0]['ket'] - expected_ket(n, ops))) < 1e-12
+    assert res[0]['exchanges'] <= 12
+
+
+def test_select_pass_and_localise_rules():
+    H = circuits.HADAMARD
+    X = circuits.PAULI_X
+    rz = circuits.z_rot(0.3)
+    g0 = make_lgate(H, [3])                 # writes 3
+    g1 = make_lgate(rz, [3])                # reads 3
+    g2 = make_lgate(X, [1], [3])            # writes 1, reads 3
+    g3 = make_lgate(H, [0])
+    assert g0.wmask == 8 and g1.wmask == 0 and g1.rmask == 8 and g2.wmask == 2 and g2.rmask == 8
+    # bit 3 not writable: g0 stays, g1 and g2 touch bit 3 written by g0 -> blocked, g3 free
+    assert select_pass([g0, g1, g2, g3], 0b0111) == [3]
+    assert select_pass([g1, g2, g0, g3], 0b0111) == [0, 1, 3]
+    mp = QubitMap(4, 1)                      # logical bit 3 selects the rank
+    assert mp.localise(g2, 0) is None
+    m, tb, cm = mp.localise(g2, 1)
+    assert tb == [1] and cm == 0 and np.array_equal(m, X)
+    m, tb, cm = mp.localise(g1, 1)           # per-rank scalar
+    assert np.allclose(m, rz[1, 1] * np.eye(2))
+    # a CZ written as a 4x4 matrix is block-diagonal in both targets
+    cz = make_lgate(np.diag([1, 1, 1, -1]).astype(complex), [3, 2])
+    assert cz.wmask == 0
+    m, tb, cm = mp.localise(cz, 1)
+    assert tb == [2] and np.allclose(m, np.diag([1, -1]))
+    with pytest.raises(RuntimeError):
+        mp.localise(g0, 0)
+
+
+def _gloo_worker(rank, world, n, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+    from qbot_b200.sharded import ShardedKet, TorchComm
+    from np_shard import NumpyShard
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        ops = circuit_ops(n, 5, 7)
+        sk = ShardedKet(n, TorchComm(), shard_factory=NumpyShard)
+        for m, t, cs in ops:
+            sk.apply_gate(m, t, cs)
+        ket = sk.gather()
+        pr = sk.probs([0, n - 1])
+        q.put((rank, ket, pr, sk.shard.exchanges))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world_size_2():
+    import torch.multiprocessing as mp
+    n, world = 7, 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, n, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = expected_ket(n, circuit_ops(n, 5, 7))
+    for rank, ket, pr, exch in got:
+        assert np.max(np.abs(ket - want)) < 1e-12
+        assert np.max(np.abs(pr - orc.ket_probs(want, n, [0, n - 1]))) < 1e-12
+        assert exch >= 1
