@@ -141,10 +141,12 @@ struct StageBuild {
 };
 
 struct SweepBuild {
+    int M = QT_MAXM;                     // tile bits
     std::vector<int> hb;                 // free tile bits (index positions), ascending
     int local_of[64];                    // index bit -> tile-local position, -1 if outside the tile
     std::vector<StageBuild> stages;
     int ngates = 0;
+    double scale = 1.0;                  // product of the 2^-1/2 factors of the unscaled H ops
 };
 
 // predicate of a gate's controls (and value-controls) split by where each bit lives in this stage
@@ -153,7 +155,8 @@ struct Pred {
     uint64_t gmask, gval;
 };
 
-Pred make_pred(const SweepBuild& sw, const QtStage& st, int R, uint64_t ones_mask, uint64_t zeros_mask) {
+Pred make_pred(const SweepBuild& sw, const QtStage& st, uint64_t ones_mask, uint64_t zeros_mask) {
+    const int R = QT_R;
     Pred p{0, 0, 0, 0, 0};
     uint32_t reg_need1 = 0, reg_need0 = 0;
     for (int b = 0; b < 64; b++) {
@@ -175,17 +178,25 @@ Pred make_pred(const SweepBuild& sw, const QtStage& st, int R, uint64_t ones_mas
     return p;
 }
 
-int reg_index(const QtStage& st, int R, int lp) {
-    for (int q = 0; q < R; q++) if (st.rb[q] == lp) return q;
+int reg_index(const QtStage& st, int lp) {
+    for (int q = 0; q < QT_R; q++) if (st.rb[q] == lp) return q;
     return -1;
 }
 
 void set_pred(QtOp& op, const Pred& p) {
     op.regsel = p.regsel; op.lmask = p.lmask; op.lval = p.lval; op.gmask = p.gmask; op.gval = p.gval;
+    op.flags = (uint16_t)((p.gmask ? QT_FLAG_GLOBAL : 0u) | (p.regsel == 0xffff ? QT_FLAG_ALLREG : 0u));
+}
+
+double phase_code(int loc, int pos) {
+    const int64_t c = (int64_t)(loc | (pos << 8));
+    double d;
+    memcpy(&d, &c, sizeof(d));
+    return d;
 }
 
 // append one gate to a stage as one or more ops
-void emit_gate(SweepBuild& sw, StageBuild& sb, int R, const QGate& g, bool merge_phases) {
+void emit_gate(SweepBuild& sw, StageBuild& sb, const QGate& g, bool merge_phases) {
     QtOp op;
     memset(&op, 0, sizeof(op));
     const QtStage& st = sb.st;
@@ -197,10 +208,10 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, int R, const QGate& g, bool merge
             int loc, pos;
             if (lp < 0) { loc = QT_LOC_GLOBAL; pos = bit; }
             else {
-                int ri = reg_index(st, R, lp);
+                int ri = reg_index(st, lp);
                 if (ri >= 0) { loc = QT_LOC_REG; pos = ri; } else { loc = QT_LOC_LOCAL; pos = lp; }
             }
-            double ent[5] = {(double)(loc | (pos << 8)), g.m[0].x, g.m[0].y, g.m[1].x, g.m[1].y};
+            double ent[5] = {phase_code(loc, pos), g.m[0].x, g.m[0].y, g.m[1].x, g.m[1].y};
             if (merge_phases) {
                 for (int x = (int)sb.ops.size() - 1; x >= 0; x--) {
                     if (sb.ops[x].type == QT_OP_PHASE && sb.ops[x].nent < 200) {
@@ -214,6 +225,7 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, int R, const QGate& g, bool merge
             op.type = QT_OP_PHASE;
             op.nent = 1;
             op.regsel = 0xffff;
+            op.flags = QT_FLAG_ALLREG;
             sb.push(op, 0, ent, 5);
             return;
         }
@@ -230,11 +242,11 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, int R, const QGate& g, bool merge
             QtOp o;
             memset(&o, 0, sizeof(o));
             o.type = QT_OP_CDIAG;
-            set_pred(o, make_pred(sw, st, R, ones, zeros));
+            set_pred(o, make_pred(sw, st, ones, zeros));
             const int lp = sw.local_of[last];
             if (lp < 0) { o.t1 = QT_LOC_GLOBAL; o.t0 = (uint8_t)last; }
             else {
-                int ri = reg_index(st, R, lp);
+                int ri = reg_index(st, lp);
                 if (ri >= 0) { o.t1 = QT_LOC_REG; o.t0 = (uint8_t)ri; } else { o.t1 = QT_LOC_LOCAL; o.t0 = (uint8_t)lp; }
             }
             double d[4] = {d0.x, d0.y, d1.x, d1.y};
@@ -242,11 +254,16 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, int R, const QGate& g, bool merge
         }
         return;
     }
-    set_pred(op, make_pred(sw, st, R, g.cmask, 0));
+    set_pred(op, make_pred(sw, st, g.cmask, 0));
     if (g.k == 1) {
-        op.t0 = (uint8_t)reg_index(st, R, sw.local_of[g.tb[0]]);
+        op.t0 = (uint8_t)reg_index(st, sw.local_of[g.tb[0]]);
         double s;
-        if (is_hadamard_like(g, &s)) { op.type = QT_OP_H; sb.push(op, g.tmask(), &s, 1); }
+        if (g.cmask == 0 && is_hadamard_like(g, &s)) {
+            // unscaled butterfly; the factor joins the sweep's scalar
+            op.type = QT_OP_H;
+            sw.scale *= s;
+            sb.push(op, g.tmask(), nullptr, 0);
+        }
         else if (is_pauli_x(g)) { op.type = QT_OP_X; sb.push(op, g.tmask(), nullptr, 0); }
         else {
             std::vector<cplx> m = dense_matrix(g);
@@ -256,30 +273,35 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, int R, const QGate& g, bool merge
     } else {
         std::vector<cplx> m = dense_matrix(g);
         op.type = QT_OP_U4;
-        op.t0 = (uint8_t)reg_index(st, R, sw.local_of[g.tb[0]]);
-        op.t1 = (uint8_t)reg_index(st, R, sw.local_of[g.tb[1]]);
+        op.t0 = (uint8_t)reg_index(st, sw.local_of[g.tb[0]]);
+        op.t1 = (uint8_t)reg_index(st, sw.local_of[g.tb[1]]);
         sb.push(op, g.tmask(), (const double*)m.data(), 32);
     }
 }
 
-void choose_thread_bits(QtStage& st, int R) {
-    bool is_reg[QT_M] = {false};
-    for (int q = 0; q < R; q++) is_reg[st.rb[q]] = true;
+void choose_thread_bits(QtStage& st, int M, bool io_stage) {
+    bool is_reg[QT_MAXM] = {false};
+    for (int q = 0; q < QT_R; q++) is_reg[st.rb[q]] = true;
     std::vector<int> freep;
-    for (int p = 0; p < QT_M; p++) if (!is_reg[p]) freep.push_back(p);
-    // the three lowest thread bits select the 16-byte bank group of an LDS.128 phase: give them
-    // tile bits of three different bank classes when available
+    for (int p = 0; p < M; p++) if (!is_reg[p]) freep.push_back(p);
     std::vector<int> order;
-    for (int cls : {1, 2, 4}) {
-        for (size_t x = 0; x < freep.size(); x++) {
-            if (bank_class(freep[x]) == cls) { order.push_back(freep[x]); freep.erase(freep.begin() + x); break; }
+    if (io_stage) {
+        // the lanes carry the contiguous low bits: every warp-wide 128-bit access is one 512-byte run
+        order = freep;       // ascending: positions 0..4 first (register bits of an IO stage are >= QT_L)
+    } else {
+        // the three lowest thread bits select the 16-byte bank group of an LDS.128 phase: give them
+        // tile bits of three different bank classes when available
+        for (int cls : {1, 2, 4}) {
+            for (size_t x = 0; x < freep.size(); x++) {
+                if (bank_class(freep[x]) == cls) { order.push_back(freep[x]); freep.erase(freep.begin() + x); break; }
+            }
         }
+        for (int p : freep) order.push_back(p);
     }
-    for (int p : freep) order.push_back(p);
-    for (int q = 0; q < QT_M - R; q++) st.tpos[q] = (uint8_t)order[q];
+    for (int q = 0; q < M - QT_R; q++) st.tpos[q] = (uint8_t)order[q];
 }
 
-std::vector<uint8_t> serialise(const SweepBuild& sw, int R) {
+std::vector<uint8_t> serialise(const SweepBuild& sw, double header_scale) {
     QtHeader h;
     memset(&h, 0, sizeof(h));
     size_t nops = 0, npool = 0;
@@ -289,13 +311,18 @@ std::vector<uint8_t> serialise(const SweepBuild& sw, int R) {
     }
     h.nstages = (uint16_t)sw.stages.size();
     h.nops = (uint16_t)nops;
-    h.R = (uint16_t)R;
+    h.M = (uint16_t)sw.M;
     h.ngates = (uint16_t)sw.ngates;
-    h.stages_off = (uint32_t)((sizeof(QtHeader) + 15) & ~size_t(15));
-    h.ops_off = (uint32_t)((h.stages_off + sizeof(QtStage) * sw.stages.size() + 15) & ~size_t(15));
-    h.pool_off = (uint32_t)((h.ops_off + sizeof(QtOp) * nops + 15) & ~size_t(15));
+    h.scale = header_scale;
+    static_assert(sizeof(QtHeader) <= QT_STAGES_OFF, "header too large");
+    static_assert(QT_STAGES_OFF + QT_MAX_STAGES * sizeof(QtStage) <= QT_OPS_OFF, "stage table too large");
+    static_assert(sizeof(QtOp) == 32, "QtOp must be 32 bytes");
+    if (sw.stages.size() > QT_MAX_STAGES || nops > QT_MAX_OPS) return {};
+    h.stages_off = QT_STAGES_OFF;
+    h.ops_off = QT_OPS_OFF;
+    h.pool_off = QT_POOL_OFF;
     h.total_bytes = (uint32_t)((h.pool_off + sizeof(double) * npool + 15) & ~size_t(15));
-    for (int i = 0; i < QT_H; i++) h.hb[i] = (uint8_t)sw.hb[i];
+    for (int i = 0; i < sw.M - QT_L; i++) h.hb[i] = (uint8_t)sw.hb[i];
     std::vector<uint8_t> out(h.total_bytes, 0);
     memcpy(out.data(), &h, sizeof(h));
     size_t first = 0, pool_at = 0;
@@ -318,78 +345,152 @@ std::vector<uint8_t> serialise(const SweepBuild& sw, int R) {
     return out;
 }
 
-// split one sweep's gates into register stages and serialise; returns false if too large
+// greedy choice of a stage's register bits among the tile-local positions [lo, M): returns the
+// index-bit mask of the chosen positions (exactly QT_R of them, filled up with the highest unused
+// positions when fewer are useful) and how many gates of `rem` the stage can run
+uint64_t choose_stage_bits(const std::vector<int>& rem, const std::vector<GInfo>& info, const uint64_t* index_of_local,
+                           int M, int lo, int* count_out) {
+    uint64_t regmask = 0;
+    int cur = 0, npicked = 0;
+    select_pass(rem, info, regmask, rem.size(), nullptr, &cur);
+    while (npicked < QT_R) {
+        int best = -1, best_count = cur;
+        for (int lp = lo; lp < M; lp++) {
+            const uint64_t bit = 1ull << index_of_local[lp];
+            if (regmask & bit) continue;
+            int c;
+            select_pass(rem, info, regmask | bit, rem.size(), nullptr, &c);
+            if (c > best_count) { best_count = c; best = lp; }
+        }
+        if (best >= 0) {
+            regmask |= 1ull << index_of_local[best];
+            cur = best_count;
+            npicked++;
+            continue;
+        }
+        // no single bit helps (e.g. a two-target gate needs both): try pairs
+        int pa = -1, pb = -1, bc = cur;
+        if (npicked + 2 <= QT_R) {
+            for (int a = lo; a < M; a++) for (int b2 = a + 1; b2 < M; b2++) {
+                const uint64_t bits = (1ull << index_of_local[a]) | (1ull << index_of_local[b2]);
+                if (regmask & bits) continue;
+                int c;
+                select_pass(rem, info, regmask | bits, rem.size(), nullptr, &c);
+                if (c > bc) { bc = c; pa = a; pb = b2; }
+            }
+        }
+        if (pa >= 0) {
+            regmask |= (1ull << index_of_local[pa]) | (1ull << index_of_local[pb]);
+            cur = bc;
+            npicked += 2;
+            continue;
+        }
+        break;
+    }
+    for (int lp = M - 1; lp >= lo && npicked < QT_R; lp--) {     // fill up
+        const uint64_t bit = 1ull << index_of_local[lp];
+        if (!(regmask & bit)) { regmask |= bit; npicked++; }
+    }
+    if (count_out) *count_out = cur;
+    return regmask;
+}
+
+StageBuild make_stage(uint64_t regmask, const uint64_t* index_of_local, int M, bool io_stage) {
+    StageBuild sb;
+    memset(&sb.st, 0, sizeof(sb.st));
+    int q = 0;
+    for (int lp = 0; lp < M; lp++) if (regmask & (1ull << index_of_local[lp])) sb.st.rb[q++] = (uint8_t)lp;
+    choose_thread_bits(sb.st, M, io_stage);
+    return sb;
+}
+
+// split one sweep's gates into register stages and serialise; returns false if too large.
+// The first and the last stage move the tile between HBM and registers, so their register bits
+// are free tile bits (positions >= QT_L) and their lanes the contiguous low bits; stages that
+// need a low bit in registers sit in between (an op-less IO stage is added when necessary).
 bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& info, const std::vector<int>& sweep_gates,
-                   const std::vector<int>& hb, int R, bool merge_phases, std::vector<uint8_t>* program) {
+                   const std::vector<int>& hb, int M, bool merge_phases, std::vector<uint8_t>* program) {
     SweepBuild sw;
+    sw.M = M;
     sw.hb = hb;
     for (int b = 0; b < 64; b++) sw.local_of[b] = -1;
     for (int b = 0; b < QT_L; b++) sw.local_of[b] = b;
-    for (int i = 0; i < QT_H; i++) sw.local_of[hb[i]] = QT_L + i;
+    for (int i = 0; i < M - QT_L; i++) sw.local_of[hb[i]] = QT_L + i;
     sw.ngates = (int)sweep_gates.size();
-    uint64_t tile_mask = 0;
-    for (int b = 0; b < 64; b++) if (sw.local_of[b] >= 0) tile_mask |= 1ull << b;
-    uint64_t index_of_local[QT_M];
+    uint64_t index_of_local[QT_MAXM];
     for (int b = 0; b < 64; b++) if (sw.local_of[b] >= 0) index_of_local[sw.local_of[b]] = (uint64_t)b;
+    uint64_t low_index_mask = 0;
+    for (int lp = 0; lp < QT_L; lp++) low_index_mask |= 1ull << index_of_local[lp];
 
     std::vector<int> rem = sweep_gates;
+    bool first = true;
     while (!rem.empty()) {
-        // greedy choice of the stage's register bits (as index-bit mask)
-        uint64_t regmask = 0;
-        int cur = 0;
-        select_pass(rem, info, regmask, rem.size(), nullptr, &cur);
-        for (int pick = 0; pick < R; pick++) {
-            int best = -1, best_count = -1;
-            for (int lp = 0; lp < QT_M; lp++) {
-                uint64_t bit = 1ull << index_of_local[lp];
-                if (regmask & bit) continue;
-                int c;
-                select_pass(rem, info, regmask | bit, rem.size(), nullptr, &c);
-                // tie-break: prefer bits that some remaining gate writes, then higher tile bits
-                if (c > best_count) { best_count = c; best = lp; }
-            }
-            if (best_count <= cur) {
-                // no single bit helps (e.g. a two-target gate needs both): try pairs for the head write set
-                int best_pair_a = -1, best_pair_b = -1, bc = cur;
-                if (pick + 1 < R) {
-                    for (int a = 0; a < QT_M; a++) for (int b2 = a + 1; b2 < QT_M; b2++) {
-                        uint64_t bits = (1ull << index_of_local[a]) | (1ull << index_of_local[b2]);
-                        if (regmask & bits) continue;
-                        int c;
-                        select_pass(rem, info, regmask | bits, rem.size(), nullptr, &c);
-                        if (c > bc) { bc = c; best_pair_a = a; best_pair_b = b2; }
-                    }
-                }
-                if (best_pair_a >= 0) {
-                    regmask |= (1ull << index_of_local[best_pair_a]) | (1ull << index_of_local[best_pair_b]);
-                    cur = bc;
-                    pick++;
-                    continue;
-                }
-            }
-            regmask |= 1ull << index_of_local[best];
-            cur = std::max(cur, best_count);
-        }
-        StageBuild sb;
-        memset(&sb.st, 0, sizeof(sb.st));
-        int q = 0;
-        for (int lp = 0; lp < QT_M; lp++) if (regmask & (1ull << index_of_local[lp])) sb.st.rb[q++] = (uint8_t)lp;
-        choose_thread_bits(sb.st, R);
+        uint64_t regmask;
+        bool io = false;
+        int c_all = 0, c_hi = 0;
+        const uint64_t m_all = choose_stage_bits(rem, info, index_of_local, M, 0, &c_all);
+        const uint64_t m_hi = choose_stage_bits(rem, info, index_of_local, M, QT_L, &c_hi);
+        if (first) {
+            // the first stage must be an IO stage; if free bits alone run nothing it stays op-less
+            regmask = m_hi; io = true;
+        } else if (c_hi >= c_all) { regmask = m_hi; io = true; }     // can serve as the last stage too
+        else regmask = m_all;
+        if ((regmask & low_index_mask) == 0) io = true;
+        StageBuild sb = make_stage(regmask, index_of_local, M, io);
         std::vector<int> picked;
         select_pass(rem, info, regmask, rem.size(), &picked, nullptr);
-        if (picked.empty()) return false;   // cannot happen: the head gate always fits
-        for (int gi : picked) emit_gate(sw, sb, R, gates[gi], merge_phases);
+        if (picked.empty() && !first) return false;   // cannot happen: the head gate always fits some stage
+        for (int gi : picked) emit_gate(sw, sb, gates[gi], merge_phases);
         std::vector<int> next;
         size_t pi = 0;
         for (int gi : rem) {
             if (pi < picked.size() && picked[pi] == gi) pi++; else next.push_back(gi);
         }
         rem.swap(next);
+        const bool empty_first = first && picked.empty();
+        first = false;
+        if (empty_first && rem.empty()) break;
         sw.stages.push_back(std::move(sb));
-        if (sw.stages.size() > 64) return false;
+        if (sw.stages.size() > QT_MAX_STAGES) return false;
     }
-    std::vector<uint8_t> prog = serialise(sw, R);
-    if (prog.size() > QT_MAX_PROGRAM_BYTES) return false;
+    if (sw.stages.empty()) return false;
+    {   // the last stage must be an IO stage
+        const QtStage& last = sw.stages.back().st;
+        bool low = false;
+        for (int q = 0; q < QT_R; q++) if (last.rb[q] < QT_L) low = true;
+        if (low) {
+            uint64_t regmask = 0;
+            for (int lp = M - 1; lp >= M - QT_R; lp--) regmask |= 1ull << index_of_local[lp];
+            sw.stages.push_back(make_stage(regmask, index_of_local, M, true));
+            if (sw.stages.size() > QT_MAX_STAGES) return false;
+        } else {
+            // make sure its thread map is the IO one (lanes = low bits)
+            choose_thread_bits(sw.stages.back().st, M, true);
+            // predicates of ops already emitted do not depend on the thread map: only on rb
+        }
+    }
+    size_t nops = 0;
+    for (const auto& sb : sw.stages) nops += sb.ops.size();
+    if (nops > QT_MAX_OPS) return false;
+    // the collected 2^-1/2 factors ride on a PHASE op when there is one, else on the header
+    double header_scale = 1.0;
+    if (sw.scale != 1.0) {
+        bool placed = false;
+        for (auto& sb : sw.stages) {
+            for (size_t x = 0; x < sb.ops.size() && !placed; x++) {
+                if (sb.ops[x].type == QT_OP_PHASE && sb.ops[x].nent < 200) {
+                    double ent[5] = {phase_code(QT_LOC_CONST, 0), sw.scale, 0.0, sw.scale, 0.0};
+                    sb.payload[x].insert(sb.payload[x].end(), ent, ent + 5);
+                    sb.ops[x].nent++;
+                    placed = true;
+                }
+            }
+            if (placed) break;
+        }
+        if (!placed) header_scale = sw.scale;
+    }
+    std::vector<uint8_t> prog = serialise(sw, header_scale);
+    if (prog.empty() || prog.size() > QT_MAX_PROGRAM_BYTES) return false;
     program->swap(prog);
     return true;
 }
@@ -398,12 +499,14 @@ bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& in
 
 std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt) {
     std::vector<QtPlanStep> steps;
-    const int R = opt.R;
+    const int M = opt.M;
+    if (M < QT_MINM || M > QT_MAXM) throw std::runtime_error("planner: tile bits out of range");
+    const int NH = M - QT_L;
     std::vector<GInfo> info(gates.size());
     for (size_t i = 0; i < gates.size(); i++) info[i] = analyse(gates[i]);
     std::vector<int> rem(gates.size());
     for (size_t i = 0; i < gates.size(); i++) rem[i] = (int)i;
-    const bool can_tile = nbits >= QT_M;
+    const bool can_tile = nbits >= M;
     const size_t WINDOW = 512;
 
     while (!rem.empty()) {
@@ -422,7 +525,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
         int cur;
         select_pass(rem, info, allowed, WINDOW, nullptr, &cur);
         std::vector<int> hb;
-        while ((int)hb.size() < QT_H) {
+        while ((int)hb.size() < NH) {
             int best = -1, best_count = cur;
             for (int b = QT_L; b < nbits; b++) {
                 if (allowed & (1ull << b)) continue;
@@ -430,7 +533,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
                 select_pass(rem, info, allowed | (1ull << b), WINDOW, nullptr, &c);
                 if (c > best_count) { best_count = c; best = b; }
             }
-            if (best < 0 && (int)hb.size() + 2 <= QT_H) {
+            if (best < 0 && (int)hb.size() + 2 <= NH) {
                 // two-target gates need both bits at once
                 int ba = -1, bb = -1;
                 for (int a = QT_L; a < nbits; a++) for (int b = a + 1; b < nbits; b++) {
@@ -453,7 +556,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
             cur = best_count;
         }
         // fill up with the lowest unused bits (longer contiguous runs in HBM)
-        for (int b = QT_L; b < nbits && (int)hb.size() < QT_H; b++) {
+        for (int b = QT_L; b < nbits && (int)hb.size() < NH; b++) {
             if (!(allowed & (1ull << b))) { allowed |= 1ull << b; hb.push_back(b); }
         }
         std::sort(hb.begin(), hb.end());
@@ -472,7 +575,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
         }
         // ---- stages + program (shrink the sweep if the program does not fit) -------------------
         std::vector<uint8_t> program;
-        while (!build_program(gates, info, picked, hb, R, opt.merge_phases, &program)) {
+        while (!build_program(gates, info, picked, hb, M, opt.merge_phases, &program)) {
             if (picked.size() <= 1) throw std::runtime_error("planner: cannot build a program for one gate");
             picked.resize(picked.size() / 2);
         }

@@ -1,17 +1,21 @@
-// qbot_b200 -- fused multi-gate sweep: persistent TMA-staged tile kernel + host engine.
+// qbot_b200 -- fused multi-gate sweep: persistent register-IO tile kernel + host engine.
 //
 // One launch = one sweep = one read + one write of the whole state (32 * 2^n bytes of HBM
 // traffic) during which every gate of the sweep's program is applied (qb_plan.h describes
-// tiles / stages / ops).  Per CTA (one per SM, persistent over tiles t = blockIdx.x + i*grid):
+// tiles / stages / ops).  A CTA of 2^(M-4) threads is persistent over tiles
+// t = blockIdx.x + i * gridDim.x and keeps a tile's 2^M amplitudes in REGISTERS, 16 per thread:
 //
-//   HBM --cp.async.bulk (128 x 512 B runs, mbarrier complete_tx)--> smem tile (3-deep ring)
-//        for each stage:  smem -> registers (2^R amplitudes / thread), ops, registers -> smem
-//   smem --cp.async.bulk.global (bulk_group)--> HBM
+//   HBM --16 x LDG.128 per thread (each warp access = one 512-byte run)--> registers
+//        stage 0 ops | STS.128 -> bar -> LDS.128 | stage 1 ops | ... | last stage ops
+//   registers --16 x STG.128 per thread (512-byte runs)--> HBM
 //
-// Loads are issued two tiles ahead and stores drain asynchronously, so the TMA engine keeps
-// HBM busy while all warps compute; the only generic-proxy global accesses are the program
-// copy.  Shared-memory placement (qt_slot) keeps every 512-byte run contiguous for the bulk
-// copies and skews runs so that any choice of register bits stays (mostly) bank-conflict free.
+// Shared memory is touched only by the transposition between two stages (padded layout
+// qt_slot, conflict-free for any choice of register bits), never for staging the HBM traffic.
+// Two (M = 12) or four (M = 11) CTAs are resident per SM, so that one CTA's loads, barriers and
+// stores overlap the other's arithmetic; the next tile of every CTA is prefetched into L2 with
+// cp.async.bulk.prefetch while the current one is computed.  Everything that does not depend on
+// the tile is computed once per launch: the per-stage thread index / shared-memory slot of every
+// thread and a 64-bit mask of the ops whose thread-local predicate holds for this thread.
 #include "qb_engine.h"
 #include "qb_plan.h"
 #include "qb_tile_ops.h"
@@ -19,136 +23,143 @@
 #include <cstring>
 #include <list>
 
-#define QT_TILE_BYTES (QT_TILE_UNITS * 16)
-#define QT_NBUF 3
-#define QT_SMEM_BYTES (QT_NBUF * QT_TILE_BYTES + QT_MAX_PROGRAM_BYTES + QT_RUNS * 8 + 64)
+template <int M> struct TileCfg {
+    static constexpr int T = 1 << (M - QT_R);
+    static constexpr int NH = M - QT_L;
+    static constexpr int CTAS_PER_SM = (M == 12) ? 2 : 4;
+    static constexpr int TILE_BYTES = QT_TILE_UNITS(M) * 16;
+    // per-thread tables: lbase + slot per stage (uint16 each), HBM offset of the thread in the
+    // first / last stage (uint64 each)
+    static constexpr int TABLE_BYTES = 2 * QT_MAX_STAGES * T * 2 + 2 * T * 8;
+    static constexpr int SMEM_BYTES = TILE_BYTES + QT_MAX_PROGRAM_BYTES + TABLE_BYTES + 64;
+};
 
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// Gray-code walk over the 16 register indices: gray(j) and the bit flipped between j-1 and j
+__device__ __forceinline__ constexpr int gray_of(int j) { return j ^ (j >> 1); }
+__device__ __forceinline__ constexpr int gray_flip(int j) {        // j >= 1
+    const int d = gray_of(j) ^ gray_of(j - 1);
+    return d == 1 ? 0 : d == 2 ? 1 : d == 4 ? 2 : 3;
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// ---- the sweep kernel ---------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(1 << (QT_M - R), 1)
-k_tile_sweep(cplx* __restrict__ psi, const uint8_t* __restrict__ prog_dev, uint64_t ntiles) {
-    constexpr int NR = 1 << R;
-    constexpr int RUN_BYTES = (1 << QT_L) * 16;
-    constexpr int RUNS_PER_LANE = QT_RUNS / 32;
+template <int M>
+__global__ void __launch_bounds__(1 << (M - QT_R), (M == 12) ? 2 : 4)
+k_tile_sweep(cplx* __restrict__ psi, const uint8_t* __restrict__ prog_dev, uint64_t ntiles, int prefetch) {
+    using Cfg = TileCfg<M>;
+    constexpr int T = Cfg::T, NH = Cfg::NH;
     extern __shared__ __align__(128) uint8_t smem[];
-    cplx* bufs = (cplx*)smem;
-    uint8_t* prog = smem + QT_NBUF * QT_TILE_BYTES;
-    uint64_t* run_off = (uint64_t*)(prog + QT_MAX_PROGRAM_BYTES);
-    uint64_t* full = run_off + QT_RUNS;
+    cplx* buf = (cplx*)smem;
+    uint8_t* prog = smem + Cfg::TILE_BYTES;
+    uint16_t* thr_lbase = (uint16_t*)(prog + QT_MAX_PROGRAM_BYTES);
+    uint16_t* thr_slot = thr_lbase + QT_MAX_STAGES * T;
+    uint64_t* thr_gin = (uint64_t*)(thr_slot + QT_MAX_STAGES * T);
+    uint64_t* thr_gout = thr_gin + T;
 
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     {
         const uint32_t total = ((const QtHeader*)prog_dev)->total_bytes;
         for (uint32_t i = tid * 16; i < total; i += T * 16) *(uint4*)(prog + i) = *(const uint4*)(prog_dev + i);
-        if (tid < QT_NBUF) mbar_init(&full[tid], 1);
     }
     __syncthreads();
     const QtHeader* h = (const QtHeader*)prog;
-    const QtStage* stages = (const QtStage*)(prog + h->stages_off);
-    const QtOp* ops = (const QtOp*)(prog + h->ops_off);
-    const double* pool = (const double*)(prog + h->pool_off);
-    if (tid < QT_RUNS) run_off[tid] = qt_run_offset((uint32_t)tid, h->hb);
-    fence_mbar_init();
-    __syncthreads();
-
-    if (blockIdx.x >= ntiles) return;
-    const uint64_t my_n = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const QtStage* stages = (const QtStage*)(prog + QT_STAGES_OFF);
+    const QtOp* ops = (const QtOp*)(prog + QT_OPS_OFF);
+    const double* pool = (const double*)(prog + QT_POOL_OFF);
     const int nstages = h->nstages;
 
-    auto issue_load = [&](uint64_t it) {      // warp 0 only
-        const int b = (int)(it % QT_NBUF);
-        const uint64_t tb = qt_tile_base(blockIdx.x + it * gridDim.x, h->hb);
-        if (lane == 0) mbar_arrive_expect_tx(&full[b], QT_RUNS * RUN_BYTES);
-        __syncwarp();
-        cplx* dst = bufs + (size_t)b * QT_TILE_UNITS;
-#pragma unroll
-        for (int r = 0; r < RUNS_PER_LANE; r++) {
-            const uint32_t k = lane + 32 * r;
-            bulk_load(dst + qt_slot(k << QT_L), psi + tb + run_off[k], RUN_BYTES, &full[b]);
-        }
-    };
-
-    if (warp == 0) {
-        issue_load(0);
-        if (my_n > 1) issue_load(1);
+    // ---- tile-independent per-thread state ----------------------------------------------------
+    uint64_t lok = 0;                                   // ops whose thread-local predicate holds here
+    for (int s = 0; s < nstages; s++) {
+        const QtStage& st = stages[s];
+        const uint32_t lb = qt_thread_lbase(st, (uint32_t)tid, M);
+        thr_lbase[s * T + tid] = (uint16_t)lb;
+        thr_slot[s * T + tid] = (uint16_t)qt_slot(lb);
+        for (int o = 0; o < st.nops; o++)
+            if (qt_op_local_ok(ops[st.first_op + o], lb)) lok |= 1ull << (st.first_op + o);
+        // HBM addressing of the first / last stage: lane = low bits, the rest through the run offsets
+        if (s == 0) thr_gin[tid] = (lb & 31u) + qt_run_offset(lb >> QT_L, h->hb, NH);
+        if (s == nstages - 1) thr_gout[tid] = (lb & 31u) + qt_run_offset(lb >> QT_L, h->hb, NH);
     }
+    __syncthreads();
 
-    for (uint64_t it = 0; it < my_n; it++) {
-        const int b = (int)(it % QT_NBUF);
-        const uint64_t tbase = qt_tile_base(blockIdx.x + it * gridDim.x, h->hb);
-        cplx* buf = bufs + (size_t)b * QT_TILE_UNITS;
-        mbar_wait(&full[b], (uint32_t)((it / QT_NBUF) & 1));
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t tbase = qt_tile_base(tile, h->hb, NH);
+        cplx a[QT_NR];
+        {
+            const QtStage& s0 = stages[0];
+            const cplx* p = psi + tbase + thr_gin[tid];
+            a[0] = __ldcs(p);
+#pragma unroll
+            for (int j = 1; j < QT_NR; j++) {
+                const int q = gray_flip(j), g = gray_of(j);
+                const int64_t step = (int64_t)1 << h->hb[s0.rb[q] - QT_L];
+                p += ((g >> q) & 1) ? step : -step;
+                a[g] = __ldcs(p);
+            }
+        }
+        if (prefetch && tid < (1 << NH)) {
+            const uint64_t nt = tile + gridDim.x;
+            if (nt < ntiles)
+                l2_prefetch_bulk(psi + qt_tile_base(nt, h->hb, NH) + qt_run_offset((uint32_t)tid, h->hb, NH), 512);
+        }
 
-        for (int s = 0; s < nstages; s++) {
+        for (int s = 0;; s++) {
             const QtStage& st = stages[s];
-            const uint32_t lbase = qt_thread_lbase<R>(st, (uint32_t)tid);
-            cplx a[NR];
-            uint32_t slot[NR];
-#pragma unroll
-            for (int i = 0; i < NR; i++) {
-                slot[i] = qt_slot(lbase | qt_reg_offset<R>(st, i));
-                a[i] = buf[slot[i]];
+            const uint32_t lbase = thr_lbase[s * T + tid];
+            const int first = st.first_op, nops = st.nops;
+            for (int o = 0; o < nops; o++) {
+                const int oi = first + o;
+                if (!((lok >> oi) & 1ull)) continue;
+                const QtOp& op = ops[oi];
+                if ((op.flags & QT_FLAG_GLOBAL) && !qt_op_global_ok(op, tbase)) continue;
+                qt_apply_op(a, op, pool, lbase, tbase);
             }
-            const int nops = st.nops;
-            const QtOp* sop = ops + st.first_op;
-            for (int o = 0; o < nops; o++) qt_apply_op<R>(a, sop[o], pool, lbase, tbase);
+            if (s + 1 == nstages) break;
+            // ---- transposition: this stage's register bits out, the next stage's in -------------
+            {
+                cplx* p = buf + thr_slot[s * T + tid];
+                if (s == 0) __syncthreads();          // the previous tile's last reads are done
+                p[0] = a[0];
 #pragma unroll
-            for (int i = 0; i < NR; i++) buf[slot[i]] = a[i];
-            if (s + 1 < nstages) __syncthreads();
+                for (int j = 1; j < QT_NR; j++) {
+                    const int q = gray_flip(j), g = gray_of(j);
+                    const int step = (int)qt_slot(1u << st.rb[q]);
+                    p += ((g >> q) & 1) ? step : -step;
+                    *p = a[g];
+                }
+            }
+            __syncthreads();
+            {
+                const QtStage& sn = stages[s + 1];
+                const cplx* p = buf + thr_slot[(s + 1) * T + tid];
+                a[0] = p[0];
+#pragma unroll
+                for (int j = 1; j < QT_NR; j++) {
+                    const int q = gray_flip(j), g = gray_of(j);
+                    const int step = (int)qt_slot(1u << sn.rb[q]);
+                    p += ((g >> q) & 1) ? step : -step;
+                    a[g] = *p;
+                }
+            }
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (warp == 0) {
+        {
+            const double scale = h->scale;
+            if (scale != 1.0) qt_scale_real(a, scale);
+            const QtStage& s1 = stages[nstages - 1];
+            cplx* p = psi + tbase + thr_gout[tid];
+            __stcs(p, a[0]);
 #pragma unroll
-            for (int r = 0; r < RUNS_PER_LANE; r++) {
-                const uint32_t k = lane + 32 * r;
-                bulk_store(psi + tbase + run_off[k], buf + qt_slot(k << QT_L), RUN_BYTES);
-            }
-            bulk_commit();
-            if (it + 2 < my_n) {
-                bulk_wait_read<1>();          // the previous tile's stores no longer read their buffer
-                __syncwarp();
-                issue_load(it + 2);
+            for (int j = 1; j < QT_NR; j++) {
+                const int q = gray_flip(j), g = gray_of(j);
+                const int64_t step = (int64_t)1 << h->hb[s1.rb[q] - QT_L];
+                p += ((g >> q) & 1) ? step : -step;
+                __stcs(p, a[g]);
             }
         }
     }
-    if (warp == 0) bulk_wait<0>();
 }
 
 // ---- host engine --------------------------------------------------------------------------------
@@ -165,7 +176,7 @@ struct CachedPlan {
 
 struct EngineState {
     std::list<CachedPlan> cache;       // most recent first
-    bool attr_set[5] = {false, false, false, false, false};
+    bool attr_set[16] = {false};
 };
 
 uint64_t fnv(uint64_t h, const void* p, size_t n) {
@@ -174,10 +185,10 @@ uint64_t fnv(uint64_t h, const void* p, size_t n) {
     return h;
 }
 
-uint64_t hash_gates(const std::vector<QGate>& gates, int nbits, int R) {
+uint64_t hash_gates(const std::vector<QGate>& gates, int nbits, int M) {
     uint64_t h = 1469598103934665603ull;
     h = fnv(h, &nbits, sizeof(nbits));
-    h = fnv(h, &R, sizeof(R));
+    h = fnv(h, &M, sizeof(M));
     for (const QGate& g : gates) {
         h = fnv(h, &g.type, sizeof(int));
         h = fnv(h, &g.k, sizeof(int));
@@ -189,13 +200,34 @@ uint64_t hash_gates(const std::vector<QGate>& gates, int nbits, int R) {
     return h;
 }
 
-int engine_R() {
-    static int r = [] {
-        const char* e = getenv("QBOT_B200_TILE_R");
-        int v = e ? atoi(e) : 4;
-        return (v == 3 || v == 4) ? v : 4;
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+int engine_M() {
+    static int m = [] {
+        int v = env_int("QBOT_B200_TILE_M", 12);
+        return (v == 11 || v == 12) ? v : 12;
     }();
-    return r;
+    return m;
+}
+
+int engine_prefetch() {
+    static int p = env_int("QBOT_B200_L2_PREFETCH", 1);
+    return p;
+}
+
+template <int M>
+void launch_sweep(qb_state* s, EngineState* es, const uint8_t* prog, uint64_t ntiles) {
+    using Cfg = TileCfg<M>;
+    if (!es->attr_set[M]) {
+        QB_CUDA(cudaFuncSetAttribute(k_tile_sweep<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        QB_CUDA(cudaFuncSetAttribute(k_tile_sweep<M>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        es->attr_set[M] = true;
+    }
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)s->sms * Cfg::CTAS_PER_SM);
+    k_tile_sweep<M><<<grid, Cfg::T, Cfg::SMEM_BYTES, s->stream>>>(s->d, prog, ntiles, engine_prefetch());
 }
 
 }  // namespace
@@ -213,8 +245,8 @@ void qb_engine_free(qb_state* s) {
 void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
     if (!s->engine) s->engine = new EngineState();
     EngineState* es = (EngineState*)s->engine;
-    const int R = engine_R();
-    const uint64_t hsh = hash_gates(gates, s->nbits, R);
+    const int M = engine_M();
+    const uint64_t hsh = hash_gates(gates, s->nbits, M);
     CachedPlan* plan = nullptr;
     for (auto it = es->cache.begin(); it != es->cache.end(); ++it) {
         if (it->hash == hsh && it->ngates == gates.size() && it->nbits == s->nbits) {
@@ -227,7 +259,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         CachedPlan cp;
         cp.hash = hsh; cp.ngates = gates.size(); cp.nbits = s->nbits;
         QtPlanOptions opt;
-        opt.R = R;
+        opt.M = M;
         cp.steps = qt_plan(gates, s->nbits, opt);
         size_t total = 0;
         cp.prog_off.resize(cp.steps.size(), 0);
@@ -253,29 +285,16 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         plan = &es->cache.front();
     }
 
-    const uint64_t ntiles = s->total() >> QT_M;
+    const uint64_t ntiles = s->total() >> M;
     for (size_t i = 0; i < plan->steps.size(); i++) {
         const QtPlanStep& st = plan->steps[i];
         if (!st.fused) {
             s->run_gate_unfused(gates[st.gate_index]);
             continue;
         }
-        const int threads = 1 << (QT_M - R);
-        const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)s->sms);
         const uint8_t* prog = plan->dev + plan->prog_off[i];
-        if (R == 3) {
-            if (!es->attr_set[3]) {
-                QB_CUDA(cudaFuncSetAttribute(k_tile_sweep<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, QT_SMEM_BYTES));
-                es->attr_set[3] = true;
-            }
-            k_tile_sweep<3><<<grid, threads, QT_SMEM_BYTES, s->stream>>>(s->d, prog, ntiles);
-        } else {
-            if (!es->attr_set[4]) {
-                QB_CUDA(cudaFuncSetAttribute(k_tile_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QT_SMEM_BYTES));
-                es->attr_set[4] = true;
-            }
-            k_tile_sweep<4><<<grid, threads, QT_SMEM_BYTES, s->stream>>>(s->d, prog, ntiles);
-        }
+        if (M == 11) launch_sweep<11>(s, es, prog, ntiles);
+        else launch_sweep<12>(s, es, prog, ntiles);
         QB_CUDA(cudaGetLastError());
         s->stats.kernel_launches++;
         s->stats.fused_passes++;

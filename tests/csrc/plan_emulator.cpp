@@ -9,44 +9,47 @@
 #include "../../qbot_b200/csrc/qb_tile_ops.h"
 
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 static std::string g_err;
 
-template <int R>
 static void run_program(const uint8_t* prog, qt_c* psi, int nbits) {
     const QtHeader* h = (const QtHeader*)prog;
     const QtStage* stages = (const QtStage*)(prog + h->stages_off);
     const QtOp* ops = (const QtOp*)(prog + h->ops_off);
     const double* pool = (const double*)(prog + h->pool_off);
-    const uint64_t ntiles = 1ull << (nbits - QT_M);
-    const int T = 1 << (QT_M - R);
-    std::vector<qt_c> buf(QT_TILE_UNITS);
+    const int M = h->M, NH = M - QT_L;
+    const uint64_t ntiles = 1ull << (nbits - M);
+    const int T = 1 << (M - QT_R);
+    std::vector<qt_c> buf(1u << M);
+    // the kernel's contract: first and last stage keep the low QT_L bits in the lanes and only
+    // free tile bits in registers
+    for (int s : {0, (int)h->nstages - 1}) {
+        for (int q = 0; q < QT_R; q++) if (stages[s].rb[q] < QT_L) throw std::runtime_error("IO stage holds a low bit in registers");
+        for (int q = 0; q < QT_L; q++) if (stages[s].tpos[q] != q) throw std::runtime_error("IO stage lanes are not the low bits");
+    }
+    if (h->nops > QT_MAX_OPS || h->nstages > QT_MAX_STAGES) throw std::runtime_error("program exceeds the kernel limits");
     for (uint64_t t = 0; t < ntiles; t++) {
-        const uint64_t tbase = qt_tile_base(t, h->hb);
-        for (uint32_t k = 0; k < QT_RUNS; k++) {
-            const qt_c* src = psi + tbase + qt_run_offset(k, h->hb);
-            for (uint32_t w = 0; w < (1u << QT_L); w++) buf[qt_slot((k << QT_L) | w)] = src[w];
-        }
+        const uint64_t tbase = qt_tile_base(t, h->hb, NH);
+        for (uint32_t j = 0; j < (1u << M); j++) buf[j] = psi[tbase + (j & 31u) + qt_run_offset(j >> QT_L, h->hb, NH)];
         for (int s = 0; s < h->nstages; s++) {
             const QtStage& st = stages[s];
             for (int tid = 0; tid < T; tid++) {
-                const uint32_t lbase = qt_thread_lbase<R>(st, (uint32_t)tid);
-                qt_c a[1 << R];
-                uint32_t slot[1 << R];
-                for (int i = 0; i < (1 << R); i++) {
-                    slot[i] = qt_slot(lbase | qt_reg_offset<R>(st, i));
-                    a[i] = buf[slot[i]];
+                const uint32_t lbase = qt_thread_lbase(st, (uint32_t)tid, M);
+                qt_c a[QT_NR];
+                for (int i = 0; i < QT_NR; i++) a[i] = buf[lbase | qt_reg_offset(st, i)];
+                for (int o = 0; o < st.nops; o++) {
+                    const QtOp& op = ops[st.first_op + o];
+                    if (!qt_op_local_ok(op, lbase) || !qt_op_global_ok(op, tbase)) continue;
+                    qt_apply_op(a, op, pool, lbase, tbase);
                 }
-                for (int o = 0; o < st.nops; o++) qt_apply_op<R>(a, ops[st.first_op + o], pool, lbase, tbase);
-                for (int i = 0; i < (1 << R); i++) buf[slot[i]] = a[i];
+                if (s + 1 == h->nstages && h->scale != 1.0) qt_scale_real(a, h->scale);
+                for (int i = 0; i < QT_NR; i++) buf[lbase | qt_reg_offset(st, i)] = a[i];
             }
         }
-        for (uint32_t k = 0; k < QT_RUNS; k++) {
-            qt_c* dst = psi + tbase + qt_run_offset(k, h->hb);
-            for (uint32_t w = 0; w < (1u << QT_L); w++) dst[w] = buf[qt_slot((k << QT_L) | w)];
-        }
+        for (uint32_t j = 0; j < (1u << M); j++) psi[tbase + (j & 31u) + qt_run_offset(j >> QT_L, h->hb, NH)] = buf[j];
     }
 }
 
@@ -80,7 +83,7 @@ const char* qbt_last_error() { return g_err.c_str(); }
 // gates: ks[g], target bits tbs[g*14..], cmasks[g], dense matrices concatenated (4^k complex each)
 // stats out: [steps, fused sweeps, unfused steps, stages, ops, program bytes max, gates in fused sweeps]
 int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t* cmasks, const double* mats,
-            double* psi, int R, int merge, int execute, long long* stats) {
+            double* psi, int M, int merge, int execute, long long* stats) {
     try {
         std::vector<QGate> gates;
         size_t moff = 0;
@@ -90,7 +93,7 @@ int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t
             if (!qb_is_identity(q)) gates.push_back(q);
         }
         QtPlanOptions opt;
-        opt.R = R;
+        opt.M = M;
         opt.merge_phases = merge != 0;
         std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
         long long st[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -105,10 +108,7 @@ int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t
                 st[4] += h->nops;
                 if ((long long)s.program.size() > st[5]) st[5] = (long long)s.program.size();
                 st[6] += s.ngates;
-                if (execute) {
-                    if (R == 3) run_program<3>(s.program.data(), (qt_c*)psi, nbits);
-                    else run_program<4>(s.program.data(), (qt_c*)psi, nbits);
-                }
+                if (execute) run_program(s.program.data(), (qt_c*)psi, nbits);
             } else {
                 st[2]++;
                 if (execute) run_unfused(gates[s.gate_index], (qt_c*)psi, nbits);

@@ -25,7 +25,7 @@ def lib():
     return _lib
 
 
-def run(nbits, gate_list, psi=None, R=4, merge=True, execute=True):
+def run(nbits, gate_list, psi=None, M=12, merge=True, execute=True):
     """gate_list: [(matrix 2^k x 2^k, target_bits (msb first), control_mask)] on index BITS.
     Returns (psi_out or None, stats dict)."""
     n = len(gate_list)
@@ -47,7 +47,7 @@ def run(nbits, gate_list, psi=None, R=4, merge=True, execute=True):
         out = np.ascontiguousarray(np.array(psi, dtype=np.complex128))
         ptr = out.ctypes.data_as(C.c_void_p)
     stats = (C.c_longlong * 7)()
-    rc = lib().qbt_run(nbits, n, ks, tbs, cms, allm.ctypes.data_as(C.c_void_p), ptr, R, 1 if merge else 0,
+    rc = lib().qbt_run(nbits, n, ks, tbs, cms, allm.ctypes.data_as(C.c_void_p), ptr, M, 1 if merge else 0,
                        1 if execute else 0, stats)
     if rc != 0:
         raise RuntimeError(lib().qbt_last_error().decode())

@@ -82,14 +82,14 @@ def random_gate_list(rng, n, count):
     return out
 
 
-@pytest.mark.parametrize('R', [3, 4])
+@pytest.mark.parametrize('M', [11, 12])
 @pytest.mark.parametrize('merge', [True, False])
-def test_random_mixed_circuits(R, merge):
-    rng = np.random.default_rng(100 + R)
+def test_random_mixed_circuits(M, merge):
+    rng = np.random.default_rng(100 + M)
     for n in (12, 13, 15):
         gl = random_gate_list(rng, n, 60)
         psi = rand_ket(rng, n)
-        out, st = plan_emu.run(n, gl, psi, R=R, merge=merge)
+        out, st = plan_emu.run(n, gl, psi, M=M, merge=merge)
         ref = psi
         for m, tb, cm in gl:
             ref = oracle_apply_bits(ref, n, m, tb, cm)
@@ -97,13 +97,13 @@ def test_random_mixed_circuits(R, merge):
         assert st['fused_gates'] + st['unfused_steps'] == len(gl)
 
 
-@pytest.mark.parametrize('R', [3, 4])
-def test_rc_circuits(R):
+@pytest.mark.parametrize('M', [11, 12])
+def test_rc_circuits(M):
     for n, depth, seed in ((12, 10, 1), (14, 12, 2), (16, 6, 3)):
         gates = rc(n, depth, seed)
         rng = np.random.default_rng(seed)
         psi = rand_ket(rng, n)
-        out, st = plan_emu.run(n, plan_emu.circuit_to_bits(n, gates), psi, R=R)
+        out, st = plan_emu.run(n, plan_emu.circuit_to_bits(n, gates), psi, M=M)
         ref = psi
         for g in gates:
             ref = orc.ket_apply(ref, n, g.target, g.matrix(), g.controls)
@@ -143,10 +143,10 @@ def test_headline_plans_are_compact():
         _, st = plan_emu.run(n, plan_emu.circuit_to_bits(n, gates), None, execute=False)
         assert st['unfused_steps'] == 0 and st['fused_gates'] == len(gates)
         assert st['fused_sweeps'] <= max_sweeps, st
-        assert st['max_program_bytes'] <= 12288
+        assert st['max_program_bytes'] <= 8192
 
 
 def test_small_states_are_not_tiled():
     gl = [(np.array([[0, 1], [1, 0]], dtype=complex), [3], 0)]
-    _, st = plan_emu.run(8, gl, np.ones(256, dtype=complex), R=4)
+    _, st = plan_emu.run(8, gl, np.ones(256, dtype=complex), M=12)
     assert st['fused_sweeps'] == 0 and st['unfused_steps'] == 1
