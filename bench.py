@@ -179,8 +179,11 @@ def run_reference_arm(args):
 # our arm
 # ---------------------------------------------------------------------------------------------
 def apply_circuit(st, gates, mats):
+    """one step: queue the whole circuit, then drain the fusion queue (the timed
+    region covers the circuit including the queue flush)"""
     for g, m in zip(gates, mats):
         st.apply_gate(m, g.target, g.controls)
+    st.flush()
 
 
 def run_single_gpu(args):
@@ -200,9 +203,13 @@ def run_single_gpu(args):
     torch.cuda.init()
     st = DeviceState.zero_state(n)
     st.set_fusion(not args.no_fusion)
+    if args.jit is not None:
+        st.set_jit(args.jit)
+    t_w = time.perf_counter()
     for _ in range(args.warmup):
         apply_circuit(st, gates, mats)
     st.sync()
+    warmup_s = time.perf_counter() - t_w
     st.reset_stats()
     sampler = ClockSampler(0)
     sampler.start()
@@ -225,7 +232,8 @@ def run_single_gpu(args):
         # dominant kernel = fused tile sweep: one read + one write of the whole ket per launch
         dom_launches = stats['fused_passes']
         dom_bytes = pass_bytes
-        dom_kernel = 'k_tile_pass (fused multi-gate sweep)'
+        dom_kernel = ('qj_kernel (structure-specialised fused sweep, NVRTC)' if stats['jit_passes'] == stats['fused_passes']
+                      else 'k_tile_sweep (generic fused sweep)' if stats['jit_passes'] == 0 else 'qj_kernel + k_tile_sweep (mixed)')
         dom_unit = "one sweep = 32*2^n B (read + write of the ket)"
     else:
         dom_launches = launches
@@ -243,7 +251,10 @@ def run_single_gpu(args):
         "config": {"workload": f"rc({n}, {depth}, seed={seed}) random circuit (H .35 / RZ .35 / CNOT .20 / Toffoli .10) on a "
                                f"{n}-qubit complex128 ket", "qubits": n, "depth": depth, "gates_per_step": ngates,
                    "state_bytes": 16 * (1 << n), "l2": "state (16*2^n B) larger than L2; no flush needed",
-                   "fusion": not args.no_fusion},
+                   "fusion": not args.no_fusion,
+                   "specialised_sweeps": f"{stats['jit_passes']}/{stats['fused_passes']}",
+                   "specialiser": dict(_lib.jit_info(), warmup_s=warmup_s,
+                                       note="sweeps of a repeated plan are NVRTC-compiled during warm-up; compile time is inside warmup_s, outside the timed region")},
         "clocks": clocks,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -308,6 +319,8 @@ def main():
     ap.add_argument('--depth', type=int, default=None)
     ap.add_argument('--seed', type=int, default=None)
     ap.add_argument('--no-fusion', action='store_true')
+    ap.add_argument('--jit', type=int, default=None, choices=[0, 1, 2],
+                    help="sweep specialisation: 0 never, 1 when a plan repeats (library default), 2 always")
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],

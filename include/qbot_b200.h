@@ -52,6 +52,7 @@ typedef struct {
     uint64_t fused_passes;      /* sweeps done by the fused tile kernel */
     uint64_t fused_gates;       /* gates executed inside fused sweeps */
     uint64_t bytes_moved;       /* bytes the launched kernels were asked to read + write */
+    uint64_t jit_passes;        /* fused sweeps run by a structure-specialised (NVRTC) kernel */
 } qb_stats;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -98,6 +99,21 @@ int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int*
 int qb_flush(qb_state* s);
 int qb_sync(qb_state* s);
 int qb_set_fusion(qb_state* s, int enabled);
+/* Sweep specialisation.  A fused sweep is normally run by the generic tile kernel, which
+ * interprets the sweep's program; when the same gate sequence is flushed again (a loop in a .qb
+ * script, a benchmark step) its sweeps are compiled once with NVRTC into kernels in which the
+ * circuit structure is constant and the gate coefficients are parameters.  mode 0: never,
+ * 1: when a plan repeats on a large state (default; env QBOT_B200_JIT), 2: always, -1: default. */
+int qb_set_jit(qb_state* s, int mode);
+/* specialiser counters of the process: kernels compiled, cache hits, total compile time (ms) */
+int qb_jit_info(uint64_t* kernels_compiled, uint64_t* cache_hits, double* compile_ms);
+/* Generate the specialised source of every fused sweep of a gate list on an nbits-bit state and
+ * compile it for sm_100a WITHOUT running it (works without a GPU: a build / CI check).  Gates as in
+ * qb_apply_gate, concatenated: ks[g], target_bits[g*14..], control_masks[g], matrices back to back.
+ * Returns the number of kernels compiled in *ncompiled; if cubin_dir is not NULL the cubins are
+ * written there as sweep_<i>.cubin (for cuobjdump). */
+int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, const uint64_t* control_masks,
+                 const double* matrices, int* ncompiled, const char* cubin_dir);
 
 /* ---- measurement ----------------------------------------------------------------------
  * computational-basis outcome weights of `m` listed bits (bits[0] = most significant outcome

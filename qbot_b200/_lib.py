@@ -18,7 +18,8 @@ c_state_p = C.c_void_p
 
 class QbStats(C.Structure):
     _fields_ = [('kernel_launches', C.c_uint64), ('gates_applied', C.c_uint64), ('state_passes', C.c_uint64),
-                ('fused_passes', C.c_uint64), ('fused_gates', C.c_uint64), ('bytes_moved', C.c_uint64)]
+                ('fused_passes', C.c_uint64), ('fused_gates', C.c_uint64), ('bytes_moved', C.c_uint64),
+                ('jit_passes', C.c_uint64)]
 
 
 class QbotB200Error(RuntimeError):
@@ -52,6 +53,10 @@ PROTOTYPES = {
     'qb_flush': (C.c_int, [c_state_p]),
     'qb_sync': (C.c_int, [c_state_p]),
     'qb_set_fusion': (C.c_int, [c_state_p, C.c_int]),
+    'qb_set_jit': (C.c_int, [c_state_p, C.c_int]),
+    'qb_jit_info': (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    'qb_jit_check': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.c_void_p,
+                               C.POINTER(C.c_int), C.c_char_p]),
     'qb_probs': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     'qb_norm2': (C.c_int, [c_state_p, C.c_void_p]),
     'qb_project_renorm': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_uint64]),
@@ -116,3 +121,34 @@ def device_count() -> int:
 def int_array(vals):
     vals = [int(v) for v in vals]
     return (C.c_int * max(len(vals), 1))(*vals)
+
+
+def jit_info() -> dict:
+    """Process-wide counters of the sweep specialiser."""
+    k, h, ms = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+    call('qb_jit_info', C.byref(k), C.byref(h), C.byref(ms))
+    return {'kernels_compiled': k.value, 'cache_hits': h.value, 'compile_ms': ms.value}
+
+
+def jit_check(nbits: int, gate_list, cubin_dir: str = None) -> int:
+    """Plan `gate_list` ([(matrix, target_bits msb-first, control_mask)] on index bits), generate
+    the specialised source of every fused sweep and NVRTC-compile it for sm_100a without running
+    it (needs no GPU).  Returns the number of kernels compiled."""
+    import numpy as np
+    n = len(gate_list)
+    ks = (C.c_int * max(n, 1))()
+    tbs = (C.c_int * (14 * max(n, 1)))()
+    cms = (C.c_uint64 * max(n, 1))()
+    mats = []
+    for i, (m, tb, cm) in enumerate(gate_list):
+        m = np.ascontiguousarray(np.asarray(m, dtype=np.complex128))
+        ks[i] = len(tb)
+        for j, b in enumerate(tb):
+            tbs[14 * i + j] = int(b)
+        cms[i] = int(cm)
+        mats.append(m.reshape(-1))
+    allm = np.ascontiguousarray(np.concatenate(mats)) if mats else np.zeros(1, dtype=np.complex128)
+    out = C.c_int(0)
+    call('qb_jit_check', nbits, n, ks, tbs, cms, allm.ctypes.data_as(C.c_void_p), C.byref(out),
+         cubin_dir.encode() if cubin_dir else None)
+    return out.value

@@ -2,6 +2,7 @@
 #include "../../include/qbot_b200.h"
 #include "qb_common.cuh"
 #include "qb_engine.h"
+#include "qb_jit_rt.h"
 
 #include <algorithm>
 #include <cmath>
@@ -464,6 +465,58 @@ int qb_set_fusion(qb_state* s, int enabled) {
     QB_REQUIRE(s, "NULL state");
     s->flush();
     s->fusion = enabled != 0;
+    QB_API_END
+}
+
+int qb_set_jit(qb_state* s, int mode) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    QB_REQUIRE(mode >= -1 && mode <= 2, "jit mode must be -1, 0, 1 or 2");
+    s->flush();
+    s->jit_mode = mode;
+    QB_API_END
+}
+
+int qb_jit_info(uint64_t* kernels_compiled, uint64_t* cache_hits, double* compile_ms) {
+    QB_API_BEGIN
+    const QbJitStats st = qb_jit_stats();
+    if (kernels_compiled) *kernels_compiled = st.kernels_compiled;
+    if (cache_hits) *cache_hits = st.cache_hits;
+    if (compile_ms) *compile_ms = st.compile_ms;
+    QB_API_END
+}
+
+int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, const uint64_t* control_masks,
+                 const double* matrices, int* ncompiled, const char* cubin_dir) {
+    QB_API_BEGIN
+    QB_REQUIRE(ks && target_bits && control_masks && matrices, "NULL argument");
+    std::vector<QGate> gates;
+    size_t moff = 0;
+    for (int g = 0; g < ngates; g++) {
+        QB_REQUIRE(ks[g] >= 1 && ks[g] <= QB_BIG_MAXK, "gate size out of range");
+        QGate q = qb_classify((const cplx*)(matrices + moff), ks[g], target_bits + (size_t)g * QB_BIG_MAXK, control_masks[g]);
+        moff += 2 * ((size_t)1 << (2 * ks[g]));
+        if (!qb_is_identity(q)) gates.push_back(q);
+    }
+    QtPlanOptions opt;
+    std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
+    int n = 0;
+    for (const QtPlanStep& st : steps) {
+        if (!st.fused) continue;
+        const std::string src = qb_jit_full_source(st.program.data(), nullptr, nullptr);
+        const std::vector<char> cubin = qb_jit_compile(src, nullptr);
+        if (cubin_dir) {
+            const std::string base = std::string(cubin_dir) + "/sweep_" + std::to_string(n);
+            FILE* f = fopen((base + ".cubin").c_str(), "wb");
+            QB_REQUIRE(f, "cannot write cubin");
+            fwrite(cubin.data(), 1, cubin.size(), f);
+            fclose(f);
+            f = fopen((base + ".cu").c_str(), "w");
+            if (f) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+        }
+        n++;
+    }
+    if (ncompiled) *ncompiled = n;
     QB_API_END
 }
 

@@ -16,6 +16,7 @@ struct qb_state {
     cudaStream_t stream = nullptr;
     bool owns_stream = true;
     bool fusion = true;
+    int jit_mode = -1;             // -1: QBOT_B200_JIT (default 1 = specialise repeated plans), 0 never, 1 on repeat, 2 always
     std::vector<QGate> queue;
     qb_stats stats = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -1,0 +1,281 @@
+// qbot_b200 -- run time of the sweep specialiser: NVRTC-compiles the text qj_generate emits for a
+// sweep program into an sm_100a cubin, loads it with the driver API and launches it.
+//
+// libnvrtc and libcuda are opened with dlopen, so that the C-ABI library itself has no link-time
+// dependency on either (it must load, and export every symbol, on a machine without a driver).
+// Compiled kernels are cached per process by the hash of their source text, i.e. by circuit
+// STRUCTURE: gate coefficients are kernel parameters (a __grid_constant__ struct, read straight
+// from the constant bank by the FP64 instructions).
+#include "qb_engine.h"
+#include "qb_jit.h"
+#include "qb_jit_rt.h"
+
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <mutex>
+
+namespace {
+
+// ---- CUDA text around the generated stage functions ---------------------------------------------
+const char* kPrelude = R"QJ(
+#define QJ_C double2
+#define QJ_DEV __device__ __forceinline__
+#define QJ_LD(p) __ldcs(p)
+#define QJ_ST(p, v) __stcs(p, v)
+#define QJ_RESTRICT __restrict__
+#define QJ_WAR_SYNC() __syncthreads()
+#define QJ_SYNC() __syncthreads()
+#ifdef QJ_POOL_GLOBAL
+#define QJ_PRELUDE
+#define QJ_POOL_PARAM const double* __restrict__ P
+#define QJ_P(i) (__ldg(P + (i)))
+#define QJ_POOL_KPARAM const double* __restrict__ P
+#else
+#define QJ_PRELUDE struct QjPool { double v[QJ_NP]; };
+#define QJ_POOL_PARAM const QjPool& P
+#define QJ_P(i) (P.v[i])
+#define QJ_POOL_KPARAM const __grid_constant__ QjPool P
+#endif
+#define QJ_PREFETCH(psi, nbase, tid)                                                               \
+    do {                                                                                           \
+        if (nbase != ~0ull && tid < (1u << QJ_NH))                                                 \
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(psi + nbase + qj_run_offset(tid)), "r"(512) : "memory"); \
+    } while (0)
+)QJ";
+
+// One CTA of QJ_T threads is persistent over tiles t = blockIdx.x + i * gridDim.x; a tile's 2^M
+// amplitudes live in registers (16 per thread) and pass through shared memory once between two
+// stages.  QJ_CTAS CTAs are resident per SM so that one CTA's loads / stores overlap another's
+// arithmetic; the next tile of a CTA is prefetched into L2 while the current one is computed.
+const char* kPostlude = R"QJ(
+extern "C" __global__ void __launch_bounds__(QJ_T, QJ_CTAS)
+qj_kernel(double2* __restrict__ psi, const unsigned long long ntiles, const int prefetch, QJ_POOL_KPARAM) {
+    extern __shared__ __align__(16) double2 buf[];
+    const unsigned tid = threadIdx.x;
+    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned long long tbase = qj_tile_base(tile);
+        const unsigned long long nt = tile + gridDim.x;
+        const unsigned long long nbase = (prefetch && nt < ntiles) ? qj_tile_base(nt) : ~0ull;
+        QJ_RUN_STAGES(tid, tbase, nbase, psi, buf, P)
+    }
+}
+)QJ";
+
+// ---- dynamically bound NVRTC + driver API ---------------------------------------------------------
+struct Nvrtc {
+    void* so = nullptr;
+    decltype(&nvrtcCreateProgram) CreateProgram = nullptr;
+    decltype(&nvrtcCompileProgram) CompileProgram = nullptr;
+    decltype(&nvrtcDestroyProgram) DestroyProgram = nullptr;
+    decltype(&nvrtcGetCUBINSize) GetCUBINSize = nullptr;
+    decltype(&nvrtcGetCUBIN) GetCUBIN = nullptr;
+    decltype(&nvrtcGetProgramLogSize) GetProgramLogSize = nullptr;
+    decltype(&nvrtcGetProgramLog) GetProgramLog = nullptr;
+    decltype(&nvrtcGetErrorString) GetErrorString = nullptr;
+    std::string why;
+};
+
+struct Driver {
+    void* so = nullptr;
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    std::string why;
+};
+
+template <class F> bool bind(void* so, const char* name, F* out) {
+    *out = (F)dlsym(so, name);
+    return *out != nullptr;
+}
+
+Nvrtc& nvrtc() {
+    static Nvrtc n = [] {
+        Nvrtc r;
+        const char* env = getenv("QBOT_B200_NVRTC");
+        const char* names[] = {env ? env : "libnvrtc.so.12", "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                               "/usr/local/cuda/lib64/libnvrtc.so"};
+        for (const char* nm : names) {
+            r.so = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (r.so) break;
+        }
+        if (!r.so) { r.why = std::string("libnvrtc not found: ") + dlerror(); return r; }
+        bool ok = bind(r.so, "nvrtcCreateProgram", &r.CreateProgram) && bind(r.so, "nvrtcCompileProgram", &r.CompileProgram) &&
+                  bind(r.so, "nvrtcDestroyProgram", &r.DestroyProgram) && bind(r.so, "nvrtcGetCUBINSize", &r.GetCUBINSize) &&
+                  bind(r.so, "nvrtcGetCUBIN", &r.GetCUBIN) && bind(r.so, "nvrtcGetProgramLogSize", &r.GetProgramLogSize) &&
+                  bind(r.so, "nvrtcGetProgramLog", &r.GetProgramLog) && bind(r.so, "nvrtcGetErrorString", &r.GetErrorString);
+        if (!ok) { r.why = "libnvrtc lacks a required symbol"; r.so = nullptr; }
+        return r;
+    }();
+    return n;
+}
+
+Driver& driver() {
+    static Driver d = [] {
+        Driver r;
+        r.so = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!r.so) { r.why = std::string("libcuda.so.1 not found: ") + dlerror(); return r; }
+        bool ok = bind(r.so, "cuModuleLoadData", &r.ModuleLoadData) && bind(r.so, "cuModuleUnload", &r.ModuleUnload) &&
+                  bind(r.so, "cuModuleGetFunction", &r.ModuleGetFunction) && bind(r.so, "cuFuncSetAttribute", &r.FuncSetAttribute) &&
+                  bind(r.so, "cuFuncGetAttribute", &r.FuncGetAttribute) && bind(r.so, "cuLaunchKernel", &r.LaunchKernel) &&
+                  bind(r.so, "cuGetErrorString", &r.GetErrorString);
+        if (!ok) { r.why = "libcuda lacks a required symbol"; r.so = nullptr; }
+        return r;
+    }();
+    return d;
+}
+
+std::string cu_err(CUresult e) {
+    const char* s = nullptr;
+    if (driver().GetErrorString) driver().GetErrorString(e, &s);
+    return s ? s : "unknown driver error";
+}
+
+struct Compiled {
+    std::vector<char> cubin;
+    QjSourceInfo info;
+    bool pool_global = false;
+    double compile_ms = 0;
+    std::map<int, std::pair<CUmodule, CUfunction>> per_device;   // loaded module per device
+};
+
+std::mutex g_mu;
+std::map<uint64_t, Compiled> g_cache;      // by hash of the full source
+std::map<uint64_t, int> g_seen;           // sightings of structures that are not compiled (yet)
+QbJitStats g_stats;
+
+constexpr int kMaxParamPoolDoubles = 480;     // 3840 bytes of coefficients + 24 bytes of scalars < 4 KB of parameters
+
+}  // namespace
+
+std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool* pool_global) {
+    QjSourceInfo li;
+    std::string body = qj_generate(program, &li);
+    const bool pg = li.npool > kMaxParamPoolDoubles;
+    if (info) *info = li;
+    if (pool_global) *pool_global = pg;
+    std::string src;
+    if (pg) src += "#define QJ_POOL_GLOBAL 1\n";
+    src += kPrelude;
+    src += body;
+    src += kPostlude;
+    return src;
+}
+
+// compile `src` to an sm_100a cubin; throws qb_error with the NVRTC log on failure
+std::vector<char> qb_jit_compile(const std::string& src, std::string* log_out) {
+    Nvrtc& n = nvrtc();
+    if (!n.so) throw qb_error(-2, "sweep specialiser: " + n.why);
+    nvrtcProgram prog = nullptr;
+    nvrtcResult r = n.CreateProgram(&prog, src.c_str(), "qbot_b200_sweep.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) throw qb_error(-2, std::string("nvrtcCreateProgram: ") + n.GetErrorString(r));
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+    r = n.CompileProgram(prog, 4, opts);
+    std::string log;
+    size_t lsz = 0;
+    if (n.GetProgramLogSize(prog, &lsz) == NVRTC_SUCCESS && lsz > 1) {
+        log.resize(lsz);
+        n.GetProgramLog(prog, &log[0]);
+    }
+    if (log_out) *log_out = log;
+    if (r != NVRTC_SUCCESS) {
+        n.DestroyProgram(&prog);
+        throw qb_error(-2, std::string("nvrtcCompileProgram: ") + n.GetErrorString(r) + "\n" + log.substr(0, 2000));
+    }
+    size_t csz = 0;
+    r = n.GetCUBINSize(prog, &csz);
+    std::vector<char> cubin(csz);
+    if (r == NVRTC_SUCCESS) r = n.GetCUBIN(prog, cubin.data());
+    n.DestroyProgram(&prog);
+    if (r != NVRTC_SUCCESS || csz == 0) throw qb_error(-2, std::string("nvrtcGetCUBIN: ") + n.GetErrorString(r));
+    return cubin;
+}
+
+bool qb_jit_available(std::string* why) {
+    if (!nvrtc().so) { if (why) *why = nvrtc().why; return false; }
+    if (!driver().so) { if (why) *why = driver().why; return false; }
+    return true;
+}
+
+int qb_jit_note(uint64_t key) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_cache.count(key)) return -1;
+    return ++g_seen[key];
+}
+
+QbJitStats qb_jit_stats() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return g_stats;
+}
+
+// the compiled kernel of `program` on `device` (compiling / loading it on first use)
+QbJitKernel qb_jit_get(const uint8_t* program, int device) {
+    QjSourceInfo info;
+    bool pg = false;
+    const std::string src = qb_jit_full_source(program, &info, &pg);
+    const uint64_t key = qj_hash(src);
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+        const auto t0 = std::chrono::steady_clock::now();
+        Compiled c;
+        c.cubin = qb_jit_compile(src, nullptr);
+        c.info = info;
+        c.pool_global = pg;
+        c.compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        g_stats.kernels_compiled++;
+        g_stats.compile_ms += c.compile_ms;
+        it = g_cache.emplace(key, std::move(c)).first;
+    } else {
+        g_stats.cache_hits++;
+    }
+    Compiled& c = it->second;
+    auto dv = c.per_device.find(device);
+    if (dv == c.per_device.end()) {
+        Driver& d = driver();
+        if (!d.so) throw qb_error(-2, "sweep specialiser: " + d.why);
+        CUmodule mod = nullptr;
+        CUfunction fn = nullptr;
+        CUresult e = d.ModuleLoadData(&mod, c.cubin.data());
+        if (e != CUDA_SUCCESS) throw qb_error(-2, "cuModuleLoadData: " + cu_err(e));
+        e = d.ModuleGetFunction(&fn, mod, "qj_kernel");
+        if (e != CUDA_SUCCESS) throw qb_error(-2, "cuModuleGetFunction: " + cu_err(e));
+        const int smem = c.info.tile_units * 16;
+        e = d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+        if (e != CUDA_SUCCESS) throw qb_error(-2, "cuFuncSetAttribute(smem): " + cu_err(e));
+        d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
+        dv = c.per_device.emplace(device, std::make_pair(mod, fn)).first;
+    }
+    QbJitKernel k;
+    k.fn = (void*)dv->second.second;
+    k.threads = c.info.threads;
+    k.smem_bytes = c.info.tile_units * 16;
+    k.npool = c.info.npool;
+    k.pool_global = c.pool_global;
+    k.ctas_per_sm = c.info.M == 12 ? 2 : 4;
+    k.M = c.info.M;
+    return k;
+}
+
+// launch: `pool` = qj_pool(program) on the host (parameter variant) or its device copy
+void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
+                   const double* pool_host, const double* pool_dev) {
+    Driver& d = driver();
+    unsigned long long nt = ntiles;
+    int pf = prefetch;
+    void* psi_arg = (void*)psi;
+    const void* pool_ptr = pool_dev;
+    void* args[4] = {&psi_arg, &nt, &pf, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * k.ctas_per_sm);
+    CUresult e = d.LaunchKernel((CUfunction)k.fn, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem_bytes, (CUstream)stream, args, nullptr);
+    if (e != CUDA_SUCCESS) throw qb_error(-2, "cuLaunchKernel(sweep): " + cu_err(e));
+}

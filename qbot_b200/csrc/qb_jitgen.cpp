@@ -1,0 +1,404 @@
+// qbot_b200 -- sweep specialiser (see qb_jit.h).  Pure host code, no CUDA dependency.
+//
+// What is resolved at generation time
+//   * the 16 amplitudes of a thread are 16 named locals (a0..a15), so a Pauli-X / CNOT / Toffoli
+//     whose controls are register bits is a RENAMING and costs no instruction at all;
+//   * every shared-memory and HBM offset is an immediate; the tile base and the thread's
+//     position are a few shifts with constant amounts;
+//   * predicates on thread bits / tile bits are tests of constant masks; ops whose predicate
+//     covers the whole tile have none;
+//   * uncontrolled diagonals merged into one PHASE op become one factor table (built once per
+//     thread and tile) and ONE complex multiply per amplitude.
+#include "qb_jit.h"
+#include "qb_plan.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <map>
+#include <vector>
+
+#define QT_NR (1 << QT_R)
+
+namespace {
+
+struct Out {
+    std::string s;
+    void f(const char* fmt, ...) {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        int n = vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        if (n > 0) s.append(buf, (size_t)std::min<int>(n, (int)sizeof(buf) - 1));
+    }
+};
+
+// expression depositing the bits of `var` (bit q, q = 0..) at positions pos[q]; consecutive runs
+// are grouped into one mask-and-shift
+std::string deposit_expr(const char* var, const int* pos, int nbits, const char* type_suffix) {
+    std::string e;
+    int q = 0;
+    while (q < nbits) {
+        int len = 1;
+        while (q + len < nbits && pos[q + len] == pos[q] + len) len++;
+        char b[160];
+        if (pos[q] >= q)
+            snprintf(b, sizeof(b), "((%s)(%s & 0x%xu) << %d)", type_suffix, var, ((1u << len) - 1u) << q, pos[q] - q);
+        else
+            snprintf(b, sizeof(b), "((%s)(%s & 0x%xu) >> %d)", type_suffix, var, ((1u << len) - 1u) << q, q - pos[q]);
+        if (!e.empty()) e += " | ";
+        e += b;
+        q += len;
+    }
+    if (e.empty()) e = "0";
+    return e;
+}
+
+struct Gen {
+    const QtHeader* h;
+    const QtStage* stages;
+    const QtOp* ops;
+    const double* pool;
+    int M, NH, T;
+    Out o;
+    std::vector<std::string> nm;     // current name of logical register i
+    int tmp = 0;
+
+    std::string P(uint32_t i) const {
+        char b[32];
+        snprintf(b, sizeof(b), "QJ_P(%u)", i);
+        return b;
+    }
+
+    std::string cond_of(const QtOp& op) const {
+        std::string c;
+        char b[128];
+        if (op.lmask) {
+            snprintf(b, sizeof(b), "(lb & 0x%xu) == 0x%xu", (unsigned)op.lmask, (unsigned)op.lval);
+            c += b;
+        }
+        if (op.gmask) {
+            snprintf(b, sizeof(b), "(tbase & 0x%llxull) == 0x%llxull", (unsigned long long)op.gmask, (unsigned long long)op.gval);
+            if (!c.empty()) c += " && ";
+            c += b;
+        }
+        return c;
+    }
+
+    // a <- f * a with f = (fr, fi) expressions
+    void cmul_into(const std::string& a, const std::string& fr, const std::string& fi) {
+        o.f("    { const double xr = %s.x, xi = %s.y; %s.x = %s * xr - %s * xi; %s.y = %s * xi + %s * xr; }\n",
+            a.c_str(), a.c_str(), a.c_str(), fr.c_str(), fi.c_str(), a.c_str(), fr.c_str(), fi.c_str());
+    }
+
+    void op_h(const QtOp& op) {
+        const int t = op.t0;
+        for (int i = 0; i < QT_NR; i++) {
+            if ((i >> t) & 1 || !((op.regsel >> i) & 1u)) continue;
+            const std::string &A = nm[i], &B = nm[i | (1 << t)];
+            o.f("    { const double xr = %s.x, xi = %s.y; %s.x = xr + %s.x; %s.y = xi + %s.y; %s.x = xr - %s.x; %s.y = xi - %s.y; }\n",
+                A.c_str(), A.c_str(), A.c_str(), B.c_str(), A.c_str(), B.c_str(), B.c_str(), B.c_str(), B.c_str(), B.c_str());
+        }
+    }
+
+    void op_x(const QtOp& op, bool conditional) {
+        const int t = op.t0;
+        for (int i = 0; i < QT_NR; i++) {
+            if ((i >> t) & 1 || !((op.regsel >> i) & 1u)) continue;
+            const int j = i | (1 << t);
+            if (conditional)
+                o.f("    { const QJ_C t_ = %s; %s = %s; %s = t_; }\n", nm[i].c_str(), nm[i].c_str(), nm[j].c_str(), nm[j].c_str());
+            else
+                std::swap(nm[i], nm[j]);
+        }
+    }
+
+    void op_u2(const QtOp& op) {
+        const int t = op.t0;
+        const uint32_t p = op.pool;
+        o.f("    { const double m0 = %s, m1 = %s, m2 = %s, m3 = %s, m4 = %s, m5 = %s, m6 = %s, m7 = %s;\n", P(p).c_str(),
+            P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str(), P(p + 4).c_str(), P(p + 5).c_str(), P(p + 6).c_str(), P(p + 7).c_str());
+        for (int i = 0; i < QT_NR; i++) {
+            if ((i >> t) & 1 || !((op.regsel >> i) & 1u)) continue;
+            const std::string &A = nm[i], &B = nm[i | (1 << t)];
+            o.f("      { const double xr = %s.x, xi = %s.y, yr = %s.x, yi = %s.y;\n", A.c_str(), A.c_str(), B.c_str(), B.c_str());
+            o.f("        %s.x = m0 * xr - m1 * xi + m2 * yr - m3 * yi; %s.y = m0 * xi + m1 * xr + m2 * yi + m3 * yr;\n", A.c_str(), A.c_str());
+            o.f("        %s.x = m4 * xr - m5 * xi + m6 * yr - m7 * yi; %s.y = m4 * xi + m5 * xr + m6 * yi + m7 * yr; }\n", B.c_str(), B.c_str());
+        }
+        o.f("    }\n");
+    }
+
+    void op_u4(const QtOp& op) {
+        const int t0 = op.t0, t1 = op.t1;
+        const uint32_t p = op.pool;
+        o.f("    {\n");
+        for (int i = 0; i < QT_NR; i++) {
+            if ((i >> t0) & 1 || (i >> t1) & 1 || !((op.regsel >> i) & 1u)) continue;
+            const int idx[4] = {i, i | (1 << t1), i | (1 << t0), i | (1 << t0) | (1 << t1)};
+            o.f("      { const QJ_C x0 = %s, x1 = %s, x2 = %s, x3 = %s;\n", nm[idx[0]].c_str(), nm[idx[1]].c_str(), nm[idx[2]].c_str(),
+                nm[idx[3]].c_str());
+            for (int r = 0; r < 4; r++) {
+                std::string re, im;
+                for (int c = 0; c < 4; c++) {
+                    const std::string mr = P(p + 8 * r + 2 * c), mi = P(p + 8 * r + 2 * c + 1);
+                    char b[256];
+                    snprintf(b, sizeof(b), "%s%s * x%d.x - %s * x%d.y", c ? " + " : "", mr.c_str(), c, mi.c_str(), c);
+                    re += b;
+                    snprintf(b, sizeof(b), "%s%s * x%d.y + %s * x%d.x", c ? " + " : "", mr.c_str(), c, mi.c_str(), c);
+                    im += b;
+                }
+                o.f("        %s.x = %s;\n        %s.y = %s;\n", nm[idx[r]].c_str(), re.c_str(), nm[idx[r]].c_str(), im.c_str());
+            }
+            o.f("      }\n");
+        }
+        o.f("    }\n");
+    }
+
+    bool pool_is_one(uint32_t p) const { return pool[p] == 1.0 && pool[p + 1] == 0.0; }
+
+    void op_cdiag(const QtOp& op) {
+        const uint32_t p = op.pool;
+        if (op.t1 == QT_LOC_REG) {
+            const bool one0 = pool_is_one(p), one1 = pool_is_one(p + 2);
+            o.f("    { const double d0r = %s, d0i = %s, d1r = %s, d1i = %s;\n", P(p).c_str(), P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str());
+            for (int i = 0; i < QT_NR; i++) {
+                if (!((op.regsel >> i) & 1u)) continue;
+                const bool hi = (i >> op.t0) & 1;
+                if (hi ? one1 : one0) continue;          // exact unit factor: structural, part of the source text
+                o.f("  ");
+                cmul_into(nm[i], hi ? "d1r" : "d0r", hi ? "d1i" : "d0i");
+            }
+            o.f("    }\n");
+        } else {
+            if (op.t1 == QT_LOC_LOCAL) o.f("    { const bool b_ = (lb >> %d) & 1u;\n", (int)op.t0);
+            else o.f("    { const bool b_ = (tbase >> %d) & 1ull;\n", (int)op.t0);
+            o.f("      const double fr = b_ ? %s : %s, fi = b_ ? %s : %s;\n", P(p + 2).c_str(), P(p).c_str(), P(p + 3).c_str(), P(p + 1).c_str());
+            for (int i = 0; i < QT_NR; i++) {
+                if (!((op.regsel >> i) & 1u)) continue;
+                o.f("  ");
+                cmul_into(nm[i], "fr", "fi");
+            }
+            o.f("    }\n");
+        }
+    }
+
+    void op_phase(const QtOp& op) {
+        const uint32_t p = op.pool;
+        const int u = tmp++;
+        o.f("    {\n");
+        bool have = false;
+        std::vector<int> reg_entries[QT_R];
+        for (int e = 0; e < op.nent; e++) {
+            const uint32_t q = p + 5 * e;
+            int64_t code;
+            memcpy(&code, pool + q, sizeof(code));
+            const int loc = (int)(code & 0xff), pos = (int)(code >> 8);
+            if (loc == QT_LOC_REG) { reg_entries[pos].push_back(e); continue; }
+            std::string fr, fi;
+            if (loc == QT_LOC_CONST) { fr = P(q + 1); fi = P(q + 2); }
+            else {
+                if (loc == QT_LOC_LOCAL) o.f("      const bool b%d_%d = (lb >> %d) & 1u;\n", u, e, pos);
+                else o.f("      const bool b%d_%d = (tbase >> %d) & 1ull;\n", u, e, pos);
+                char b[160];
+                snprintf(b, sizeof(b), "(b%d_%d ? %s : %s)", u, e, P(q + 3).c_str(), P(q + 1).c_str());
+                fr = b;
+                snprintf(b, sizeof(b), "(b%d_%d ? %s : %s)", u, e, P(q + 4).c_str(), P(q + 2).c_str());
+                fi = b;
+            }
+            if (!have) { o.f("      double cr = %s, ci = %s;\n", fr.c_str(), fi.c_str()); have = true; }
+            else
+                o.f("      { const double fr = %s, fi = %s; const double tr = cr * fr - ci * fi; ci = cr * fi + ci * fr; cr = tr; }\n",
+                    fr.c_str(), fi.c_str());
+        }
+        // factor table over the register bits that carry entries
+        struct Ent { int mask; std::string r, i; };
+        std::vector<Ent> table;
+        if (have) table.push_back({0, "cr", "ci"});
+        int regbits = 0;
+        for (int q = 0; q < QT_R; q++) {
+            if (reg_entries[q].empty()) continue;
+            regbits |= 1 << q;
+            // product of this bit's entries
+            char d0r[32], d0i[32], d1r[32], d1i[32];
+            snprintf(d0r, sizeof(d0r), "d0r_%d", q); snprintf(d0i, sizeof(d0i), "d0i_%d", q);
+            snprintf(d1r, sizeof(d1r), "d1r_%d", q); snprintf(d1i, sizeof(d1i), "d1i_%d", q);
+            const uint32_t q0 = p + 5 * reg_entries[q][0];
+            o.f("      double %s = %s, %s = %s, %s = %s, %s = %s;\n", d0r, P(q0 + 1).c_str(), d0i, P(q0 + 2).c_str(), d1r, P(q0 + 3).c_str(),
+                d1i, P(q0 + 4).c_str());
+            for (size_t x = 1; x < reg_entries[q].size(); x++) {
+                const uint32_t qx = p + 5 * reg_entries[q][x];
+                o.f("      { const double t0 = %s * %s - %s * %s; %s = %s * %s + %s * %s; %s = t0; }\n", d0r, P(qx + 1).c_str(), d0i,
+                    P(qx + 2).c_str(), d0i, d0r, P(qx + 2).c_str(), d0i, P(qx + 1).c_str(), d0r);
+                o.f("      { const double t1 = %s * %s - %s * %s; %s = %s * %s + %s * %s; %s = t1; }\n", d1r, P(qx + 3).c_str(), d1i,
+                    P(qx + 4).c_str(), d1i, d1r, P(qx + 4).c_str(), d1i, P(qx + 3).c_str(), d1r);
+            }
+            std::vector<Ent> next;
+            if (table.empty()) {
+                next.push_back({0, d0r, d0i});
+                next.push_back({1 << q, d1r, d1i});
+            } else {
+                for (const Ent& t : table) {
+                    for (int v = 0; v < 2; v++) {
+                        char nr[48], ni[48];
+                        const int mk = t.mask | (v << q);
+                        snprintf(nr, sizeof(nr), "f%d_%dr", q, mk);
+                        snprintf(ni, sizeof(ni), "f%d_%di", q, mk);
+                        o.f("      const double %s = %s * %s - %s * %s, %s = %s * %s + %s * %s;\n", nr, t.r.c_str(), v ? d1r : d0r, t.i.c_str(),
+                            v ? d1i : d0i, ni, t.r.c_str(), v ? d1i : d0i, t.i.c_str(), v ? d1r : d0r);
+                        next.push_back({mk, nr, ni});
+                    }
+                }
+            }
+            table.swap(next);
+        }
+        if (!table.empty()) {
+            for (int i = 0; i < QT_NR; i++) {
+                const int mk = i & regbits;
+                for (const Ent& t : table)
+                    if (t.mask == mk) { o.f("  "); cmul_into(nm[i], t.r, t.i); break; }
+            }
+        }
+        o.f("    }\n");
+    }
+
+    void emit_op(const QtOp& op) {
+        const std::string c = cond_of(op);
+        const bool conditional = !c.empty();
+        if (op.type == QT_OP_X && !conditional) { op_x(op, false); return; }
+        if (conditional) o.f("    if (%s) {\n", c.c_str());
+        switch (op.type) {
+            case QT_OP_H: op_h(op); break;
+            case QT_OP_X: op_x(op, true); break;
+            case QT_OP_U2: op_u2(op); break;
+            case QT_OP_U4: op_u4(op); break;
+            case QT_OP_CDIAG: op_cdiag(op); break;
+            case QT_OP_PHASE: op_phase(op); break;
+            default: break;
+        }
+        if (conditional) o.f("    }\n");
+    }
+
+    uint64_t hbm_reg_offset(const QtStage& st, int i) const {
+        uint64_t off = 0;
+        for (int q = 0; q < QT_R; q++) if ((i >> q) & 1) off |= 1ull << h->hb[st.rb[q] - QT_L];
+        return off;
+    }
+    uint32_t smem_reg_offset(const QtStage& st, int i) const {
+        uint32_t off = 0;
+        for (int q = 0; q < QT_R; q++) if ((i >> q) & 1) off += qt_slot(1u << st.rb[q]);
+        return off;
+    }
+
+    void emit_stage(int s) {
+        const QtStage& st = stages[s];
+        const bool first = s == 0, last = s + 1 == h->nstages;
+        nm.resize(QT_NR);
+        for (int i = 0; i < QT_NR; i++) nm[i] = "a" + std::to_string(i);
+        o.f("QJ_DEV void qj_stage%d(const unsigned tid, const unsigned long long tbase, const unsigned long long nbase,\n"
+            "                      QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT buf, QJ_POOL_PARAM) {\n", s);
+        int tpos[QT_MAXM];
+        for (int q = 0; q < M - QT_R; q++) tpos[q] = st.tpos[q];
+        o.f("    const unsigned lb = %s;\n", deposit_expr("tid", tpos, M - QT_R, "unsigned").c_str());
+        o.f("    (void)lb; (void)tbase; (void)nbase; (void)psi; (void)buf;\n");
+        if (first || last) {
+            // HBM position of the thread: lane = low bits, run bits deposited at the tile-bit positions
+            int hpos[QT_MAXM];
+            for (int i = 0; i < NH; i++) hpos[i] = h->hb[i];
+            o.f("    const unsigned run = lb >> %d;\n", QT_L);
+            o.f("    QJ_C* const gp = psi + (tbase + (unsigned long long)(lb & 31u) + (%s));\n",
+                deposit_expr("run", hpos, NH, "unsigned long long").c_str());
+        }
+        if (!(first && last)) o.f("    QJ_C* const sp = buf + (lb + (lb >> 5) + (lb >> 8) + (lb >> 11));\n");
+        o.f("    QJ_C a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15;\n");
+        if (first) {
+            for (int i = 0; i < QT_NR; i++) o.f("    a%d = QJ_LD(gp + 0x%llxull);\n", i, (unsigned long long)hbm_reg_offset(st, i));
+            o.f("    QJ_PREFETCH(psi, nbase, tid);\n");
+        } else {
+            for (int i = 0; i < QT_NR; i++) o.f("    a%d = sp[%u];\n", i, smem_reg_offset(st, i));
+        }
+        for (int x = 0; x < st.nops; x++) emit_op(ops[st.first_op + x]);
+        if (last) {
+            if (h->scale != 1.0) {
+                const uint32_t sidx = (uint32_t)npool_prog;      // the header scale rides behind the program's pool
+                o.f("    { const double s_ = %s;\n", P(sidx).c_str());
+                for (int i = 0; i < QT_NR; i++) o.f("      %s.x *= s_; %s.y *= s_;\n", nm[i].c_str(), nm[i].c_str());
+                o.f("    }\n");
+            }
+            for (int i = 0; i < QT_NR; i++) o.f("    QJ_ST(gp + 0x%llxull, %s);\n", (unsigned long long)hbm_reg_offset(st, i), nm[i].c_str());
+        } else {
+            if (first) o.f("    QJ_WAR_SYNC();\n");
+            for (int i = 0; i < QT_NR; i++) o.f("    sp[%u] = %s;\n", smem_reg_offset(st, i), nm[i].c_str());
+        }
+        o.f("}\n\n");
+    }
+
+    int npool_prog = 0;
+};
+
+}  // namespace
+
+std::vector<double> qj_pool(const uint8_t* program) {
+    const QtHeader* h = (const QtHeader*)program;
+    const double* pool = (const double*)(program + h->pool_off);
+    const size_t n = (h->total_bytes - h->pool_off) / sizeof(double);
+    std::vector<double> out(pool, pool + n);
+    out.push_back(h->scale);
+    return out;
+}
+
+uint64_t qj_hash(const std::string& src) {
+    uint64_t hsh = 1469598103934665603ull;
+    for (unsigned char c : src) { hsh ^= c; hsh *= 1099511628211ull; }
+    return hsh;
+}
+
+std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
+    Gen g;
+    g.h = (const QtHeader*)program;
+    g.stages = (const QtStage*)(program + g.h->stages_off);
+    g.ops = (const QtOp*)(program + g.h->ops_off);
+    g.pool = (const double*)(program + g.h->pool_off);
+    g.M = g.h->M;
+    g.NH = g.M - QT_L;
+    g.T = 1 << (g.M - QT_R);
+    g.npool_prog = (int)((g.h->total_bytes - g.h->pool_off) / sizeof(double));
+    const int npool = g.npool_prog + 1;      // + header scale
+    Out& o = g.o;
+    o.f("// generated by qbot_b200 qj_generate: M=%d stages=%d ops=%d gates=%d\n", g.M, (int)g.h->nstages, (int)g.h->nops, (int)g.h->ngates);
+    o.f("#define QJ_M %d\n#define QJ_T %d\n#define QJ_NH %d\n#define QJ_NP %d\n#define QJ_NSTAGES %d\n", g.M, g.T, g.NH, npool, (int)g.h->nstages);
+    o.f("#define QJ_TILE_UNITS %d\n#define QJ_CTAS %d\n", QT_TILE_UNITS(g.M), g.M == 12 ? 2 : 4);
+    o.f("QJ_PRELUDE\n\n");
+    // tile base: the tile number's bits deposited into the positions outside the tile
+    o.f("QJ_DEV unsigned long long qj_tile_base(const unsigned long long t) {\n    unsigned long long b = t << %d;\n", QT_L);
+    for (int i = 0; i < g.NH; i++) {
+        const int p = g.h->hb[i];
+        o.f("    b = ((b >> %d) << %d) | (b & 0x%llxull);\n", p, p + 1, (unsigned long long)((1ull << p) - 1ull));
+    }
+    o.f("    return b;\n}\n");
+    {
+        int hpos[QT_MAXM];
+        for (int i = 0; i < g.NH; i++) hpos[i] = g.h->hb[i];
+        o.f("QJ_DEV unsigned long long qj_run_offset(const unsigned k) { return %s; }\n\n",
+            deposit_expr("k", hpos, g.NH, "unsigned long long").c_str());
+    }
+    for (int s = 0; s < g.h->nstages; s++) g.emit_stage(s);
+    o.f("#define QJ_RUN_STAGES(tid, tbase, nbase, psi, buf, P) \\\n");
+    for (int s = 0; s < g.h->nstages; s++) {
+        if (s) o.f("    QJ_SYNC(); \\\n");
+        o.f("    qj_stage%d(tid, tbase, nbase, psi, buf, P); \\\n", s);
+    }
+    o.f("\n");
+    o.f("#ifdef QJ_WANT_DISPATCH\nQJ_DEV void qj_stage(const int s, const unsigned tid, const unsigned long long tbase, QJ_C* psi, QJ_C* buf, QJ_POOL_PARAM) {\n    switch (s) {\n");
+    for (int s = 0; s < g.h->nstages; s++) o.f("        case %d: qj_stage%d(tid, tbase, ~0ull, psi, buf, P); break;\n", s, s);
+    o.f("        default: break;\n    }\n}\n#endif\n");
+    if (info) {
+        info->M = g.M;
+        info->threads = g.T;
+        info->npool = npool;
+        info->nstages = g.h->nstages;
+        info->tile_units = QT_TILE_UNITS(g.M);
+    }
+    return o.s;
+}

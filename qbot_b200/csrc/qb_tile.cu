@@ -19,6 +19,7 @@
 #include "qb_engine.h"
 #include "qb_plan.h"
 #include "qb_tile_ops.h"
+#include "qb_jit_rt.h"
 
 #include <cstring>
 #include <list>
@@ -172,6 +173,21 @@ struct CachedPlan {
     std::vector<QtPlanStep> steps;
     std::vector<size_t> prog_off;      // per step offset into dev (fused steps)
     uint8_t* dev = nullptr;
+    // specialised (NVRTC-compiled) kernel of each fused step, resolved when its STRUCTURE has been
+    // seen before (in this plan, an earlier plan or another state)
+    struct StepJit {
+        uint64_t key = 0;              // hash of the specialised source (0: not generated yet)
+        bool ready = false, failed = false;
+        QbJitKernel k;
+        std::vector<double> pool;      // run-time coefficients (host copy, passed as kernel parameters)
+        double* pool_dev = nullptr;    // device copy when they do not fit the parameter space
+    };
+    std::vector<StepJit> jit;
+    void release() {
+        if (dev) cudaFree(dev);
+        dev = nullptr;
+        for (auto& j : jit) if (j.pool_dev) { cudaFree(j.pool_dev); j.pool_dev = nullptr; }
+    }
 };
 
 struct EngineState {
@@ -218,6 +234,42 @@ int engine_prefetch() {
     return p;
 }
 
+// 0: never specialise; 1 (default): specialise a plan when it is run again on a state of at least
+// QBOT_B200_JIT_MIN_BITS index bits (compile time is amortised by repetition); 2: always
+int engine_jit_default() {
+    static int m = env_int("QBOT_B200_JIT", 1);
+    return m;
+}
+int engine_jit_min_bits() {
+    static int b = env_int("QBOT_B200_JIT_MIN_BITS", 22);
+    return b;
+}
+
+// decide (once per step and run, until resolved) whether fused step i runs specialised
+bool step_jit(qb_state* s, CachedPlan* plan, size_t i, int jit_mode) {
+    CachedPlan::StepJit& j = plan->jit[i];
+    if (j.ready) return true;
+    if (j.failed) return false;
+    if (jit_mode == 1 && s->nbits + (s->nbranch > 1 ? 4 : 0) < engine_jit_min_bits()) return false;
+    const uint8_t* program = plan->steps[i].program.data();
+    try {
+        if (!j.key) j.key = qj_hash(qb_jit_full_source(program, nullptr, nullptr));
+        const int seen = qb_jit_note(j.key);          // sightings of this structure so far (this one included) or -1 if compiled
+        if (jit_mode != 2 && seen >= 0 && seen < 2) return false;
+        j.k = qb_jit_get(program, s->device);
+        j.pool = qj_pool(program);
+        if (j.k.pool_global) {
+            QB_CUDA(cudaMalloc((void**)&j.pool_dev, j.pool.size() * sizeof(double)));
+            QB_CUDA(cudaMemcpyAsync(j.pool_dev, j.pool.data(), j.pool.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        }
+        j.ready = true;
+    } catch (const qb_error&) {
+        j.failed = true;
+        if (jit_mode == 2) throw;       // explicitly requested: fail loudly
+    }
+    return j.ready;
+}
+
 template <int M>
 void launch_sweep(qb_state* s, EngineState* es, const uint8_t* prog, uint64_t ntiles) {
     using Cfg = TileCfg<M>;
@@ -237,7 +289,7 @@ bool qb_engine_available() { return getenv("QBOT_B200_NO_FUSION") == nullptr; }
 void qb_engine_free(qb_state* s) {
     EngineState* es = (EngineState*)s->engine;
     if (!es) return;
-    for (auto& c : es->cache) if (c.dev) cudaFree(c.dev);
+    for (auto& c : es->cache) c.release();
     delete es;
     s->engine = nullptr;
 }
@@ -278,12 +330,15 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         }
         if (es->cache.size() >= 8) {
             QB_CUDA(cudaStreamSynchronize(s->stream));
-            if (es->cache.back().dev) cudaFree(es->cache.back().dev);
+            es->cache.back().release();
             es->cache.pop_back();
         }
         es->cache.push_front(std::move(cp));
         plan = &es->cache.front();
     }
+
+    const int jit_mode = s->jit_mode >= 0 ? s->jit_mode : engine_jit_default();
+    if (plan->jit.size() != plan->steps.size()) plan->jit.assign(plan->steps.size(), CachedPlan::StepJit());
 
     const uint64_t ntiles = s->total() >> M;
     for (size_t i = 0; i < plan->steps.size(); i++) {
@@ -292,10 +347,16 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
             s->run_gate_unfused(gates[st.gate_index]);
             continue;
         }
-        const uint8_t* prog = plan->dev + plan->prog_off[i];
-        if (M == 11) launch_sweep<11>(s, es, prog, ntiles);
-        else launch_sweep<12>(s, es, prog, ntiles);
-        QB_CUDA(cudaGetLastError());
+        if (jit_mode != 0 && step_jit(s, plan, i, jit_mode)) {
+            const CachedPlan::StepJit& j = plan->jit[i];
+            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_prefetch(), j.pool.data(), j.pool_dev);
+            s->stats.jit_passes++;
+        } else {
+            const uint8_t* prog = plan->dev + plan->prog_off[i];
+            if (M == 11) launch_sweep<11>(s, es, prog, ntiles);
+            else launch_sweep<12>(s, es, prog, ntiles);
+            QB_CUDA(cudaGetLastError());
+        }
         s->stats.kernel_launches++;
         s->stats.fused_passes++;
         s->stats.state_passes++;

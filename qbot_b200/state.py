@@ -301,6 +301,10 @@ class DeviceState:
     def set_fusion(self, on: bool):
         _lib.call('qb_set_fusion', self._h, 1 if on else 0)
 
+    def set_jit(self, mode: int):
+        """Sweep specialisation: 0 never, 1 when a plan repeats on a large state (default), 2 always."""
+        _lib.call('qb_set_jit', self._h, int(mode))
+
     # ---- measurement ------------------------------------------------------------------------------
     def probs(self, qubits: Sequence[int]) -> np.ndarray:
         """Computational-basis outcome weights of the listed qubits (first listed = most

@@ -7,6 +7,7 @@
 #include "../../qbot_b200/csrc/qb_gate.h"
 #include "../../qbot_b200/csrc/qb_plan.h"
 #include "../../qbot_b200/csrc/qb_tile_ops.h"
+#include "../../qbot_b200/csrc/qb_jit.h"
 
 #include <cstring>
 #include <stdexcept>
@@ -121,5 +122,56 @@ int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t
         g_err = e.what();
         return -2;
     }
+}
+
+// plan only: fused flag / gate index per step and the fused steps' programs, concatenated
+int qbt_plan(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t* cmasks, const double* mats, int M, int merge,
+             int max_steps, int* nsteps, int* step_fused, int* step_gate, long long* prog_off, long long* prog_len,
+             unsigned char* prog_buf, long long prog_cap) {
+    try {
+        std::vector<QGate> gates;
+        size_t moff = 0;
+        for (int g = 0; g < ngates; g++) {
+            QGate q = qb_classify((const cplx*)(mats + moff), ks[g], tbs + (size_t)g * QB_BIG_MAXK, cmasks[g]);
+            moff += 2 * ((size_t)1 << (2 * ks[g]));
+            if (!qb_is_identity(q)) gates.push_back(q);
+        }
+        QtPlanOptions opt;
+        opt.M = M;
+        opt.merge_phases = merge != 0;
+        std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
+        if ((int)steps.size() > max_steps) { g_err = "too many steps"; return -1; }
+        long long at = 0;
+        for (size_t i = 0; i < steps.size(); i++) {
+            step_fused[i] = steps[i].fused ? 1 : 0;
+            step_gate[i] = steps[i].gate_index;
+            prog_off[i] = at;
+            prog_len[i] = (long long)steps[i].program.size();
+            if (steps[i].fused) {
+                if (at + (long long)steps[i].program.size() > prog_cap) { g_err = "program buffer too small"; return -1; }
+                memcpy(prog_buf + at, steps[i].program.data(), steps[i].program.size());
+                at += ((long long)steps[i].program.size() + 15) & ~15ll;
+            }
+        }
+        *nsteps = (int)steps.size();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+
+// specialised source of one program (valid until the next call) and its run-time coefficients
+const char* qbt_jit_source(const unsigned char* program) {
+    static std::string src;
+    src = qj_generate(program, nullptr);
+    return src.c_str();
+}
+
+int qbt_jit_pool(const unsigned char* program, double* out, int cap) {
+    std::vector<double> p = qj_pool(program);
+    if ((int)p.size() > cap) return -1;
+    memcpy(out, p.data(), p.size() * sizeof(double));
+    return (int)p.size();
 }
 }

@@ -7,8 +7,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, 'build', 'libqb_plan_test.so')
-SRCS = [os.path.join(ROOT, 'tests', 'csrc', 'plan_emulator.cpp'), os.path.join(ROOT, 'qbot_b200', 'csrc', 'qb_plan.cpp')]
-DEPS = SRCS + [os.path.join(ROOT, 'qbot_b200', 'csrc', f) for f in ('qb_plan.h', 'qb_tile_ops.h', 'qb_gate.h')]
+SRCS = [os.path.join(ROOT, 'tests', 'csrc', 'plan_emulator.cpp'), os.path.join(ROOT, 'qbot_b200', 'csrc', 'qb_plan.cpp'),
+        os.path.join(ROOT, 'qbot_b200', 'csrc', 'qb_jitgen.cpp')]
+DEPS = SRCS + [os.path.join(ROOT, 'qbot_b200', 'csrc', f) for f in ('qb_plan.h', 'qb_tile_ops.h', 'qb_gate.h', 'qb_jit.h')]
 
 _lib = None
 
@@ -25,9 +26,7 @@ def lib():
     return _lib
 
 
-def run(nbits, gate_list, psi=None, M=12, merge=True, execute=True):
-    """gate_list: [(matrix 2^k x 2^k, target_bits (msb first), control_mask)] on index BITS.
-    Returns (psi_out or None, stats dict)."""
+def pack_gates(gate_list):
     n = len(gate_list)
     ks = (C.c_int * max(n, 1))()
     tbs = (C.c_int * (14 * max(n, 1)))()
@@ -41,6 +40,14 @@ def run(nbits, gate_list, psi=None, M=12, merge=True, execute=True):
         cms[i] = int(cm)
         mats.append(m.reshape(-1))
     allm = np.ascontiguousarray(np.concatenate(mats)) if mats else np.zeros(1, dtype=np.complex128)
+    return ks, tbs, cms, allm
+
+
+def run(nbits, gate_list, psi=None, M=12, merge=True, execute=True):
+    """gate_list: [(matrix 2^k x 2^k, target_bits (msb first), control_mask)] on index BITS.
+    Returns (psi_out or None, stats dict)."""
+    n = len(gate_list)
+    ks, tbs, cms, allm = pack_gates(gate_list)
     out = None
     ptr = None
     if execute:

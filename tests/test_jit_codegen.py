@@ -1,0 +1,103 @@
+"""CPU: the sweep specialiser (qbot_b200/csrc/qb_jitgen.cpp).  The source text it generates for
+the planner's sweep programs -- the text NVRTC compiles into the sm_100a kernel -- is compiled
+with g++ over CPU definitions of its macros and executed against the oracle: register renaming
+of X / CNOT / Toffoli, constant tile addressing, predicates on thread / tile bits, merged phase
+tables, controlled diagonals, two-qubit blocks.  One test also NVRTC-compiles the real CUDA
+text for sm_100a (no GPU needed for that)."""
+import numpy as np
+import pytest
+
+import jit_emu
+import plan_emu
+from oracle import qbot_oracle as orc
+from qbot_b200.circuits import rc
+from conftest import close
+from test_planner import random_gate_list, oracle_apply_bits, rand_ket
+
+
+def tileable(gl):
+    """the generated kernels only ever see gates the planner fuses"""
+    out = []
+    for m, tb, cm in gl:
+        m = np.asarray(m)
+        diag = np.count_nonzero(m - np.diag(np.diagonal(m))) == 0
+        if (diag and len(tb) <= 3) or (not diag and len(tb) <= 2):
+            out.append((m, tb, cm))
+    return out
+
+
+@pytest.mark.parametrize('M', [11, 12])
+def test_generated_source_rc(M):
+    for n, depth, seed in ((12, 10, 1), (14, 12, 2), (16, 5, 3)):
+        gates = rc(n, depth, seed)
+        psi = rand_ket(np.random.default_rng(seed), n)
+        out, info = jit_emu.run(n, plan_emu.circuit_to_bits(n, gates), psi, M=M)
+        ref = psi
+        for g in gates:
+            ref = orc.ket_apply(ref, n, g.target, g.matrix(), g.controls)
+        assert close(out, ref, 1e-12), (n, info)
+
+
+@pytest.mark.parametrize('M,merge', [(12, True), (11, True), (12, False)])
+def test_generated_source_mixed(M, merge):
+    rng = np.random.default_rng(300 + M)
+    for n in (12, 13, 15):
+        gl = tileable(random_gate_list(rng, n, 70))
+        psi = rand_ket(rng, n)
+        out, info = jit_emu.run(n, gl, psi, M=M, merge=merge)
+        ref = psi
+        for m, tb, cm in gl:
+            ref = oracle_apply_bits(ref, n, m, tb, cm)
+        assert close(out, ref, 1e-12), (n, info)
+
+
+def test_generated_source_matches_interpreter_semantics():
+    """same plan, two executors: the op interpreter shared with the generic kernel
+    (qb_tile_ops.h) and the generated straight-line code"""
+    n = 15
+    gl = plan_emu.circuit_to_bits(n, rc(n, 8, 3))
+    psi = rand_ket(np.random.default_rng(5), n)
+    a, _ = plan_emu.run(n, gl, psi)
+    b, _ = jit_emu.run(n, gl, psi)
+    assert close(b, a, 1e-14)
+
+
+def test_structure_only_source():
+    """angles are run-time coefficients: two circuits that differ only in their RZ angles and
+    general 2x2 entries generate identical text"""
+    n = 14
+    a = plan_emu.circuit_to_bits(n, rc(n, 6, 9))
+    b = []
+    rng = np.random.default_rng(1)
+    for m, tb, cm in a:
+        m = np.asarray(m)
+        if abs(m[0, 1]) == 0 and abs(m[0, 0] - 1) > 1e-9:      # an RZ: new angle
+            th = rng.uniform(0.1, 6.0)
+            m = np.diag([np.exp(-0.5j * th), np.exp(0.5j * th)])
+        b.append((m, tb, cm))
+    sa = [jit_emu.source_of(p) for f, _, p in jit_emu.plan(n, a) if f]
+    sb = [jit_emu.source_of(p) for f, _, p in jit_emu.plan(n, b) if f]
+    assert sa == sb and len(sa) > 0
+    pa = [jit_emu.pool_of(p) for f, _, p in jit_emu.plan(n, a) if f]
+    pb = [jit_emu.pool_of(p) for f, _, p in jit_emu.plan(n, b) if f]
+    assert any(not np.array_equal(x, y) for x, y in zip(pa, pb))
+
+
+def test_nvrtc_compiles_generated_kernels(tmp_path):
+    """the real CUDA text through NVRTC for sm_100a, via the C ABI (qb_jit_check)"""
+    import ctypes
+    try:
+        ctypes.CDLL('libnvrtc.so.12')
+    except OSError:
+        try:
+            ctypes.CDLL('/usr/local/cuda/lib64/libnvrtc.so.12')
+        except OSError:
+            pytest.skip('libnvrtc not present')
+    from qbot_b200 import _lib
+    n = 24
+    rng = np.random.default_rng(4)
+    gl = plan_emu.circuit_to_bits(n, rc(n, 3, 24)) + tileable(random_gate_list(rng, n, 30))
+    k = _lib.jit_check(n, gl, str(tmp_path))
+    assert k >= 2
+    cubins = sorted(tmp_path.glob('sweep_*.cubin'))
+    assert len(cubins) == k and all(c.stat().st_size > 4096 for c in cubins)
