@@ -166,8 +166,12 @@ int qb_ipc_close(int device, void* dev);
  * sum_d bit_d(j) << src_bit_of_dst_bit[d]  (a permutation of the index bits), and is written to
  * chunk_dst[j >> (nbits - chunk_bits)][j & (2^(nbits-chunk_bits) - 1)].  The chunk pointers
  * may be local (the second shard buffer, followed by an NCCL all-to-all) or IPC mappings of
- * peer buffers (the exchange then happens inside this kernel, as stores over NVLink). */
-int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst);
+ * peer buffers (the exchange then happens inside this kernel, as stores over NVLink).
+ * Chunks are visited interleaved (64 KB units round-robin over the chunks) starting with chunk
+ * `first_chunk` (unit w goes to chunk (w mod 2^chunk_bits) ^ first_chunk): a rank passes its own
+ * chunk number, which makes concurrent ranks follow a pairwise-exchange schedule -- no two of
+ * them store to the same peer at the same time. */
+int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst, int first_chunk);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 int qb_get_stats(const qb_state* s, qb_stats* out);

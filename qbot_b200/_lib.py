@@ -72,7 +72,7 @@ PROTOTYPES = {
     'qb_ipc_export': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     'qb_ipc_open': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     'qb_ipc_close': (C.c_int, [C.c_int, C.c_void_p]),
-    'qb_permute_scatter': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    'qb_permute_scatter': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p), C.c_int]),
     'qb_get_stats': (C.c_int, [c_state_p, C.POINTER(QbStats)]),
     'qb_reset_stats': (C.c_int, [c_state_p]),
     'qb_timer_start': (C.c_int, [c_state_p]),

@@ -499,6 +499,7 @@ int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, c
         if (!qb_is_identity(q)) gates.push_back(q);
     }
     QtPlanOptions opt;
+    if (const char* e = getenv("QBOT_B200_TILE_M")) { const int v = atoi(e); if (v == 11 || v == 12) opt.M = v; }
     std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
     int n = 0;
     for (const QtPlanStep& st : steps) {
@@ -820,9 +821,11 @@ int qb_ipc_close(int device, void* dev) {
     QB_API_END
 }
 
-int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst) {
+int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst, int first_chunk) {
     QB_API_BEGIN
     QB_REQUIRE(s && src_bit_of_dst_bit && chunk_dst, "NULL argument");
+    QB_REQUIRE(first_chunk >= 0 && first_chunk < (1 << chunk_bits), "permute_scatter: first_chunk out of range");
+    QB_REQUIRE(s->nbits - chunk_bits >= 8, "permute_scatter: chunks must hold at least 256 amplitudes");
     QB_REQUIRE(s->kind == QB_KET && s->nbranch == 1, "permute_scatter: single-branch kets only");
     QB_REQUIRE(chunk_bits >= 0 && chunk_bits <= 4 && chunk_bits <= s->nbits, "permute_scatter: chunk_bits must be 0..4");
     s->flush();
@@ -843,6 +846,9 @@ int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bit
     a.in = s->d;
     a.total = s->per_branch();
     a.chunk_shift = s->nbits - chunk_bits;
+    a.chunk_bits = chunk_bits;
+    a.unit_bits = std::min(12, a.chunk_shift);
+    a.first_chunk = first_chunk;
     for (int c = 0; c < (1 << chunk_bits); c++) {
         QB_REQUIRE(chunk_dst[c], "permute_scatter: NULL chunk destination");
         QB_REQUIRE(chunk_dst[c] != (void*)s->d, "permute_scatter: destination aliases the source");

@@ -144,6 +144,9 @@ struct PermArgs {
     uint64_t total;               // amplitudes of the shard
     uint64_t fixed_mask;          // index bits that keep their position
     int chunk_shift;              // nbits - chunk_bits
+    int chunk_bits;
+    int unit_bits;                // 2^unit_bits consecutive destination amplitudes per work unit (8..12)
+    int first_chunk;              // rotation of the chunk visiting order
     int nmoved;
     uint8_t from[QB_PERM_MAXMOVED];   // source bit of moved destination bit to[i]
     uint8_t to[QB_PERM_MAXMOVED];

@@ -60,7 +60,7 @@ qj_kernel(double2* __restrict__ psi, const unsigned long long ntiles, const int 
     const unsigned tid = threadIdx.x;
     for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const unsigned long long tbase = qj_tile_base(tile);
-        const unsigned long long nt = tile + gridDim.x;
+        const unsigned long long nt = tile + (unsigned long long)prefetch * gridDim.x;     // prefetch = distance in tiles (0: off)
         const unsigned long long nbase = (prefetch && nt < ntiles) ? qj_tile_base(nt) : ~0ull;
         QJ_RUN_STAGES(tid, tbase, nbase, psi, buf, P)
     }
@@ -153,6 +153,14 @@ std::map<uint64_t, Compiled> g_cache;      // by hash of the full source
 std::map<uint64_t, int> g_seen;           // sightings of structures that are not compiled (yet)
 QbJitStats g_stats;
 
+// resident CTAs per SM the kernel is compiled for (register budget = 65536 / (threads * CTAs));
+// 0 = the generator's default (2 for 256-thread tiles, 4 for 128-thread tiles)
+int jit_ctas_override(int M) {
+    const char* e = getenv(M == 12 ? "QBOT_B200_JIT_CTAS12" : "QBOT_B200_JIT_CTAS11");
+    const int v = e ? atoi(e) : 0;
+    return (v >= 1 && v <= 8) ? v : 0;
+}
+
 constexpr int kMaxParamPoolDoubles = 480;     // 3840 bytes of coefficients + 24 bytes of scalars < 4 KB of parameters
 
 }  // namespace
@@ -165,6 +173,7 @@ std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool*
     if (pool_global) *pool_global = pg;
     std::string src;
     if (pg) src += "#define QJ_POOL_GLOBAL 1\n";
+    if (const int c = jit_ctas_override(li.M)) src += "#define QJ_CTAS " + std::to_string(c) + "\n";
     src += kPrelude;
     src += body;
     src += kPostlude;
@@ -261,7 +270,7 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
     k.smem_bytes = c.info.tile_units * 16;
     k.npool = c.info.npool;
     k.pool_global = c.pool_global;
-    k.ctas_per_sm = c.info.M == 12 ? 2 : 4;
+    k.ctas_per_sm = jit_ctas_override(c.info.M) ? jit_ctas_override(c.info.M) : (c.info.M == 12 ? 2 : 4);
     k.M = c.info.M;
     return k;
 }

@@ -368,7 +368,7 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     Out& o = g.o;
     o.f("// generated by qbot_b200 qj_generate: M=%d stages=%d ops=%d gates=%d\n", g.M, (int)g.h->nstages, (int)g.h->nops, (int)g.h->ngates);
     o.f("#define QJ_M %d\n#define QJ_T %d\n#define QJ_NH %d\n#define QJ_NP %d\n#define QJ_NSTAGES %d\n", g.M, g.T, g.NH, npool, (int)g.h->nstages);
-    o.f("#define QJ_TILE_UNITS %d\n#define QJ_CTAS %d\n", QT_TILE_UNITS(g.M), g.M == 12 ? 2 : 4);
+    o.f("#define QJ_TILE_UNITS %d\n#ifndef QJ_CTAS\n#define QJ_CTAS %d\n#endif\n", QT_TILE_UNITS(g.M), g.M == 12 ? 2 : 4);
     o.f("QJ_PRELUDE\n\n");
     // tile base: the tile number's bits deposited into the positions outside the tile
     o.f("QJ_DEV unsigned long long qj_tile_base(const unsigned long long t) {\n    unsigned long long b = t << %d;\n", QT_L);

@@ -513,18 +513,40 @@ void qb_launch_project(const LaunchCtx& c, cplx* psi, uint64_t total, uint64_t m
 // iteration; the planner keeps the low 5 bits in place so that warps read and write whole
 // 512-byte runs.
 // ---------------------------------------------------------------------------------------------
+// Work is cut into UNITS of 2^ub consecutive destination amplitudes (64 KB when the chunk allows).
+// Unit w goes to chunk (w mod 2^k) ^ first_chunk, so that (a) a GPU streams to all its peers at
+// the same time and (b) ranks that run this kernel concurrently never all target one peer (the
+// rotation is the rank's own chunk number: a pairwise-exchange schedule, no incast on a link).
+// The source offset of a thread's amplitudes inside a unit does not depend on the unit, so the
+// bit permutation is evaluated once per thread (low bits) and once per unit (high bits).
+__device__ __forceinline__ uint64_t perm_bits(const PermArgs& a, uint64_t j) {
+    uint64_t src = j & a.fixed_mask;
+    for (int i = 0; i < a.nmoved; i++) src |= ((j >> a.to[i]) & 1ull) << a.from[i];
+    return src;
+}
+
 __global__ void __launch_bounds__(256) k_permute_scatter(PermArgs a) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t cmask = (1ull << a.chunk_shift) - 1ull;
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.total; j += stride) {
-        uint64_t src = j & a.fixed_mask;
-        for (int i = 0; i < a.nmoved; i++) src |= ((j >> a.to[i]) & 1ull) << a.from[i];
-        const cplx v = __ldcs(&a.in[src]);
-        __stcs(&a.dst[j >> a.chunk_shift][j & cmask], v);
+    const int ub = a.unit_bits, k = a.chunk_bits;
+    const uint32_t per_thread = (1u << ub) >> 8;               // amplitudes per thread and unit (ub >= 8): 1..16
+    uint64_t soff[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) soff[t] = perm_bits(a, (uint64_t)threadIdx.x + 256ull * t);
+    const uint64_t nunits = a.total >> ub;
+    const uint64_t cmask = (1ull << k) - 1ull;
+    for (uint64_t w = blockIdx.x; w < nunits; w += gridDim.x) {
+        const uint64_t c = (w & cmask) ^ (uint64_t)a.first_chunk;
+        const uint64_t o = (w >> k) << ub;                      // offset of the unit inside its chunk
+        const uint64_t ubase = perm_bits(a, (c << a.chunk_shift) | o);
+        cplx* __restrict__ out = a.dst[c] + o + threadIdx.x;
+        cplx v[16];
+#pragma unroll
+        for (int t = 0; t < 16; t++) if ((uint32_t)t < per_thread) v[t] = __ldcs(&a.in[ubase | soff[t]]);
+#pragma unroll
+        for (int t = 0; t < 16; t++) if ((uint32_t)t < per_thread) __stcs(out + 256 * t, v[t]);
     }
 }
 
 void qb_launch_permute_scatter(const LaunchCtx& c, const PermArgs& a) {
-    k_permute_scatter<<<grid_for(c, a.total, 256), 256, 0, c.stream>>>(a);
+    k_permute_scatter<<<grid_for(c, a.total >> 4, 256, 4), 256, 0, c.stream>>>(a);
     COUNT_LAUNCH(c);
 }

@@ -497,6 +497,99 @@ bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& in
 
 }  // namespace
 
+namespace {
+
+struct Lcg {            // deterministic: the same circuit always gets the same plan
+    uint64_t s;
+    uint32_t next() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 33); }
+};
+
+// greedy choice of one sweep's free tile bits: repeatedly add the bit (or pair of bits, for
+// two-target gates) that admits the most queued gates.  With `rng` the choice is randomised
+// among the best two candidates (plan search, see qt_plan).
+std::vector<int> choose_tile_bits(const std::vector<int>& rem, const std::vector<GInfo>& info, int nbits, int NH, size_t window, Lcg* rng) {
+    const uint64_t low = (1ull << QT_L) - 1ull;
+    uint64_t allowed = low;
+    int cur;
+    select_pass(rem, info, allowed, window, nullptr, &cur);
+    std::vector<int> hb;
+    while ((int)hb.size() < NH) {
+        int best = -1, best_count = cur, second = -1, second_count = cur;
+        for (int b = QT_L; b < nbits; b++) {
+            if (allowed & (1ull << b)) continue;
+            int c;
+            select_pass(rem, info, allowed | (1ull << b), window, nullptr, &c);
+            if (c > best_count) { second = best; second_count = best_count; best_count = c; best = b; }
+            else if (c > second_count) { second_count = c; second = b; }
+        }
+        if (rng && second >= 0 && (rng->next() & 3u) == 0) { best = second; best_count = second_count; }
+        if (best < 0 && (int)hb.size() + 2 <= NH) {
+            // two-target gates need both bits at once
+            int ba = -1, bb = -1;
+            for (int a = QT_L; a < nbits; a++) for (int b = a + 1; b < nbits; b++) {
+                uint64_t bits = (1ull << a) | (1ull << b);
+                if (allowed & bits) continue;
+                int c;
+                select_pass(rem, info, allowed | bits, window, nullptr, &c);
+                if (c > best_count) { best_count = c; ba = a; bb = b; }
+            }
+            if (ba >= 0) {
+                allowed |= (1ull << ba) | (1ull << bb);
+                hb.push_back(ba); hb.push_back(bb);
+                cur = best_count;
+                continue;
+            }
+        }
+        if (best < 0) break;
+        allowed |= 1ull << best;
+        hb.push_back(best);
+        cur = best_count;
+    }
+    // fill up with the lowest unused bits (longer contiguous runs in HBM)
+    for (int b = QT_L; b < nbits && (int)hb.size() < NH; b++) {
+        if (!(allowed & (1ull << b))) { allowed |= 1ull << b; hb.push_back(b); }
+    }
+    std::sort(hb.begin(), hb.end());
+    return hb;
+}
+
+uint64_t allowed_of(const std::vector<int>& hb) {
+    uint64_t a = (1ull << QT_L) - 1ull;
+    for (int b : hb) a |= 1ull << b;
+    return a;
+}
+
+void remove_picked(std::vector<int>& rem, const std::vector<int>& picked) {
+    std::vector<int> next;
+    size_t pi = 0;
+    for (int gi : rem) {
+        if (pi < picked.size() && picked[pi] == gi) pi++; else next.push_back(gi);
+    }
+    rem.swap(next);
+}
+
+// one trial of the plan search: tile bits of every fused sweep, without building programs
+// (returns the number of steps)
+size_t trial_plan(const std::vector<GInfo>& info, int nbits, int NH, size_t window, Lcg* rng, std::vector<std::vector<int>>* guide) {
+    std::vector<int> rem(info.size());
+    for (size_t i = 0; i < info.size(); i++) rem[i] = (int)i;
+    size_t steps = 0;
+    guide->clear();
+    while (!rem.empty()) {
+        steps++;
+        if (!info[rem[0]].tileable) { rem.erase(rem.begin()); continue; }
+        std::vector<int> hb = choose_tile_bits(rem, info, nbits, NH, window, rng);
+        std::vector<int> picked;
+        select_pass(rem, info, allowed_of(hb), window, &picked, nullptr);
+        if (picked.empty()) { rem.erase(rem.begin()); continue; }
+        guide->push_back(hb);
+        remove_picked(rem, picked);
+    }
+    return steps;
+}
+
+}  // namespace
+
 std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt) {
     std::vector<QtPlanStep> steps;
     const int M = opt.M;
@@ -509,6 +602,23 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
     const bool can_tile = nbits >= M;
     const size_t WINDOW = 512;
 
+    // ---- plan search: the greedy tile-bit choice is a local optimum per sweep; a few randomised
+    //      trials (deterministic seed) usually save one or two of ~14 sweeps.  Every sweep is a
+    //      full pass over HBM, so the search is worth its milliseconds on large states only.
+    std::vector<std::vector<int>> guide;
+    bool have_guide = false;
+    if (can_tile && opt.search_trials > 1 && gates.size() >= 8) {
+        size_t best = trial_plan(info, nbits, NH, WINDOW, nullptr, &guide);
+        Lcg rng{0x9E3779B97F4A7C15ull ^ (uint64_t)gates.size()};
+        std::vector<std::vector<int>> g2;
+        for (int t = 1; t < opt.search_trials; t++) {
+            const size_t n = trial_plan(info, nbits, NH, WINDOW, &rng, &g2);
+            if (n < best) { best = n; guide.swap(g2); }
+        }
+        have_guide = true;
+    }
+    size_t guide_at = 0;
+
     while (!rem.empty()) {
         if (!can_tile || !info[rem[0]].tileable) {
             QtPlanStep st;
@@ -519,49 +629,12 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
             rem.erase(rem.begin());
             continue;
         }
-        // ---- choose the sweep's free tile bits greedily ---------------------------------------
-        uint64_t low = (1ull << QT_L) - 1ull;
-        uint64_t allowed = low;
-        int cur;
-        select_pass(rem, info, allowed, WINDOW, nullptr, &cur);
+        // ---- the sweep's free tile bits: from the search, or greedy ----------------------------
         std::vector<int> hb;
-        while ((int)hb.size() < NH) {
-            int best = -1, best_count = cur;
-            for (int b = QT_L; b < nbits; b++) {
-                if (allowed & (1ull << b)) continue;
-                int c;
-                select_pass(rem, info, allowed | (1ull << b), WINDOW, nullptr, &c);
-                if (c > best_count) { best_count = c; best = b; }
-            }
-            if (best < 0 && (int)hb.size() + 2 <= NH) {
-                // two-target gates need both bits at once
-                int ba = -1, bb = -1;
-                for (int a = QT_L; a < nbits; a++) for (int b = a + 1; b < nbits; b++) {
-                    uint64_t bits = (1ull << a) | (1ull << b);
-                    if (allowed & bits) continue;
-                    int c;
-                    select_pass(rem, info, allowed | bits, WINDOW, nullptr, &c);
-                    if (c > best_count) { best_count = c; ba = a; bb = b; }
-                }
-                if (ba >= 0) {
-                    allowed |= (1ull << ba) | (1ull << bb);
-                    hb.push_back(ba); hb.push_back(bb);
-                    cur = best_count;
-                    continue;
-                }
-            }
-            if (best < 0) break;
-            allowed |= 1ull << best;
-            hb.push_back(best);
-            cur = best_count;
-        }
-        // fill up with the lowest unused bits (longer contiguous runs in HBM)
-        for (int b = QT_L; b < nbits && (int)hb.size() < NH; b++) {
-            if (!(allowed & (1ull << b))) { allowed |= 1ull << b; hb.push_back(b); }
-        }
-        std::sort(hb.begin(), hb.end());
+        if (have_guide && guide_at < guide.size()) hb = guide[guide_at];
+        else hb = choose_tile_bits(rem, info, nbits, NH, WINDOW, nullptr);
         std::vector<int> picked;
-        select_pass(rem, info, allowed, WINDOW, &picked, nullptr);
+        select_pass(rem, info, allowed_of(hb), WINDOW, &picked, nullptr);
         if (picked.empty()) {
             // the head gate is tileable and unblocked, so this only happens if it needs more
             // high bits than the tile has; run it unfused
@@ -573,11 +646,13 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
             rem.erase(rem.begin());
             continue;
         }
+        guide_at++;
         // ---- stages + program (shrink the sweep if the program does not fit) -------------------
         std::vector<uint8_t> program;
         while (!build_program(gates, info, picked, hb, M, opt.merge_phases, &program)) {
             if (picked.size() <= 1) throw std::runtime_error("planner: cannot build a program for one gate");
             picked.resize(picked.size() / 2);
+            have_guide = false;       // the searched plan assumed the whole sweep ran: fall back to greedy
         }
         QtPlanStep st;
         st.fused = true;
@@ -585,12 +660,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
         st.ngates = (int)picked.size();
         st.program.swap(program);
         steps.push_back(std::move(st));
-        std::vector<int> next;
-        size_t pi = 0;
-        for (int gi : rem) {
-            if (pi < picked.size() && picked[pi] == gi) pi++; else next.push_back(gi);
-        }
-        rem.swap(next);
+        remove_picked(rem, picked);
     }
     return steps;
 }

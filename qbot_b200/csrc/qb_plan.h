@@ -120,6 +120,7 @@ struct QtPlanStep {
 struct QtPlanOptions {
     int M = 12;
     bool merge_phases = true;
+    int search_trials = 1;      // > 1: randomised search over the tile-bit choices, fewest steps wins
 };
 
 // Plan the execution of `gates` (in order) on a state with `nbits` index bits per branch.

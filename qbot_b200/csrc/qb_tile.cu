@@ -312,6 +312,9 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         cp.hash = hsh; cp.ngates = gates.size(); cp.nbits = s->nbits;
         QtPlanOptions opt;
         opt.M = M;
+        // plan search effort grows with the cost of a sweep (env QBOT_B200_PLAN_TRIALS overrides)
+        const int total_bits = s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0);
+        opt.search_trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);
         cp.steps = qt_plan(gates, s->nbits, opt);
         size_t total = 0;
         cp.prog_off.resize(cp.steps.size(), 0);

@@ -352,7 +352,8 @@ class CudaShard:
             t0 = time.perf_counter()
             for c in range(1 << k):
                 dst[c] = self.peer[peer_rank(c)][other] + my_s * chunk_bytes
-            lib.call('qb_permute_scatter', self.state._h, perm, k, dst)
+            # chunk order rotated by this rank's own chunk number: a pairwise-exchange schedule
+            lib.call('qb_permute_scatter', self.state._h, perm, k, dst, my_s)
             self.state.sync()
             self.exchange_seconds += time.perf_counter() - t0
             comm.barrier()
@@ -363,7 +364,7 @@ class CudaShard:
             t0 = time.perf_counter()
             for c in range(1 << k):
                 dst[c] = self.buf[other].value + c * chunk_bytes
-            lib.call('qb_permute_scatter', self.state._h, perm, k, dst)
+            lib.call('qb_permute_scatter', self.state._h, perm, k, dst, 0)
             self.state.sync()
             dev = f'cuda:{self.device}'
             nf = 2 << nl

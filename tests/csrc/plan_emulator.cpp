@@ -9,6 +9,7 @@
 #include "../../qbot_b200/csrc/qb_tile_ops.h"
 #include "../../qbot_b200/csrc/qb_jit.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -96,6 +97,7 @@ int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t
         QtPlanOptions opt;
         opt.M = M;
         opt.merge_phases = merge != 0;
+        if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
         std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
         long long st[7] = {0, 0, 0, 0, 0, 0, 0};
         int covered = 0;
@@ -139,6 +141,7 @@ int qbt_plan(int nbits, int ngates, const int* ks, const int* tbs, const uint64_
         QtPlanOptions opt;
         opt.M = M;
         opt.merge_phases = merge != 0;
+        if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
         std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
         if ((int)steps.size() > max_steps) { g_err = "too many steps"; return -1; }
         long long at = 0;

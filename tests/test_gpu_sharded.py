@@ -35,7 +35,7 @@ def test_permute_scatter_matches_numpy():
         chunk = (16 << nl) >> k
         # chunks deliberately placed in reverse order
         dst = (C.c_void_p * (1 << k))(*[buf.value + ((1 << k) - 1 - c) * chunk for c in range(1 << k)])
-        _lib.call('qb_permute_scatter', st._h, _lib.int_array(perm), k, dst)
+        _lib.call('qb_permute_scatter', st._h, _lib.int_array(perm), k, dst, (3 * nl) % (1 << k))
         st.sync()
         h = C.c_void_p()
         _lib.call('qb_create_external', C.byref(h), 0, nl, 1, 0, buf, None)

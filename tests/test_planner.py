@@ -150,3 +150,26 @@ def test_small_states_are_not_tiled():
     gl = [(np.array([[0, 1], [1, 0]], dtype=complex), [3], 0)]
     _, st = plan_emu.run(8, gl, np.ones(256, dtype=complex), M=12)
     assert st['fused_sweeps'] == 0 and st['unfused_steps'] == 1
+
+
+def test_plan_search_never_worse_and_still_correct(monkeypatch):
+    """randomised plan search (qt_plan search_trials): trial 0 is the greedy plan, so the result
+    can only have fewer steps; the searched plan executes to the same state"""
+    n = 16
+    gates = rc(n, 14, 5)
+    gl = plan_emu.circuit_to_bits(n, gates)
+    psi = rand_ket(np.random.default_rng(2), n)
+    monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '1')
+    base, st1 = plan_emu.run(n, gl, psi)
+    monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '24')
+    out, st2 = plan_emu.run(n, gl, psi)
+    assert st2['steps'] <= st1['steps']
+    assert st2['fused_gates'] == len(gl) and st2['unfused_steps'] == 0
+    assert close(out, base, 1e-13)
+    for nn, d, s in ((30, 20, 30), (34, 10, 34)):
+        gl = plan_emu.circuit_to_bits(nn, rc(nn, d, s))
+        monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '1')
+        _, a = plan_emu.run(nn, gl, None, execute=False)
+        monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '16')
+        _, b = plan_emu.run(nn, gl, None, execute=False)
+        assert b['fused_sweeps'] < a['fused_sweeps'], (a, b)
