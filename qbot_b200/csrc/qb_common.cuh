@@ -91,6 +91,8 @@ struct BinArgs {
     int foldbits[16];
     int ml;
     int lowt[16];                 // low target bit positions, ascending
+    int ngroup;                   // chunks that differ only in these (non-target) chunk-index bits are
+    int groupbits[8];             //   summed by ONE block before the fold (positions in the chunk index, ascending)
 };
 
 struct BinFinalArgs {
@@ -103,6 +105,7 @@ struct BinFinalArgs {
     int ml;
     int tbits[QB_MAX_BITS];       // target bits, MSB-first as listed
     int lowrank[QB_MAX_BITS];     // for target t with bit < c: its rank among low targets, else -1
+    uint64_t groupmask;           // chunk-index bits already summed by k_bins (only representatives hold data)
 };
 
 struct PtraceArgs {

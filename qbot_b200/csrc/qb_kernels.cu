@@ -260,15 +260,28 @@ void qb_launch_dense_batched(const LaunchCtx& c, int K, cplx* psi, int nbits, in
 __global__ void __launch_bounds__(256) k_bins(BinArgs a) {
     __shared__ double sre[1 << BIN_C];
     __shared__ double sim[1 << BIN_C];
-    const uint64_t blk = blockIdx.x;                 // = branch * nchunks + chunk
-    const uint64_t branch = blk / a.nchunks, q = blk % a.nchunks;
+    // block = branch * (nchunks >> ngroup) + group; the group's representative chunk has zeros at
+    // the group bits, its 2^ngroup members are summed element-wise in registers (ascending order)
+    const uint64_t ngrp = a.nchunks >> a.ngroup;
+    const uint64_t branch = blockIdx.x / ngrp;
+    uint64_t q = blockIdx.x % ngrp;
+    for (int x = 0; x < a.ngroup; x++) q = qb_insert_zero(q, a.groupbits[x]);
+    const uint64_t blk = branch * a.nchunks + q;
     const int C = 1 << a.c;
     const cplx* src = a.src + branch * a.branch_stride;
+    const int G = 1 << a.ngroup;
     for (int l = threadIdx.x; l < C; l += blockDim.x) {
-        uint64_t i = (q << a.c) | (uint64_t)l;
-        cplx v = src[i * a.elem_stride];
-        if (a.mode == 0) { sre[l] = v.x * v.x + v.y * v.y; sim[l] = 0.0; }
-        else { sre[l] = v.x; sim[l] = v.y; }
+        double re = 0.0, im = 0.0;
+#pragma unroll 4
+        for (int gi = 0; gi < G; gi++) {
+            uint64_t qq = q;
+            for (int x = 0; x < a.ngroup; x++) qq |= (uint64_t)((gi >> x) & 1) << a.groupbits[x];
+            const uint64_t i = (qq << a.c) | (uint64_t)l;
+            const cplx v = __ldcs(&src[i * a.elem_stride]);
+            if (a.mode == 0) re += v.x * v.x + v.y * v.y;
+            else { re += v.x; im += v.y; }
+        }
+        sre[l] = re; sim[l] = im;
     }
     __syncthreads();
     unsigned folded = 0;
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(256) k_bins(BinArgs a) {
 }
 
 void qb_launch_bins(const LaunchCtx& c, const BinArgs& a, int64_t nbranch) {
-    uint64_t blocks = a.nchunks * (uint64_t)nbranch;
+    uint64_t blocks = (a.nchunks >> a.ngroup) * (uint64_t)nbranch;
     QB_REQUIRE(blocks < (1ull << 31), "probs: too many chunks");
     k_bins<<<(unsigned)blocks, 256, 0, c.stream>>>(a);
     COUNT_LAUNCH(c);
@@ -309,6 +322,7 @@ __global__ void __launch_bounds__(256) k_bins_final(BinFinalArgs a) {
         else { hfix |= v << (a.tbits[t] - a.c); hmask |= 1ull << (a.tbits[t] - a.c); }
     }
     const int qbits = a.nb - a.c > 0 ? a.nb - a.c : 0;
+    hmask |= a.groupmask;              // summed by k_bins already: only the representatives (zeros there) hold data
     int nfix = __popcll(hmask);
     const uint64_t nfree = 1ull << (qbits - nfix);
     const uint64_t ML = 1ull << a.ml;
