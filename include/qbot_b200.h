@@ -127,7 +127,8 @@ int qb_project_renorm(qb_state* s, const int* bits, int m, uint64_t outcome);
 
 /* ---- density-matrix structure ops -----------------------------------------------------
  * density.partialTraceArbitrary (density.py:122-148): keep the listed qubit-bits (keep_bits[0]
- * = most significant bit of the result), trace the others.  Returns a new DM handle. */
+ * = most significant bit of the result), trace the others.  Returns a new DM handle.  For a ket
+ * the result is Tr_rest |psi><psi|, computed from the amplitudes (nkeep <= 13). */
 int qb_ptrace(qb_state* s, const int* keep_bits, int nkeep, qb_state** out);
 /* density.interweaveDensities / replaceArbitrary (density.py:150-227): out = A (x) B with A's
  * i-th qubit-bit (most significant first) placed at bit a_bits[i] of the result and B's at

@@ -2,6 +2,9 @@
 #include "../../include/qbot_b200.h"
 #include "qb_common.cuh"
 #include "qb_engine.h"
+#include <algorithm>
+#include <mutex>
+#include <tuple>
 #include "qb_jit_rt.h"
 
 #include <algorithm>
@@ -37,10 +40,64 @@ static int sm_count_of(int dev) {
     return v;
 }
 
+// Large register buffers are recycled instead of returned to the driver: cudaMalloc / cudaFree of
+// a 16 GiB ket cost tens of milliseconds each, and every executeTxt call creates and drops one
+// register.  At most two buffers per device are kept, each at most a third of the device memory;
+// an allocation failure empties the cache and retries.
+namespace {
+struct BufCache {
+    std::mutex mu;
+    std::vector<std::tuple<int, size_t, void*>> free_list;      // (device, bytes, pointer)
+};
+BufCache g_bufs;
+constexpr size_t kCacheMinBytes = 64u << 20;
+
+void* cached_alloc(int device, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_bufs.mu);
+        for (size_t i = 0; i < g_bufs.free_list.size(); i++) {
+            if (std::get<0>(g_bufs.free_list[i]) == device && std::get<1>(g_bufs.free_list[i]) == bytes) {
+                void* p = std::get<2>(g_bufs.free_list[i]);
+                g_bufs.free_list.erase(g_bufs.free_list.begin() + i);
+                return p;
+            }
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(g_bufs.mu);
+        for (auto& b : g_bufs.free_list) if (std::get<0>(b) == device) cudaFree(std::get<2>(b));
+        g_bufs.free_list.erase(std::remove_if(g_bufs.free_list.begin(), g_bufs.free_list.end(),
+                                              [&](const std::tuple<int, size_t, void*>& b) { return std::get<0>(b) == device; }),
+                               g_bufs.free_list.end());
+        e = cudaMalloc(&p, bytes);
+    }
+    QB_CUDA(e);
+    return p;
+}
+
+void cached_free(int device, size_t bytes, void* p, cudaStream_t stream) {
+    if (bytes >= kCacheMinBytes) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes <= total_b / 3) {
+            if (stream) cudaStreamSynchronize(stream);            // nothing may still be writing into it
+            std::lock_guard<std::mutex> lk(g_bufs.mu);
+            int mine = 0;
+            for (auto& b : g_bufs.free_list) if (std::get<0>(b) == device) mine++;
+            if (mine < 2) { g_bufs.free_list.emplace_back(device, bytes, p); return; }
+        }
+    }
+    cudaFree(p);
+}
+}  // namespace
+
 qb_state::~qb_state() {
     qb_engine_free(this);
-    if (d && owns) cudaFree(d);
+    if (d && owns) { DevGuard g(device); cached_free(device, bytes(), d, stream); }
     if (scratch) cudaFree(scratch);
+    if (stage) cudaFree(stage);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream && owns_stream) cudaStreamDestroy(stream);
@@ -62,7 +119,7 @@ static qb_state* new_state(int kind, int nq, int64_t nbranch, int device, void* 
     if (ext_stream) { s->stream = (cudaStream_t)ext_stream; s->owns_stream = false; }
     else { QB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->owns_stream = true; }
     if (ext) { s->d = (cplx*)ext; s->owns = false; }
-    else { QB_CUDA(cudaMalloc((void**)&s->d, s->bytes())); s->owns = true; }
+    else { s->d = (cplx*)cached_alloc(device, s->bytes()); s->owns = true; }
     return s.release();
 }
 
@@ -223,8 +280,7 @@ int qb_destroy(qb_state* s) {
     if (s) {
         DevGuard g(s->device);
         cudaStreamSynchronize(s->stream);
-        if (s->stage) cudaFree(s->stage);
-        delete s;
+        delete s;                                   // the destructor releases stage / scratch / the register buffer
     }
     QB_API_END
 }
@@ -620,8 +676,9 @@ int qb_project_renorm(qb_state* s, const int* bits, int m, uint64_t outcome) {
 int qb_ptrace(qb_state* s, const int* keep_bits, int nkeep, qb_state** out) {
     QB_API_BEGIN
     QB_REQUIRE(s && out && (keep_bits || nkeep == 0), "NULL argument");
-    QB_REQUIRE(s->kind == QB_DM && s->nbranch == 1, "ptrace needs a single-branch density matrix");
+    QB_REQUIRE(s->nbranch == 1, "ptrace needs a single-branch state");
     QB_REQUIRE(nkeep >= 0 && nkeep <= s->nq, "ptrace: bad keep count");
+    QB_REQUIRE(s->kind == QB_DM || nkeep <= 13, "ptrace of a ket: at most 13 kept qubits");
     s->flush();
     DevGuard g(s->device);
     PtraceArgs a;
@@ -639,7 +696,8 @@ int qb_ptrace(qb_state* s, const int* keep_bits, int nkeep, qb_state** out) {
     o->fusion = s->fusion;
     a.rho = s->d; a.out = o->d;
     // order the new handle's stream after ours
-    qb_launch_ptrace(s->ctx(), a);
+    if (s->kind == QB_DM) qb_launch_ptrace(s->ctx(), a);
+    else qb_launch_ket_rdm(s->ctx(), a);          // Tr_rest |psi><psi| straight from the amplitudes
     QB_CUDA(cudaStreamSynchronize(s->stream));
     s->stats.bytes_moved += (sizeof(cplx) << (s->nq + nkeep)) + o->bytes();
     *out = o;

@@ -404,6 +404,41 @@ __global__ void __launch_bounds__(256) k_ptrace_blk(PtraceArgs a) {
     }
 }
 
+// reduced density matrix of a KET: out[i][j] = sum_t psi[dep(i)|sp(t)] * conj(psi[dep(j)|sp(t)])
+// (the partial trace of |psi><psi| without ever forming it).  One block per output entry,
+// fixed-shape tree; meant for a handful of kept qubits (the measured system of a `peek`).
+__global__ void __launch_bounds__(256) k_ket_rdm(PtraceArgs a) {
+    __shared__ double sre[256];
+    __shared__ double sim[256];
+    const uint64_t A = 1ull << a.nkeep, total = A * A, T = 1ull << a.ntr;
+    for (uint64_t e = blockIdx.x; e < total; e += gridDim.x) {
+        const uint64_t rb = pt_spread(e >> a.nkeep, a.keepb, a.nkeep, true);
+        const uint64_t cb = pt_spread(e & (A - 1), a.keepb, a.nkeep, true);
+        double re = 0.0, im = 0.0;
+        for (uint64_t t = threadIdx.x; t < T; t += blockDim.x) {
+            const uint64_t sp = pt_spread(t, a.trb, a.ntr, false);
+            const cplx x = a.rho[rb | sp], y = a.rho[cb | sp];
+            re += x.x * y.x + x.y * y.y;
+            im += x.y * y.x - x.x * y.y;
+        }
+        sre[threadIdx.x] = re; sim[threadIdx.x] = im;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) { sre[threadIdx.x] += sre[threadIdx.x + s]; sim[threadIdx.x] += sim[threadIdx.x + s]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) a.out[e] = make_double2(sre[0], sim[0]);
+        __syncthreads();
+    }
+}
+
+void qb_launch_ket_rdm(const LaunchCtx& c, const PtraceArgs& a) {
+    const uint64_t total = 1ull << (2 * a.nkeep);
+    const uint64_t blocks = total < (uint64_t)c.sms * 16 ? total : (uint64_t)c.sms * 16;
+    k_ket_rdm<<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+    COUNT_LAUNCH(c);
+}
+
 void qb_launch_ptrace(const LaunchCtx& c, const PtraceArgs& a) {
     uint64_t total = 1ull << (2 * a.nkeep);
     if (a.ntr <= 6) {

@@ -23,6 +23,8 @@
 
 #include <cstring>
 #include <list>
+#include <map>
+#include <mutex>
 
 template <int M> struct TileCfg {
     static constexpr int T = 1 << (M - QT_R);
@@ -190,10 +192,16 @@ struct CachedPlan {
     }
 };
 
+// One plan cache per DEVICE and process (not per state handle): a program that is run again
+// on a fresh register -- every executeTxt call creates one -- finds its plans, device-side sweep
+// programs and specialised kernels ready.
 struct EngineState {
     std::list<CachedPlan> cache;       // most recent first
     bool attr_set[16] = {false};
 };
+constexpr size_t kMaxCachedPlans = 32;
+std::mutex g_engine_mu;                // guards the caches and the lazily resolved StepJit records
+std::map<int, EngineState> g_engines;
 
 uint64_t fnv(uint64_t h, const void* p, size_t n) {
     const uint8_t* b = (const uint8_t*)p;
@@ -286,17 +294,11 @@ void launch_sweep(qb_state* s, EngineState* es, const uint8_t* prog, uint64_t nt
 
 bool qb_engine_available() { return getenv("QBOT_B200_NO_FUSION") == nullptr; }
 
-void qb_engine_free(qb_state* s) {
-    EngineState* es = (EngineState*)s->engine;
-    if (!es) return;
-    for (auto& c : es->cache) c.release();
-    delete es;
-    s->engine = nullptr;
-}
+void qb_engine_free(qb_state* s) { s->engine = nullptr; }      // plans belong to the device, not to the handle
 
 void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
-    if (!s->engine) s->engine = new EngineState();
-    EngineState* es = (EngineState*)s->engine;
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    EngineState* es = &g_engines[s->device];
     const int M = engine_M();
     const uint64_t hsh = hash_gates(gates, s->nbits, M);
     CachedPlan* plan = nullptr;
@@ -331,7 +333,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
             QB_CUDA(cudaMemcpyAsync(cp.dev, hostbuf.data(), total, cudaMemcpyHostToDevice, s->stream));
             QB_CUDA(cudaStreamSynchronize(s->stream));     // hostbuf dies here
         }
-        if (es->cache.size() >= 8) {
+        if (es->cache.size() >= kMaxCachedPlans) {
             QB_CUDA(cudaStreamSynchronize(s->stream));
             es->cache.back().release();
             es->cache.pop_back();
@@ -356,6 +358,10 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
             s->stats.jit_passes++;
         } else {
             const uint8_t* prog = plan->dev + plan->prog_off[i];
+            {   // a stale error of an earlier unchecked runtime call must not be blamed on this launch
+                const cudaError_t stale = cudaGetLastError();
+                if (stale != cudaSuccess) throw qb_error(-2, std::string("stale CUDA error before the sweep launch: ") + cudaGetErrorString(stale));
+            }
             if (M == 11) launch_sweep<11>(s, es, prog, ntiles);
             else launch_sweep<12>(s, es, prog, ntiles);
             QB_CUDA(cudaGetLastError());

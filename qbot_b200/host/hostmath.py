@@ -91,13 +91,79 @@ def shift_matrix(num_qubits: int, up: bool = True, shifts: int = 1):
 
 
 # ---- tensor helpers -----------------------------------------------------------------------------
+LAZY_MIN_QUBITS = 14      # smaller products are built on the host exactly as the reference does
+
+
+class LazyProduct:
+    """kron(factors[0], factors[1], ...) kept as a descriptor.
+
+    The reference builds initial states with kron chains on the host (density.py:7-29), which
+    stops being possible around 14 qubits (a 2^n x 2^n complex128 array).  From LAZY_MIN_QUBITS
+    on, tensorProd / tensorExp return this ndarray-like object instead; `qset` hands its
+    factors to the device-side constructor (qb_init_product) and no 2^n array ever exists on
+    the host.  All factors are kets (1-D) or all are density matrices (2-D)."""
+    _qb_lazy_product = True
+
+    def __init__(self, factors):
+        flat = []
+        for f in factors:
+            if getattr(f, '_qb_lazy_product', False):
+                flat.extend(f.factors)
+            else:
+                flat.append(np.asarray(f, dtype=complex))
+        nd = {f.ndim for f in flat}
+        if len(nd) != 1 or next(iter(nd)) not in (1, 2):
+            raise ValueError("tensor product of kets with density matrices")
+        self.factors = flat
+        self.ndim = flat[0].ndim
+        self.num_qubits = sum(ilog2(f.shape[0]) for f in flat)
+        self.dtype = np.dtype(complex)
+
+    @property
+    def shape(self):
+        d = 1 << self.num_qubits
+        return (d,) if self.ndim == 1 else (d, d)
+
+    @property
+    def size(self):
+        return (1 << self.num_qubits) ** self.ndim
+
+    def single_qubit_factors(self):
+        """per-qubit 2-vectors / 2x2 matrices, qubit 0 first, or None if a factor spans several qubits"""
+        if all(f.shape[0] == 2 for f in self.factors):
+            return self.factors
+        return None
+
+    def materialize(self):
+        out = self.factors[0]
+        for f in self.factors[1:]:
+            out = np.kron(out, f)
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.materialize()
+        return a if dtype is None else a.astype(dtype)
+
+    def __repr__(self):
+        return f"LazyProduct({len(self.factors)} factors, {self.num_qubits} qubits, {'ket' if self.ndim == 1 else 'density'})"
+
+
+def is_lazy(x) -> bool:
+    return getattr(x, '_qb_lazy_product', False)
+
+
 def tensor_prod(*parts):
+    parts = [p for p in parts if p.size != 0]
+    if not parts:
+        return np.array([], dtype=complex)
+    if len({p.ndim for p in parts}) == 1 and parts[0].ndim in (1, 2) and \
+            sum(ilog2(p.shape[0]) for p in parts) >= LAZY_MIN_QUBITS:
+        return LazyProduct(parts)
     out = None
     for p in parts:
-        if p.size == 0:
-            continue
+        p = np.asarray(p)
         out = p if out is None else np.kron(out, p)
-    return out if out is not None else np.array([], dtype=complex)
+    return out
 
 
 def tensor_exp(state, n: int):

@@ -74,8 +74,16 @@ def build_namespace():
 globalNameSpace = build_namespace()
 
 
+_code_cache = {}
+
+
 def evaluate(expression: str, localNameSpace: dict):
-    return eval(compile(expression, "<string>", "eval"), globalNameSpace, localNameSpace)
+    code = _code_cache.get(expression)
+    if code is None:
+        code = compile(expression, "<string>", "eval")
+        if len(_code_cache) < 65536:
+            _code_cache[expression] = code       # the same source lines are evaluated again by loops and re-runs
+    return eval(code, globalNameSpace, localNameSpace)
 
 
 def evaluateWrapper(lines, lineNum, expression: str, localNameSpace: dict):

@@ -234,6 +234,14 @@ def make_ops(host: Host) -> dict:
         SURVEY.md F1 -- this is the new representation); empty values stay as they are."""
         if is_state(val):
             return val
+        if hm.is_lazy(val):
+            # product state described by its factors: built on the device (qb_init_product), the
+            # 2^n array never exists on the host
+            from ..state import KET, DM
+            fs = val.single_qubit_factors()
+            if fs is not None:
+                return State.product(fs, KET if val.ndim == 1 else DM)
+            return State.from_host(val.materialize())
         if val.size == 0 or val.ndim not in (1, 2):
             return val
         return State.from_host(val)
@@ -244,7 +252,7 @@ def make_ops(host: Host) -> dict:
                 return val.toDensityMatrix()
             except Exception:
                 err.raiseFormattedError(err.customTypeError(lines, lineNum, ['np.ndarray', 'ProbVal<np.ndarray>'], val.typeString()))
-        if not isinstance(val, np.ndarray) and not is_state(val):
+        if not isinstance(val, np.ndarray) and not is_state(val) and not hm.is_lazy(val):
             err.raiseFormattedError(err.customTypeError(lines, lineNum, ['np.ndarray', 'ProbVal<np.ndarray>'], type(val).__name__))
         return val
 
@@ -508,6 +516,39 @@ def make_ops(host: Host) -> dict:
                 newState = State.scatter_product(measured, sysB_dev, targets_sorted, rest)
         return Result(unmeasured, probs, basisStates, basisSymbols, newState)
 
+    KET_AS_DENSITY_MAX = 13    # larger ket-mode registers are never expanded to 4^n density matrices
+
+    def measure_ket(st, basis, toMeasure):
+        """`peek` on a large ket-mode register (new representation): outcome weights
+        straight from the amplitudes (qb_probs); rho_A is computed only if somebody reads it.  The
+        reference's collapse (F7) yields a mixed product state, which a ket cannot hold -- `meas`
+        on such a register is refused."""
+        numQubits = st.nq
+        if toMeasure is None:
+            toMeasure = list(range(numQubits))
+        toMeasure = list(toMeasure) if isinstance(toMeasure, set) else list(set(toMeasure))
+        for target in toMeasure:
+            if target < 0 or target > numQubits - 1:
+                raise MeasurementIndexError(f"measurement target {target} outside of valid range [{0}, {numQubits - 1}]",
+                                            target, 0, numQubits - 1)
+        numTargets = len(toMeasure)
+        if numTargets == 0:
+            raise ValueError("measurement must have targets")
+        if basis.numQubits != 1 or not _is_computational(basis):
+            raise NotImplementedError("a ket-mode register is measured in the computational basis")
+        if numTargets > 26:
+            raise NotImplementedError("too many outcome qubits")
+        targets_sorted = sorted(toMeasure)
+        w = st.probs(targets_sorted)
+        s = 0
+        probs = []
+        for x in w.reshape(-1):
+            probs.append(float(x))
+            s += probs[-1]
+        probs = [p / s for p in probs]
+        return Result(_LazyReducedDensity(st, targets_sorted), probs, _LazyProjectors(numTargets, basis),
+                      _LazySymbols(numTargets, basis), None)
+
     def meas(ns, lines, lineNum, tokens, changeState=True):
         varName = tokens[1]
         if not varName.isidentifier():
@@ -516,15 +557,20 @@ def make_ops(host: Host) -> dict:
         if not isinstance(measBasis, host.Basis):
             err.raiseFormattedError(err.customTypeError(lines, lineNum, ['Basis'], type(measBasis).__name__))
         try:
-            st = current_dm(ns)
+            raw = current(ns)
+            big_ket = is_state(raw) and raw.kind == 0 and raw.nq > KET_AS_DENSITY_MAX
+            if big_ket and changeState:
+                raise NotImplementedError(f"meas on a {raw.nq}-qubit ket-mode register: the reference's collapse is a mixed "
+                                          "product state (4^n entries); use peek, or a density-matrix register")
+            st = raw if big_ket else current_dm(ns)
             if len(tokens) < 4:
-                result = measure(st, measBasis, None, changeState)
+                result = measure_ket(st, measBasis, None) if big_ket else measure(st, measBasis, None, changeState)
             else:
                 targets = ensureContainer(lines, lineNum, evaluateWrapper(lines, lineNum, tokens[3], ns))
                 if isinstance(targets, ProbVal):
                     # the reference crashes here (MeasurementResult.fromProbVal)
                     raise AttributeError("type object 'ProbVal' has no attribute 'probs'")
-                result = measure(st, measBasis, targets, changeState)
+                result = measure_ket(st, measBasis, targets) if big_ket else measure(st, measBasis, targets, changeState)
         except MeasurementIndexError as e:
             err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', e.args[1], e.args[3]))
         except Exception as e:
@@ -560,6 +606,23 @@ class _LazyProjectors:
         if i < 0 or i >= len(self):
             raise IndexError(i)
         return hm.permute_basis(self.factors, i, self.basis)[0]
+
+
+class _LazyReducedDensity:
+    """rho_A of a ket-mode register, computed on the device when somebody looks at it."""
+
+    def __init__(self, ket_state, keep):
+        self._snapshot = ket_state.clone() if ket_state.nq <= 24 else ket_state   # large kets: a view of the live register
+        self._keep = list(keep)
+        self._val = None
+        d = 1 << len(self._keep)
+        self.shape, self.ndim, self.size, self.dtype = (d, d), 2, d * d, np.dtype(complex)
+
+    def __array__(self, dtype=None, copy=None):
+        if self._val is None:
+            self._val = np.asarray(self._snapshot.ptrace_keep(self._keep))
+            self._snapshot = None
+        return self._val if dtype is None else self._val.astype(dtype)
 
 
 class _LazySymbols(_LazyProjectors):

@@ -33,9 +33,18 @@ def install(qbot_module=None, state_cls=None):
                 MeasurementResult=meas_mod.MeasurementResult)
     new = make_ops(host)
     table = ops_mod.operations
+    gns = getattr(ev_mod, 'globalNameSpace', None)
     _saved = dict(table={k: table[k] for k in ('qset', 'gate', 'disc', 'swap', 'meas', 'peek')},
                   valsClose=pv_mod.valsClose, toDensityMatrix=pv_mod.ProbVal.toDensityMatrix,
-                  convert=ops_mod.convertToDensity, mods=(ops_mod, pv_mod))
+                  convert=ops_mod.convertToDensity, mods=(ops_mod, pv_mod), gns=gns,
+                  tensor={k: gns[k] for k in ('tensorProd', 'tensorExp') if gns is not None and k in gns})
+    if _saved['tensor']:
+        # state constructors of >= 14 qubits stay descriptors and are built on the device
+        # (SURVEY.md row f1); below that they are the reference's host kron chains
+        from .host import hostmath as hm
+        fw = pv_mod.funcWrapper
+        gns['tensorProd'] = lambda *a, **k: fw(hm.tensor_prod, *a, **k)
+        gns['tensorExp'] = lambda *a, **k: fw(hm.tensor_exp, *a, **k)
     for name in _saved['table']:
         _, lo, hi = table[name]
         table[name] = (new[name], lo, hi)
@@ -68,6 +77,8 @@ def uninstall():
     ops_mod, pv_mod = _saved['mods']
     for name, entry in _saved['table'].items():
         ops_mod.operations[name] = entry
+    for k, v in _saved.get('tensor', {}).items():
+        _saved['gns'][k] = v
     pv_mod.valsClose = _saved['valsClose']
     pv_mod.ProbVal.toDensityMatrix = _saved['toDensityMatrix']
     ops_mod.convertToDensity = _saved['convert']

@@ -28,6 +28,13 @@ class FakeState:
             return cls(a, DM, orc.ilog2(a.shape[0]))
         return cls(a, KET, orc.ilog2(a.shape[0]))
 
+    @classmethod
+    def product(cls, factors, kind=KET, device=0):
+        out = np.asarray(factors[0], dtype=complex)
+        for f in factors[1:]:
+            out = np.kron(out, np.asarray(f, dtype=complex))
+        return cls(out, kind, len(factors))
+
     def clone(self):
         return FakeState(self.data.copy(), self.kind, self.nq, self.nbranch)
 
@@ -111,6 +118,11 @@ class FakeState:
 
     def ptrace_keep(self, keep):
         keep = list(keep)
+        if self.kind == KET:          # Tr_rest |psi><psi| straight from the amplitudes
+            t = self.data.reshape((2,) * self.nq)
+            rest = [q for q in range(self.nq) if q not in keep]
+            t = np.transpose(t, keep + rest).reshape(1 << len(keep), -1)
+            return FakeState(t @ t.conj().T, DM, len(keep))
         if not keep:
             return FakeState(np.trace(self.data).reshape(1, 1), DM, 0)
         assert keep == sorted(keep)

@@ -2,6 +2,7 @@
 README examples, outputs recorded from the real reference) through the interpreter mirror on
 the CUDA backend -- final register, measurement results, ProbVal-driven mixtures, control
 flow and error text."""
+import numpy as np
 import pytest
 
 from test_host_logic import check_script
@@ -24,3 +25,34 @@ def test_exact_equality_cases_stay_exact(golden):
     for name in ('gate_h', 'cgate_00', 'cgate_01_list', 'cgate_01_int', 'disc_plain', 'toffoli_slot', 'toffoli_upside_down'):
         ns = qbot_b200.executeTxt(by[name]['text'], state_cls=DeviceState)
         assert np.array_equal(np.asarray(ns['state']), golden.scripts_arr[by[name]['state']]), name
+
+
+def test_large_ket_register_through_the_dsl():
+    """a 24-qubit program runs through the unchanged DSL surface -- device-side
+    `tensorExp` constructor, ket-mode register, fused + specialised gate application, `peek` --
+    and agrees with the oracle's ket path; the reduced density of the peeked qubits is computed
+    from the amplitudes on demand."""
+    import qbot_b200
+    from qbot_b200.circuits import rc
+    from oracle import qbot_oracle as orc
+    n = 24
+    gates = rc(n, 4, 24)
+    qs = [0, 7, 15, 23]
+    prog = "\n".join([f"qset tensorExp(comp.kets[0], {n})"] + [g.dsl() for g in gates] +
+                     [f"peek r ; comp ; {qs}", "cdef rhoA ; r.unMeasuredDensity"])
+    ns = qbot_b200.executeTxt(prog)
+    st = ns['state']
+    assert st.kind == 0 and st.nq == n
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[0] = 1
+    for g in gates:
+        psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+    want = orc.ket_probs(psi, n, qs)
+    want = want / want.sum()
+    assert np.max(np.abs(np.array(ns['r'].probs) - want)) < 1e-12
+    t = np.transpose(psi.reshape((2,) * n), qs + [q for q in range(n) if q not in qs]).reshape(16, -1)
+    rho = np.asarray(ns['rhoA'])
+    assert rho.shape == (16, 16) and np.max(np.abs(rho - t @ t.conj().T)) < 1e-12
+    idx = np.random.default_rng(0).integers(0, 1 << n, size=64)
+    got = np.array([st.download_range(int(i), 1)[0] for i in idx])
+    assert np.max(np.abs(got - psi[idx])) < 1e-12

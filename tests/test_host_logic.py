@@ -111,3 +111,28 @@ def test_ket_register_new_representation():
     assert psi.shape == (4,) and close(psi, np.array([1, 0, 0, 1]) / np.sqrt(2))
     ns, _, _ = run_script("qset np_array([1, 0, 0, 0]) * (1+0j)\ngate hadamardGate ; 0\ngate pauliXGate ; 1 ; [0]\nmeas x ; bell\n", FakeState)
     assert ns['x'].probs == [1.0, 0.0, 0.0, 0.0]
+
+
+def test_lazy_product_states_and_ket_peek():
+    """tensorProd / tensorExp results of >= 14 qubits stay descriptors and are
+    built by the device-side constructor; a large ket-mode register can be `peek`ed (outcome
+    weights from the amplitudes, rho_A on demand) while `meas` -- whose reference collapse is a
+    mixed product state -- is refused with the reference's error formatting."""
+    import qbot_b200
+    from qbot_b200.host import hostmath as hm
+    from fake_backend import FakeState
+    lp = hm.tensor_exp(np.array([1, 0], dtype=complex), 16)
+    assert hm.is_lazy(lp) and lp.shape == (1 << 16,) and lp.ndim == 1 and lp.size == 1 << 16
+    assert not hm.is_lazy(hm.tensor_exp(np.array([1, 0], dtype=complex), 13))
+    mixed = hm.tensor_prod(hm.tensor_exp(np.array([1, 0], dtype=complex), 14), np.array([0, 1], dtype=complex))
+    assert hm.is_lazy(mixed) and len(mixed.factors) == 15 and np.asarray(mixed)[1] == 1
+    n = 14
+    prog = "\n".join([f"qset tensorExp(comp.kets[0], {n})", "gate hadamardGate ; 3", "gate pauliXGate ; 9 ; [3]",
+                      "gate zRotGate(0.7) ; 9", "peek r ; comp ; [9, 3]", "cdef rhoA ; r.unMeasuredDensity"])
+    ns = qbot_b200.executeTxt(prog, state_cls=FakeState)
+    assert ns['state'].kind == 0 and ns['state'].shape == (1 << n,)
+    assert ns['r'].probs == [0.5, 0.0, 0.0, 0.5] and ns['r'].newState is None
+    rho = np.asarray(ns['rhoA'])
+    assert rho.shape == (4, 4) and abs(np.trace(rho) - 1) < 1e-14 and abs(abs(rho[0, 3]) - 0.5) < 1e-14
+    with pytest.raises(SystemExit):
+        qbot_b200.executeTxt(prog + "\nmeas m ; comp ; [0]", state_cls=FakeState)
