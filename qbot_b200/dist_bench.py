@@ -96,6 +96,34 @@ def run_multi_gpu(args):
     dist.all_reduce(agg, op=dist.ReduceOp.MAX)
     launches, passes, fused_passes, ex_s, jit_passes = [float(x) for x in agg.tolist()]
     norm = sk.norm2()
+    # ---- end to end: a fresh |0...0> register, the circuit through the public ShardedKet API with
+    #      host matrices, outcome weights of 4 qubits all-reduced and read back to the host ----------
+    e2e = None
+    if not getattr(args, 'no_e2e', False):
+        import time as _t
+        qs = [0, n // 3, (2 * n) // 3, n - 1]
+
+        def e2e_step():
+            sk.reset_zero()
+            step()
+            return sk.probs(qs)
+
+        e2e_step()
+        e2e_step()            # the identity-map start has its own sweep structures: compile them outside the timing
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = _t.perf_counter()
+        for _ in range(args.steps):
+            pr = e2e_step()
+        torch.cuda.synchronize()
+        tt = torch.tensor([_t.perf_counter() - t0], dtype=torch.float64, device=f'cuda:{local}')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+        e2e = {"value": ngates * args.steps / e2e_s * 2.0 ** (n - 30), "unit": "gates/s (30-qubit equivalents)",
+               "h2d_bytes_per_step": int(sum(m.nbytes for m in mats)), "d2h_bytes_per_step": int(pr.nbytes),
+               "ms_per_step": 1e3 * e2e_s / args.steps, "probs_sum": float(pr.sum()),
+               "what": "ShardedKet.reset_zero() + apply_gate per gate (host matrices -> C ABI) + flush (fused sweeps, "
+                       "NVLink exchanges) + probs of 4 qubits (local reduce + all-reduce -> host); wall clock, max over ranks"}
     secs = ms_max / 1e3
     raw = ngates * args.steps / secs                 # gates/s on the n-qubit ket
     value = raw * 2.0 ** (n - 30)                    # in units of the single-GPU workload: one gate on 2^30 amplitudes
@@ -132,7 +160,7 @@ def run_multi_gpu(args):
                          "nvlink_gbs_per_gpu_per_direction": (exb / ex_s / 1e9) if ex_s > 0 else None,
                          "nvlink_peak_gbs": 900.0, "frac": (exb / ex_s / 1e9 / 900.0) if ex_s > 0 else None,
                          "share_of_step": ex_s / secs},
-            "amp_updates_per_s": raw * (1 << n), "norm_check": norm,
+            "e2e": e2e, "amp_updates_per_s": raw * (1 << n), "norm_check": norm,
         }
         print(json.dumps(out))
     sk.close()

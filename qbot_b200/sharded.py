@@ -481,6 +481,14 @@ class ShardedKet:
         self.flush()
         self.shard.sync()
 
+    def reset_zero(self):
+        """|0...0> again, identity qubit map (a fresh register without re-allocating the shards)."""
+        self.queue = []
+        self.shard.sync()
+        self.comm.barrier()
+        self.map = QubitMap(self.nq, self.map.g)
+        self.shard.init_basis(self.rank == 0, 0)
+
     # -- read-outs -----------------------------------------------------------------------------
     def probs(self, qubits: Sequence[int]) -> np.ndarray:
         """Outcome weights of the listed qubits (first listed = most significant outcome bit);

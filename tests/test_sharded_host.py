@@ -104,6 +104,30 @@ def test_virtual_ranks_match_oracle(n, world):
     assert res[0]['exchanges'] >= 1          # the circuit does need global qubits
 
 
+def test_reset_zero_gives_a_fresh_register():
+    """reset_zero: |0...0> and the identity qubit map again (used by the multi-GPU e2e loop)"""
+    n, world = 8, 4
+    ops = circuit_ops(n, 5, 7)
+    want = expected_ket(n, ops)
+    shared = VirtualComm.Shared(world)
+    out = [None] * world
+
+    def work(rank):
+        sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard)
+        for rep in range(2):
+            sk.reset_zero()
+            assert sk.map.at == list(range(n))
+            for m, t, cs in ops:
+                sk.apply_gate(m, t, cs)
+            out[rank] = sk.gather()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for r in range(world):
+        assert out[r] is not None and np.max(np.abs(out[r] - want)) < 1e-12
+
+
 def test_exchange_count_is_small():
     # rc(12, 10): every layer writes ~2/3 of the qubits; farthest-next-use eviction keeps the
     # number of exchanges well below one per layer-and-rank-bit
