@@ -98,6 +98,7 @@ qb_state::~qb_state() {
     if (d && owns) { DevGuard g(device); cached_free(device, bytes(), d, stream); }
     if (scratch) cudaFree(scratch);
     if (stage) cudaFree(stage);
+    if (sm_arrivals) cudaFree(sm_arrivals);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream && owns_stream) cudaStreamDestroy(stream);
@@ -556,6 +557,8 @@ int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, c
     }
     QtPlanOptions opt;
     if (const char* e = getenv("QBOT_B200_TILE_M")) { const int v = atoi(e); if (v == 11 || v == 12) opt.M = v; }
+    opt.R = QT_MAXR;          // the specialiser's own plan shape (32 amplitudes per thread) unless overridden
+    if (const char* e = getenv("QBOT_B200_JIT_R")) { const int v = atoi(e); if (v == 4 || v == 5) opt.R = v; }
     std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
     int n = 0;
     for (const QtPlanStep& st : steps) {

@@ -26,11 +26,54 @@ namespace {
 const char* kPrelude = R"QJ(
 #define QJ_C double2
 #define QJ_DEV __device__ __forceinline__
+#ifdef QJ_DEBUG_NOLOAD
+#define QJ_LD(p) make_double2(1.0 + (double)(tid & 7u), 0.5)
+#else
 #define QJ_LD(p) __ldcs(p)
+#endif
+#ifdef QJ_DEBUG_NOSTORE
+#define QJ_ST(p, v) do { if ((v).x == 1.2345e-300) __stcs(p, v); } while (0)
+#else
 #define QJ_ST(p, v) __stcs(p, v)
+#endif
 #define QJ_RESTRICT __restrict__
-#define QJ_WAR_SYNC() __syncthreads()
 #define QJ_SYNC() __syncthreads()
+// one mbarrier per CTA counts the bytes of the next tile's bulk copies
+__device__ __forceinline__ unsigned qj_mbar() {
+    __shared__ __align__(8) unsigned long long bar;
+    return (unsigned)__cvta_generic_to_shared(&bar);
+}
+#define QJ_MBAR_INIT()                                                                             \
+    do {                                                                                           \
+        if (threadIdx.x == 0) {                                                                    \
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(qj_mbar()) : "memory");  \
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                     \
+        }                                                                                          \
+        __syncthreads();                                                                           \
+    } while (0)
+#define QJ_BULK_COPY(sdst, gsrc)                                                                   \
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];" ::"r"( \
+                     (unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(qj_mbar()) : "memory")
+#define QJ_ASYNC_WAIT(parity)                                                                      \
+    do {                                                                                           \
+        unsigned done_;                                                                            \
+        do {                                                                                       \
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" \
+                         : "=r"(done_) : "r"(qj_mbar()), "r"(parity) : "memory");                  \
+        } while (!done_);                                                                          \
+    } while (0)
+// every thread of the CTA has read its amplitudes out of the buffer (barrier); order those generic
+// reads before the TMA's writes (proxy fence); one thread announces the byte count
+#define QJ_ISSUE_NEXT(tid, nbase, psi, buf)                                                        \
+    do {                                                                                           \
+        __syncthreads();                                                                           \
+        if (nbase != ~0ull) {                                                                      \
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                           \
+            if (tid == 0)                                                                          \
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qj_mbar()), "r"(QJ_RUNS * 512) : "memory"); \
+            qj_issue_next(tid, nbase, psi, buf);                                                   \
+        }                                                                                          \
+    } while (0)
 #ifdef QJ_POOL_GLOBAL
 #define QJ_PRELUDE
 #define QJ_POOL_PARAM const double* __restrict__ P
@@ -55,14 +98,46 @@ const char* kPrelude = R"QJ(
 // arithmetic; the next tile of a CTA is prefetched into L2 while the current one is computed.
 const char* kPostlude = R"QJ(
 extern "C" __global__ void __launch_bounds__(QJ_T, QJ_CTAS)
-qj_kernel(double2* __restrict__ psi, const unsigned long long ntiles, const int prefetch, QJ_POOL_KPARAM) {
+qj_kernel(double2* __restrict__ psi, const unsigned long long ntiles, const int prefetch,
+          unsigned* __restrict__ sm_arrivals, const unsigned stagger_ns, QJ_POOL_KPARAM) {
     extern __shared__ __align__(16) double2 buf[];
     const unsigned tid = threadIdx.x;
+    // De-phase the CTAs that share an SM.  All CTAs of a launch start together and, sharing the
+    // L2 path and the FP64 pipe fairly, stay in lock-step: both load, both compute, both store --
+    // the SM<->L2 transfer time ADDS to the arithmetic (measured: +0.11 ms per Hadamard at 30
+    // qubits, exactly the FP64 pipe rate, zero overlap).  The k-th CTA to arrive on an SM waits
+    // k * stagger_ns once; a phase difference between two fairly sharing cyclic processes is
+    // conserved, so from then on one CTA's transfers overlap the other's arithmetic.
+    if (stagger_ns) {
+        __shared__ unsigned arrival;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            arrival = atomicAdd(&sm_arrivals[smid], 1u);
+        }
+        __syncthreads();
+        const unsigned long long wait = (unsigned long long)(arrival % QJ_CTAS) * stagger_ns;
+        if (wait) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                __nanosleep(256);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (t1 - t0 < wait);
+        }
+    }
+    // prefetch bit 0: L2 prefetch of the CTA's next tile at the start of a tile; bit 1: asynchronous
+    // copy of the next tile into the transposition buffer during the last stage
+    unsigned pre = 0, phase = 0;
+    QJ_MBAR_INIT();
     for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const unsigned long long tbase = qj_tile_base(tile);
-        const unsigned long long nt = tile + (unsigned long long)prefetch * gridDim.x;     // prefetch = distance in tiles (0: off)
-        const unsigned long long nbase = (prefetch && nt < ntiles) ? qj_tile_base(nt) : ~0ull;
-        QJ_RUN_STAGES(tid, tbase, nbase, psi, buf, P)
+        const unsigned long long nt = tile + gridDim.x;
+        const unsigned long long next = nt < ntiles ? qj_tile_base(nt) : ~0ull;
+        const unsigned long long pfbase = (prefetch & 1) ? next : ~0ull;
+        const unsigned long long nbase = (prefetch & 2) ? next : ~0ull;
+        QJ_RUN_STAGES(tid, tbase, nbase, pfbase, pre, psi, buf, P)
+        if (nbase != ~0ull) { pre = 1u + phase; phase ^= 1u; } else pre = 0;
     }
 }
 )QJ";
@@ -173,6 +248,9 @@ std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool*
     if (pool_global) *pool_global = pg;
     std::string src;
     if (pg) src += "#define QJ_POOL_GLOBAL 1\n";
+    // diagnostics only (wrong results!): drop the HBM loads and / or stores of the sweep to time its parts
+    if (getenv("QBOT_B200_DEBUG_NOLOAD")) src += "#define QJ_DEBUG_NOLOAD 1\n";
+    if (getenv("QBOT_B200_DEBUG_NOSTORE")) src += "#define QJ_DEBUG_NOSTORE 1\n";
     if (const int c = jit_ctas_override(li.M)) src += "#define QJ_CTAS " + std::to_string(c) + "\n";
     src += kPrelude;
     src += body;
@@ -270,20 +348,22 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
     k.smem_bytes = c.info.tile_units * 16;
     k.npool = c.info.npool;
     k.pool_global = c.pool_global;
-    k.ctas_per_sm = jit_ctas_override(c.info.M) ? jit_ctas_override(c.info.M) : (c.info.M == 12 ? 2 : 4);
+    k.ctas_per_sm = jit_ctas_override(c.info.M) ? jit_ctas_override(c.info.M) : qj_default_ctas(c.info.M, c.info.R);
     k.M = c.info.M;
     return k;
 }
 
 // launch: `pool` = qj_pool(program) on the host (parameter variant) or its device copy
 void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
-                   const double* pool_host, const double* pool_dev) {
+                   const double* pool_host, const double* pool_dev, unsigned* sm_arrivals, unsigned stagger_ns) {
     Driver& d = driver();
     unsigned long long nt = ntiles;
     int pf = prefetch;
     void* psi_arg = (void*)psi;
     const void* pool_ptr = pool_dev;
-    void* args[4] = {&psi_arg, &nt, &pf, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
+    if (!sm_arrivals || k.ctas_per_sm < 2) stagger_ns = 0;
+    if (stagger_ns) QB_CUDA(cudaMemsetAsync(sm_arrivals, 0, 1024 * sizeof(unsigned), stream));
+    void* args[6] = {&psi_arg, &nt, &pf, &sm_arrivals, &stagger_ns, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * k.ctas_per_sm);
     CUresult e = d.LaunchKernel((CUfunction)k.fn, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem_bytes, (CUstream)stream, args, nullptr);
     if (e != CUDA_SUCCESS) throw qb_error(-2, "cuLaunchKernel(sweep): " + cu_err(e));

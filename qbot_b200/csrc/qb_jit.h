@@ -15,6 +15,7 @@
 
 struct QjSourceInfo {
     int M = 0;            // tile bits
+    int R = 4;            // register bits per stage (2^R amplitudes per thread)
     int threads = 0;      // 2^(M-4)
     int npool = 0;        // doubles of run-time coefficients
     int nstages = 0;
@@ -27,6 +28,8 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info);
 // the run-time coefficients the generated code reads through QJ_P(i): the program's pool followed
 // by the header scale (info->npool doubles)
 std::vector<double> qj_pool(const uint8_t* program);
+
+int qj_default_ctas(int M, int R);
 
 // 64-bit FNV-1a of a source text (the key of the compiled-kernel cache)
 uint64_t qj_hash(const std::string& src);

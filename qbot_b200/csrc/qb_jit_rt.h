@@ -24,7 +24,7 @@ std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool*
 std::vector<char> qb_jit_compile(const std::string& src, std::string* log_out);
 QbJitKernel qb_jit_get(const uint8_t* program, int device);
 void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
-                   const double* pool_host, const double* pool_dev);
+                   const double* pool_host, const double* pool_dev, unsigned* sm_arrivals, unsigned stagger_ns);
 QbJitStats qb_jit_stats();
 // record one sighting of a specialised source (by hash): returns the number of sightings so far,
 // or -1 when a kernel for it is already compiled

@@ -19,8 +19,6 @@
 #include <map>
 #include <vector>
 
-#define QT_NR (1 << QT_R)
-
 namespace {
 
 struct Out {
@@ -62,6 +60,7 @@ struct Gen {
     const QtOp* ops;
     const double* pool;
     int M, NH, T;
+    int R, NR;                       // register bits per stage, amplitudes per thread
     Out o;
     std::vector<std::string> nm;     // current name of logical register i
     int tmp = 0;
@@ -95,7 +94,7 @@ struct Gen {
 
     void op_h(const QtOp& op) {
         const int t = op.t0;
-        for (int i = 0; i < QT_NR; i++) {
+        for (int i = 0; i < NR; i++) {
             if ((i >> t) & 1 || !((op.regsel >> i) & 1u)) continue;
             const std::string &A = nm[i], &B = nm[i | (1 << t)];
             o.f("    { const double xr = %s.x, xi = %s.y; %s.x = xr + %s.x; %s.y = xi + %s.y; %s.x = xr - %s.x; %s.y = xi - %s.y; }\n",
@@ -105,7 +104,7 @@ struct Gen {
 
     void op_x(const QtOp& op, bool conditional) {
         const int t = op.t0;
-        for (int i = 0; i < QT_NR; i++) {
+        for (int i = 0; i < NR; i++) {
             if ((i >> t) & 1 || !((op.regsel >> i) & 1u)) continue;
             const int j = i | (1 << t);
             if (conditional)
@@ -120,7 +119,7 @@ struct Gen {
         const uint32_t p = op.pool;
         o.f("    { const double m0 = %s, m1 = %s, m2 = %s, m3 = %s, m4 = %s, m5 = %s, m6 = %s, m7 = %s;\n", P(p).c_str(),
             P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str(), P(p + 4).c_str(), P(p + 5).c_str(), P(p + 6).c_str(), P(p + 7).c_str());
-        for (int i = 0; i < QT_NR; i++) {
+        for (int i = 0; i < NR; i++) {
             if ((i >> t) & 1 || !((op.regsel >> i) & 1u)) continue;
             const std::string &A = nm[i], &B = nm[i | (1 << t)];
             o.f("      { const double xr = %s.x, xi = %s.y, yr = %s.x, yi = %s.y;\n", A.c_str(), A.c_str(), B.c_str(), B.c_str());
@@ -134,7 +133,7 @@ struct Gen {
         const int t0 = op.t0, t1 = op.t1;
         const uint32_t p = op.pool;
         o.f("    {\n");
-        for (int i = 0; i < QT_NR; i++) {
+        for (int i = 0; i < NR; i++) {
             if ((i >> t0) & 1 || (i >> t1) & 1 || !((op.regsel >> i) & 1u)) continue;
             const int idx[4] = {i, i | (1 << t1), i | (1 << t0), i | (1 << t0) | (1 << t1)};
             o.f("      { const QJ_C x0 = %s, x1 = %s, x2 = %s, x3 = %s;\n", nm[idx[0]].c_str(), nm[idx[1]].c_str(), nm[idx[2]].c_str(),
@@ -163,7 +162,7 @@ struct Gen {
         if (op.t1 == QT_LOC_REG) {
             const bool one0 = pool_is_one(p), one1 = pool_is_one(p + 2);
             o.f("    { const double d0r = %s, d0i = %s, d1r = %s, d1i = %s;\n", P(p).c_str(), P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str());
-            for (int i = 0; i < QT_NR; i++) {
+            for (int i = 0; i < NR; i++) {
                 if (!((op.regsel >> i) & 1u)) continue;
                 const bool hi = (i >> op.t0) & 1;
                 if (hi ? one1 : one0) continue;          // exact unit factor: structural, part of the source text
@@ -175,7 +174,7 @@ struct Gen {
             if (op.t1 == QT_LOC_LOCAL) o.f("    { const bool b_ = (lb >> %d) & 1u;\n", (int)op.t0);
             else o.f("    { const bool b_ = (tbase >> %d) & 1ull;\n", (int)op.t0);
             o.f("      const double fr = b_ ? %s : %s, fi = b_ ? %s : %s;\n", P(p + 2).c_str(), P(p).c_str(), P(p + 3).c_str(), P(p + 1).c_str());
-            for (int i = 0; i < QT_NR; i++) {
+            for (int i = 0; i < NR; i++) {
                 if (!((op.regsel >> i) & 1u)) continue;
                 o.f("  ");
                 cmul_into(nm[i], "fr", "fi");
@@ -189,7 +188,7 @@ struct Gen {
         const int u = tmp++;
         o.f("    {\n");
         bool have = false;
-        std::vector<int> reg_entries[QT_R];
+        std::vector<int> reg_entries[QT_MAXR];
         for (int e = 0; e < op.nent; e++) {
             const uint32_t q = p + 5 * e;
             int64_t code;
@@ -217,7 +216,7 @@ struct Gen {
         std::vector<Ent> table;
         if (have) table.push_back({0, "cr", "ci"});
         int regbits = 0;
-        for (int q = 0; q < QT_R; q++) {
+        for (int q = 0; q < R; q++) {
             if (reg_entries[q].empty()) continue;
             regbits |= 1 << q;
             // product of this bit's entries
@@ -254,7 +253,7 @@ struct Gen {
             table.swap(next);
         }
         if (!table.empty()) {
-            for (int i = 0; i < QT_NR; i++) {
+            for (int i = 0; i < NR; i++) {
                 const int mk = i & regbits;
                 for (const Ent& t : table)
                     if (t.mask == mk) { o.f("  "); cmul_into(nm[i], t.r, t.i); break; }
@@ -282,54 +281,90 @@ struct Gen {
 
     uint64_t hbm_reg_offset(const QtStage& st, int i) const {
         uint64_t off = 0;
-        for (int q = 0; q < QT_R; q++) if ((i >> q) & 1) off |= 1ull << h->hb[st.rb[q] - QT_L];
+        for (int q = 0; q < R; q++) if ((i >> q) & 1) off |= 1ull << h->hb[st.rb[q] - QT_L];
         return off;
     }
     uint32_t smem_reg_offset(const QtStage& st, int i) const {
         uint32_t off = 0;
-        for (int q = 0; q < QT_R; q++) if ((i >> q) & 1) off += qt_slot(1u << st.rb[q]);
+        for (int q = 0; q < R; q++) if ((i >> q) & 1) off += qt_slot(1u << st.rb[q]);
         return off;
+    }
+
+    // thread-position expressions of a stage (lb = tile-local index with the register bits clear)
+    std::string lb_expr(const QtStage& st) const {
+        int tpos[QT_MAXM];
+        for (int q = 0; q < M - R; q++) tpos[q] = st.tpos[q];
+        return deposit_expr("tid", tpos, M - R, "unsigned");
+    }
+    std::string run_deposit_expr() const {
+        int hpos[QT_MAXM];
+        for (int i = 0; i < NH; i++) hpos[i] = h->hb[i];
+        return deposit_expr("run", hpos, NH, "unsigned long long");
+    }
+
+    // The next tile of the CTA is fetched ASYNCHRONOUSLY by the TMA engine (cp.async.bulk, one
+    // 512-byte run per copy, completion counted on an mbarrier) into the transposition buffer while
+    // the last stage of the current tile computes and stores.  Per-thread loads (LDG or cp.async)
+    // cannot do this: the LSU only keeps a few KB of requests in flight per SM, so a warp that
+    // asks for its share of a 64 KB tile is stuck at issue for the whole transfer (measured:
+    // arithmetic overlaps the stores and the L2 prefetch perfectly but ADDS to the load time).
+    // Bulk copies occupy no LSU slot and no register; stage 0 of the next tile waits on the
+    // mbarrier and reads its amplitudes out of the buffer like after any transposition.
+    void emit_issue_next() {
+        o.f("#define QJ_RUNS %d\n", 1 << NH);
+        o.f("QJ_DEV void qj_issue_next(const unsigned tid, const unsigned long long nbase, QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT buf) {\n");
+        o.f("    if (nbase == ~0ull) return;\n");
+        o.f("    for (unsigned k = tid; k < QJ_RUNS; k += QJ_T)\n");
+        o.f("        QJ_BULK_COPY(buf + (32u * k + k + (k >> 3) + (k >> 6)), psi + (nbase + qj_run_offset(k)));\n");
+        o.f("}\n\n");
     }
 
     void emit_stage(int s) {
         const QtStage& st = stages[s];
         const bool first = s == 0, last = s + 1 == h->nstages;
-        nm.resize(QT_NR);
-        for (int i = 0; i < QT_NR; i++) nm[i] = "a" + std::to_string(i);
+        nm.resize(NR);
+        for (int i = 0; i < NR; i++) nm[i] = "a" + std::to_string(i);
         o.f("QJ_DEV void qj_stage%d(const unsigned tid, const unsigned long long tbase, const unsigned long long nbase,\n"
+            "                      const unsigned long long pfbase, const unsigned pre,\n"
             "                      QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT buf, QJ_POOL_PARAM) {\n", s);
-        int tpos[QT_MAXM];
-        for (int q = 0; q < M - QT_R; q++) tpos[q] = st.tpos[q];
-        o.f("    const unsigned lb = %s;\n", deposit_expr("tid", tpos, M - QT_R, "unsigned").c_str());
-        o.f("    (void)lb; (void)tbase; (void)nbase; (void)psi; (void)buf;\n");
+        o.f("    const unsigned lb = %s;\n", lb_expr(st).c_str());
+        o.f("    (void)lb; (void)tbase; (void)nbase; (void)pfbase; (void)pre; (void)psi; (void)buf;\n");
         if (first || last) {
             // HBM position of the thread: lane = low bits, run bits deposited at the tile-bit positions
-            int hpos[QT_MAXM];
-            for (int i = 0; i < NH; i++) hpos[i] = h->hb[i];
             o.f("    const unsigned run = lb >> %d;\n", QT_L);
-            o.f("    QJ_C* const gp = psi + (tbase + (unsigned long long)(lb & 31u) + (%s));\n",
-                deposit_expr("run", hpos, NH, "unsigned long long").c_str());
+            o.f("    QJ_C* const gp = psi + (tbase + (unsigned long long)(lb & 31u) + (%s));\n", run_deposit_expr().c_str());
         }
-        if (!(first && last)) o.f("    QJ_C* const sp = buf + (lb + (lb >> 5) + (lb >> 8) + (lb >> 11));\n");
-        o.f("    QJ_C a0, a1, a2, a3, a4, a5, a6, a7, a8, a9, a10, a11, a12, a13, a14, a15;\n");
+        o.f("    QJ_C* const sp = buf + (lb + (lb >> 5) + (lb >> 8) + (lb >> 11));\n    (void)sp;\n");
+        o.f("    QJ_C a0");
+        for (int i = 1; i < NR; i++) o.f(", a%d", i);
+        o.f(";\n");
         if (first) {
-            for (int i = 0; i < QT_NR; i++) o.f("    a%d = QJ_LD(gp + 0x%llxull);\n", i, (unsigned long long)hbm_reg_offset(st, i));
-            o.f("    QJ_PREFETCH(psi, nbase, tid);\n");
+            // the tile is already in the buffer (bulk copies issued during the previous tile; pre - 1 is the
+            // mbarrier phase parity to wait for), or comes straight from HBM (first tile of the CTA)
+            o.f("    if (pre) {\n        QJ_ASYNC_WAIT(pre - 1u);\n");
+            for (int i = 0; i < NR; i++) o.f("        a%d = sp[%u];\n", i, smem_reg_offset(st, i));
+            o.f("    } else {\n");
+            for (int i = 0; i < NR; i++) o.f("        a%d = QJ_LD(gp + 0x%llxull);\n", i, (unsigned long long)hbm_reg_offset(st, i));
+            o.f("    }\n    QJ_PREFETCH(psi, pfbase, tid);\n");
         } else {
-            for (int i = 0; i < QT_NR; i++) o.f("    a%d = sp[%u];\n", i, smem_reg_offset(st, i));
+            for (int i = 0; i < NR; i++) o.f("    a%d = sp[%u];\n", i, smem_reg_offset(st, i));
         }
+        // last stage: every thread of the CTA has read its amplitudes out of the buffer -> it is free
+        // for the next tile's asynchronous copies (this barrier replaces the one before stage 0's stores)
+        if (last) o.f("    QJ_ISSUE_NEXT(tid, nbase, psi, buf);\n");
         for (int x = 0; x < st.nops; x++) emit_op(ops[st.first_op + x]);
         if (last) {
             if (h->scale != 1.0) {
                 const uint32_t sidx = (uint32_t)npool_prog;      // the header scale rides behind the program's pool
                 o.f("    { const double s_ = %s;\n", P(sidx).c_str());
-                for (int i = 0; i < QT_NR; i++) o.f("      %s.x *= s_; %s.y *= s_;\n", nm[i].c_str(), nm[i].c_str());
+                for (int i = 0; i < NR; i++) o.f("      %s.x *= s_; %s.y *= s_;\n", nm[i].c_str(), nm[i].c_str());
                 o.f("    }\n");
             }
-            for (int i = 0; i < QT_NR; i++) o.f("    QJ_ST(gp + 0x%llxull, %s);\n", (unsigned long long)hbm_reg_offset(st, i), nm[i].c_str());
+            for (int i = 0; i < NR; i++) o.f("    QJ_ST(gp + 0x%llxull, %s);\n", (unsigned long long)hbm_reg_offset(st, i), nm[i].c_str());
         } else {
-            if (first) o.f("    QJ_WAR_SYNC();\n");
-            for (int i = 0; i < QT_NR; i++) o.f("    sp[%u] = %s;\n", smem_reg_offset(st, i), nm[i].c_str());
+            // stage 0 stores into the very slots this thread has just read (or, for the CTA's first tile,
+            // into a buffer nobody has touched yet): no barrier needed before them
+            for (int i = 0; i < NR; i++) o.f("    sp[%u] = %s;\n", smem_reg_offset(st, i), nm[i].c_str());
         }
         o.f("}\n\n");
     }
@@ -348,6 +383,14 @@ std::vector<double> qj_pool(const uint8_t* program) {
     return out;
 }
 
+// resident CTAs per SM a kernel is compiled for: threads = 2^(M-R); 16 amplitudes per thread need
+// ~128 registers (512 threads per SM); 32 amplitudes per thread spill at 168 registers (measured:
+// 10.6 ms per 30-qubit sweep with 384 threads per SM against 7.85 ms with 256 threads at 255 registers)
+int qj_default_ctas(int M, int R) {
+    const int threads = 1 << (M - R);
+    return R >= 5 ? 256 / threads : 512 / threads;
+}
+
 uint64_t qj_hash(const std::string& src) {
     uint64_t hsh = 1469598103934665603ull;
     for (unsigned char c : src) { hsh ^= c; hsh *= 1099511628211ull; }
@@ -362,13 +405,15 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     g.pool = (const double*)(program + g.h->pool_off);
     g.M = g.h->M;
     g.NH = g.M - QT_L;
-    g.T = 1 << (g.M - QT_R);
+    g.R = g.h->R ? g.h->R : QT_R;
+    g.NR = 1 << g.R;
+    g.T = 1 << (g.M - g.R);
     g.npool_prog = (int)((g.h->total_bytes - g.h->pool_off) / sizeof(double));
     const int npool = g.npool_prog + 1;      // + header scale
     Out& o = g.o;
-    o.f("// generated by qbot_b200 qj_generate: M=%d stages=%d ops=%d gates=%d\n", g.M, (int)g.h->nstages, (int)g.h->nops, (int)g.h->ngates);
+    o.f("// generated by qbot_b200 qj_generate: M=%d R=%d stages=%d ops=%d gates=%d\n", g.M, g.R, (int)g.h->nstages, (int)g.h->nops, (int)g.h->ngates);
     o.f("#define QJ_M %d\n#define QJ_T %d\n#define QJ_NH %d\n#define QJ_NP %d\n#define QJ_NSTAGES %d\n", g.M, g.T, g.NH, npool, (int)g.h->nstages);
-    o.f("#define QJ_TILE_UNITS %d\n#ifndef QJ_CTAS\n#define QJ_CTAS %d\n#endif\n", QT_TILE_UNITS(g.M), g.M == 12 ? 2 : 4);
+    o.f("#define QJ_TILE_UNITS %d\n#ifndef QJ_CTAS\n#define QJ_CTAS %d\n#endif\n", QT_TILE_UNITS(g.M), qj_default_ctas(g.M, g.R));
     o.f("QJ_PRELUDE\n\n");
     // tile base: the tile number's bits deposited into the positions outside the tile
     o.f("QJ_DEV unsigned long long qj_tile_base(const unsigned long long t) {\n    unsigned long long b = t << %d;\n", QT_L);
@@ -383,18 +428,20 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
         o.f("QJ_DEV unsigned long long qj_run_offset(const unsigned k) { return %s; }\n\n",
             deposit_expr("k", hpos, g.NH, "unsigned long long").c_str());
     }
+    g.emit_issue_next();
     for (int s = 0; s < g.h->nstages; s++) g.emit_stage(s);
-    o.f("#define QJ_RUN_STAGES(tid, tbase, nbase, psi, buf, P) \\\n");
+    o.f("#define QJ_RUN_STAGES(tid, tbase, nbase, pfbase, pre, psi, buf, P) \\\n");
     for (int s = 0; s < g.h->nstages; s++) {
         if (s) o.f("    QJ_SYNC(); \\\n");
-        o.f("    qj_stage%d(tid, tbase, nbase, psi, buf, P); \\\n", s);
+        o.f("    qj_stage%d(tid, tbase, nbase, pfbase, pre, psi, buf, P); \\\n", s);
     }
     o.f("\n");
-    o.f("#ifdef QJ_WANT_DISPATCH\nQJ_DEV void qj_stage(const int s, const unsigned tid, const unsigned long long tbase, QJ_C* psi, QJ_C* buf, QJ_POOL_PARAM) {\n    switch (s) {\n");
-    for (int s = 0; s < g.h->nstages; s++) o.f("        case %d: qj_stage%d(tid, tbase, ~0ull, psi, buf, P); break;\n", s, s);
+    o.f("#ifdef QJ_WANT_DISPATCH\nQJ_DEV void qj_stage(const int s, const unsigned tid, const unsigned long long tbase, const unsigned long long nbase, const unsigned pre, QJ_C* psi, QJ_C* buf, QJ_POOL_PARAM) {\n    switch (s) {\n");
+    for (int s = 0; s < g.h->nstages; s++) o.f("        case %d: qj_stage%d(tid, tbase, nbase, ~0ull, pre, psi, buf, P); break;\n", s, s);
     o.f("        default: break;\n    }\n}\n#endif\n");
     if (info) {
         info->M = g.M;
+        info->R = g.R;
         info->threads = g.T;
         info->npool = npool;
         info->nstages = g.h->nstages;

@@ -142,6 +142,7 @@ struct StageBuild {
 
 struct SweepBuild {
     int M = QT_MAXM;                     // tile bits
+    int R = QT_R;                        // register bits per stage
     std::vector<int> hb;                 // free tile bits (index positions), ascending
     int local_of[64];                    // index bit -> tile-local position, -1 if outside the tile
     std::vector<StageBuild> stages;
@@ -151,12 +152,13 @@ struct SweepBuild {
 
 // predicate of a gate's controls (and value-controls) split by where each bit lives in this stage
 struct Pred {
-    uint16_t regsel, lmask, lval;
+    uint32_t regsel;
+    uint16_t lmask, lval;
     uint64_t gmask, gval;
 };
 
 Pred make_pred(const SweepBuild& sw, const QtStage& st, uint64_t ones_mask, uint64_t zeros_mask) {
-    const int R = QT_R;
+    const int R = sw.R;
     Pred p{0, 0, 0, 0, 0};
     uint32_t reg_need1 = 0, reg_need0 = 0;
     for (int b = 0; b < 64; b++) {
@@ -174,18 +176,20 @@ Pred make_pred(const SweepBuild& sw, const QtStage& st, uint64_t ones_mask, uint
         else { p.lmask |= (uint16_t)(1u << lp); if (one) p.lval |= (uint16_t)(1u << lp); }
     }
     for (int i = 0; i < (1 << R); i++)
-        if ((i & reg_need1) == reg_need1 && (i & reg_need0) == 0) p.regsel |= (uint16_t)(1u << i);
+        if ((i & reg_need1) == reg_need1 && (i & reg_need0) == 0) p.regsel |= 1u << i;
     return p;
 }
 
-int reg_index(const QtStage& st, int lp) {
-    for (int q = 0; q < QT_R; q++) if (st.rb[q] == lp) return q;
+int reg_index(const QtStage& st, int lp, int R) {
+    for (int q = 0; q < R; q++) if (st.rb[q] == lp) return q;
     return -1;
 }
 
-void set_pred(QtOp& op, const Pred& p) {
+uint32_t all_regs(int R) { return R >= 5 ? 0xffffffffu : (1u << (1 << R)) - 1u; }
+
+void set_pred(QtOp& op, const Pred& p, int R) {
     op.regsel = p.regsel; op.lmask = p.lmask; op.lval = p.lval; op.gmask = p.gmask; op.gval = p.gval;
-    op.flags = (uint16_t)((p.gmask ? QT_FLAG_GLOBAL : 0u) | (p.regsel == 0xffff ? QT_FLAG_ALLREG : 0u));
+    op.flags = (uint16_t)((p.gmask ? QT_FLAG_GLOBAL : 0u) | (p.regsel == all_regs(R) ? QT_FLAG_ALLREG : 0u));
 }
 
 double phase_code(int loc, int pos) {
@@ -208,7 +212,7 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, const QGate& g, bool merge_phases
             int loc, pos;
             if (lp < 0) { loc = QT_LOC_GLOBAL; pos = bit; }
             else {
-                int ri = reg_index(st, lp);
+                int ri = reg_index(st, lp, sw.R);
                 if (ri >= 0) { loc = QT_LOC_REG; pos = ri; } else { loc = QT_LOC_LOCAL; pos = lp; }
             }
             double ent[5] = {phase_code(loc, pos), g.m[0].x, g.m[0].y, g.m[1].x, g.m[1].y};
@@ -224,7 +228,7 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, const QGate& g, bool merge_phases
             }
             op.type = QT_OP_PHASE;
             op.nent = 1;
-            op.regsel = 0xffff;
+            op.regsel = all_regs(sw.R);
             op.flags = QT_FLAG_ALLREG;
             sb.push(op, 0, ent, 5);
             return;
@@ -242,11 +246,11 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, const QGate& g, bool merge_phases
             QtOp o;
             memset(&o, 0, sizeof(o));
             o.type = QT_OP_CDIAG;
-            set_pred(o, make_pred(sw, st, ones, zeros));
+            set_pred(o, make_pred(sw, st, ones, zeros), sw.R);
             const int lp = sw.local_of[last];
             if (lp < 0) { o.t1 = QT_LOC_GLOBAL; o.t0 = (uint8_t)last; }
             else {
-                int ri = reg_index(st, lp);
+                int ri = reg_index(st, lp, sw.R);
                 if (ri >= 0) { o.t1 = QT_LOC_REG; o.t0 = (uint8_t)ri; } else { o.t1 = QT_LOC_LOCAL; o.t0 = (uint8_t)lp; }
             }
             double d[4] = {d0.x, d0.y, d1.x, d1.y};
@@ -254,9 +258,9 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, const QGate& g, bool merge_phases
         }
         return;
     }
-    set_pred(op, make_pred(sw, st, g.cmask, 0));
+    set_pred(op, make_pred(sw, st, g.cmask, 0), sw.R);
     if (g.k == 1) {
-        op.t0 = (uint8_t)reg_index(st, sw.local_of[g.tb[0]]);
+        op.t0 = (uint8_t)reg_index(st, sw.local_of[g.tb[0]], sw.R);
         double s;
         if (g.cmask == 0 && is_hadamard_like(g, &s)) {
             // unscaled butterfly; the factor joins the sweep's scalar
@@ -273,15 +277,15 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, const QGate& g, bool merge_phases
     } else {
         std::vector<cplx> m = dense_matrix(g);
         op.type = QT_OP_U4;
-        op.t0 = (uint8_t)reg_index(st, sw.local_of[g.tb[0]]);
-        op.t1 = (uint8_t)reg_index(st, sw.local_of[g.tb[1]]);
+        op.t0 = (uint8_t)reg_index(st, sw.local_of[g.tb[0]], sw.R);
+        op.t1 = (uint8_t)reg_index(st, sw.local_of[g.tb[1]], sw.R);
         sb.push(op, g.tmask(), (const double*)m.data(), 32);
     }
 }
 
-void choose_thread_bits(QtStage& st, int M, bool io_stage) {
+void choose_thread_bits(QtStage& st, int M, int R, bool io_stage) {
     bool is_reg[QT_MAXM] = {false};
-    for (int q = 0; q < QT_R; q++) is_reg[st.rb[q]] = true;
+    for (int q = 0; q < R; q++) is_reg[st.rb[q]] = true;
     std::vector<int> freep;
     for (int p = 0; p < M; p++) if (!is_reg[p]) freep.push_back(p);
     std::vector<int> order;
@@ -298,7 +302,7 @@ void choose_thread_bits(QtStage& st, int M, bool io_stage) {
         }
         for (int p : freep) order.push_back(p);
     }
-    for (int q = 0; q < M - QT_R; q++) st.tpos[q] = (uint8_t)order[q];
+    for (int q = 0; q < M - R; q++) st.tpos[q] = (uint8_t)order[q];
 }
 
 std::vector<uint8_t> serialise(const SweepBuild& sw, double header_scale) {
@@ -312,11 +316,12 @@ std::vector<uint8_t> serialise(const SweepBuild& sw, double header_scale) {
     h.nstages = (uint16_t)sw.stages.size();
     h.nops = (uint16_t)nops;
     h.M = (uint16_t)sw.M;
+    h.R = (uint8_t)sw.R;
     h.ngates = (uint16_t)sw.ngates;
     h.scale = header_scale;
     static_assert(sizeof(QtHeader) <= QT_STAGES_OFF, "header too large");
     static_assert(QT_STAGES_OFF + QT_MAX_STAGES * sizeof(QtStage) <= QT_OPS_OFF, "stage table too large");
-    static_assert(sizeof(QtOp) == 32, "QtOp must be 32 bytes");
+    static_assert(sizeof(QtOp) == 40, "QtOp must be 40 bytes");
     if (sw.stages.size() > QT_MAX_STAGES || nops > QT_MAX_OPS) return {};
     h.stages_off = QT_STAGES_OFF;
     h.ops_off = QT_OPS_OFF;
@@ -346,14 +351,14 @@ std::vector<uint8_t> serialise(const SweepBuild& sw, double header_scale) {
 }
 
 // greedy choice of a stage's register bits among the tile-local positions [lo, M): returns the
-// index-bit mask of the chosen positions (exactly QT_R of them, filled up with the highest unused
+// index-bit mask of the chosen positions (exactly R of them, filled up with the highest unused
 // positions when fewer are useful) and how many gates of `rem` the stage can run
 uint64_t choose_stage_bits(const std::vector<int>& rem, const std::vector<GInfo>& info, const uint64_t* index_of_local,
-                           int M, int lo, int* count_out) {
+                           int M, int R, int lo, int* count_out) {
     uint64_t regmask = 0;
     int cur = 0, npicked = 0;
     select_pass(rem, info, regmask, rem.size(), nullptr, &cur);
-    while (npicked < QT_R) {
+    while (npicked < R) {
         int best = -1, best_count = cur;
         for (int lp = lo; lp < M; lp++) {
             const uint64_t bit = 1ull << index_of_local[lp];
@@ -370,7 +375,7 @@ uint64_t choose_stage_bits(const std::vector<int>& rem, const std::vector<GInfo>
         }
         // no single bit helps (e.g. a two-target gate needs both): try pairs
         int pa = -1, pb = -1, bc = cur;
-        if (npicked + 2 <= QT_R) {
+        if (npicked + 2 <= R) {
             for (int a = lo; a < M; a++) for (int b2 = a + 1; b2 < M; b2++) {
                 const uint64_t bits = (1ull << index_of_local[a]) | (1ull << index_of_local[b2]);
                 if (regmask & bits) continue;
@@ -387,7 +392,7 @@ uint64_t choose_stage_bits(const std::vector<int>& rem, const std::vector<GInfo>
         }
         break;
     }
-    for (int lp = M - 1; lp >= lo && npicked < QT_R; lp--) {     // fill up
+    for (int lp = M - 1; lp >= lo && npicked < R; lp--) {     // fill up
         const uint64_t bit = 1ull << index_of_local[lp];
         if (!(regmask & bit)) { regmask |= bit; npicked++; }
     }
@@ -395,12 +400,12 @@ uint64_t choose_stage_bits(const std::vector<int>& rem, const std::vector<GInfo>
     return regmask;
 }
 
-StageBuild make_stage(uint64_t regmask, const uint64_t* index_of_local, int M, bool io_stage) {
+StageBuild make_stage(uint64_t regmask, const uint64_t* index_of_local, int M, int R, bool io_stage) {
     StageBuild sb;
     memset(&sb.st, 0, sizeof(sb.st));
     int q = 0;
     for (int lp = 0; lp < M; lp++) if (regmask & (1ull << index_of_local[lp])) sb.st.rb[q++] = (uint8_t)lp;
-    choose_thread_bits(sb.st, M, io_stage);
+    choose_thread_bits(sb.st, M, R, io_stage);
     return sb;
 }
 
@@ -409,9 +414,10 @@ StageBuild make_stage(uint64_t regmask, const uint64_t* index_of_local, int M, b
 // are free tile bits (positions >= QT_L) and their lanes the contiguous low bits; stages that
 // need a low bit in registers sit in between (an op-less IO stage is added when necessary).
 bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& info, const std::vector<int>& sweep_gates,
-                   const std::vector<int>& hb, int M, bool merge_phases, std::vector<uint8_t>* program) {
+                   const std::vector<int>& hb, int M, int R, bool merge_phases, std::vector<uint8_t>* program) {
     SweepBuild sw;
     sw.M = M;
+    sw.R = R;
     sw.hb = hb;
     for (int b = 0; b < 64; b++) sw.local_of[b] = -1;
     for (int b = 0; b < QT_L; b++) sw.local_of[b] = b;
@@ -428,15 +434,15 @@ bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& in
         uint64_t regmask;
         bool io = false;
         int c_all = 0, c_hi = 0;
-        const uint64_t m_all = choose_stage_bits(rem, info, index_of_local, M, 0, &c_all);
-        const uint64_t m_hi = choose_stage_bits(rem, info, index_of_local, M, QT_L, &c_hi);
+        const uint64_t m_all = choose_stage_bits(rem, info, index_of_local, M, R, 0, &c_all);
+        const uint64_t m_hi = choose_stage_bits(rem, info, index_of_local, M, R, QT_L, &c_hi);
         if (first) {
             // the first stage must be an IO stage; if free bits alone run nothing it stays op-less
             regmask = m_hi; io = true;
         } else if (c_hi >= c_all) { regmask = m_hi; io = true; }     // can serve as the last stage too
         else regmask = m_all;
         if ((regmask & low_index_mask) == 0) io = true;
-        StageBuild sb = make_stage(regmask, index_of_local, M, io);
+        StageBuild sb = make_stage(regmask, index_of_local, M, R, io);
         std::vector<int> picked;
         select_pass(rem, info, regmask, rem.size(), &picked, nullptr);
         if (picked.empty() && !first) return false;   // cannot happen: the head gate always fits some stage
@@ -457,15 +463,15 @@ bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& in
     {   // the last stage must be an IO stage
         const QtStage& last = sw.stages.back().st;
         bool low = false;
-        for (int q = 0; q < QT_R; q++) if (last.rb[q] < QT_L) low = true;
+        for (int q = 0; q < R; q++) if (last.rb[q] < QT_L) low = true;
         if (low) {
             uint64_t regmask = 0;
-            for (int lp = M - 1; lp >= M - QT_R; lp--) regmask |= 1ull << index_of_local[lp];
-            sw.stages.push_back(make_stage(regmask, index_of_local, M, true));
+            for (int lp = M - 1; lp >= M - R; lp--) regmask |= 1ull << index_of_local[lp];
+            sw.stages.push_back(make_stage(regmask, index_of_local, M, R, true));
             if (sw.stages.size() > QT_MAX_STAGES) return false;
         } else {
             // make sure its thread map is the IO one (lanes = low bits)
-            choose_thread_bits(sw.stages.back().st, M, true);
+            choose_thread_bits(sw.stages.back().st, M, R, true);
             // predicates of ops already emitted do not depend on the thread map: only on rb
         }
     }
@@ -594,6 +600,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
     std::vector<QtPlanStep> steps;
     const int M = opt.M;
     if (M < QT_MINM || M > QT_MAXM) throw std::runtime_error("planner: tile bits out of range");
+    if (opt.R != QT_R && opt.R != QT_MAXR) throw std::runtime_error("planner: register bits per stage must be 4 or 5");
     const int NH = M - QT_L;
     std::vector<GInfo> info(gates.size());
     for (size_t i = 0; i < gates.size(); i++) info[i] = analyse(gates[i]);
@@ -649,7 +656,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
         guide_at++;
         // ---- stages + program (shrink the sweep if the program does not fit) -------------------
         std::vector<uint8_t> program;
-        while (!build_program(gates, info, picked, hb, M, opt.merge_phases, &program)) {
+        while (!build_program(gates, info, picked, hb, M, opt.R, opt.merge_phases, &program)) {
             if (picked.size() <= 1) throw std::runtime_error("planner: cannot build a program for one gate");
             picked.resize(picked.size() / 2);
             have_guide = false;       // the searched plan assumed the whole sweep ran: fall back to greedy

@@ -17,7 +17,8 @@
 #include <vector>
 
 #define QT_L 5                  // contiguous low bits of a tile (2^5 * 16 B = 512 B runs)
-#define QT_R 4                  // register bits per stage
+#define QT_R 4                  // register bits per stage of programs the GENERIC kernel runs (16 amplitudes per thread)
+#define QT_MAXR 5               // specialised kernels may hold 32 amplitudes per thread (QtHeader.R says which)
 #define QT_MAXM 12              // largest tile (bits)
 #define QT_MINM 11
 #define QT_MAXH (QT_MAXM - QT_L)
@@ -27,7 +28,7 @@
 // fixed layout of a program (lets the kernel address stages / ops / pool with constant offsets)
 #define QT_STAGES_OFF 64
 #define QT_OPS_OFF 256
-#define QT_POOL_OFF (QT_OPS_OFF + QT_MAX_OPS * 32)
+#define QT_POOL_OFF (QT_OPS_OFF + QT_MAX_OPS * 40)
 
 enum QtOpType : uint8_t {
     QT_OP_H = 1,        // UNSCALED butterfly [[1,1],[1,-1]] on register bit t0 (the 2^-1/2 factors
@@ -42,16 +43,18 @@ enum QtOpType : uint8_t {
 enum QtLoc : uint8_t { QT_LOC_REG = 0, QT_LOC_LOCAL = 1, QT_LOC_GLOBAL = 2, QT_LOC_CONST = 3 };
 
 #define QT_FLAG_GLOBAL 1u       // the op has a predicate on bits outside the tile
-#define QT_FLAG_ALLREG 2u       // regsel covers all 16 registers
+#define QT_FLAG_ALLREG 2u       // regsel covers all 2^R registers
 
-struct QtOp {             // 32 bytes: the first 16 are all an op without out-of-tile controls needs
+struct QtOp {             // 40 bytes
     uint8_t type;
     uint8_t t0, t1;       // register-bit indices of the targets (CDIAG: t0 = position, t1 = QtLoc)
     uint8_t nent;         // PHASE: entries
-    uint16_t regsel;      // register indices (bit i <-> a[i]) that satisfy the register-bit part of the predicate
+    uint32_t regsel;      // register indices (bit i <-> a[i]) that satisfy the register-bit part of the predicate
     uint16_t lmask, lval; // predicate on the thread's tile-local index bits
     uint16_t flags;
+    uint16_t pad_;
     uint32_t pool;        // offset of the payload in the program's pool, in doubles
+    uint32_t pad2_;
     uint64_t gmask, gval; // predicate on index bits outside the tile (uniform per tile)
 };
 
@@ -61,8 +64,8 @@ struct QtPhaseEntry {     // 5 doubles in the pool; `code` holds loc | pos << 8 
 };
 
 struct QtStage {
-    uint8_t rb[QT_R];          // tile-local positions of the register bits (a[i]: bit q of i <-> rb[q])
-    uint8_t tpos[QT_MAXM];     // tile-local position carried by thread-index bit q (M - 4 entries used)
+    uint8_t rb[QT_MAXR];       // tile-local positions of the register bits (a[i]: bit q of i <-> rb[q]; R used)
+    uint8_t tpos[QT_MAXM];     // tile-local position carried by thread-index bit q (M - R entries used)
     uint16_t first_op, nops;
 };
 
@@ -73,7 +76,7 @@ struct QtHeader {
     uint16_t ngates;           // gates of the circuit executed by this sweep
     uint32_t stages_off, ops_off, pool_off;    // byte offsets from the start of the program
     uint8_t hb[QT_MAXH];       // index-bit positions of the free tile bits, ascending (M - QT_L used)
-    uint8_t pad_[1];
+    uint8_t R;                 // register bits per stage: 4 (16 amplitudes per thread) or 5 (32; specialised kernels only)
     double scale;              // every amplitude is multiplied by this before the store (1.0: skipped)
 };
 
@@ -119,6 +122,7 @@ struct QtPlanStep {
 
 struct QtPlanOptions {
     int M = 12;
+    int R = QT_R;               // register bits per stage (5: for the sweep specialiser only)
     bool merge_phases = true;
     int search_trials = 1;      // > 1: randomised search over the tile-bit choices, fewest steps wins
 };

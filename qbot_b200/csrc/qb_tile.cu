@@ -172,6 +172,9 @@ struct CachedPlan {
     uint64_t hash = 0;
     size_t ngates = 0;
     int nbits = 0;
+    int R = QT_R;                      // register bits per stage the plan was built for (5: specialised kernels only)
+    uint64_t uses = 0;
+    bool upgrade_failed = false;       // building / compiling the 32-amplitudes-per-thread variant failed once
     std::vector<QtPlanStep> steps;
     std::vector<size_t> prog_off;      // per step offset into dev (fused steps)
     uint8_t* dev = nullptr;
@@ -241,6 +244,15 @@ int engine_prefetch() {
     static int p = env_int("QBOT_B200_L2_PREFETCH", 1);
     return p;
 }
+// specialised sweeps: bit 0 = L2 prefetch of the next tile, bit 1 = asynchronous copy of the next
+// tile into the transposition buffer during the last stage (env QBOT_B200_ASYNC_LOAD=0 disables)
+int engine_jit_prefetch() {
+    // measured at 30 qubits (ms per sweep): bulk copy only 7.44 | bulk copy + L2 prefetch 7.80 |
+    // L2 prefetch + LDG 7.96 | plain LDG 10.1
+    const int async = env_int("QBOT_B200_ASYNC_LOAD", 1) ? 2 : 0;
+    const int l2 = env_int("QBOT_B200_JIT_L2_PREFETCH", async ? 0 : 1) ? 1 : 0;
+    return async | l2;
+}
 
 // 0: never specialise; 1 (default): specialise a plan when it is run again on a state of at least
 // QBOT_B200_JIT_MIN_BITS index bits (compile time is amortised by repetition); 2: always
@@ -251,6 +263,12 @@ int engine_jit_default() {
 int engine_jit_min_bits() {
     static int b = env_int("QBOT_B200_JIT_MIN_BITS", 22);
     return b;
+}
+// plan shape of specialised sweeps: 5 register bits per stage (32 amplitudes per thread, 128-thread
+// CTAs, 3 per SM: fewer shared-memory transpositions, smaller barrier domains) or 4 (same plan as the
+// generic kernel's)
+int engine_jit_R() {
+    return env_int("QBOT_B200_JIT_R", QT_MAXR) == QT_R ? QT_R : QT_MAXR;      // read every time: tests flip it
 }
 
 // decide (once per step and run, until resolved) whether fused step i runs specialised
@@ -290,9 +308,55 @@ void launch_sweep(qb_state* s, EngineState* es, const uint8_t* prog, uint64_t nt
     k_tile_sweep<M><<<grid, Cfg::T, Cfg::SMEM_BYTES, s->stream>>>(s->d, prog, ntiles, engine_prefetch());
 }
 
+bool qb_engine_available_impl() { return getenv("QBOT_B200_NO_FUSION") == nullptr; }
+
+// the cached plan of `gates` for R register bits per stage (planning it on a miss)
+CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gates, int M, int R) {
+    uint64_t hsh = hash_gates(gates, s->nbits, M);
+    hsh = fnv(hsh, &R, sizeof(R));
+    for (auto it = es->cache.begin(); it != es->cache.end(); ++it) {
+        if (it->hash == hsh && it->ngates == gates.size() && it->nbits == s->nbits && it->R == R) {
+            es->cache.splice(es->cache.begin(), es->cache, it);
+            return &es->cache.front();
+        }
+    }
+    CachedPlan cp;
+    cp.hash = hsh; cp.ngates = gates.size(); cp.nbits = s->nbits; cp.R = R;
+    QtPlanOptions opt;
+    opt.M = M;
+    opt.R = R;
+    // plan search effort grows with the cost of a sweep (env QBOT_B200_PLAN_TRIALS overrides)
+    const int total_bits = s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0);
+    opt.search_trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);
+    cp.steps = qt_plan(gates, s->nbits, opt);
+    size_t total = 0;
+    cp.prog_off.resize(cp.steps.size(), 0);
+    for (size_t i = 0; i < cp.steps.size(); i++) {
+        if (!cp.steps[i].fused) continue;
+        cp.prog_off[i] = total;
+        total += (cp.steps[i].program.size() + 255) & ~size_t(255);
+    }
+    if (total && R == QT_R) {          // device copies of the programs: read by the generic kernel only
+        std::vector<uint8_t> hostbuf(total, 0);
+        for (size_t i = 0; i < cp.steps.size(); i++)
+            if (cp.steps[i].fused) memcpy(hostbuf.data() + cp.prog_off[i], cp.steps[i].program.data(), cp.steps[i].program.size());
+        QB_CUDA(cudaMalloc((void**)&cp.dev, total));
+        QB_CUDA(cudaMemcpyAsync(cp.dev, hostbuf.data(), total, cudaMemcpyHostToDevice, s->stream));
+        QB_CUDA(cudaStreamSynchronize(s->stream));     // hostbuf dies here
+    }
+    if (es->cache.size() >= kMaxCachedPlans) {
+        QB_CUDA(cudaStreamSynchronize(s->stream));
+        es->cache.back().release();
+        es->cache.pop_back();
+    }
+    cp.jit.assign(cp.steps.size(), CachedPlan::StepJit());
+    es->cache.push_front(std::move(cp));
+    return &es->cache.front();
+}
+
 }  // namespace
 
-bool qb_engine_available() { return getenv("QBOT_B200_NO_FUSION") == nullptr; }
+bool qb_engine_available() { return qb_engine_available_impl(); }
 
 void qb_engine_free(qb_state* s) { s->engine = nullptr; }      // plans belong to the device, not to the handle
 
@@ -300,50 +364,35 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
     std::lock_guard<std::mutex> lk(g_engine_mu);
     EngineState* es = &g_engines[s->device];
     const int M = engine_M();
-    const uint64_t hsh = hash_gates(gates, s->nbits, M);
-    CachedPlan* plan = nullptr;
-    for (auto it = es->cache.begin(); it != es->cache.end(); ++it) {
-        if (it->hash == hsh && it->ngates == gates.size() && it->nbits == s->nbits) {
-            es->cache.splice(es->cache.begin(), es->cache, it);
-            plan = &es->cache.front();
-            break;
-        }
-    }
-    if (!plan) {
-        CachedPlan cp;
-        cp.hash = hsh; cp.ngates = gates.size(); cp.nbits = s->nbits;
-        QtPlanOptions opt;
-        opt.M = M;
-        // plan search effort grows with the cost of a sweep (env QBOT_B200_PLAN_TRIALS overrides)
-        const int total_bits = s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0);
-        opt.search_trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);
-        cp.steps = qt_plan(gates, s->nbits, opt);
-        size_t total = 0;
-        cp.prog_off.resize(cp.steps.size(), 0);
-        for (size_t i = 0; i < cp.steps.size(); i++) {
-            if (!cp.steps[i].fused) continue;
-            cp.prog_off[i] = total;
-            total += (cp.steps[i].program.size() + 255) & ~size_t(255);
-        }
-        if (total) {
-            std::vector<uint8_t> hostbuf(total, 0);
-            for (size_t i = 0; i < cp.steps.size(); i++)
-                if (cp.steps[i].fused) memcpy(hostbuf.data() + cp.prog_off[i], cp.steps[i].program.data(), cp.steps[i].program.size());
-            QB_CUDA(cudaMalloc((void**)&cp.dev, total));
-            QB_CUDA(cudaMemcpyAsync(cp.dev, hostbuf.data(), total, cudaMemcpyHostToDevice, s->stream));
-            QB_CUDA(cudaStreamSynchronize(s->stream));     // hostbuf dies here
-        }
-        if (es->cache.size() >= kMaxCachedPlans) {
-            QB_CUDA(cudaStreamSynchronize(s->stream));
-            es->cache.back().release();
-            es->cache.pop_back();
-        }
-        es->cache.push_front(std::move(cp));
-        plan = &es->cache.front();
-    }
+    int jit_mode = s->jit_mode >= 0 ? s->jit_mode : engine_jit_default();
+    const bool tiled = s->nbits >= M;
+    const bool big = s->nbits + (s->nbranch > 1 ? 4 : 0) >= engine_jit_min_bits();
 
-    const int jit_mode = s->jit_mode >= 0 ? s->jit_mode : engine_jit_default();
-    if (plan->jit.size() != plan->steps.size()) plan->jit.assign(plan->steps.size(), CachedPlan::StepJit());
+    // Which plan runs: the generic 16-amplitudes-per-thread plan (any executor), or -- when the
+    // sweeps are going to be specialised anyway -- the specialiser's own 32-amplitudes-per-thread
+    // plan.  Mode 2 takes the latter at first sight; mode 1 when the SAME gate list is flushed a
+    // second time on a large state (every kernel of the variant is compiled before anything is
+    // launched, so a failure leaves the generic plan in charge).
+    CachedPlan* plan = nullptr;
+    if (tiled && jit_mode == 2 && engine_jit_R() == QT_MAXR) {
+        plan = get_plan(s, es, gates, M, QT_MAXR);
+    } else {
+        plan = get_plan(s, es, gates, M, QT_R);
+        plan->uses++;
+        if (tiled && jit_mode == 1 && big && engine_jit_R() == QT_MAXR && plan->uses >= 2 && !plan->upgrade_failed) {
+            CachedPlan* base = plan;
+            try {
+                CachedPlan* p5 = get_plan(s, es, gates, M, QT_MAXR);
+                for (size_t i = 0; i < p5->steps.size(); i++)
+                    if (p5->steps[i].fused && !step_jit(s, p5, i, 2)) throw qb_error(-2, "specialised variant unavailable");
+                plan = p5;
+            } catch (const qb_error&) {
+                base->upgrade_failed = true;
+                plan = base;
+            }
+        }
+    }
+    if (plan->R != QT_R) jit_mode = 2;          // only specialised kernels can run this plan shape
 
     const uint64_t ntiles = s->total() >> M;
     for (size_t i = 0; i < plan->steps.size(); i++) {
@@ -354,9 +403,13 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         }
         if (jit_mode != 0 && step_jit(s, plan, i, jit_mode)) {
             const CachedPlan::StepJit& j = plan->jit[i];
-            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_prefetch(), j.pool.data(), j.pool_dev);
+            if (plan->R != QT_R && !j.ready) throw qb_error(-2, "no specialised kernel for a 32-amplitudes-per-thread sweep");
+            if (!s->sm_arrivals) QB_CUDA(cudaMalloc((void**)&s->sm_arrivals, 1024 * sizeof(unsigned)));
+            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_jit_prefetch(), j.pool.data(), j.pool_dev, s->sm_arrivals,
+                          (unsigned)env_int("QBOT_B200_STAGGER_NS", 0));
             s->stats.jit_passes++;
         } else {
+            if (plan->R != QT_R) throw qb_error(-2, "the generic sweep kernel cannot run a 32-amplitudes-per-thread plan");
             const uint8_t* prog = plan->dev + plan->prog_off[i];
             {   // a stale error of an earlier unchecked runtime call must not be blamed on this launch
                 const cudaError_t stale = cudaGetLastError();

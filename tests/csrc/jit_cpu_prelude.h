@@ -3,6 +3,7 @@
 // functions over every tile and thread the way the CUDA kernel schedules them (one stage for all
 // threads of a tile, then the next -- the barriers of the kernel).
 #pragma once
+#include <cstring>
 #include <vector>
 struct QjC { double x, y; };
 #define QJ_C QjC
@@ -12,8 +13,10 @@ struct QjC { double x, y; };
 #define QJ_P(i) (P[i])
 #define QJ_POOL_PARAM const double* P
 #define QJ_RESTRICT
-#define QJ_WAR_SYNC()
 #define QJ_SYNC()
+#define QJ_BULK_COPY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
+#define QJ_ASYNC_WAIT(parity)
+#define QJ_ISSUE_NEXT(tid, nbase, psi, buf)      /* the harness runs qj_issue_next after the last stage (the kernel's barrier) */
 #define QJ_PREFETCH(psi, nbase, tid)
 #define QJ_PRELUDE
 #define QJ_WANT_DISPATCH
@@ -22,9 +25,13 @@ struct QjC { double x, y; };
     extern "C" void NAME(QjC* psi, int nbits, const double* pool) {                                  \
         const unsigned long long ntiles = 1ull << (nbits - QJ_M);                                    \
         std::vector<QjC> buf(QJ_TILE_UNITS);                                                         \
+        /* one "CTA" walks all tiles: the first tile comes from HBM, every later one through the    \
+           asynchronous copies its predecessor's last stage issued into the buffer */               \
         for (unsigned long long t = 0; t < ntiles; t++) {                                            \
             const unsigned long long tbase = qj_tile_base(t);                                        \
+            const unsigned long long nbase = t + 1 < ntiles ? qj_tile_base(t + 1) : ~0ull;           \
             for (int s = 0; s < QJ_NSTAGES; s++)                                                     \
-                for (unsigned tid = 0; tid < QJ_T; tid++) qj_stage(s, tid, tbase, psi, buf.data(), pool); \
+                for (unsigned tid = 0; tid < QJ_T; tid++) qj_stage(s, tid, tbase, nbase, t > 0, psi, buf.data(), pool); \
+            for (unsigned tid = 0; tid < QJ_T; tid++) qj_issue_next(tid, nbase, psi, buf.data());    \
         }                                                                                            \
     }

@@ -33,6 +33,7 @@ static void run_program(const uint8_t* prog, qt_c* psi, int nbits) {
         for (int q = 0; q < QT_L; q++) if (stages[s].tpos[q] != q) throw std::runtime_error("IO stage lanes are not the low bits");
     }
     if (h->nops > QT_MAX_OPS || h->nstages > QT_MAX_STAGES) throw std::runtime_error("program exceeds the kernel limits");
+    if (h->R != QT_R) throw std::runtime_error("the op interpreter (generic kernel) runs programs with 16 amplitudes per thread only");
     for (uint64_t t = 0; t < ntiles; t++) {
         const uint64_t tbase = qt_tile_base(t, h->hb, NH);
         for (uint32_t j = 0; j < (1u << M); j++) buf[j] = psi[tbase + (j & 31u) + qt_run_offset(j >> QT_L, h->hb, NH)];
@@ -142,6 +143,7 @@ int qbt_plan(int nbits, int ngates, const int* ks, const int* tbs, const uint64_
         opt.M = M;
         opt.merge_phases = merge != 0;
         if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
+        if (const char* e = getenv("QBOT_B200_PLAN_R")) opt.R = atoi(e);
         std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
         if ((int)steps.size() > max_steps) { g_err = "too many steps"; return -1; }
         long long at = 0;

@@ -18,7 +18,14 @@ def DS():
     return DeviceState
 
 
-def test_jit_mixed_circuits_vs_oracle(DS):
+@pytest.fixture(params=['5', '4'], ids=['R5', 'R4'])
+def jit_R(request, monkeypatch):
+    """plan shape of the specialised sweeps: 32 amplitudes per thread (default) or the generic 16"""
+    monkeypatch.setenv('QBOT_B200_JIT_R', request.param)
+    return int(request.param)
+
+
+def test_jit_mixed_circuits_vs_oracle(DS, jit_R):
     rng = np.random.default_rng(21)
     for n in (12, 13, 15, 17):
         gl = random_gate_list(rng, n, 80)
@@ -36,7 +43,7 @@ def test_jit_mixed_circuits_vs_oracle(DS):
         assert close(got, ref, 1e-12), n
 
 
-def test_jit_equals_unfused_rc(DS):
+def test_jit_equals_unfused_rc(DS, jit_R):
     from qbot_b200.circuits import rc
     n = 22
     gates = rc(n, 12, 22)
@@ -94,7 +101,7 @@ def test_jit_on_repeat_and_coefficient_reuse(DS):
     assert after['kernels_compiled'] == mid['kernels_compiled'] and after['cache_hits'] > mid['cache_hits'], (mid, after)
 
 
-def test_jit_density_and_batch(DS):
+def test_jit_density_and_batch(DS, jit_R):
     rng = np.random.default_rng(22)
     n = 7
     v, w = rand_ket(rng, n), rand_ket(rng, n)

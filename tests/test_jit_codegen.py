@@ -26,8 +26,16 @@ def tileable(gl):
     return out
 
 
+@pytest.fixture(params=[4, 5], ids=['R4', 'R5'])
+def plan_R(request, monkeypatch):
+    """register bits per stage of the plans: 4 (16 amplitudes per thread, also run by the generic
+    kernel) and 5 (32 per thread, the specialiser's own plan shape)"""
+    monkeypatch.setenv('QBOT_B200_PLAN_R', str(request.param))
+    return request.param
+
+
 @pytest.mark.parametrize('M', [11, 12])
-def test_generated_source_rc(M):
+def test_generated_source_rc(M, plan_R):
     for n, depth, seed in ((12, 10, 1), (14, 12, 2), (16, 5, 3)):
         gates = rc(n, depth, seed)
         psi = rand_ket(np.random.default_rng(seed), n)
@@ -39,7 +47,7 @@ def test_generated_source_rc(M):
 
 
 @pytest.mark.parametrize('M,merge', [(12, True), (11, True), (12, False)])
-def test_generated_source_mixed(M, merge):
+def test_generated_source_mixed(M, merge, plan_R):
     rng = np.random.default_rng(300 + M)
     for n in (12, 13, 15):
         gl = tileable(random_gate_list(rng, n, 70))
