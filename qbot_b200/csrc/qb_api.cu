@@ -47,10 +47,43 @@ static int sm_count_of(int dev) {
 namespace {
 struct BufCache {
     std::mutex mu;
-    std::vector<std::tuple<int, size_t, void*>> free_list;      // (device, bytes, pointer)
+    std::vector<std::tuple<int, size_t, void*>> free_list;      // (device, bytes, pointer): registers
+    std::vector<std::tuple<int, size_t, void*>> small_list;     // work buffers in power-of-two size classes
 };
 BufCache g_bufs;
 constexpr size_t kCacheMinBytes = 64u << 20;
+
+// short-lived work buffers (partials of a probability reduction, ...): cudaMalloc / cudaFree cost
+// from a few to hundreds of milliseconds next to multi-GiB allocations, so they are recycled too
+size_t work_class(size_t bytes) {
+    size_t c = 64u << 10;
+    while (c < bytes) c <<= 1;
+    return c;
+}
+void* work_alloc(int device, size_t bytes) {
+    const size_t c = work_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(g_bufs.mu);
+        for (size_t i = 0; i < g_bufs.small_list.size(); i++) {
+            if (std::get<0>(g_bufs.small_list[i]) == device && std::get<1>(g_bufs.small_list[i]) == c) {
+                void* p = std::get<2>(g_bufs.small_list[i]);
+                g_bufs.small_list.erase(g_bufs.small_list.begin() + i);
+                return p;
+            }
+        }
+    }
+    void* p = nullptr;
+    QB_CUDA(cudaMalloc(&p, c));
+    return p;
+}
+void work_free(int device, size_t bytes, void* p) {
+    const size_t c = work_class(bytes);
+    if (c <= (256u << 20)) {
+        std::lock_guard<std::mutex> lk(g_bufs.mu);
+        if (g_bufs.small_list.size() < 16) { g_bufs.small_list.emplace_back(device, c, p); return; }
+    }
+    cudaFree(p);
+}
 
 void* cached_alloc(int device, size_t bytes) {
     {
@@ -353,12 +386,12 @@ int qb_init_product(qb_state* s, const double* vecs, int per_branch) {
     DevGuard g(s->device);
     size_t per = (s->kind == QB_KET ? 2 : 4) * (size_t)s->nq;
     size_t count = per * (per_branch ? (size_t)s->nbranch : 1);
-    cplx* dv = nullptr;
-    QB_CUDA(cudaMalloc((void**)&dv, sizeof(cplx) * std::max<size_t>(count, 1)));
+    const size_t dv_bytes = sizeof(cplx) * std::max<size_t>(count, 1);
+    cplx* dv = (cplx*)work_alloc(s->device, dv_bytes);
     QB_CUDA(cudaMemcpyAsync(dv, vecs, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));
     qb_launch_init_product(s->ctx(), s->d, s->kind, s->nq, s->nbranch, dv, per_branch);
     QB_CUDA(cudaStreamSynchronize(s->stream));
-    cudaFree(dv);
+    work_free(s->device, dv_bytes, dv);
     s->stats.bytes_moved += s->bytes();
     QB_API_END
 }
@@ -472,7 +505,7 @@ int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int*
     char* buf = nullptr;
     size_t off_tb = (mat_bytes + 255) & ~size_t(255), off_cm = (off_tb + tb_bytes + 255) & ~size_t(255),
            off_en = (off_cm + cm_bytes + 255) & ~size_t(255), tot = off_en + B + 256;
-    QB_CUDA(cudaMalloc((void**)&buf, tot));
+    buf = (char*)work_alloc(s->device, tot);
     std::vector<cplx> hm((const cplx*)matrices, (const cplx*)matrices + D2 * B);
     std::vector<int> htb(target_bits, target_bits + (size_t)k * B);
     std::vector<uint64_t> hcm(B, 0);
@@ -496,7 +529,7 @@ int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int*
         s->stats.bytes_moved += s->bytes() * 2;
         s->stats.state_passes++;
     }
-    cudaFree(buf);
+    work_free(s->device, tot, buf);
     s->stats.gates_applied += B;
     QB_API_END
 }
@@ -561,6 +594,19 @@ int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, c
     if (const char* e = getenv("QBOT_B200_JIT_R")) { const int v = atoi(e); if (v == 4 || v == 5) opt.R = v; }
     std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
     int n = 0;
+    if (!cubin_dir) {
+        // no artefacts wanted: compile through the parallel path the engine uses
+        std::vector<const uint8_t*> progs;
+        for (const QtPlanStep& st : steps) if (st.fused) progs.push_back(st.program.data());
+        const uint64_t before = qb_jit_stats().kernels_compiled;
+        qb_jit_precompile(progs);
+        for (const uint8_t* p : progs) {          // whatever the pool did not take (single program, duplicates) compiles here
+            const std::string src = qb_jit_full_source(p, nullptr, nullptr);
+            (void)src;
+        }
+        if (ncompiled) *ncompiled = (int)(qb_jit_stats().kernels_compiled - before);
+        return QB_OK;
+    }
     for (const QtPlanStep& st : steps) {
         if (!st.fused) continue;
         const std::string src = qb_jit_full_source(st.program.data(), nullptr, nullptr);
@@ -622,16 +668,16 @@ static void run_bins(qb_state* s, const int* bits, int m, std::vector<cplx>& hos
     }
     size_t npartial = (size_t)s->nbranch * a.nchunks << a.ml;
     size_t nout = (size_t)s->nbranch << m;
-    cplx *dpart = nullptr, *dout = nullptr;
-    QB_CUDA(cudaMalloc((void**)&dpart, sizeof(cplx) * npartial));
-    QB_CUDA(cudaMalloc((void**)&dout, sizeof(cplx) * nout));
+    cplx* dpart = (cplx*)work_alloc(s->device, sizeof(cplx) * npartial);
+    cplx* dout = (cplx*)work_alloc(s->device, sizeof(cplx) * nout);
     a.partial = dpart; f.partial = dpart; f.out = dout;
     qb_launch_bins(s->ctx(), a, s->nbranch);
     qb_launch_bins_final(s->ctx(), f, s->nbranch);
     host_out.resize(nout);
     QB_CUDA(cudaMemcpyAsync(host_out.data(), dout, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, s->stream));
     QB_CUDA(cudaStreamSynchronize(s->stream));
-    cudaFree(dpart); cudaFree(dout);
+    work_free(s->device, sizeof(cplx) * npartial, dpart);
+    work_free(s->device, sizeof(cplx) * nout, dout);
     s->stats.bytes_moved += (s->kind == QB_KET ? s->bytes() : (sizeof(cplx) * (size_t)s->nbranch << s->nq));
 }
 

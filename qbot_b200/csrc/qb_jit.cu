@@ -18,7 +18,9 @@
 #include <chrono>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 namespace {
 
@@ -54,6 +56,9 @@ __device__ __forceinline__ unsigned qj_mbar() {
 #define QJ_BULK_COPY(sdst, gsrc)                                                                   \
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];" ::"r"( \
                      (unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(qj_mbar()) : "memory")
+#ifdef QJ_DEBUG_NOWAIT
+#define QJ_ASYNC_WAIT(parity)
+#else
 #define QJ_ASYNC_WAIT(parity)                                                                      \
     do {                                                                                           \
         unsigned done_;                                                                            \
@@ -62,6 +67,7 @@ __device__ __forceinline__ unsigned qj_mbar() {
                          : "=r"(done_) : "r"(qj_mbar()), "r"(parity) : "memory");                  \
         } while (!done_);                                                                          \
     } while (0)
+#endif
 // every thread of the CTA has read its amplitudes out of the buffer (barrier); order those generic
 // reads before the TMA's writes (proxy fence); one thread announces the byte count
 #define QJ_ISSUE_NEXT(tid, nbase, psi, buf)                                                        \
@@ -251,6 +257,7 @@ std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool*
     // diagnostics only (wrong results!): drop the HBM loads and / or stores of the sweep to time its parts
     if (getenv("QBOT_B200_DEBUG_NOLOAD")) src += "#define QJ_DEBUG_NOLOAD 1\n";
     if (getenv("QBOT_B200_DEBUG_NOSTORE")) src += "#define QJ_DEBUG_NOSTORE 1\n";
+    if (getenv("QBOT_B200_DEBUG_NOWAIT")) src += "#define QJ_DEBUG_NOWAIT 1\n";
     if (const int c = jit_ctas_override(li.M)) src += "#define QJ_CTAS " + std::to_string(c) + "\n";
     src += kPrelude;
     src += body;
@@ -302,6 +309,56 @@ int qb_jit_note(uint64_t key) {
 QbJitStats qb_jit_stats() {
     std::lock_guard<std::mutex> lk(g_mu);
     return g_stats;
+}
+
+// Compile the kernels of several sweep programs that are not cached yet, NVRTC running on up to 8
+// host threads (one program per thread at a time): a 13-sweep circuit costs one compile latency
+// (~0.7 s) instead of thirteen.  Failures are left to qb_jit_get, which reports them.
+void qb_jit_precompile(const std::vector<const uint8_t*>& programs) {
+    struct Job { std::string src; uint64_t key; QjSourceInfo info; bool pg; std::vector<char> cubin; double ms = 0; bool ok = false; };
+    std::vector<Job> jobs;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (const uint8_t* p : programs) {
+            Job j;
+            j.src = qb_jit_full_source(p, &j.info, &j.pg);
+            j.key = qj_hash(j.src);
+            bool dup = g_cache.count(j.key) != 0;
+            for (const Job& o : jobs) dup = dup || o.key == j.key;
+            if (!dup) jobs.push_back(std::move(j));
+        }
+    }
+    if (jobs.size() < 2 || !nvrtc().so) return;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = std::min<size_t>(jobs.size(), std::max(1u, std::min(8u, hw ? hw : 1u)));
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nthreads; t++) {
+        pool.emplace_back([&] {
+            for (size_t i = next++; i < jobs.size(); i = next++) {
+                const auto t0 = std::chrono::steady_clock::now();
+                try {
+                    jobs[i].cubin = qb_jit_compile(jobs[i].src, nullptr);
+                    jobs[i].ok = true;
+                } catch (...) {
+                }
+                jobs[i].ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (Job& j : jobs) {
+        if (!j.ok || g_cache.count(j.key)) continue;
+        Compiled c;
+        c.cubin = std::move(j.cubin);
+        c.info = j.info;
+        c.pool_global = j.pg;
+        c.compile_ms = j.ms;
+        g_stats.kernels_compiled++;
+        g_stats.compile_ms += j.ms;
+        g_cache.emplace(j.key, std::move(c));
+    }
 }
 
 // the compiled kernel of `program` on `device` (compiling / loading it on first use)

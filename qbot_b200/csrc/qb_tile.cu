@@ -354,6 +354,14 @@ CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gat
     return &es->cache.front();
 }
 
+// all kernels of a plan that is going to run specialised, compiled in parallel on the host cores
+void precompile_plan(CachedPlan* plan) {
+    std::vector<const uint8_t*> progs;
+    for (size_t i = 0; i < plan->steps.size(); i++)
+        if (plan->steps[i].fused && !plan->jit[i].ready && !plan->jit[i].failed) progs.push_back(plan->steps[i].program.data());
+    if (progs.size() >= 2) qb_jit_precompile(progs);
+}
+
 }  // namespace
 
 bool qb_engine_available() { return qb_engine_available_impl(); }
@@ -376,6 +384,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
     CachedPlan* plan = nullptr;
     if (tiled && jit_mode == 2 && engine_jit_R() == QT_MAXR) {
         plan = get_plan(s, es, gates, M, QT_MAXR);
+        precompile_plan(plan);
     } else {
         plan = get_plan(s, es, gates, M, QT_R);
         plan->uses++;
@@ -383,6 +392,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
             CachedPlan* base = plan;
             try {
                 CachedPlan* p5 = get_plan(s, es, gates, M, QT_MAXR);
+                precompile_plan(p5);
                 for (size_t i = 0; i < p5->steps.size(); i++)
                     if (p5->steps[i].fused && !step_jit(s, p5, i, 2)) throw qb_error(-2, "specialised variant unavailable");
                 plan = p5;
@@ -404,9 +414,9 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         if (jit_mode != 0 && step_jit(s, plan, i, jit_mode)) {
             const CachedPlan::StepJit& j = plan->jit[i];
             if (plan->R != QT_R && !j.ready) throw qb_error(-2, "no specialised kernel for a 32-amplitudes-per-thread sweep");
-            if (!s->sm_arrivals) QB_CUDA(cudaMalloc((void**)&s->sm_arrivals, 1024 * sizeof(unsigned)));
-            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_jit_prefetch(), j.pool.data(), j.pool_dev, s->sm_arrivals,
-                          (unsigned)env_int("QBOT_B200_STAGGER_NS", 0));
+            const unsigned stagger = (unsigned)env_int("QBOT_B200_STAGGER_NS", 0);     // CTA de-phasing experiment: no effect measured
+            if (stagger && !s->sm_arrivals) QB_CUDA(cudaMalloc((void**)&s->sm_arrivals, 1024 * sizeof(unsigned)));
+            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_jit_prefetch(), j.pool.data(), j.pool_dev, s->sm_arrivals, stagger);
             s->stats.jit_passes++;
         } else {
             if (plan->R != QT_R) throw qb_error(-2, "the generic sweep kernel cannot run a 32-amplitudes-per-thread plan");
