@@ -95,6 +95,8 @@ def run_multi_gpu(args):
                         sk.shard.exchange_seconds - es0, stats['jit_passes']], dtype=torch.float64, device=f'cuda:{local}')
     dist.all_reduce(agg, op=dist.ReduceOp.MAX)
     launches, passes, fused_passes, ex_s, jit_passes = [float(x) for x in agg.tolist()]
+    nex = sk.shard.exchanges - ex0                   # (before the e2e loop below adds its own exchanges)
+    exb = sk.shard.exchanged_bytes - eb0
     norm = sk.norm2()
     # ---- end to end: a fresh |0...0> register, the circuit through the public ShardedKet API with
     #      host matrices, outcome weights of 4 qubits all-reduced and read back to the host ----------
@@ -127,8 +129,6 @@ def run_multi_gpu(args):
     secs = ms_max / 1e3
     raw = ngates * args.steps / secs                 # gates/s on the n-qubit ket
     value = raw * 2.0 ** (n - 30)                    # in units of the single-GPU workload: one gate on 2^30 amplitudes
-    nex = sk.shard.exchanges - ex0
-    exb = sk.shard.exchanged_bytes - eb0
     shard_bytes = 16 << (n - (world.bit_length() - 1))
     # dominant kernel of the local work: one fused sweep = read + write of the shard
     local_s = max(secs - ex_s, 1e-9)
