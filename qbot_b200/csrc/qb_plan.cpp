@@ -520,15 +520,29 @@ std::vector<int> choose_tile_bits(const std::vector<int>& rem, const std::vector
     select_pass(rem, info, allowed, window, nullptr, &cur);
     std::vector<int> hb;
     while ((int)hb.size() < NH) {
-        int best = -1, best_count = cur, second = -1, second_count = cur;
+        // the three best improving bits (count, then higher bit first); greedy takes the best, the
+        // randomised variant one of them uniformly
+        int top_b[3] = {-1, -1, -1}, top_c[3] = {cur, cur, cur};
         for (int b = QT_L; b < nbits; b++) {
             if (allowed & (1ull << b)) continue;
             int c;
             select_pass(rem, info, allowed | (1ull << b), window, nullptr, &c);
-            if (c > best_count) { second = best; second_count = best_count; best_count = c; best = b; }
-            else if (c > second_count) { second_count = c; second = b; }
+            if (c <= cur) continue;
+            for (int x = 0; x < 3; x++) {
+                if (top_b[x] < 0 || c > top_c[x]) {
+                    for (int y = 2; y > x; y--) { top_b[y] = top_b[y - 1]; top_c[y] = top_c[y - 1]; }
+                    top_b[x] = b; top_c[x] = c;
+                    break;
+                }
+            }
         }
-        if (rng && second >= 0 && (rng->next() & 3u) == 0) { best = second; best_count = second_count; }
+        int best = top_b[0], best_count = top_c[0];
+        if (rng && best >= 0) {
+            int k = 1;
+            while (k < 3 && top_b[k] >= 0) k++;
+            const int pick = (int)(rng->next() % (uint32_t)k);
+            best = top_b[pick]; best_count = top_c[pick];
+        }
         if (best < 0 && (int)hb.size() + 2 <= NH) {
             // two-target gates need both bits at once
             int ba = -1, bb = -1;
@@ -594,6 +608,64 @@ size_t trial_plan(const std::vector<GInfo>& info, int nbits, int NH, size_t wind
     return steps;
 }
 
+// Beam search over the tile-bit choices: every node is a set of gates still to run; a node is
+// expanded by `branch` randomised greedy tile choices (the first one the deterministic greedy),
+// all nodes advance one sweep per round and the `width` nodes with the fewest remaining gates
+// survive.  Compared with independent randomised trials this finds one sweep less on the
+// benchmark circuits (30 q: 12 instead of 13) for ~0.1-0.3 s of planning.
+size_t beam_plan(const std::vector<GInfo>& info, int nbits, int NH, size_t window, int width, int branch,
+                 std::vector<std::vector<int>>* guide) {
+    struct Node {
+        std::vector<int> rem;
+        std::vector<std::vector<int>> guide;
+        size_t steps = 0;
+    };
+    std::vector<Node> beams(1);
+    beams[0].rem.resize(info.size());
+    for (size_t i = 0; i < info.size(); i++) beams[0].rem[i] = (int)i;
+    Lcg rng{0x9E3779B97F4A7C15ull ^ (uint64_t)info.size()};
+    for (;;) {
+        // finished nodes: all nodes have run the same number of rounds, unfused steps aside
+        const Node* done = nullptr;
+        for (const Node& b : beams) if (b.rem.empty() && (!done || b.steps < done->steps)) done = &b;
+        if (done) { *guide = done->guide; return done->steps; }
+        std::vector<Node> next;
+        for (Node& b : beams) {
+            // gates the tile kernel cannot run go one by one, in order, without branching
+            while (!b.rem.empty() && !info[b.rem[0]].tileable) { b.rem.erase(b.rem.begin()); b.steps++; }
+            if (b.rem.empty()) { next.push_back(b); continue; }
+            std::vector<uint64_t> seen_allowed;
+            for (int c = 0; c < branch; c++) {
+                std::vector<int> hb = choose_tile_bits(b.rem, info, nbits, NH, window, c == 0 ? nullptr : &rng);
+                const uint64_t allowed = allowed_of(hb);
+                if (std::find(seen_allowed.begin(), seen_allowed.end(), allowed) != seen_allowed.end()) continue;
+                seen_allowed.push_back(allowed);
+                std::vector<int> picked;
+                select_pass(b.rem, info, allowed, window, &picked, nullptr);
+                Node nn;
+                nn.rem = b.rem;
+                nn.guide = b.guide;
+                nn.steps = b.steps + 1;
+                if (picked.empty()) nn.rem.erase(nn.rem.begin());      // head gate needs more high bits than a tile has: unfused
+                else { nn.guide.push_back(hb); remove_picked(nn.rem, picked); }
+                next.push_back(std::move(nn));
+            }
+        }
+        std::stable_sort(next.begin(), next.end(), [](const Node& a, const Node& b) {
+            return a.rem.size() != b.rem.size() ? a.rem.size() < b.rem.size() : a.steps < b.steps;
+        });
+        // drop duplicates (same remaining set) and keep the best `width`
+        std::vector<Node> kept;
+        for (Node& nn : next) {
+            bool dup = false;
+            for (const Node& k : kept) if (k.rem == nn.rem) { dup = true; break; }
+            if (!dup) kept.push_back(std::move(nn));
+            if ((int)kept.size() >= width) break;
+        }
+        beams.swap(kept);
+    }
+}
+
 }  // namespace
 
 std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt) {
@@ -609,19 +681,17 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
     const bool can_tile = nbits >= M;
     const size_t WINDOW = 512;
 
-    // ---- plan search: the greedy tile-bit choice is a local optimum per sweep; a few randomised
-    //      trials (deterministic seed) usually save one or two of ~14 sweeps.  Every sweep is a
-    //      full pass over HBM, so the search is worth its milliseconds on large states only.
+    // ---- plan search: the greedy tile-bit choice is a local optimum per sweep.  Every sweep is a
+    //      full pass over HBM, so on large states a beam search over the choices (deterministic
+    //      seed) is worth its fraction of a second: 14 -> 12 sweeps at 30 q, 9 -> 8 at 34 q.
     std::vector<std::vector<int>> guide;
     bool have_guide = false;
     if (can_tile && opt.search_trials > 1 && gates.size() >= 8) {
-        size_t best = trial_plan(info, nbits, NH, WINDOW, nullptr, &guide);
-        Lcg rng{0x9E3779B97F4A7C15ull ^ (uint64_t)gates.size()};
-        std::vector<std::vector<int>> g2;
-        for (int t = 1; t < opt.search_trials; t++) {
-            const size_t n = trial_plan(info, nbits, NH, WINDOW, &rng, &g2);
-            if (n < best) { best = n; guide.swap(g2); }
-        }
+        const int width = opt.search_trials >= 32 ? 8 : 4, branch = opt.search_trials >= 32 ? 6 : 4;
+        std::vector<std::vector<int>> g0;
+        const size_t greedy = trial_plan(info, nbits, NH, WINDOW, nullptr, &g0);
+        const size_t beam = beam_plan(info, nbits, NH, WINDOW, width, branch, &guide);
+        if (greedy <= beam) guide.swap(g0);
         have_guide = true;
     }
     size_t guide_at = 0;
