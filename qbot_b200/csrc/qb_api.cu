@@ -3,6 +3,7 @@
 #include "qb_common.cuh"
 #include "qb_engine.h"
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <tuple>
 #include "qb_jit_rt.h"
@@ -42,7 +43,7 @@ static int sm_count_of(int dev) {
 
 // Large register buffers are recycled instead of returned to the driver: cudaMalloc / cudaFree of
 // a 16 GiB ket cost tens of milliseconds each, and every executeTxt call creates and drops one
-// register.  At most two buffers per device are kept, each at most a third of the device memory;
+// register.  A few buffers per device are kept, together at most a third of the device memory;
 // an allocation failure empties the cache and retries.
 namespace {
 struct BufCache {
@@ -80,12 +81,13 @@ void work_free(int device, size_t bytes, void* p) {
     const size_t c = work_class(bytes);
     if (c <= (256u << 20)) {
         std::lock_guard<std::mutex> lk(g_bufs.mu);
-        if (g_bufs.small_list.size() < 16) { g_bufs.small_list.emplace_back(device, c, p); return; }
+        if (g_bufs.small_list.size() < 64) { g_bufs.small_list.emplace_back(device, c, p); return; }
     }
     cudaFree(p);
 }
 
 void* cached_alloc(int device, size_t bytes) {
+    if (bytes < kCacheMinBytes) return work_alloc(device, bytes);        // small registers: power-of-two size classes
     {
         std::lock_guard<std::mutex> lk(g_bufs.mu);
         for (size_t i = 0; i < g_bufs.free_list.size(); i++) {
@@ -111,15 +113,35 @@ void* cached_alloc(int device, size_t bytes) {
     return p;
 }
 
+size_t device_total_mem(int device) {           // asked once per device (cudaMemGetInfo is not cheap)
+    static std::mutex mu;
+    static std::map<int, size_t> total;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = total.find(device);
+    if (it != total.end()) return it->second;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); total_b = 0; }
+    total[device] = total_b;
+    return total_b;
+}
+
 void cached_free(int device, size_t bytes, void* p, cudaStream_t stream) {
+    if (bytes < kCacheMinBytes) {
+        if (stream) cudaStreamSynchronize(stream);
+        work_free(device, bytes, p);
+        return;
+    }
     if (bytes >= kCacheMinBytes) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && bytes <= total_b / 3) {
+        const size_t total_b = device_total_mem(device);
+        if (bytes <= total_b / 3) {
             if (stream) cudaStreamSynchronize(stream);            // nothing may still be writing into it
             std::lock_guard<std::mutex> lk(g_bufs.mu);
             int mine = 0;
-            for (auto& b : g_bufs.free_list) if (std::get<0>(b) == device) mine++;
-            if (mine < 2) { g_bufs.free_list.emplace_back(device, bytes, p); return; }
+            size_t held = 0;
+            for (auto& b : g_bufs.free_list) if (std::get<0>(b) == device) { mine++; held += std::get<1>(b); }
+            // a few registers (density-matrix ops create a new one per partial trace / scatter / mix),
+            // never more than a third of the device memory in total
+            if (mine < 8 && held + bytes <= total_b / 3) { g_bufs.free_list.emplace_back(device, bytes, p); return; }
         }
     }
     cudaFree(p);
@@ -129,7 +151,7 @@ void cached_free(int device, size_t bytes, void* p, cudaStream_t stream) {
 qb_state::~qb_state() {
     qb_engine_free(this);
     if (d && owns) { DevGuard g(device); cached_free(device, bytes(), d, stream); }
-    if (scratch) cudaFree(scratch);
+    if (scratch) { DevGuard g(device); cached_free(device, bytes(), scratch, stream); }   // same allocator as `d`: the two may have been swapped
     if (stage) cudaFree(stage);
     if (sm_arrivals) cudaFree(sm_arrivals);
     if (ev0) cudaEventDestroy(ev0);
@@ -160,7 +182,7 @@ static qb_state* new_state(int kind, int nq, int64_t nbranch, int device, void* 
 LaunchCtx qb_state::ctx() { return LaunchCtx{stream, sms, &stats.kernel_launches}; }
 
 cplx* qb_state::get_scratch() {
-    if (!scratch) QB_CUDA(cudaMalloc((void**)&scratch, bytes()));
+    if (!scratch) scratch = (cplx*)cached_alloc(device, bytes());       // interchangeable with `d` (out-of-place gates swap them)
     return scratch;
 }
 

@@ -34,31 +34,64 @@ void qb_launch_fill_basis(const LaunchCtx& c, cplx* d, uint64_t per_branch, int6
     COUNT_LAUNCH(c);
 }
 
-// ket: psi[i] = prod_q v_q[bit_q(i)]   dm: rho[r][c] = prod_q D_q[r_q][c_q]   (qubit 0 first,
-// multiplied left to right like the reference's kron chain, density.py:7-24)
-__global__ void __launch_bounds__(256) k_init_product(cplx* d, int kind, int nq, uint64_t per_branch, uint64_t total,
+// ket: psi[i] = prod_q v_q[bit_q(i)]   dm: rho[r][c] = prod_q D_q[r_q][c_q]   (qubit 0 first; the
+// reference builds these with a kron chain on the host, density.py:7-24).
+// The qubits are cut into groups of up to 8 (ket) / 4 (density matrix) consecutive qubits; a
+// block builds the 256-entry factor table of every group of ITS branch in shared memory (each
+// entry the left-to-right product of the group's factors) and then writes a 2^16-amplitude
+// chunk with one complex multiply per group and amplitude -- the kernel is a pure HBM write
+// instead of nq dependent loads + multiplies per amplitude.
+#define IP_MAXG 5
+#define IP_CHUNK_BITS 16
+__global__ void __launch_bounds__(256) k_init_product(cplx* d, int kind, int nq, int nbits, uint64_t chunks_per_branch,
                                                       const cplx* __restrict__ vecs, int per_branch_vecs) {
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    int per = kind == 0 ? 2 : 4;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        uint64_t b = i / per_branch, l = i % per_branch;
-        const cplx* v = vecs + (per_branch_vecs ? b * (uint64_t)nq * per : 0);
-        cplx acc = make_double2(1.0, 0.0);
-        for (int q = 0; q < nq; q++) {
-            int sel;
-            if (kind == 0) sel = (int)((l >> (nq - 1 - q)) & 1);
-            else sel = (int)((((l >> (2 * nq - 1 - q)) & 1) << 1) | ((l >> (nq - 1 - q)) & 1));
-            cplx f = v[q * per + sel];
-            acc = q == 0 ? f : qb_cmul(acc, f);
+    __shared__ cplx T[IP_MAXG][256];
+    const int per = kind == 0 ? 2 : 4;
+    const int gq = kind == 0 ? 8 : 4;                       // qubits per group
+    const int ng = (nq + gq - 1) / gq;
+    const uint64_t b = blockIdx.x / chunks_per_branch, chunk = blockIdx.x % chunks_per_branch;
+    const cplx* v = vecs + (per_branch_vecs ? b * (uint64_t)nq * per : 0);
+    for (int g = 0; g < ng; g++) {
+        const int q0 = g * gq, len = min(gq, nq - q0);
+        const int entries = kind == 0 ? (1 << len) : (1 << (2 * len));
+        for (int e = threadIdx.x; e < entries; e += blockDim.x) {
+            cplx acc = make_double2(1.0, 0.0);
+            for (int j = 0; j < len; j++) {
+                int sel;
+                if (kind == 0) sel = (e >> (len - 1 - j)) & 1;
+                else sel = (((e >> (2 * len - 1 - j)) & 1) << 1) | ((e >> (len - 1 - j)) & 1);
+                const cplx f = v[(q0 + j) * per + sel];
+                acc = j == 0 ? f : qb_cmul(acc, f);
+            }
+            T[g][e] = acc;
         }
-        d[i] = acc;
+    }
+    __syncthreads();
+    const uint64_t per_branch = 1ull << nbits;
+    const uint64_t lo = chunk << IP_CHUNK_BITS;
+    const uint64_t hi = per_branch < lo + (1ull << IP_CHUNK_BITS) ? per_branch : lo + (1ull << IP_CHUNK_BITS);
+    cplx* out = d + b * per_branch;
+    for (uint64_t l = lo + threadIdx.x; l < hi; l += blockDim.x) {
+        cplx acc;
+        for (int g = 0; g < ng; g++) {
+            const int q0 = g * gq, len = min(gq, nq - q0);
+            unsigned e;
+            if (kind == 0) e = (unsigned)(l >> (nq - q0 - len)) & ((1u << len) - 1u);
+            else e = (((unsigned)(l >> (2 * nq - q0 - len)) & ((1u << len) - 1u)) << len) | ((unsigned)(l >> (nq - q0 - len)) & ((1u << len) - 1u));
+            acc = g == 0 ? T[0][e] : qb_cmul(acc, T[g][e]);
+        }
+        __stcs(out + l, acc);
     }
 }
 
 void qb_launch_init_product(const LaunchCtx& c, cplx* d, int kind, int nq, int64_t nbranch, const cplx* vecs_dev, int per_branch) {
-    uint64_t per = 1ull << (kind == 0 ? nq : 2 * nq);
-    uint64_t total = per * (uint64_t)nbranch;
-    k_init_product<<<grid_for(c, total, 256), 256, 0, c.stream>>>(d, kind, nq, per, total, vecs_dev, per_branch);
+    const int nbits = kind == 0 ? nq : 2 * nq;
+    QB_REQUIRE(nq <= (kind == 0 ? 8 : 4) * IP_MAXG, "init_product: too many qubits");
+    const uint64_t per = 1ull << nbits;
+    const uint64_t chunks = per >> IP_CHUNK_BITS ? per >> IP_CHUNK_BITS : 1;
+    const uint64_t blocks = chunks * (uint64_t)nbranch;
+    QB_REQUIRE(blocks < (1ull << 31), "init_product: state too large");
+    k_init_product<<<(unsigned)blocks, 256, 0, c.stream>>>(d, kind, nq, nbits, chunks, vecs_dev, per_branch);
     COUNT_LAUNCH(c);
 }
 
@@ -504,9 +537,22 @@ __global__ void __launch_bounds__(256) k_mix_branches(const cplx* __restrict__ s
                                                       int64_t nbranch, uint64_t per, cplx* out) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += stride) {
+        // list order, no FMA contraction (bit-identical to the numpy loop); the loads of 8 branches
+        // are in flight at once, only the additions are sequential
         double re = 0.0, im = 0.0;
-        for (int64_t b = 0; b < nbranch; b++) {
-            cplx v = src[(uint64_t)b * per + e];
+        int64_t b = 0;
+        for (; b + 8 <= nbranch; b += 8) {
+            cplx v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = __ldcs(&src[(uint64_t)(b + u) * per + e]);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                re = __dadd_rn(re, __dmul_rn(p[b + u], v[u].x));
+                im = __dadd_rn(im, __dmul_rn(p[b + u], v[u].y));
+            }
+        }
+        for (; b < nbranch; b++) {
+            const cplx v = src[(uint64_t)b * per + e];
             re = __dadd_rn(re, __dmul_rn(p[b], v.x));
             im = __dadd_rn(im, __dmul_rn(p[b], v.y));
         }
