@@ -246,19 +246,33 @@ k_dense_batched(cplx* psi, int nbits, const cplx* __restrict__ mats, const int* 
     const uint64_t nwork = 1ull << (nbits - nins);
     cplx* base_ptr = psi + (b << nbits);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwork; w += stride) {
-        uint64_t base = w;
-        for (int i = 0; i < nins; i++) base = qb_insert_zero(base, s_ins[i]);
-        base |= cmask;
-        cplx x[D];
+    // U independent work items per iteration: all their loads are issued before the first multiply
+    // (one block walks a whole branch, so memory-level parallelism has to come from the thread)
+    constexpr int U = K == 1 ? 4 : K == 2 ? 2 : 1;
+    for (uint64_t w0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w0 < nwork; w0 += stride * U) {
+        uint64_t base[U];
+        cplx x[U][D];
 #pragma unroll
-        for (int j = 0; j < D; j++) x[j] = base_ptr[base | sub_offset<K>(j, tbm)];
+        for (int u = 0; u < U; u++) {
+            const uint64_t w = w0 + (uint64_t)u * stride;
+            uint64_t bs = w;
+            for (int i = 0; i < nins; i++) bs = qb_insert_zero(bs, s_ins[i]);
+            base[u] = bs | cmask;
+            if (w < nwork) {
+#pragma unroll
+                for (int j = 0; j < D; j++) x[u][j] = __ldcs(&base_ptr[base[u] | sub_offset<K>(j, tbm)]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (w0 + (uint64_t)u * stride >= nwork) continue;
 #pragma unroll(K <= 2 ? D : 1)
-        for (int i = 0; i < D; i++) {
-            cplx acc = qb_cmul(sm[i * D], x[0]);
+            for (int i = 0; i < D; i++) {
+                cplx acc = qb_cmul(sm[i * D], x[u][0]);
 #pragma unroll
-            for (int j = 1; j < D; j++) acc = qb_cfma(sm[i * D + j], x[j], acc);
-            base_ptr[base | sub_offset<K>(i, tbm)] = acc;
+                for (int j = 1; j < D; j++) acc = qb_cfma(sm[i * D + j], x[u][j], acc);
+                __stcs(&base_ptr[base[u] | sub_offset<K>(i, tbm)], acc);
+            }
         }
     }
 }

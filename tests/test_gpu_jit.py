@@ -134,3 +134,24 @@ def test_jit_density_and_batch(DS, jit_R):
         refs.append(r)
     assert close(np.asarray(bs), np.stack(refs), 1e-12)
     assert bs.stats()['jit_passes'] > 0
+
+
+def test_jit_large_coefficient_pool(DS, jit_R):
+    """a sweep with more run-time coefficients than fit the kernel-parameter struct (> 480
+    doubles: ~60 general 2x2 gates) reads them from a device array instead"""
+    rng = np.random.default_rng(31)
+    n = 13
+    psi = rand_ket(rng, n)
+    st = DS.from_host(psi)
+    st.set_jit(2)
+    gl = []
+    for i in range(62):
+        gl.append((rand_u(rng, 1), [int(rng.integers(0, 12))], 0))
+    for m, tb, cm in gl:
+        st.apply_gate_bits(m, tb, cm)
+    got = np.asarray(st)
+    assert st.stats()['jit_passes'] >= 1
+    ref = psi
+    for m, tb, cm in gl:
+        ref = oracle_apply_bits(ref, n, m, tb, cm)
+    assert close(got, ref, 1e-12)
