@@ -687,7 +687,8 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
     std::vector<std::vector<int>> guide;
     bool have_guide = false;
     if (can_tile && opt.search_trials > 1 && gates.size() >= 8) {
-        const int width = opt.search_trials >= 32 ? 8 : 4, branch = opt.search_trials >= 32 ? 6 : 4;
+        const int width = opt.search_trials >= 128 ? 24 : opt.search_trials >= 32 ? 8 : 4;
+        const int branch = opt.search_trials >= 128 ? 10 : opt.search_trials >= 32 ? 6 : 4;
         std::vector<std::vector<int>> g0;
         const size_t greedy = trial_plan(info, nbits, NH, WINDOW, nullptr, &g0);
         const size_t beam = beam_plan(info, nbits, NH, WINDOW, width, branch, &guide);
