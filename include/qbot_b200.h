@@ -89,6 +89,12 @@ int qb_download_range(qb_state* s, uint64_t first_amp, uint64_t count, void* hos
  * to target_bits when every bit of control_mask is 1.  target_bits[0] carries the matrix's
  * most significant index bit.  Gates are queued and fused; qb_flush drains the queue. */
 int qb_apply_gate(qb_state* s, const double* matrix, int k, const int* target_bits, uint64_t control_mask);
+/* A whole gate list in one call (same semantics as `ngates` calls of qb_apply_gate, in order):
+ * ks[g], target_bits[g*14 .. g*14+ks[g]-1] (14 = the largest gate), control_masks[g], matrices back to
+ * back (4^ks[g] complex each).  For hosts whose per-call overhead matters (a 20-qubit circuit of
+ * 2913 gates is bound by ~4 us of Python per qb_apply_gate call). */
+int qb_apply_gates(qb_state* s, int ngates, const int* ks, const int* target_bits, const uint64_t* control_masks,
+                   const double* matrices);
 /* replaces genSwapGate (qgates.py:77-133) + applyGate as used by operators._swap / swap (364-393) */
 int qb_apply_swap(qb_state* s, int bit_a, int bit_b);
 /* piece (5): one launch over all branches, each with its own gate (probVal.funcWrapper loop,

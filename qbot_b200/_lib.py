@@ -48,6 +48,7 @@ PROTOTYPES = {
     'qb_download': (C.c_int, [c_state_p, C.c_void_p, C.c_size_t]),
     'qb_download_range': (C.c_int, [c_state_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     'qb_apply_gate': (C.c_int, [c_state_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_uint64]),
+    'qb_apply_gates': (C.c_int, [c_state_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.c_void_p]),
     'qb_apply_swap': (C.c_int, [c_state_p, C.c_int, C.c_int]),
     'qb_apply_gate_batched': (C.c_int, [c_state_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.c_void_p]),
     'qb_flush': (C.c_int, [c_state_p]),

@@ -23,6 +23,11 @@ static thread_local std::string g_err;
     catch (const std::exception& e) { g_err = e.what(); return QB_ERR_ARG; }                   \
     catch (...) { g_err = "unknown error"; return QB_ERR_ARG; }
 
+#define QB_REQUIRE_API(cond)                                                                   \
+    do {                                                                                       \
+        if (!(cond)) { g_err = "bad argument: " #cond; return QB_ERR_ARG; }                    \
+    } while (0)
+
 static inline cplx C(double re, double im) { return make_double2(re, im); }
 #include "qb_plan.h"
 
@@ -478,6 +483,19 @@ int qb_apply_gate(qb_state* s, const double* matrix, int k, const int* target_bi
         s->enqueue(qb_classify(mc.data(), k, target_bits, control_mask));
     }
     QB_API_END
+}
+
+int qb_apply_gates(qb_state* s, int ngates, const int* ks, const int* target_bits, const uint64_t* control_masks,
+                   const double* matrices) {
+    QB_REQUIRE_API(s && ks && target_bits && control_masks && matrices && ngates >= 0);
+    size_t moff = 0;
+    for (int g = 0; g < ngates; g++) {
+        if (ks[g] < 1 || ks[g] > QB_BIG_MAXK) { g_err = "gate size out of range"; return QB_ERR_ARG; }
+        const int rc = qb_apply_gate(s, matrices + moff, ks[g], target_bits + (size_t)g * QB_BIG_MAXK, control_masks[g]);
+        if (rc != QB_OK) return rc;
+        moff += 2 * ((size_t)1 << (2 * ks[g]));
+    }
+    return QB_OK;
 }
 
 int qb_apply_swap(qb_state* s, int bit_a, int bit_b) {

@@ -219,6 +219,38 @@ class DeviceState:
         self._dirty()
         return self
 
+    @staticmethod
+    def pack_circuit(nq: int, items) -> tuple:
+        """items: [(matrix, first_target, controls)] in reference qubit numbering -> the argument
+        block of qb_apply_gates (build it once for a circuit that is applied repeatedly)."""
+        n = len(items)
+        ks = (C.c_int * max(n, 1))()
+        tbs = (C.c_int * (14 * max(n, 1)))()
+        cms = (C.c_uint64 * max(n, 1))()
+        mats = []
+        for i, (m, t, controls) in enumerate(items):
+            m = np.ascontiguousarray(np.asarray(m, dtype=np.complex128))
+            k = int(m.shape[0]).bit_length() - 1
+            if t < 0 or t + k - 1 >= nq:
+                raise IndexError(f"{k} qubit gate does not fit the {nq} qubit hilbertspace when started on qubit {t}")
+            ks[i] = k
+            for j in range(k):
+                tbs[14 * i + j] = nq - 1 - (t + j)
+            cm = 0
+            for c in controls:
+                cm |= 1 << (nq - 1 - int(c))
+            cms[i] = cm
+            mats.append(m.reshape(-1))
+        allm = np.ascontiguousarray(np.concatenate(mats)) if mats else np.zeros(1, dtype=np.complex128)
+        return n, ks, tbs, cms, allm
+
+    def apply_circuit(self, packed) -> "DeviceState":
+        """Queue a whole packed circuit with ONE call into the library (qb_apply_gates)."""
+        n, ks, tbs, cms, allm = packed
+        _lib.call('qb_apply_gates', self._h, n, ks, tbs, cms, _cptr(allm))
+        self._dirty()
+        return self
+
     def apply_swap(self, qubit_a: int, qubit_b: int) -> "DeviceState":
         _lib.call('qb_apply_swap', self._h, self._bit(qubit_a), self._bit(qubit_b))
         self._dirty()

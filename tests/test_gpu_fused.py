@@ -94,3 +94,18 @@ def test_plan_cache_replay(DS):
             psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
         st.flush()
     assert close(np.asarray(st), psi, 1e-12)
+
+
+def test_apply_circuit_equals_per_gate_calls(DS):
+    """qb_apply_gates (one call for a whole gate list) == the same gates through qb_apply_gate"""
+    from qbot_b200.circuits import rc
+    n = 14
+    gates = rc(n, 10, 77)
+    items = [(g.matrix(), g.target, g.controls) for g in gates]
+    a, b = DS.zero_state(n), DS.zero_state(n)
+    a.apply_circuit(DS.pack_circuit(n, items))
+    for m, t, c in items:
+        b.apply_gate(m, t, c)
+    assert np.array_equal(np.asarray(a), np.asarray(b))
+    with pytest.raises(IndexError):
+        DS.pack_circuit(n, [(np.eye(4), n - 1, [])])
