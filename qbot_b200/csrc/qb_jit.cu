@@ -40,44 +40,64 @@ const char* kPrelude = R"QJ(
 #endif
 #define QJ_RESTRICT __restrict__
 #define QJ_SYNC() __syncthreads()
-// one mbarrier per CTA counts the bytes of the next tile's bulk copies
-__device__ __forceinline__ unsigned qj_mbar() {
-    __shared__ __align__(8) unsigned long long bar;
-    return (unsigned)__cvta_generic_to_shared(&bar);
+// two mbarriers per CTA count the bytes of the next tile's bulk copies: [0] the early half (landing
+// buffer behind the transposition buffer), [1] the late half (transposition buffer)
+__device__ __forceinline__ unsigned qj_mbar(const int which) {
+    __shared__ __align__(8) unsigned long long bar[2];
+    return (unsigned)__cvta_generic_to_shared(&bar[which]);
 }
 #define QJ_MBAR_INIT()                                                                             \
     do {                                                                                           \
         if (threadIdx.x == 0) {                                                                    \
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(qj_mbar()) : "memory");  \
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(qj_mbar(0)) : "memory"); \
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(qj_mbar(1)) : "memory"); \
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                     \
         }                                                                                          \
         __syncthreads();                                                                           \
     } while (0)
-#define QJ_BULK_COPY(sdst, gsrc)                                                                   \
+#define QJ_BULK_COPY_TO(sdst, gsrc, which)                                                         \
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];" ::"r"( \
-                     (unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(qj_mbar()) : "memory")
-#ifdef QJ_DEBUG_NOWAIT
-#define QJ_ASYNC_WAIT(parity)
-#else
-#define QJ_ASYNC_WAIT(parity)                                                                      \
+                     (unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(qj_mbar(which)) : "memory")
+#define QJ_BULK_COPY_EARLY(sdst, gsrc) QJ_BULK_COPY_TO(sdst, gsrc, 0)
+#define QJ_BULK_COPY(sdst, gsrc) QJ_BULK_COPY_TO(sdst, gsrc, 1)
+#define QJ_MBAR_WAIT(which, parity)                                                                \
     do {                                                                                           \
         unsigned done_;                                                                            \
         do {                                                                                       \
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" \
-                         : "=r"(done_) : "r"(qj_mbar()), "r"(parity) : "memory");                  \
+                         : "=r"(done_) : "r"(qj_mbar(which)), "r"(parity) : "memory");             \
         } while (!done_);                                                                          \
     } while (0)
-#endif
-// every thread of the CTA has read its amplitudes out of the buffer (barrier); order those generic
-// reads before the TMA's writes (proxy fence); one thread announces the byte count
+#define QJ_ASYNC_WAIT(parity)                                                                      \
+    do {                                                                                           \
+        QJ_MBAR_WAIT(0, parity);                                                                   \
+        QJ_MBAR_WAIT(1, parity);                                                                   \
+    } while (0)
+#define QJ_EXPECT(which)                                                                           \
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qj_mbar(which)), "r"(QJ_HALF_RUNS * 512) : "memory")
+// early half: issued right after the first barrier of a tile (everybody has read the landing buffer)
+#define QJ_ISSUE_EARLY(tid, nbase, psi, buf)                                                       \
+    do {                                                                                           \
+        if (nbase != ~0ull) {                                                                      \
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                           \
+            if (tid == 0) QJ_EXPECT(0);                                                            \
+            qj_issue_early(tid, nbase, psi, buf + QJ_TILE_UNITS);                                  \
+        }                                                                                          \
+    } while (0)
+// late half: every thread of the CTA has read its amplitudes out of the transposition buffer
+// (barrier); order those generic reads before the TMA's writes (proxy fence).  A one-stage sweep
+// has no earlier barrier, so its early half goes out here too.
 #define QJ_ISSUE_NEXT(tid, nbase, psi, buf)                                                        \
     do {                                                                                           \
         __syncthreads();                                                                           \
         if (nbase != ~0ull) {                                                                      \
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                           \
-            if (tid == 0)                                                                          \
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qj_mbar()), "r"(QJ_RUNS * 512) : "memory"); \
+            if (tid == 0) QJ_EXPECT(1);                                                            \
             qj_issue_next(tid, nbase, psi, buf);                                                   \
+            if (!QJ_NSTAGES_GT1) {                                                                 \
+                if (tid == 0) QJ_EXPECT(0);                                                        \
+                qj_issue_early(tid, nbase, psi, buf + QJ_TILE_UNITS);                              \
+            }                                                                                      \
         }                                                                                          \
     } while (0)
 #ifdef QJ_POOL_GLOBAL
@@ -393,7 +413,7 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
         if (e != CUDA_SUCCESS) throw qb_error(-2, "cuModuleLoadData: " + cu_err(e));
         e = d.ModuleGetFunction(&fn, mod, "qj_kernel");
         if (e != CUDA_SUCCESS) throw qb_error(-2, "cuModuleGetFunction: " + cu_err(e));
-        const int smem = c.info.tile_units * 16;
+        const int smem = c.info.tile_units * 16 + (8 << c.info.M);      // transposition buffer + landing buffer of half a tile
         e = d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
         if (e != CUDA_SUCCESS) throw qb_error(-2, "cuFuncSetAttribute(smem): " + cu_err(e));
         d.FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT, 100);
@@ -402,7 +422,7 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
     QbJitKernel k;
     k.fn = (void*)dv->second.second;
     k.threads = c.info.threads;
-    k.smem_bytes = c.info.tile_units * 16;
+    k.smem_bytes = c.info.tile_units * 16 + (8 << c.info.M);
     k.npool = c.info.npool;
     k.pool_global = c.pool_global;
     k.ctas_per_sm = jit_ctas_override(c.info.M) ? jit_ctas_override(c.info.M) : qj_default_ctas(c.info.M, c.info.R);

@@ -310,13 +310,27 @@ struct Gen {
     // arithmetic overlaps the stores and the L2 prefetch perfectly but ADDS to the load time).
     // Bulk copies occupy no LSU slot and no register; stage 0 of the next tile waits on the
     // mbarrier and reads its amplitudes out of the buffer like after any transposition.
+    // run-index bit that splits the next tile into an EARLY half (landing buffer behind the
+    // transposition buffer, fetched a whole tile ahead) and a LATE half (into the transposition
+    // buffer once the last stage has emptied it): the run bit of stage 0's highest register bit,
+    // so that which half a register comes from is known at generation time
+    int early_bit() const { return stages[0].rb[R - 1] - QT_L; }
+    static unsigned squeeze(unsigned k, int eb) { return (k & ((1u << eb) - 1u)) | ((k >> (eb + 1)) << eb); }
+
     void emit_issue_next() {
-        o.f("#define QJ_RUNS %d\n", 1 << NH);
+        const int eb = early_bit();
+        o.f("#define QJ_RUNS %d\n#define QJ_HALF_RUNS %d\n", 1 << NH, 1 << (NH - 1));
+        // k' enumerates the runs of one half; the full run index gets a 0 (early) / 1 (late) at bit eb
+        o.f("QJ_DEV void qj_issue_early(const unsigned tid, const unsigned long long nbase, QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT inb) {\n");
+        o.f("    if (nbase == ~0ull) return;\n");
+        o.f("    for (unsigned kp = tid; kp < QJ_HALF_RUNS; kp += QJ_T) {\n");
+        o.f("        const unsigned k = (kp & 0x%xu) | ((kp >> %d) << %d);\n", (1u << eb) - 1u, eb, eb + 1);
+        o.f("        QJ_BULK_COPY_EARLY(inb + 32u * kp, psi + (nbase + qj_run_offset(k)));\n    }\n}\n\n");
         o.f("QJ_DEV void qj_issue_next(const unsigned tid, const unsigned long long nbase, QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT buf) {\n");
         o.f("    if (nbase == ~0ull) return;\n");
-        o.f("    for (unsigned k = tid; k < QJ_RUNS; k += QJ_T)\n");
-        o.f("        QJ_BULK_COPY(buf + (32u * k + k + (k >> 3) + (k >> 6)), psi + (nbase + qj_run_offset(k)));\n");
-        o.f("}\n\n");
+        o.f("    for (unsigned kp = tid; kp < QJ_HALF_RUNS; kp += QJ_T) {\n");
+        o.f("        const unsigned k = (kp & 0x%xu) | ((kp >> %d) << %d) | 0x%xu;\n", (1u << eb) - 1u, eb, eb + 1, 1u << eb);
+        o.f("        QJ_BULK_COPY(buf + (32u * k + k + (k >> 3) + (k >> 6)), psi + (nbase + qj_run_offset(k)));\n    }\n}\n\n");
     }
 
     void emit_stage(int s) {
@@ -341,8 +355,21 @@ struct Gen {
         if (first) {
             // the tile is already in the buffer (bulk copies issued during the previous tile; pre - 1 is the
             // mbarrier phase parity to wait for), or comes straight from HBM (first tile of the CTA)
+            // registers whose top register bit is 0 belong to the early half (landing buffer, runs stored
+            // back to back in squeezed run order), the others to the late half (transposition buffer)
+            const int eb = early_bit();
             o.f("    if (pre) {\n        QJ_ASYNC_WAIT(pre - 1u);\n");
-            for (int i = 0; i < NR; i++) o.f("        a%d = sp[%u];\n", i, smem_reg_offset(st, i));
+            o.f("        const unsigned kb = lb >> %d;\n", QT_L);
+            o.f("        const QJ_C* const ip = buf + QJ_TILE_UNITS + 32u * ((kb & 0x%xu) | ((kb >> %d) << %d)) + (lb & 31u);\n",
+                (1u << eb) - 1u, eb + 1, eb);
+            for (int i = 0; i < NR; i++) {
+                if ((i >> (R - 1)) & 1) o.f("        a%d = sp[%u];\n", i, smem_reg_offset(st, i));
+                else {
+                    unsigned rr = 0;
+                    for (int q = 0; q < R; q++) if ((i >> q) & 1) rr |= 1u << (st.rb[q] - QT_L);
+                    o.f("        a%d = ip[%u];\n", i, 32u * squeeze(rr, eb));
+                }
+            }
             o.f("    } else {\n");
             for (int i = 0; i < NR; i++) o.f("        a%d = QJ_LD(gp + 0x%llxull);\n", i, (unsigned long long)hbm_reg_offset(st, i));
             o.f("    }\n    QJ_PREFETCH(psi, pfbase, tid);\n");
@@ -414,6 +441,7 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     o.f("// generated by qbot_b200 qj_generate: M=%d R=%d stages=%d ops=%d gates=%d\n", g.M, g.R, (int)g.h->nstages, (int)g.h->nops, (int)g.h->ngates);
     o.f("#define QJ_M %d\n#define QJ_T %d\n#define QJ_NH %d\n#define QJ_NP %d\n#define QJ_NSTAGES %d\n", g.M, g.T, g.NH, npool, (int)g.h->nstages);
     o.f("#define QJ_TILE_UNITS %d\n#ifndef QJ_CTAS\n#define QJ_CTAS %d\n#endif\n", QT_TILE_UNITS(g.M), qj_default_ctas(g.M, g.R));
+    o.f("#define QJ_NSTAGES_GT1 %d\n", g.h->nstages > 1 ? 1 : 0);
     o.f("QJ_PRELUDE\n\n");
     // tile base: the tile number's bits deposited into the positions outside the tile
     o.f("QJ_DEV unsigned long long qj_tile_base(const unsigned long long t) {\n    unsigned long long b = t << %d;\n", QT_L);
@@ -430,9 +458,12 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     }
     g.emit_issue_next();
     for (int s = 0; s < g.h->nstages; s++) g.emit_stage(s);
+    // after the first barrier of a tile nobody reads the landing buffer any more: the early half of
+    // the NEXT tile starts to arrive while stages 1.. of this tile run
     o.f("#define QJ_RUN_STAGES(tid, tbase, nbase, pfbase, pre, psi, buf, P) \\\n");
     for (int s = 0; s < g.h->nstages; s++) {
         if (s) o.f("    QJ_SYNC(); \\\n");
+        if (s == 1) o.f("    QJ_ISSUE_EARLY(tid, nbase, psi, buf); \\\n");
         o.f("    qj_stage%d(tid, tbase, nbase, pfbase, pre, psi, buf, P); \\\n", s);
     }
     o.f("\n");

@@ -15,6 +15,8 @@ struct QjC { double x, y; };
 #define QJ_RESTRICT
 #define QJ_SYNC()
 #define QJ_BULK_COPY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
+#define QJ_BULK_COPY_EARLY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
+#define QJ_ISSUE_EARLY(tid, nbase, psi, buf)     /* the harness runs qj_issue_early at the end of the tile */
 #define QJ_ASYNC_WAIT(parity)
 #define QJ_ISSUE_NEXT(tid, nbase, psi, buf)      /* the harness runs qj_issue_next after the last stage (the kernel's barrier) */
 #define QJ_PREFETCH(psi, nbase, tid)
@@ -24,7 +26,7 @@ struct QjC { double x, y; };
 #define QJ_CPU_HARNESS(NAME)                                                                         \
     extern "C" void NAME(QjC* psi, int nbits, const double* pool) {                                  \
         const unsigned long long ntiles = 1ull << (nbits - QJ_M);                                    \
-        std::vector<QjC> buf(QJ_TILE_UNITS);                                                         \
+        std::vector<QjC> buf(QJ_TILE_UNITS + 32 * QJ_HALF_RUNS);   /* transposition + landing buffer */ \
         /* one "CTA" walks all tiles: the first tile comes from HBM, every later one through the    \
            asynchronous copies its predecessor's last stage issued into the buffer */               \
         for (unsigned long long t = 0; t < ntiles; t++) {                                            \
@@ -33,5 +35,6 @@ struct QjC { double x, y; };
             for (int s = 0; s < QJ_NSTAGES; s++)                                                     \
                 for (unsigned tid = 0; tid < QJ_T; tid++) qj_stage(s, tid, tbase, nbase, t > 0, psi, buf.data(), pool); \
             for (unsigned tid = 0; tid < QJ_T; tid++) qj_issue_next(tid, nbase, psi, buf.data());    \
+            for (unsigned tid = 0; tid < QJ_T; tid++) qj_issue_early(tid, nbase, psi, buf.data() + QJ_TILE_UNITS); \
         }                                                                                            \
     }
