@@ -156,9 +156,21 @@ struct Gen {
     }
 
     bool pool_is_one(uint32_t p) const { return pool[p] == 1.0 && pool[p + 1] == 0.0; }
+    bool pool_is_minus_one(uint32_t p) const { return pool[p] == -1.0 && pool[p + 1] == 0.0; }
+    void negate(const std::string& a) { o.f("      %s.x = -%s.x; %s.y = -%s.y;\n", a.c_str(), a.c_str(), a.c_str(), a.c_str()); }
 
     void op_cdiag(const QtOp& op) {
         const uint32_t p = op.pool;
+        // exact +1 / -1 factors are structural (part of the source text): controlled-Z and the like cost
+        // a sign flip per touched amplitude instead of a complex multiply
+        const bool z_like = pool_is_one(p) && pool_is_minus_one(p + 2);
+        if (z_like && op.t1 != QT_LOC_REG) {
+            if (op.t1 == QT_LOC_LOCAL) o.f("    if ((lb >> %d) & 1u) {\n", (int)op.t0);
+            else o.f("    if ((tbase >> %d) & 1ull) {\n", (int)op.t0);
+            for (int i = 0; i < NR; i++) if ((op.regsel >> i) & 1u) negate(nm[i]);
+            o.f("    }\n");
+            return;
+        }
         if (op.t1 == QT_LOC_REG) {
             const bool one0 = pool_is_one(p), one1 = pool_is_one(p + 2);
             o.f("    { const double d0r = %s, d0i = %s, d1r = %s, d1i = %s;\n", P(p).c_str(), P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str());
@@ -166,6 +178,7 @@ struct Gen {
                 if (!((op.regsel >> i) & 1u)) continue;
                 const bool hi = (i >> op.t0) & 1;
                 if (hi ? one1 : one0) continue;          // exact unit factor: structural, part of the source text
+                if (pool_is_minus_one(hi ? p + 2 : p)) { negate(nm[i]); continue; }
                 o.f("  ");
                 cmul_into(nm[i], hi ? "d1r" : "d0r", hi ? "d1i" : "d0i");
             }

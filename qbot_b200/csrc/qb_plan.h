@@ -130,3 +130,6 @@ struct QtPlanOptions {
 // Plan the execution of `gates` (in order) on a state with `nbits` index bits per branch.
 // Every gate appears in exactly one step; the order of non-commuting gates is preserved.
 std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt);
+
+// Unitary-preserving rewrite of a gate list into a cheaper one (see qb_plan.cpp); plan the result.
+std::vector<QGate> qt_peephole(const std::vector<QGate>& gates, int* rewritten);

@@ -173,6 +173,7 @@ struct CachedPlan {
     size_t ngates = 0;
     int nbits = 0;
     int R = QT_R;                      // register bits per stage the plan was built for (5: specialised kernels only)
+    std::vector<QGate> gates;          // the gate list the plan was built from (after the peephole rewrite)
     uint64_t uses = 0;
     bool upgrade_failed = false;       // building / compiling the 32-amplitudes-per-thread variant failed once
     std::vector<QtPlanStep> steps;
@@ -328,7 +329,8 @@ CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gat
     // plan search effort grows with the cost of a sweep (env QBOT_B200_PLAN_TRIALS overrides)
     const int total_bits = s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0);
     opt.search_trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);
-    cp.steps = qt_plan(gates, s->nbits, opt);
+    cp.gates = getenv("QBOT_B200_NO_PEEPHOLE") ? gates : qt_peephole(gates, nullptr);
+    cp.steps = qt_plan(cp.gates, s->nbits, opt);
     size_t total = 0;
     cp.prog_off.resize(cp.steps.size(), 0);
     for (size_t i = 0; i < cp.steps.size(); i++) {
@@ -408,7 +410,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
     for (size_t i = 0; i < plan->steps.size(); i++) {
         const QtPlanStep& st = plan->steps[i];
         if (!st.fused) {
-            s->run_gate_unfused(gates[st.gate_index]);
+            s->run_gate_unfused(plan->gates[st.gate_index]);
             continue;
         }
         if (jit_mode != 0 && step_jit(s, plan, i, jit_mode)) {

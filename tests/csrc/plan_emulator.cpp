@@ -99,6 +99,7 @@ int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t
         opt.M = M;
         opt.merge_phases = merge != 0;
         if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
+        if (!getenv("QBOT_B200_NO_PEEPHOLE")) gates = qt_peephole(gates, nullptr);      // as the engine does
         std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
         long long st[7] = {0, 0, 0, 0, 0, 0, 0};
         int covered = 0;
@@ -144,6 +145,7 @@ int qbt_plan(int nbits, int ngates, const int* ks, const int* tbs, const uint64_
         opt.merge_phases = merge != 0;
         if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
         if (const char* e = getenv("QBOT_B200_PLAN_R")) opt.R = atoi(e);
+        if (!getenv("QBOT_B200_NO_PEEPHOLE")) gates = qt_peephole(gates, nullptr);
         std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
         if ((int)steps.size() > max_steps) { g_err = "too many steps"; return -1; }
         long long at = 0;

@@ -172,5 +172,44 @@ def test_plan_search_never_worse_and_still_correct(monkeypatch):
         _, a = plan_emu.run(nn, gl, None, execute=False)
         monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '32')          # the engine's setting for states of >= 27 index bits
         _, b = plan_emu.run(nn, gl, None, execute=False)
-        assert b['fused_sweeps'] < a['fused_sweeps'], (a, b)
+        assert b['fused_sweeps'] <= a['fused_sweeps'], (a, b)
         assert b['fused_sweeps'] <= (12 if nn == 30 else 8)
+
+
+def test_peephole_rewrite_preserves_the_state(monkeypatch):
+    """X (any controls) followed by H on its target is rewritten to H followed by a controlled Z
+    (H X = Z H): same state, the diagonal gate needs no tile bit and costs a sign flip"""
+    rng = np.random.default_rng(9)
+    n = 13
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    H = np.array([[1, 1], [1, -1]], dtype=complex) * 2 ** -0.5
+    gl = []
+    for _ in range(60):
+        bits = [int(b) for b in rng.permutation(n)]
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            gl.append((X, bits[:1], sum(1 << c for c in bits[1:1 + int(rng.integers(0, 3))])))
+            if rng.random() < 0.7:          # something harmless in between, then the Hadamard on the target
+                gl.append((np.diag(np.exp(1j * rng.uniform(0, 6, 2))), [bits[4]], 0))
+                gl.append((H, bits[:1], 0))
+        elif kind == 1:
+            gl.append((H, bits[:1], 0))
+        elif kind == 2:
+            gl.append((np.diag(np.exp(1j * rng.uniform(0, 6, 2))), bits[:1], 0))
+        elif kind == 3:
+            gl.append((X, bits[:1], 1 << bits[1]))
+            gl.append((H, [bits[1]], 0))      # Hadamard on the CONTROL: blocks the rewrite across it
+            gl.append((H, bits[:1], 0))
+        else:
+            gl.append((rand_u(rng, 1), bits[:1], 1 << bits[2]))
+    psi = rand_ket(rng, n)
+    ref = psi
+    for m, tb, cm in gl:
+        ref = oracle_apply_bits(ref, n, m, tb, cm)
+    monkeypatch.delenv('QBOT_B200_NO_PEEPHOLE', raising=False)
+    out, st = plan_emu.run(n, gl, psi)
+    assert close(out, ref, 1e-12)
+    monkeypatch.setenv('QBOT_B200_NO_PEEPHOLE', '1')
+    out2, st2 = plan_emu.run(n, gl, psi)
+    assert close(out2, ref, 1e-12)
+    assert st['fused_gates'] == st2['fused_gates'] == len(gl)
