@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -613,33 +614,13 @@ void remove_picked(std::vector<int>& rem, const std::vector<int>& picked) {
     rem.swap(next);
 }
 
-// one trial of the plan search: tile bits of every fused sweep, without building programs
-// (returns the number of steps)
-size_t trial_plan(const std::vector<GInfo>& info, int nbits, int NH, size_t window, Lcg* rng, std::vector<std::vector<int>>* guide) {
-    std::vector<int> rem(info.size());
-    for (size_t i = 0; i < info.size(); i++) rem[i] = (int)i;
-    size_t steps = 0;
-    guide->clear();
-    while (!rem.empty()) {
-        steps++;
-        if (!info[rem[0]].tileable) { rem.erase(rem.begin()); continue; }
-        std::vector<int> hb = choose_tile_bits(rem, info, nbits, NH, window, rng);
-        std::vector<int> picked;
-        select_pass(rem, info, allowed_of(hb), window, &picked, nullptr);
-        if (picked.empty()) { rem.erase(rem.begin()); continue; }
-        guide->push_back(hb);
-        remove_picked(rem, picked);
-    }
-    return steps;
-}
-
 // Beam search over the tile-bit choices: every node is a set of gates still to run; a node is
 // expanded by `branch` randomised greedy tile choices (the first one the deterministic greedy),
 // all nodes advance one sweep per round and the `width` nodes with the fewest remaining gates
 // survive.  Compared with independent randomised trials this finds one sweep less on the
 // benchmark circuits (30 q: 12 instead of 13) for ~0.1-0.3 s of planning.
 size_t beam_plan(const std::vector<GInfo>& info, int nbits, int NH, size_t window, int width, int branch,
-                 std::vector<std::vector<int>>* guide) {
+                 std::vector<std::vector<std::vector<int>>>* guides) {
     struct Node {
         std::vector<int> rem;
         std::vector<std::vector<int>> guide;
@@ -653,7 +634,11 @@ size_t beam_plan(const std::vector<GInfo>& info, int nbits, int NH, size_t windo
         // finished nodes: all nodes have run the same number of rounds, unfused steps aside
         const Node* done = nullptr;
         for (const Node& b : beams) if (b.rem.empty() && (!done || b.steps < done->steps)) done = &b;
-        if (done) { *guide = done->guide; return done->steps; }
+        if (done) {
+            guides->clear();
+            for (const Node& b : beams) if (b.rem.empty() && b.steps == done->steps) guides->push_back(b.guide);
+            return done->steps;
+        }
         std::vector<Node> next;
         for (Node& b : beams) {
             // gates the tile kernel cannot run go one by one, in order, without branching
@@ -695,15 +680,17 @@ size_t beam_plan(const std::vector<GInfo>& info, int nbits, int NH, size_t windo
 
 // Peephole rewrite of the queued gate list (same unitary, cheaper gates):
 //   X_t (any controls C) ... H_t   ==   ... H_t  Z_t (controls C)       because  H X = Z H
+//   H_t ... X_t (controls C)       ==   Z_t (controls C)  H_t ...       because  X H = H Z
 // when nothing between the two touches t and nothing acts non-diagonally on a control in C.
 // The controlled X would need its target bit inside the tile and costs a (predicated) exchange of
 // half of every thread's amplitudes; the controlled Z is diagonal -- a free rider on any sweep,
 // wherever its bits live, costing one negation per touched amplitude.  In the random benchmark
-// circuits a third of the CNOT / Toffoli gates are followed by a Hadamard on their target.
-std::vector<QGate> qt_peephole(const std::vector<QGate>& in, int* rewritten) {
+// circuits more than half of the CNOT / Toffoli gates have a Hadamard next to them on their target.
+std::vector<QGate> qt_peephole(const std::vector<QGate>& in, int level, int* rewritten) {
     std::vector<QGate> g = in;
     int count = 0;
     const size_t LOOKAHEAD = 512;
+    if (level <= 0) { if (rewritten) *rewritten = 0; return g; }
     for (size_t i = 0; i < g.size(); i++) {
         if (!is_pauli_x(g[i])) continue;
         const int t = g[i].tb[0];
@@ -733,39 +720,56 @@ std::vector<QGate> qt_peephole(const std::vector<QGate>& in, int* rewritten) {
         count++;
         i--;                                        // re-examine the gate that moved into slot i
     }
+    // the mirror image:  H_t ... X_t (controls C)   ==   Z_t (controls C) H_t ...   (X H = H Z read
+    // the other way round), for the X gates the forward rule left
+    const bool backward = level >= 2;
+    for (size_t i = 0; backward && i < g.size(); i++) {
+        if (!is_pauli_x(g[i])) continue;
+        const int t = g[i].tb[0];
+        const uint64_t C = g[i].cmask, tbit = 1ull << t;
+        bool found = false;
+        size_t j = i;
+        while (j > 0 && i - j < LOOKAHEAD) {
+            j--;
+            const QGate& h = g[j];
+            const uint64_t touched = h.tmask() | h.cmask;
+            if (touched & tbit) {
+                double sc;
+                found = h.cmask == 0 && h.k == 1 && is_hadamard_like(h, &sc);
+                break;
+            }
+            const uint64_t writes = h.type == QB_G_DIAG ? 0ull : h.tmask();
+            if (writes & C) break;
+        }
+        if (!found) continue;
+        QGate z;
+        z.type = QB_G_DIAG;
+        z.k = 1;
+        z.tb[0] = t;
+        z.cmask = C;
+        z.m = {cplx{1.0, 0.0}, cplx{-1.0, 0.0}};
+        g.erase(g.begin() + (long)i);
+        g.insert(g.begin() + (long)j, z);            // before the Hadamard; slot i now holds the gate that followed the X's predecessor
+        count++;
+    }
     if (rewritten) *rewritten = count;
     return g;
 }
 
-std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt) {
+namespace {
+
+// build the steps (sweep programs + unfused gates) following `guide` (tile bits of the fused sweeps in
+// order; greedy wherever the guide ends or stops being valid)
+std::vector<QtPlanStep> build_steps(const std::vector<QGate>& gates, const std::vector<GInfo>& info, int nbits,
+                                    const QtPlanOptions& opt, const std::vector<std::vector<int>>* guide) {
     std::vector<QtPlanStep> steps;
-    const int M = opt.M;
-    if (M < QT_MINM || M > QT_MAXM) throw std::runtime_error("planner: tile bits out of range");
-    if (opt.R != QT_R && opt.R != QT_MAXR) throw std::runtime_error("planner: register bits per stage must be 4 or 5");
-    const int NH = M - QT_L;
-    std::vector<GInfo> info(gates.size());
-    for (size_t i = 0; i < gates.size(); i++) info[i] = analyse(gates[i]);
-    std::vector<int> rem(gates.size());
-    for (size_t i = 0; i < gates.size(); i++) rem[i] = (int)i;
+    const int M = opt.M, NH = M - QT_L;
     const bool can_tile = nbits >= M;
     const size_t WINDOW = 512;
-
-    // ---- plan search: the greedy tile-bit choice is a local optimum per sweep.  Every sweep is a
-    //      full pass over HBM, so on large states a beam search over the choices (deterministic
-    //      seed) is worth its fraction of a second: 14 -> 12 sweeps at 30 q, 9 -> 8 at 34 q.
-    std::vector<std::vector<int>> guide;
-    bool have_guide = false;
-    if (can_tile && opt.search_trials > 1 && gates.size() >= 8) {
-        const int width = opt.search_trials >= 128 ? 24 : opt.search_trials >= 32 ? 8 : 4;
-        const int branch = opt.search_trials >= 128 ? 10 : opt.search_trials >= 32 ? 6 : 4;
-        std::vector<std::vector<int>> g0;
-        const size_t greedy = trial_plan(info, nbits, NH, WINDOW, nullptr, &g0);
-        const size_t beam = beam_plan(info, nbits, NH, WINDOW, width, branch, &guide);
-        if (greedy <= beam) guide.swap(g0);
-        have_guide = true;
-    }
+    std::vector<int> rem(gates.size());
+    for (size_t i = 0; i < gates.size(); i++) rem[i] = (int)i;
+    bool have_guide = guide != nullptr;
     size_t guide_at = 0;
-
     while (!rem.empty()) {
         if (!can_tile || !info[rem[0]].tileable) {
             QtPlanStep st;
@@ -778,7 +782,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
         }
         // ---- the sweep's free tile bits: from the search, or greedy ----------------------------
         std::vector<int> hb;
-        if (have_guide && guide_at < guide.size()) hb = guide[guide_at];
+        if (have_guide && guide_at < guide->size()) hb = (*guide)[guide_at];
         else hb = choose_tile_bits(rem, info, nbits, NH, WINDOW, nullptr);
         std::vector<int> picked;
         select_pass(rem, info, allowed_of(hb), WINDOW, &picked, nullptr);
@@ -810,4 +814,78 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
         remove_picked(rem, picked);
     }
     return steps;
+}
+
+// what a plan costs, lexicographically: passes over the state, then shared-memory transpositions
+// (stages), then ops
+struct PlanCost {
+    size_t steps = 0, stages = 0, ops = 0;
+    bool operator<(const PlanCost& o) const {
+        if (steps != o.steps) return steps < o.steps;
+        if (stages != o.stages) return stages < o.stages;
+        return ops < o.ops;
+    }
+};
+PlanCost cost_of(const std::vector<QtPlanStep>& steps) {
+    PlanCost c;
+    c.steps = steps.size();
+    for (const QtPlanStep& st : steps) {
+        if (!st.fused) continue;
+        const QtHeader* h = (const QtHeader*)st.program.data();
+        c.stages += h->nstages;
+        c.ops += h->nops;
+    }
+    return c;
+}
+
+}  // namespace
+
+std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt) {
+    const int M = opt.M;
+    if (M < QT_MINM || M > QT_MAXM) throw std::runtime_error("planner: tile bits out of range");
+    if (opt.R != QT_R && opt.R != QT_MAXR) throw std::runtime_error("planner: register bits per stage must be 4 or 5");
+    const int NH = M - QT_L;
+    std::vector<GInfo> info(gates.size());
+    for (size_t i = 0; i < gates.size(); i++) info[i] = analyse(gates[i]);
+    const bool can_tile = nbits >= M;
+    const size_t WINDOW = 512;
+
+    // ---- plan search: the greedy tile-bit choice is a local optimum per sweep.  Every sweep is a
+    //      full pass over HBM, so on large states a beam search over the choices (deterministic
+    //      seed) is worth its fraction of a second: 14 -> 12 sweeps at 30 q, 9 -> 8 at 34 q.  The
+    //      programs of the best few candidates are built and the cheapest plan wins (passes, then
+    //      stages, then ops).
+    std::vector<QtPlanStep> best = build_steps(gates, info, nbits, opt, nullptr);
+    if (can_tile && opt.search_trials > 1 && gates.size() >= 8) {
+        const int width = opt.search_trials >= 128 ? 24 : opt.search_trials >= 32 ? 8 : 4;
+        const int branch = opt.search_trials >= 128 ? 10 : opt.search_trials >= 32 ? 6 : 4;
+        std::vector<std::vector<std::vector<int>>> guides;
+        beam_plan(info, nbits, NH, WINDOW, width, branch, &guides);
+        PlanCost best_cost = cost_of(best);
+        for (const auto& g : guides) {
+            std::vector<QtPlanStep> cand = build_steps(gates, info, nbits, opt, &g);
+            const PlanCost c = cost_of(cand);
+            if (c < best_cost) { best_cost = c; best.swap(cand); }
+        }
+    }
+    return best;
+}
+
+// Plan the cheapest of the rewritten variants of a gate list (forward rule only / both rules; env
+// QBOT_B200_PEEPHOLE = 0, 1 or 2 pins one): passes over the state first, then stages, then ops.
+std::vector<QtPlanStep> qt_plan_best(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt, std::vector<QGate>* planned) {
+    const char* pin = getenv("QBOT_B200_NO_PEEPHOLE") ? "0" : getenv("QBOT_B200_PEEPHOLE");
+    std::vector<int> levels;
+    if (pin) levels.push_back(atoi(pin));
+    else { levels.push_back(1); levels.push_back(2); }
+    std::vector<QtPlanStep> best;
+    PlanCost best_cost;
+    bool have = false;
+    for (int lvl : levels) {
+        std::vector<QGate> g = qt_peephole(gates, lvl, nullptr);
+        std::vector<QtPlanStep> steps = qt_plan(g, nbits, opt);
+        const PlanCost c = cost_of(steps);
+        if (!have || c < best_cost) { have = true; best_cost = c; best.swap(steps); planned->swap(g); }
+    }
+    return best;
 }

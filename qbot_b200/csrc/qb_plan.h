@@ -132,4 +132,7 @@ struct QtPlanOptions {
 std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt);
 
 // Unitary-preserving rewrite of a gate list into a cheaper one (see qb_plan.cpp); plan the result.
-std::vector<QGate> qt_peephole(const std::vector<QGate>& gates, int* rewritten);
+// level 0: none, 1: X..H -> H Z, 2: also H..X -> Z H
+std::vector<QGate> qt_peephole(const std::vector<QGate>& gates, int level, int* rewritten);
+// the cheapest plan over the rewrite levels; *planned = the gate list the returned steps refer to
+std::vector<QtPlanStep> qt_plan_best(const std::vector<QGate>& gates, int nbits, const QtPlanOptions& opt, std::vector<QGate>* planned);

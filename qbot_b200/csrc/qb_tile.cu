@@ -329,8 +329,7 @@ CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gat
     // plan search effort grows with the cost of a sweep (env QBOT_B200_PLAN_TRIALS overrides)
     const int total_bits = s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0);
     opt.search_trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);
-    cp.gates = getenv("QBOT_B200_NO_PEEPHOLE") ? gates : qt_peephole(gates, nullptr);
-    cp.steps = qt_plan(cp.gates, s->nbits, opt);
+    cp.steps = qt_plan_best(gates, s->nbits, opt, &cp.gates);
     size_t total = 0;
     cp.prog_off.resize(cp.steps.size(), 0);
     for (size_t i = 0; i < cp.steps.size(); i++) {

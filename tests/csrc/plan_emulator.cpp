@@ -99,8 +99,9 @@ int qbt_run(int nbits, int ngates, const int* ks, const int* tbs, const uint64_t
         opt.M = M;
         opt.merge_phases = merge != 0;
         if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
-        if (!getenv("QBOT_B200_NO_PEEPHOLE")) gates = qt_peephole(gates, nullptr);      // as the engine does
-        std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
+        std::vector<QGate> planned;
+        std::vector<QtPlanStep> steps = qt_plan_best(gates, nbits, opt, &planned);        // as the engine does
+        gates.swap(planned);
         long long st[7] = {0, 0, 0, 0, 0, 0, 0};
         int covered = 0;
         for (const QtPlanStep& s : steps) {
@@ -145,8 +146,9 @@ int qbt_plan(int nbits, int ngates, const int* ks, const int* tbs, const uint64_
         opt.merge_phases = merge != 0;
         if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
         if (const char* e = getenv("QBOT_B200_PLAN_R")) opt.R = atoi(e);
-        if (!getenv("QBOT_B200_NO_PEEPHOLE")) gates = qt_peephole(gates, nullptr);
-        std::vector<QtPlanStep> steps = qt_plan(gates, nbits, opt);
+        std::vector<QGate> planned;
+        std::vector<QtPlanStep> steps = qt_plan_best(gates, nbits, opt, &planned);
+        gates.swap(planned);
         if ((int)steps.size() > max_steps) { g_err = "too many steps"; return -1; }
         long long at = 0;
         for (size_t i = 0; i < steps.size(); i++) {
