@@ -152,6 +152,10 @@ struct SweepBuild {
     std::vector<StageBuild> stages;
     int ngates = 0;
     double scale = 1.0;                  // product of the 2^-1/2 factors of the unscaled H ops
+    // uncontrolled 1-qubit diagonals are not emitted where they were picked: they commute with
+    // everything except writes of their own bit, so they are PLACED after the stages are known
+    struct PendingDiag { int stage, pos, bit; double d[4]; };
+    std::vector<PendingDiag> pending;
 };
 
 // predicate of a gate's controls (and value-controls) split by where each bit lives in this stage
@@ -221,14 +225,8 @@ void emit_gate(SweepBuild& sw, StageBuild& sb, const QGate& g, bool merge_phases
             }
             double ent[5] = {phase_code(loc, pos), g.m[0].x, g.m[0].y, g.m[1].x, g.m[1].y};
             if (merge_phases) {
-                for (int x = (int)sb.ops.size() - 1; x >= 0; x--) {
-                    if (sb.ops[x].type == QT_OP_PHASE && sb.ops[x].nent < 200) {
-                        sb.payload[x].insert(sb.payload[x].end(), ent, ent + 5);
-                        sb.ops[x].nent++;
-                        return;
-                    }
-                    if (sb.op_w[x] & (1ull << bit)) break;       // cannot move before a write of this bit
-                }
+                sw.pending.push_back({(int)sw.stages.size(), (int)sb.ops.size(), bit, {g.m[0].x, g.m[0].y, g.m[1].x, g.m[1].y}});
+                return;
             }
             op.type = QT_OP_PHASE;
             op.nent = 1;
@@ -435,6 +433,144 @@ StageBuild make_stage(uint64_t regmask, const uint64_t* index_of_local, int M, i
     return sb;
 }
 
+// Placement of the sweep's uncontrolled 1-qubit diagonals (RZ, Z, S, T, ...).  An entry may sit
+// anywhere between the previous and the next WRITE of its bit; at the end of a stage it commutes
+// with the whole stage as long as no later op of that stage writes the bit.  One PHASE op costs a
+// complex multiply per amplitude however many entries it carries, and entries on register bits
+// cost a factor table on top -- so every entry goes to the tail of ONE stage inside its window,
+// preferably a stage where its bit is not a register bit and that already has a tail PHASE op.
+// Only entries sandwiched between two writes inside one stage stay where they were.
+void place_diagonals(SweepBuild& sw) {
+    if (sw.pending.empty()) return;
+    const int ns = (int)sw.stages.size();
+    std::vector<std::vector<const SweepBuild::PendingDiag*>> tail(ns);
+    std::vector<std::vector<const SweepBuild::PendingDiag*>> inplace(ns);
+    // first pass: windows
+    struct Win { int lo, hi; };
+    std::vector<Win> win(sw.pending.size());
+    for (size_t x = 0; x < sw.pending.size(); x++) {
+        const auto& e = sw.pending[x];
+        const uint64_t b = 1ull << e.bit;
+        const int es = std::min(e.stage, ns - 1);            // (a trailing op-less IO stage may have been appended later)
+        int ps = -1, nsx = ns;                               // stage of the previous / next write of the bit
+        for (int s = es; s >= 0 && ps < 0; s--) {
+            const auto& ow = sw.stages[s].op_w;
+            const int from = s == e.stage ? std::min(e.pos, (int)ow.size()) : (int)ow.size();
+            for (int o = from - 1; o >= 0; o--) if (ow[o] & b) { ps = s; break; }
+        }
+        for (int s = e.stage; s < ns && nsx == ns; s++) {
+            const auto& ow = sw.stages[s].op_w;
+            const int from = s == e.stage ? std::min(e.pos, (int)ow.size()) : 0;
+            for (int o = from; o < (int)ow.size(); o++) if (ow[o] & b) { nsx = s; break; }
+        }
+        win[x] = {ps < 0 ? 0 : ps, nsx - 1};
+        if (e.stage >= ns) win[x].lo = std::min(win[x].lo, ns - 1);
+    }
+    // second pass: sandwiched entries stay, the others go to a stage tail
+    std::vector<int> tail_count(ns, 0);
+    for (size_t x = 0; x < sw.pending.size(); x++) {
+        const auto& e = sw.pending[x];
+        if (win[x].lo > win[x].hi) { inplace[std::min(e.stage, ns - 1)].push_back(&e); continue; }
+        const int lp = sw.local_of[e.bit];
+        int best = -1, best_score = -1;
+        for (int s = win[x].lo; s <= win[x].hi; s++) {
+            const bool is_reg = lp >= 0 && reg_index(sw.stages[s].st, lp, sw.R) >= 0;
+            const int score = (is_reg ? 0 : 2) + (tail_count[s] > 0 ? 1 : 0);
+            if (score > best_score || (score == best_score && s > best)) { best_score = score; best = s; }
+        }
+        tail[best].push_back(&e);
+        tail_count[best]++;
+    }
+    auto entry_of = [&](const StageBuild& sb, const SweepBuild::PendingDiag& e, double* ent) {
+        const int lp = sw.local_of[e.bit];
+        int loc, pos;
+        if (lp < 0) { loc = QT_LOC_GLOBAL; pos = e.bit; }
+        else {
+            const int ri = reg_index(sb.st, lp, sw.R);
+            if (ri >= 0) { loc = QT_LOC_REG; pos = ri; } else { loc = QT_LOC_LOCAL; pos = lp; }
+        }
+        ent[0] = phase_code(loc, pos);
+        for (int i = 0; i < 4; i++) ent[1 + i] = e.d[i];
+    };
+    auto phase_op = [&](const StageBuild& sb, const std::vector<const SweepBuild::PendingDiag*>& es, QtOp* op, std::vector<double>* pl) {
+        memset(op, 0, sizeof(*op));
+        op->type = QT_OP_PHASE;
+        op->nent = (uint8_t)es.size();
+        op->regsel = all_regs(sw.R);
+        op->flags = QT_FLAG_ALLREG;
+        pl->clear();
+        for (const auto* e : es) {
+            double ent[5];
+            entry_of(sb, *e, ent);
+            pl->insert(pl->end(), ent, ent + 5);
+        }
+    };
+    for (int s = 0; s < ns; s++) {
+        StageBuild& sb = sw.stages[s];
+        if (!inplace[s].empty()) {
+            // rebuild the op list with the sandwiched entries at their original positions (entries at
+            // the same position share one PHASE op)
+            StageBuild nb;
+            nb.st = sb.st;
+            size_t at = 0;
+            for (size_t o = 0; o <= sb.ops.size(); o++) {
+                while (at < inplace[s].size() && (size_t)std::min(inplace[s][at]->pos, (int)sb.ops.size()) == o) {
+                    const SweepBuild::PendingDiag* e = inplace[s][at++];
+                    double ent[5];
+                    entry_of(nb, *e, ent);
+                    // merge backwards into an earlier PHASE op as long as no write of this bit is crossed
+                    bool merged = false;
+                    for (int x = (int)nb.ops.size() - 1; x >= 0; x--) {
+                        if (nb.ops[x].type == QT_OP_PHASE && nb.ops[x].nent < 200) {
+                            nb.payload[x].insert(nb.payload[x].end(), ent, ent + 5);
+                            nb.ops[x].nent++;
+                            merged = true;
+                            break;
+                        }
+                        if (nb.op_w[x] & (1ull << e->bit)) break;
+                    }
+                    if (!merged) {
+                        QtOp op;
+                        std::vector<double> pl;
+                        phase_op(nb, {e}, &op, &pl);
+                        nb.push(op, 0, pl.data(), pl.size());
+                    }
+                }
+                if (o < sb.ops.size()) nb.push(sb.ops[o], sb.op_w[o], sb.payload[o].data(), sb.payload[o].size());
+            }
+            sb.ops.swap(nb.ops);
+            sb.op_w.swap(nb.op_w);
+            sb.payload.swap(nb.payload);
+        }
+        // tail entries: into an existing PHASE op of the stage when no write of the bit follows it, else
+        // into one PHASE op at the end of the stage
+        std::vector<const SweepBuild::PendingDiag*> rest;
+        for (const auto* e : tail[s]) {
+            double ent[5];
+            entry_of(sb, *e, ent);
+            bool merged = false;
+            for (int x = (int)sb.ops.size() - 1; x >= 0; x--) {
+                if (sb.ops[x].type == QT_OP_PHASE && sb.ops[x].nent < 200) {
+                    sb.payload[x].insert(sb.payload[x].end(), ent, ent + 5);
+                    sb.ops[x].nent++;
+                    merged = true;
+                    break;
+                }
+                if (sb.op_w[x] & (1ull << e->bit)) break;
+            }
+            if (!merged) rest.push_back(e);
+        }
+        for (size_t g0 = 0; g0 < rest.size(); g0 += 200) {
+            std::vector<const SweepBuild::PendingDiag*> part(rest.begin() + g0, rest.begin() + std::min(rest.size(), g0 + 200));
+            QtOp op;
+            std::vector<double> pl;
+            phase_op(sb, part, &op, &pl);
+            sb.push(op, 0, pl.data(), pl.size());
+        }
+    }
+    sw.pending.clear();
+}
+
 // split one sweep's gates into register stages and serialise; returns false if too large.
 // The first and the last stage move the tile between HBM and registers, so their register bits
 // are free tile bits (positions >= QT_L) and their lanes the contiguous low bits; stages that
@@ -501,6 +637,7 @@ bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& in
             // predicates of ops already emitted do not depend on the thread map: only on rb
         }
     }
+    place_diagonals(sw);
     size_t nops = 0;
     for (const auto& sb : sw.stages) nops += sb.ops.size();
     if (nops > QT_MAX_OPS) return false;
