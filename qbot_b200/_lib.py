@@ -84,6 +84,23 @@ _lock = threading.Lock()
 _lib = None
 
 
+def _locate_nvrtc():
+    """The sweep specialiser dlopens libnvrtc.so.12 by name, then from /usr/local/cuda/lib64; if
+    neither exists point it (QBOT_B200_NVRTC) at the copy that ships with the CUDA wheels."""
+    if os.environ.get('QBOT_B200_NVRTC'):
+        return
+    import glob
+    import sys
+    for pat in ('/usr/local/cuda/lib64/libnvrtc.so.12', '/usr/local/cuda*/lib64/libnvrtc.so.12'):
+        if glob.glob(pat):
+            return
+    for base in sys.path:
+        hits = glob.glob(os.path.join(base, 'nvidia', 'cuda_nvrtc', 'lib', 'libnvrtc.so.12'))
+        if hits:
+            os.environ['QBOT_B200_NVRTC'] = hits[0]
+            return
+
+
 def load():
     """Load the shared library (once).  Raises if it has not been built."""
     global _lib
@@ -95,6 +112,7 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise QbotB200Error(-2, f"{LIB_PATH} not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'`; "
                                     "there is no CPU fallback")
+        _locate_nvrtc()
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)        # AttributeError here = header / library mismatch
