@@ -158,7 +158,6 @@ qb_state::~qb_state() {
     if (d && owns) { DevGuard g(device); cached_free(device, bytes(), d, stream); }
     if (scratch) { DevGuard g(device); cached_free(device, bytes(), scratch, stream); }   // same allocator as `d`: the two may have been swapped
     if (stage) cudaFree(stage);
-    if (sm_arrivals) cudaFree(sm_arrivals);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream && owns_stream) cudaStreamDestroy(stream);

@@ -24,7 +24,6 @@ struct qb_state {
     static constexpr size_t STAGE_BYTES = 4u << 20;
     void* stage = nullptr;
     size_t stage_off = 0;
-    unsigned* sm_arrivals = nullptr;   // per-SM CTA arrival counters of the specialised sweeps (1024 entries)
     // fused engine state (plan cache, device copies of the sweep programs)
     void* engine = nullptr;
 

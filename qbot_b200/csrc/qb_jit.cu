@@ -119,39 +119,16 @@ __device__ __forceinline__ unsigned qj_mbar(const int which) {
 )QJ";
 
 // One CTA of QJ_T threads is persistent over tiles t = blockIdx.x + i * gridDim.x; a tile's 2^M
-// amplitudes live in registers (16 per thread) and pass through shared memory once between two
-// stages.  QJ_CTAS CTAs are resident per SM so that one CTA's loads / stores overlap another's
-// arithmetic; the next tile of a CTA is prefetched into L2 while the current one is computed.
+// amplitudes live in registers (2^R per thread) and pass through shared memory once between two
+// stages.  QJ_CTAS CTAs are resident per SM so that one CTA's transfers overlap another's
+// arithmetic; the next tile of a CTA arrives by TMA bulk copies while the current one is computed
+// (early half: landing buffer, issued after the first barrier; late half: transposition buffer,
+// issued in the last stage); only a CTA's first tile is loaded with LDG.
 const char* kPostlude = R"QJ(
 extern "C" __global__ void __launch_bounds__(QJ_T, QJ_CTAS)
-qj_kernel(double2* __restrict__ psi, const unsigned long long ntiles, const int prefetch,
-          unsigned* __restrict__ sm_arrivals, const unsigned stagger_ns, QJ_POOL_KPARAM) {
+qj_kernel(double2* __restrict__ psi, const unsigned long long ntiles, const int prefetch, QJ_POOL_KPARAM) {
     extern __shared__ __align__(16) double2 buf[];
     const unsigned tid = threadIdx.x;
-    // De-phase the CTAs that share an SM.  All CTAs of a launch start together and, sharing the
-    // L2 path and the FP64 pipe fairly, stay in lock-step: both load, both compute, both store --
-    // the SM<->L2 transfer time ADDS to the arithmetic (measured: +0.11 ms per Hadamard at 30
-    // qubits, exactly the FP64 pipe rate, zero overlap).  The k-th CTA to arrive on an SM waits
-    // k * stagger_ns once; a phase difference between two fairly sharing cyclic processes is
-    // conserved, so from then on one CTA's transfers overlap the other's arithmetic.
-    if (stagger_ns) {
-        __shared__ unsigned arrival;
-        if (tid == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            arrival = atomicAdd(&sm_arrivals[smid], 1u);
-        }
-        __syncthreads();
-        const unsigned long long wait = (unsigned long long)(arrival % QJ_CTAS) * stagger_ns;
-        if (wait) {
-            unsigned long long t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            do {
-                __nanosleep(256);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            } while (t1 - t0 < wait);
-        }
-    }
     // prefetch bit 0: L2 prefetch of the CTA's next tile at the start of a tile; bit 1: asynchronous
     // copy of the next tile into the transposition buffer during the last stage
     unsigned pre = 0, phase = 0;
@@ -432,15 +409,13 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
 
 // launch: `pool` = qj_pool(program) on the host (parameter variant) or its device copy
 void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
-                   const double* pool_host, const double* pool_dev, unsigned* sm_arrivals, unsigned stagger_ns) {
+                   const double* pool_host, const double* pool_dev) {
     Driver& d = driver();
     unsigned long long nt = ntiles;
     int pf = prefetch;
     void* psi_arg = (void*)psi;
     const void* pool_ptr = pool_dev;
-    if (!sm_arrivals || k.ctas_per_sm < 2) stagger_ns = 0;
-    if (stagger_ns) QB_CUDA(cudaMemsetAsync(sm_arrivals, 0, 1024 * sizeof(unsigned), stream));
-    void* args[6] = {&psi_arg, &nt, &pf, &sm_arrivals, &stagger_ns, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
+    void* args[4] = {&psi_arg, &nt, &pf, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
     const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * k.ctas_per_sm);
     CUresult e = d.LaunchKernel((CUfunction)k.fn, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem_bytes, (CUstream)stream, args, nullptr);
     if (e != CUDA_SUCCESS) throw qb_error(-2, "cuLaunchKernel(sweep): " + cu_err(e));

@@ -25,7 +25,7 @@ std::vector<char> qb_jit_compile(const std::string& src, std::string* log_out);
 void qb_jit_precompile(const std::vector<const uint8_t*>& programs);
 QbJitKernel qb_jit_get(const uint8_t* program, int device);
 void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
-                   const double* pool_host, const double* pool_dev, unsigned* sm_arrivals, unsigned stagger_ns);
+                   const double* pool_host, const double* pool_dev);
 QbJitStats qb_jit_stats();
 // record one sighting of a specialised source (by hash): returns the number of sightings so far,
 // or -1 when a kernel for it is already compiled

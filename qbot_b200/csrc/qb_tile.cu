@@ -415,9 +415,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         if (jit_mode != 0 && step_jit(s, plan, i, jit_mode)) {
             const CachedPlan::StepJit& j = plan->jit[i];
             if (plan->R != QT_R && !j.ready) throw qb_error(-2, "no specialised kernel for a 32-amplitudes-per-thread sweep");
-            const unsigned stagger = (unsigned)env_int("QBOT_B200_STAGGER_NS", 0);     // CTA de-phasing experiment: no effect measured
-            if (stagger && !s->sm_arrivals) QB_CUDA(cudaMalloc((void**)&s->sm_arrivals, 1024 * sizeof(unsigned)));
-            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_jit_prefetch(), j.pool.data(), j.pool_dev, s->sm_arrivals, stagger);
+            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_jit_prefetch(), j.pool.data(), j.pool_dev);
             s->stats.jit_passes++;
         } else {
             if (plan->R != QT_R) throw qb_error(-2, "the generic sweep kernel cannot run a 32-amplitudes-per-thread plan");
