@@ -111,3 +111,56 @@ def test_exchange_one_rank_per_gpu(tmp_path, mode):
     nproc = 1 << (ng.bit_length() - 1)
     out = _run_ranks(nproc, mode, 'nccl', 16, tmp_path)
     assert out.count('"err"') == nproc
+
+
+BATCH_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+from qbot_b200.sharded import ShardedBranchBatch, TorchComm
+from qbot_b200.circuits import rc, z_rot
+from oracle import qbot_oracle as orc
+rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE'])
+torch.cuda.set_device(0)
+dist.init_process_group('gloo')
+n, B = 10, 64
+rng = np.random.default_rng(16)
+th = rng.uniform(0, np.pi, size=(B, n)); ph = rng.uniform(0, 2 * np.pi, size=(B, n))
+fac = np.stack([np.cos(th / 2), np.exp(1j * ph) * np.sin(th / 2)], axis=-1)
+gates = rc(n, 6, 16)
+ang = rng.uniform(0, 6, B); tg = [int(t) for t in rng.integers(0, n, B)]
+mats = np.stack([z_rot(a) for a in ang])
+bb = ShardedBranchBatch(n, B, TorchComm(), 0, fac)
+for g in gates:
+    bb.apply_gate(g.matrix(), g.target, g.controls)
+bb.apply_gate_per_branch(mats, tg)
+targets = [1, 4, 9]
+pr = bb.probs(targets)
+assert pr.shape == (B, 8)
+worst = 0.0
+for b in range(B):                       # every rank checks ALL branches: the gather keeps the global branch order
+    psi = np.array([1.0 + 0j])
+    for q in range(n):
+        psi = np.kron(psi, fac[b, q])
+    for g in gates:
+        psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+    psi = orc.ket_apply(psi, n, tg[b], mats[b])
+    worst = max(worst, float(np.max(np.abs(pr[b] - orc.ket_probs(psi, n, targets)))))
+print(json.dumps(dict(rank=rank, worst=worst, first=bb.first, per=bb.per)))
+dist.barrier()
+dist.destroy_process_group()
+assert worst < 1e-12
+'''
+
+
+def test_branch_batch_sharded_over_ranks(tmp_path):
+    """BASELINE config 4's sharding: contiguous blocks of branches per rank, no data-path
+    communication, one all-gather of the outcome weights in global branch order."""
+    script = tmp_path / 'batch_worker.py'
+    script.write_text(BATCH_WORKER.format(root=ROOT))
+    port = 29300 + (os.getpid() % 300)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=4',
+           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count('"worst"') == 4
