@@ -639,12 +639,9 @@ int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, c
         std::vector<const uint8_t*> progs;
         for (const QtPlanStep& st : steps) if (st.fused) progs.push_back(st.program.data());
         const uint64_t before = qb_jit_stats().kernels_compiled;
-        qb_jit_precompile(progs);
-        for (const uint8_t* p : progs) {          // whatever the pool did not take (single program, duplicates) compiles here
-            const std::string src = qb_jit_full_source(p, nullptr, nullptr);
-            (void)src;
-        }
-        if (ncompiled) *ncompiled = (int)(qb_jit_stats().kernels_compiled - before);
+        if (progs.size() == 1) qb_jit_compile(qb_jit_full_source(progs[0], nullptr, nullptr), nullptr);      // the pool takes >= 2
+        else qb_jit_precompile(progs);
+        if (ncompiled) *ncompiled = progs.size() == 1 ? 1 : (int)(qb_jit_stats().kernels_compiled - before);
         return QB_OK;
     }
     for (const QtPlanStep& st : steps) {
