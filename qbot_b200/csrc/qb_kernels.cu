@@ -317,16 +317,30 @@ __global__ void __launch_bounds__(256) k_bins(BinArgs a) {
     const int C = 1 << a.c;
     const cplx* src = a.src + branch * a.branch_stride;
     const int G = 1 << a.ngroup;
+    // element offset of every group member, computed once per block (the inner loop is then one
+    // add + one load per element instead of re-depositing the group bits)
+    __shared__ uint64_t goff[64];
+    for (int gi = threadIdx.x; gi < G; gi += blockDim.x) {
+        uint64_t qq = q;
+        for (int x = 0; x < a.ngroup; x++) qq |= (uint64_t)((gi >> x) & 1) << a.groupbits[x];
+        goff[gi] = (qq << a.c) * a.elem_stride;
+    }
+    __syncthreads();
     for (int l = threadIdx.x; l < C; l += blockDim.x) {
         double re = 0.0, im = 0.0;
-#pragma unroll 4
-        for (int gi = 0; gi < G; gi++) {
-            uint64_t qq = q;
-            for (int x = 0; x < a.ngroup; x++) qq |= (uint64_t)((gi >> x) & 1) << a.groupbits[x];
-            const uint64_t i = (qq << a.c) | (uint64_t)l;
-            const cplx v = __ldcs(&src[i * a.elem_stride]);
-            if (a.mode == 0) re += v.x * v.x + v.y * v.y;
-            else { re += v.x; im += v.y; }
+        const cplx* p = src + (uint64_t)l * a.elem_stride;
+        if (a.mode == 0) {
+#pragma unroll 8
+            for (int gi = 0; gi < G; gi++) {
+                const cplx v = __ldcs(p + goff[gi]);
+                re += v.x * v.x + v.y * v.y;
+            }
+        } else {
+#pragma unroll 8
+            for (int gi = 0; gi < G; gi++) {
+                const cplx v = __ldcs(p + goff[gi]);
+                re += v.x; im += v.y;
+            }
         }
         sre[l] = re; sim[l] = im;
     }
