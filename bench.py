@@ -48,7 +48,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
                                           '-i', str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -94,7 +94,7 @@ def cpu_reference_algorithm(n_ref: int, budget_s: float, seed: int):
     same generator's circuit at the largest size that representation allows."""
     from oracle import qbot_oracle as orc
     from qbot_b200.circuits import rc
-    gates = rc(n_ref, 4, seed)
+    gates = rc(n_ref, 16, seed)          # more than the budget can consume: the loop below stops on time
     rho = np.zeros((1 << n_ref, 1 << n_ref), dtype=complex)
     rho[0, 0] = 1
     rho = orc.reference_style_gate(rho, n_ref, gates[0].target, gates[0].matrix(), gates[0].controls)   # warm-up
@@ -352,7 +352,7 @@ def run_single_gpu(args):
         kv, kdone, kdt = cpu_ket_port(24, 6.0, 24)
         out["cpu_baseline"] = {
             "value": v, "unit": "gates/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{done} gates of rc({args.ref_qubits_default}, 4, 12) in {dt:.1f}s with the reference's algorithm (full 2^n x 2^n unitary, "
+            "sample": f"{done} gates of rc({args.ref_qubits_default}, 16, 12) in {dt:.1f}s with the reference's algorithm (full 2^n x 2^n unitary, "
                       f"U rho U^dagger) on a {args.ref_qubits_default}-qubit density matrix; the reference cannot represent n={n}",
             "ket_port": {"value": kv, "unit": "gates/s", "qubits": 24,
                          "sample": f"{kdone} gates of rc(24, 2, 24) in {kdt:.1f}s, numpy strided ket update (not a reference code path)"}}
