@@ -224,7 +224,8 @@ struct Gen {
                 o.f("      { const double fr = %s, fi = %s; const double tr = cr * fr - ci * fi; ci = cr * fi + ci * fr; cr = tr; }\n",
                     fr.c_str(), fi.c_str());
         }
-        // factor table over the register bits that carry entries
+        // factor table over the register bits that carry entries; an entry with an empty name is
+        // exactly 1 (register-bit diagonals arrive as diag(1, d1/d0)): nothing to multiply
         struct Ent { int mask; std::string r, i; };
         std::vector<Ent> table;
         if (have) table.push_back({0, "cr", "ci"});
@@ -246,15 +247,20 @@ struct Gen {
                 o.f("      { const double t1 = %s * %s - %s * %s; %s = %s * %s + %s * %s; %s = t1; }\n", d1r, P(qx + 3).c_str(), d1i,
                     P(qx + 4).c_str(), d1i, d1r, P(qx + 4).c_str(), d1i, P(qx + 3).c_str(), d1r);
             }
+            // is the (product) d0 of this bit exactly one?  (structural: single entries come in as (1, 0))
+            bool d0_one = reg_entries[q].size() >= 1;
+            for (int ex : reg_entries[q]) d0_one = d0_one && pool_is_one(p + 5 * ex + 1);
             std::vector<Ent> next;
             if (table.empty()) {
-                next.push_back({0, d0r, d0i});
+                if (d0_one) next.push_back({0, "", ""}); else next.push_back({0, d0r, d0i});
                 next.push_back({1 << q, d1r, d1i});
             } else {
                 for (const Ent& t : table) {
                     for (int v = 0; v < 2; v++) {
                         char nr[48], ni[48];
                         const int mk = t.mask | (v << q);
+                        if (v == 0 && d0_one) { next.push_back({mk, t.r, t.i}); continue; }      // times one
+                        if (t.r.empty()) { next.push_back({mk, v ? d1r : d0r, v ? d1i : d0i}); continue; }   // one times d
                         snprintf(nr, sizeof(nr), "f%d_%dr", q, mk);
                         snprintf(ni, sizeof(ni), "f%d_%di", q, mk);
                         o.f("      const double %s = %s * %s - %s * %s, %s = %s * %s + %s * %s;\n", nr, t.r.c_str(), v ? d1r : d0r, t.i.c_str(),
@@ -269,7 +275,10 @@ struct Gen {
             for (int i = 0; i < NR; i++) {
                 const int mk = i & regbits;
                 for (const Ent& t : table)
-                    if (t.mask == mk) { o.f("  "); cmul_into(nm[i], t.r, t.i); break; }
+                    if (t.mask == mk) {
+                        if (!t.r.empty()) { o.f("  "); cmul_into(nm[i], t.r, t.i); }
+                        break;
+                    }
             }
         }
         o.f("    }\n");

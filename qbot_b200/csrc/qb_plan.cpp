@@ -152,6 +152,7 @@ struct SweepBuild {
     std::vector<StageBuild> stages;
     int ngates = 0;
     double scale = 1.0;                  // product of the 2^-1/2 factors of the unscaled H ops
+    double gph_re = 1.0, gph_im = 0.0;   // product of the d0 factors pulled out of register-bit diagonals
     // uncontrolled 1-qubit diagonals are not emitted where they were picked: they commute with
     // everything except writes of their own bit, so they are PLACED after the stages are known
     struct PendingDiag { int stage, pos, bit; double d[4]; };
@@ -481,6 +482,7 @@ void place_diagonals(SweepBuild& sw) {
         tail[best].push_back(&e);
         tail_count[best]++;
     }
+    std::vector<const SweepBuild::PendingDiag*> counted;       // entries whose d0 already joined the global factor
     auto entry_of = [&](const StageBuild& sb, const SweepBuild::PendingDiag& e, double* ent) {
         const int lp = sw.local_of[e.bit];
         int loc, pos;
@@ -491,6 +493,23 @@ void place_diagonals(SweepBuild& sw) {
         }
         ent[0] = phase_code(loc, pos);
         for (int i = 0; i < 4; i++) ent[1 + i] = e.d[i];
+        if (loc == QT_LOC_REG) {
+            // diag(d0, d1) = d0 * diag(1, d1/d0): the scalar joins the sweep's global factor (applied once,
+            // where a thread-level factor is multiplied in anyway), and the specialised kernel then has
+            // nothing to do for the amplitudes whose register bit is 0
+            const double d0r = e.d[0], d0i = e.d[1], d1r = e.d[2], d1i = e.d[3];
+            const double n2 = d0r * d0r + d0i * d0i;
+            if (n2 > 0.0) {
+                ent[1] = 1.0; ent[2] = 0.0;
+                ent[3] = (d1r * d0r + d1i * d0i) / n2;
+                ent[4] = (d1i * d0r - d1r * d0i) / n2;
+                if (std::find(counted.begin(), counted.end(), &e) == counted.end()) {      // (an entry is encoded more than once)
+                    counted.push_back(&e);
+                    const double gr = sw.gph_re * d0r - sw.gph_im * d0i, gi = sw.gph_re * d0i + sw.gph_im * d0r;
+                    sw.gph_re = gr; sw.gph_im = gi;
+                }
+            }
+        }
     };
     auto phase_op = [&](const StageBuild& sb, const std::vector<const SweepBuild::PendingDiag*>& es, QtOp* op, std::vector<double>* pl) {
         memset(op, 0, sizeof(*op));
@@ -641,22 +660,35 @@ bool build_program(const std::vector<QGate>& gates, const std::vector<GInfo>& in
     size_t nops = 0;
     for (const auto& sb : sw.stages) nops += sb.ops.size();
     if (nops > QT_MAX_OPS) return false;
-    // the collected 2^-1/2 factors ride on a PHASE op when there is one, else on the header
+    // the collected 2^-1/2 factors and the d0 factors pulled out of register-bit diagonals ride as
+    // ONE constant on a PHASE op -- preferably one that multiplies a thread-level factor into every
+    // amplitude anyway (it has an entry that is not on a register bit) -- else on the header
     double header_scale = 1.0;
-    if (sw.scale != 1.0) {
-        bool placed = false;
+    const double cre = sw.scale * sw.gph_re, cim = sw.scale * sw.gph_im;
+    if (cre != 1.0 || cim != 0.0) {
+        StageBuild* best_sb = nullptr;
+        size_t best_x = 0;
+        int best_score = -1;
         for (auto& sb : sw.stages) {
-            for (size_t x = 0; x < sb.ops.size() && !placed; x++) {
-                if (sb.ops[x].type == QT_OP_PHASE && sb.ops[x].nent < 200) {
-                    double ent[5] = {phase_code(QT_LOC_CONST, 0), sw.scale, 0.0, sw.scale, 0.0};
-                    sb.payload[x].insert(sb.payload[x].end(), ent, ent + 5);
-                    sb.ops[x].nent++;
-                    placed = true;
+            for (size_t x = 0; x < sb.ops.size(); x++) {
+                if (sb.ops[x].type != QT_OP_PHASE || sb.ops[x].nent >= 200) continue;
+                int nonreg = 0, reg = 0;
+                for (int e = 0; e < sb.ops[x].nent; e++) {
+                    int64_t code;
+                    memcpy(&code, &sb.payload[x][5 * e], sizeof(code));
+                    if ((code & 0xff) == QT_LOC_REG) reg++; else nonreg++;
                 }
+                const int score = nonreg > 0 ? 1000 : reg;
+                if (score > best_score) { best_score = score; best_sb = &sb; best_x = x; }
             }
-            if (placed) break;
         }
-        if (!placed) header_scale = sw.scale;
+        if (best_sb) {
+            double ent[5] = {phase_code(QT_LOC_CONST, 0), cre, cim, cre, cim};
+            best_sb->payload[best_x].insert(best_sb->payload[best_x].end(), ent, ent + 5);
+            best_sb->ops[best_x].nent++;
+        } else {
+            header_scale = sw.scale;         // no PHASE op => no register-bit diagonal => the factor is the real scale
+        }
     }
     std::vector<uint8_t> prog = serialise(sw, header_scale);
     if (prog.empty() || prog.size() > QT_MAX_PROGRAM_BYTES) return false;
