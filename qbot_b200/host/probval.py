@@ -54,8 +54,59 @@ class ProbVal:
                 self.values.append(v)
         self.normalize()
 
+    @staticmethod
+    def _exact_keys(values):
+        """Hashable keys that are equal exactly when valsClose is true, for the value kinds whose
+        equality is exact (same-shape ndarrays, gate descriptors, ints / bools / strings); None when
+        the list holds anything else (floats compare with a tolerance, which is not an equivalence
+        relation).  SURVEY.md row f4: the pairwise loop below is O(B^2) -- 8 million descriptor
+        comparisons for a 4096-branch ProbVal."""
+        if len(values) < 32:
+            return None
+        keys = []
+        shape = None
+        for x in values:
+            if isinstance(x, np.ndarray):
+                if x.dtype == object or (shape is not None and x.shape != shape):
+                    return None
+                shape = x.shape
+                c = np.ascontiguousarray(x, dtype=complex) + 0.0          # -0.0 == 0.0 must hash alike
+                if np.isnan(c.real).any() or np.isnan(c.imag).any():
+                    return None
+                keys.append(('a', x.shape, c.tobytes()))
+            elif hasattr(x, 'canonical') and hasattr(x, 'controls'):      # GateDesc: equality of the full-space unitaries
+                sup, m = x.canonical()
+                m = np.ascontiguousarray(m, dtype=complex) + 0.0
+                if np.isnan(m.real).any() or np.isnan(m.imag).any():
+                    return None
+                keys.append(('g', tuple(sup), m.shape, m.tobytes()))
+            elif isinstance(x, (bool, int, str)) and not isinstance(x, float):
+                keys.append(('s', x))
+            else:
+                return None
+        kinds = {k[0] for k in keys}
+        return keys if len(kinds) == 1 else None
+
     def normalize(self):
         p, v = self.probs, self.values
+        keys = self._exact_keys(v)
+        if keys is not None:
+            # same outcome as the pairwise loop: an entry below smallVal is dropped when reached, a
+            # kept entry removes every later equal one (whatever its probability)
+            seen = set()
+            np_, nv = [], []
+            for pi, vi, ki in zip(p, v, keys):
+                if pi < smallVal or ki in seen:
+                    continue
+                seen.add(ki)
+                np_.append(pi)
+                nv.append(vi)
+            p[:] = np_
+            v[:] = nv
+            total = sum(p)
+            for i in range(len(p)):
+                p[i] = round(p[i] / total, probRounding)
+            return
         i = 0
         while i < len(p):
             if p[i] < smallVal:

@@ -136,3 +136,55 @@ def test_lazy_product_states_and_ket_peek():
     assert rho.shape == (4, 4) and abs(np.trace(rho) - 1) < 1e-14 and abs(abs(rho[0, 3]) - 0.5) < 1e-14
     with pytest.raises(SystemExit):
         qbot_b200.executeTxt(prog + "\nmeas m ; comp ; [0]", state_cls=FakeState)
+
+
+def test_probval_normalize_fast_path_equals_pairwise_loop():
+    """row f4: for exact-equality value kinds normalize uses hashing (O(B)); it must keep exactly
+    what the reference's pairwise loop keeps -- first occurrence wins, later duplicates are dropped
+    (their probability is NOT added), entries below 1e-5 are dropped when reached"""
+    from qbot_b200.host import probval as pv
+    from qbot_b200.host.ops import GateDesc
+    rng = np.random.default_rng(3)
+
+    def slow(probs, values):
+        p, v = list(probs), list(values)
+        i = 0
+        while i < len(p):
+            if p[i] < pv.smallVal:
+                del p[i], v[i]
+                continue
+            j = i + 1
+            while j < len(p):
+                if pv.valsClose(v[i], v[j]):
+                    del p[j], v[j]
+                else:
+                    j += 1
+            i += 1
+        t = sum(p)
+        return [round(x / t, pv.probRounding) for x in p], v
+
+    H = np.array([[1, 1], [1, -1]], dtype=complex) * 2 ** -0.5
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    pools = {
+        'ints': [int(x) for x in rng.integers(0, 12, 200)],
+        'arrays': [np.array([[1, 0], [0, np.exp(1j * float(k))]]) for k in rng.integers(0, 9, 150)] + [np.array([[0.0, -0.0], [0, 1]]), np.array([[-0.0, 0.0], [0, 1]])] * 20,
+        'gates': [GateDesc(H if k % 2 else X, int(k) % 5, [7] if k % 3 == 0 else []) for k in rng.integers(0, 30, 120)],
+    }
+    for name, vals in pools.items():
+        probs = list(rng.uniform(0, 1, len(vals)))
+        for k in rng.integers(0, len(vals), 15):
+            probs[int(k)] = 1e-7                                     # entries below smallVal
+        assert pv.ProbVal._exact_keys(vals) is not None, name
+        got = pv.ProbVal(list(probs), list(vals))
+        wp, wv = slow(probs, vals)
+        assert got.probs == wp, name
+        assert len(got.values) == len(wv) and all(pv.valsClose(a, b) for a, b in zip(got.values, wv)), name
+    # floats compare with a tolerance: never the fast path
+    assert pv.ProbVal._exact_keys([0.1 * k for k in range(40)]) is None
+    # the 4096-branch case of config 4: descriptors with many duplicates, well under a second
+    import time
+    vals = [GateDesc(np.diag([1, np.exp(1j * (k % 64))]), k % 16, []) for k in range(4096)]
+    t0 = time.perf_counter()
+    r = pv.ProbVal([1.0 / 4096] * 4096, vals)
+    assert len(r.values) == 64 * 16 // np.gcd(64, 16) or len(r.values) <= 1024
+    assert time.perf_counter() - t0 < 5.0
