@@ -358,6 +358,29 @@ void qb_jit_precompile(const std::vector<const uint8_t*>& programs) {
     }
 }
 
+// compile one program into the cache without loading it on any device (host work only)
+void qb_jit_compile_cached(const uint8_t* program) {
+    QjSourceInfo info;
+    bool pg = false;
+    const std::string src = qb_jit_full_source(program, &info, &pg);
+    const uint64_t key = qj_hash(src);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_cache.count(key)) return;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    Compiled c;
+    c.cubin = qb_jit_compile(src, nullptr);
+    c.info = info;
+    c.pool_global = pg;
+    c.compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_cache.count(key)) return;
+    g_stats.kernels_compiled++;
+    g_stats.compile_ms += c.compile_ms;
+    g_cache.emplace(key, std::move(c));
+}
+
 // the compiled kernel of `program` on `device` (compiling / loading it on first use)
 QbJitKernel qb_jit_get(const uint8_t* program, int device) {
     QjSourceInfo info;

@@ -23,6 +23,7 @@ bool qb_jit_available(std::string* why);
 std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool* pool_global);
 std::vector<char> qb_jit_compile(const std::string& src, std::string* log_out);
 void qb_jit_precompile(const std::vector<const uint8_t*>& programs);
+void qb_jit_compile_cached(const uint8_t* program);
 QbJitKernel qb_jit_get(const uint8_t* program, int device);
 void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
                    const double* pool_host, const double* pool_dev);

@@ -21,10 +21,12 @@
 #include "qb_tile_ops.h"
 #include "qb_jit_rt.h"
 
+#include <algorithm>
 #include <cstring>
 #include <list>
 #include <map>
 #include <mutex>
+#include <thread>
 
 template <int M> struct TileCfg {
     static constexpr int T = 1 << (M - QT_R);
@@ -355,6 +357,59 @@ CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gat
     return &es->cache.front();
 }
 
+// First sight of a gate list on a large state (default specialisation mode): the generic kernel
+// runs it now; meanwhile a host thread plans the specialiser's variant and NVRTC-compiles its
+// kernels into the process-wide cache, so that a second run starts specialised without waiting.
+// Pure host work (planner + NVRTC); at most two such jobs at a time; joined at process exit.
+struct Warmers {
+    std::mutex mu;
+    std::vector<std::thread> threads;
+    std::vector<uint64_t> started;
+    int running = 0;
+    ~Warmers() {
+        for (auto& t : threads) if (t.joinable()) t.join();
+    }
+};
+Warmers g_warmers;
+
+// the upgrade path waits for a warm-up of the same gate list instead of compiling the same kernels twice
+void wait_for_warm(uint64_t plan_hash) {
+    std::thread t;
+    {
+        std::lock_guard<std::mutex> lk(g_warmers.mu);
+        for (size_t i = 0; i < g_warmers.started.size() && i < g_warmers.threads.size(); i++)
+            if (g_warmers.started[i] == plan_hash && g_warmers.threads[i].joinable()) { t.swap(g_warmers.threads[i]); break; }
+    }
+    if (t.joinable()) t.join();
+}
+
+void warm_in_background(const std::vector<QGate>& gates, int nbits, int total_bits, int M, uint64_t plan_hash) {
+    if (!qb_jit_available(nullptr)) return;
+    std::lock_guard<std::mutex> lk(g_warmers.mu);
+    if (g_warmers.running >= 2) return;
+    if (std::find(g_warmers.started.begin(), g_warmers.started.end(), plan_hash) != g_warmers.started.end()) return;
+    g_warmers.started.push_back(plan_hash);
+    g_warmers.running++;
+    const int trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);   // as get_plan
+    g_warmers.threads.emplace_back([gates, nbits, M, trials]() {
+        try {
+            QtPlanOptions opt;
+            opt.M = M;
+            opt.R = QT_MAXR;
+            opt.search_trials = trials;
+            std::vector<QGate> planned;
+            const std::vector<QtPlanStep> steps = qt_plan_best(gates, nbits, opt, &planned);
+            std::vector<const uint8_t*> progs;
+            for (const QtPlanStep& st : steps) if (st.fused) progs.push_back(st.program.data());
+            if (progs.size() == 1) qb_jit_compile_cached(progs[0]);
+            else if (!progs.empty()) qb_jit_precompile(progs);
+        } catch (...) {
+        }
+        std::lock_guard<std::mutex> lk2(g_warmers.mu);
+        g_warmers.running--;
+    });
+}
+
 // all kernels of a plan that is going to run specialised, compiled in parallel on the host cores
 void precompile_plan(CachedPlan* plan) {
     std::vector<const uint8_t*> progs;
@@ -389,9 +444,13 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
     } else {
         plan = get_plan(s, es, gates, M, QT_R);
         plan->uses++;
+        if (tiled && jit_mode == 1 && big && engine_jit_R() == QT_MAXR && plan->uses == 1 && env_int("QBOT_B200_JIT_BACKGROUND", 1))
+            warm_in_background(gates, s->nbits, s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0), M,
+                               plan->hash);     // a second run will find its kernels compiled
         if (tiled && jit_mode == 1 && big && engine_jit_R() == QT_MAXR && plan->uses >= 2 && !plan->upgrade_failed) {
             CachedPlan* base = plan;
             try {
+                wait_for_warm(base->hash);
                 CachedPlan* p5 = get_plan(s, es, gates, M, QT_MAXR);
                 precompile_plan(p5);
                 for (size_t i = 0; i < p5->steps.size(); i++)
