@@ -226,10 +226,12 @@ struct Compiled {
     std::map<int, std::pair<CUmodule, CUfunction>> per_device;   // loaded module per device
 };
 
-std::mutex g_mu;
-std::map<uint64_t, Compiled> g_cache;      // by hash of the full source
-std::map<uint64_t, int> g_seen;           // sightings of structures that are not compiled (yet)
-QbJitStats g_stats;
+// never destroyed: background warm-up threads (qb_tile.cu) may still be compiling into the cache while
+// the process runs its static destructors
+std::mutex& g_mu = *new std::mutex;
+std::map<uint64_t, Compiled>& g_cache = *new std::map<uint64_t, Compiled>;      // by hash of the full source
+std::map<uint64_t, int>& g_seen = *new std::map<uint64_t, int>;                // sightings of structures that are not compiled (yet)
+QbJitStats& g_stats = *new QbJitStats;
 
 // resident CTAs per SM the kernel is compiled for (register budget = 65536 / (threads * CTAs));
 // 0 = the generator's default (2 for 256-thread tiles, 4 for 128-thread tiles)
