@@ -468,7 +468,7 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     // tile base: the tile number's bits deposited into the positions outside the tile
     o.f("QJ_DEV unsigned long long qj_tile_base(const unsigned long long t) {\n    unsigned long long b = t << %d;\n", QT_L);
     for (int i = 0; i < g.NH; i++) {
-        const int p = g.h->hb[i];
+        const int p = g.h->hbs[i];
         o.f("    b = ((b >> %d) << %d) | (b & 0x%llxull);\n", p, p + 1, (unsigned long long)((1ull << p) - 1ull));
     }
     o.f("    return b;\n}\n");

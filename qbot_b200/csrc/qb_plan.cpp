@@ -330,7 +330,8 @@ std::vector<uint8_t> serialise(const SweepBuild& sw, double header_scale) {
     h.ops_off = QT_OPS_OFF;
     h.pool_off = QT_POOL_OFF;
     h.total_bytes = (uint32_t)((h.pool_off + sizeof(double) * npool + 15) & ~size_t(15));
-    for (int i = 0; i < sw.M - QT_L; i++) h.hb[i] = (uint8_t)sw.hb[i];
+    for (int i = 0; i < sw.M - QT_L; i++) h.hb[i] = h.hbs[i] = (uint8_t)sw.hb[i];
+    std::sort(h.hbs, h.hbs + (sw.M - QT_L));
     std::vector<uint8_t> out(h.total_bytes, 0);
     memcpy(out.data(), &h, sizeof(h));
     size_t first = 0, pool_at = 0;
@@ -927,6 +928,20 @@ std::vector<QGate> qt_peephole(const std::vector<QGate>& in, int level, int* rew
 
 namespace {
 
+// number of stages of a program whose three lowest thread bits do not cover the three bank classes
+// (IO stages always do: their lanes are the low index bits)
+int conflicting_stages(const std::vector<uint8_t>& program) {
+    const QtHeader* h = (const QtHeader*)program.data();
+    const QtStage* st = (const QtStage*)(program.data() + h->stages_off);
+    int bad = 0;
+    for (int s = 0; s < h->nstages; s++) {
+        int seen = 0;
+        for (int q = 0; q < 3; q++) seen |= bank_class(st[s].tpos[q]);
+        if (seen != 7) bad++;
+    }
+    return bad;
+}
+
 // build the steps (sweep programs + unfused gates) following `guide` (tile bits of the fused sweeps in
 // order; greedy wherever the guide ends or stops being valid)
 std::vector<QtPlanStep> build_steps(const std::vector<QGate>& gates, const std::vector<GInfo>& info, int nbits,
@@ -973,6 +988,25 @@ std::vector<QtPlanStep> build_steps(const std::vector<QGate>& gates, const std::
             if (picked.size() <= 1) throw std::runtime_error("planner: cannot build a program for one gate");
             picked.resize(picked.size() / 2);
             have_guide = false;       // the searched plan assumed the whole sweep ran: fall back to greedy
+        }
+        // Which tile-local position a free tile bit gets decides its shared-memory bank class; if some
+        // stage's register bits exhaust a class (2-way conflicts on every transposition access of that
+        // stage), try other orders of the same bits.
+        if (conflicting_stages(program) > 0) {
+            std::vector<int> order = hb, best_order = hb;
+            int best_conf = conflicting_stages(program);
+            std::sort(order.begin(), order.end());
+            int tries = 0;
+            while (best_conf > 0 && tries < 200 && std::next_permutation(order.begin(), order.end())) {
+                tries++;
+                std::vector<uint8_t> cand;
+                if (!build_program(gates, info, picked, order, M, opt.R, opt.merge_phases, &cand)) continue;
+                const QtHeader* hc = (const QtHeader*)cand.data();
+                const QtHeader* hp = (const QtHeader*)program.data();
+                if (hc->nstages > hp->nstages) continue;                 // never pay a stage for it
+                const int conf = conflicting_stages(cand);
+                if (conf < best_conf) { best_conf = conf; program.swap(cand); best_order = order; }
+            }
         }
         QtPlanStep st;
         st.fused = true;

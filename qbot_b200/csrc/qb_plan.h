@@ -75,9 +75,12 @@ struct QtHeader {
     uint16_t M;                // tile bits of this program
     uint16_t ngates;           // gates of the circuit executed by this sweep
     uint32_t stages_off, ops_off, pool_off;    // byte offsets from the start of the program
-    uint8_t hb[QT_MAXH];       // index-bit positions of the free tile bits, ascending (M - QT_L used)
+    uint8_t hb[QT_MAXH];       // index-bit positions of the free tile bits (M - QT_L used): hb[i] sits at tile-local
+                               // position QT_L + i.  Any order: the planner permutes it so that no stage's register bits
+                               // exhaust a shared-memory bank class (see qt_slot)
     uint8_t R;                 // register bits per stage: 4 (16 amplitudes per thread) or 5 (32; specialised kernels only)
     double scale;              // every amplitude is multiplied by this before the store (1.0: skipped)
+    uint8_t hbs[QT_MAXH];      // the same positions in ascending order (what qt_tile_base needs)
 };
 
 // padded placement of a tile-local index in the shared-memory tile (in 16-byte units): run k
@@ -95,6 +98,7 @@ QT_HD uint32_t qt_slot(uint32_t j) {
 #define QT_TILE_UNITS(M) ((1 << (M)) + (1 << ((M) - QT_L)) + (1 << ((M) - QT_L - 3)) + 8)
 
 // index of the first amplitude of tile t: t's bits deposited into the non-tile positions
+// (hb in ASCENDING order: QtHeader.hbs)
 QT_HD uint64_t qt_tile_base(uint64_t t, const uint8_t* hb, int nh) {
     uint64_t b = t << QT_L;
     for (int i = 0; i < nh; i++) {

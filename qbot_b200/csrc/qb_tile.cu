@@ -91,7 +91,7 @@ k_tile_sweep(cplx* __restrict__ psi, const uint8_t* __restrict__ prog_dev, uint6
     __syncthreads();
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t tbase = qt_tile_base(tile, h->hb, NH);
+        const uint64_t tbase = qt_tile_base(tile, h->hbs, NH);
         cplx a[QT_NR];
         {
             const QtStage& s0 = stages[0];
@@ -108,7 +108,7 @@ k_tile_sweep(cplx* __restrict__ psi, const uint8_t* __restrict__ prog_dev, uint6
         if (prefetch && tid < (1 << NH)) {
             const uint64_t nt = tile + gridDim.x;
             if (nt < ntiles)
-                l2_prefetch_bulk(psi + qt_tile_base(nt, h->hb, NH) + qt_run_offset((uint32_t)tid, h->hb, NH), 512);
+                l2_prefetch_bulk(psi + qt_tile_base(nt, h->hbs, NH) + qt_run_offset((uint32_t)tid, h->hb, NH), 512);
         }
 
         for (int s = 0;; s++) {

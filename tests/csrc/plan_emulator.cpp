@@ -35,7 +35,7 @@ static void run_program(const uint8_t* prog, qt_c* psi, int nbits) {
     if (h->nops > QT_MAX_OPS || h->nstages > QT_MAX_STAGES) throw std::runtime_error("program exceeds the kernel limits");
     if (h->R != QT_R) throw std::runtime_error("the op interpreter (generic kernel) runs programs with 16 amplitudes per thread only");
     for (uint64_t t = 0; t < ntiles; t++) {
-        const uint64_t tbase = qt_tile_base(t, h->hb, NH);
+        const uint64_t tbase = qt_tile_base(t, h->hbs, NH);
         for (uint32_t j = 0; j < (1u << M); j++) buf[j] = psi[tbase + (j & 31u) + qt_run_offset(j >> QT_L, h->hb, NH)];
         for (int s = 0; s < h->nstages; s++) {
             const QtStage& st = stages[s];
