@@ -13,6 +13,7 @@
 #include "qb_plan.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -64,6 +65,46 @@ struct Gen {
     Out o;
     std::vector<std::string> nm;     // current name of logical register i
     int tmp = 0;
+    // Lazy conditional X: an X on register bit T under a run-time predicate (control on a thread or
+    // tile bit) normally exchanges half of the thread's amplitudes with predicated moves.  When the
+    // next thing that looks at bit T in the stage is the stage's store, the exchange becomes a choice
+    // of store address (two base pointers); when it is an unconditional Hadamard on T, H X = Z H
+    // turns it into a sign flip of half the outputs.  flags[T] = the predicate variable.
+    std::map<int, std::string> flags;
+    int cur_stage_first = 0, cur_stage_nops = 0, cur_op = 0;
+    bool lazy_x = true;
+
+    static bool symmetric_in(uint32_t regsel, int T, int NR) {
+        for (int i = 0; i < NR; i++) if (((regsel >> i) & 1u) != ((regsel >> (i ^ (1 << T))) & 1u)) return false;
+        return true;
+    }
+    bool touches(const QtOp& op2, int T) const {
+        switch (op2.type) {
+            case QT_OP_X: if (op2.t0 == T) return false; break;        // swaps of the same pairs commute with the flip
+            case QT_OP_H: case QT_OP_U2: if (op2.t0 == T) return true; break;
+            case QT_OP_U4: if (op2.t0 == T || op2.t1 == T) return true; break;
+            case QT_OP_CDIAG: if (op2.t1 == QT_LOC_REG && op2.t0 == T) return true; break;
+            case QT_OP_PHASE:
+                for (int e = 0; e < op2.nent; e++) {
+                    int64_t code;
+                    memcpy(&code, pool + op2.pool + 5 * e, sizeof(code));
+                    if ((code & 0xff) == QT_LOC_REG && (int)(code >> 8) == T) return true;
+                }
+                break;
+            default: break;
+        }
+        return !symmetric_in(op2.regsel, T, NR);
+    }
+    // 0: nothing else looks at bit T in this stage, 1: an unconditional full Hadamard on T comes first, 2: anything else
+    int lookahead(int T) const {
+        for (int y = cur_op + 1; y < cur_stage_nops; y++) {
+            const QtOp& op2 = ops[cur_stage_first + y];
+            if (!touches(op2, T)) continue;
+            if (op2.type == QT_OP_H && op2.t0 == T && (op2.flags & QT_FLAG_ALLREG) && !op2.lmask && !op2.gmask) return 1;
+            return 2;
+        }
+        return 0;
+    }
 
     std::string P(uint32_t i) const {
         char b[32];
@@ -99,6 +140,14 @@ struct Gen {
             const std::string &A = nm[i], &B = nm[i | (1 << t)];
             o.f("    { const double xr = %s.x, xi = %s.y; %s.x = xr + %s.x; %s.y = xi + %s.y; %s.x = xr - %s.x; %s.y = xi - %s.y; }\n",
                 A.c_str(), A.c_str(), A.c_str(), B.c_str(), A.c_str(), B.c_str(), B.c_str(), B.c_str(), B.c_str(), B.c_str());
+        }
+        auto fl = flags.find(t);
+        if (fl != flags.end()) {
+            // pending conditional X on this bit: H X = Z H -> flip the sign of the "1" outputs where it holds
+            o.f("    if (%s) {\n", fl->second.c_str());
+            for (int i = 0; i < NR; i++) if ((i >> t) & 1) negate(nm[i]);
+            o.f("    }\n");
+            flags.erase(fl);
         }
     }
 
@@ -288,6 +337,17 @@ struct Gen {
         const std::string c = cond_of(op);
         const bool conditional = !c.empty();
         if (op.type == QT_OP_X && !conditional) { op_x(op, false); return; }
+        if (op.type == QT_OP_X && lazy_x && (op.flags & QT_FLAG_ALLREG) && lookahead(op.t0) != 2) {
+            auto fl = flags.find(op.t0);
+            if (fl != flags.end()) o.f("    %s ^= (%s);\n", fl->second.c_str(), c.c_str());
+            else {
+                char nmf[32];
+                snprintf(nmf, sizeof(nmf), "fx%d", tmp++);
+                o.f("    bool %s = (%s);\n", nmf, c.c_str());
+                flags[op.t0] = nmf;
+            }
+            return;
+        }
         if (conditional) o.f("    if (%s) {\n", c.c_str());
         switch (op.type) {
             case QT_OP_H: op_h(op); break;
@@ -401,7 +461,34 @@ struct Gen {
         // last stage: every thread of the CTA has read its amplitudes out of the buffer -> it is free
         // for the next tile's asynchronous copies (this barrier replaces the one before stage 0's stores)
         if (last) o.f("    QJ_ISSUE_NEXT(tid, nbase, psi, buf);\n");
-        for (int x = 0; x < st.nops; x++) emit_op(ops[st.first_op + x]);
+        flags.clear();
+        cur_stage_first = st.first_op;
+        cur_stage_nops = st.nops;
+        for (int x = 0; x < st.nops; x++) { cur_op = x; emit_op(ops[st.first_op + x]); }
+        // pending conditional X exchanges become a choice of store address: register i of a thread whose
+        // flag holds goes where register i ^ (1 << T) would have gone
+        int fmask = 0;
+        for (const auto& fl : flags) {
+            const int T = fl.first;
+            fmask |= 1 << T;
+            if (last) {
+                const unsigned long long hT = 1ull << h->hb[st.rb[T] - QT_L];
+                o.f("    const unsigned long long e%d_0 = %s ? 0x%llxull : 0ull, e%d_1 = %s ? 0ull : 0x%llxull;\n", T, fl.second.c_str(), hT, T,
+                    fl.second.c_str(), hT);
+            } else {
+                const unsigned sT = qt_slot(1u << st.rb[T]);
+                o.f("    const unsigned e%d_0 = %s ? %uu : 0u, e%d_1 = %s ? 0u : %uu;\n", T, fl.second.c_str(), sT, T, fl.second.c_str(), sT);
+            }
+        }
+        auto flag_terms = [&](int i) {
+            std::string t;
+            for (const auto& fl : flags) {
+                char b[32];
+                snprintf(b, sizeof(b), " + e%d_%d", fl.first, (i >> fl.first) & 1);
+                t += b;
+            }
+            return t;
+        };
         if (last) {
             if (h->scale != 1.0) {
                 const uint32_t sidx = (uint32_t)npool_prog;      // the header scale rides behind the program's pool
@@ -409,12 +496,14 @@ struct Gen {
                 for (int i = 0; i < NR; i++) o.f("      %s.x *= s_; %s.y *= s_;\n", nm[i].c_str(), nm[i].c_str());
                 o.f("    }\n");
             }
-            for (int i = 0; i < NR; i++) o.f("    QJ_ST(gp + 0x%llxull, %s);\n", (unsigned long long)hbm_reg_offset(st, i), nm[i].c_str());
+            for (int i = 0; i < NR; i++)
+                o.f("    QJ_ST(gp + (0x%llxull%s), %s);\n", (unsigned long long)hbm_reg_offset(st, i & ~fmask), flag_terms(i).c_str(), nm[i].c_str());
         } else {
             // stage 0 stores into the very slots this thread has just read (or, for the CTA's first tile,
             // into a buffer nobody has touched yet): no barrier needed before them
-            for (int i = 0; i < NR; i++) o.f("    sp[%u] = %s;\n", smem_reg_offset(st, i), nm[i].c_str());
+            for (int i = 0; i < NR; i++) o.f("    sp[%uu%s] = %s;\n", smem_reg_offset(st, i & ~fmask), flag_terms(i).c_str(), nm[i].c_str());
         }
+        flags.clear();
         o.f("}\n\n");
     }
 
@@ -458,6 +547,7 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     g.NR = 1 << g.R;
     g.T = 1 << (g.M - g.R);
     g.npool_prog = (int)((g.h->total_bytes - g.h->pool_off) / sizeof(double));
+    g.lazy_x = getenv("QBOT_B200_EAGER_X") == nullptr;
     const int npool = g.npool_prog + 1;      // + header scale
     Out& o = g.o;
     o.f("// generated by qbot_b200 qj_generate: M=%d R=%d stages=%d ops=%d gates=%d\n", g.M, g.R, (int)g.h->nstages, (int)g.h->nops, (int)g.h->ngates);
