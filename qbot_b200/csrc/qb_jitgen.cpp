@@ -65,45 +65,203 @@ struct Gen {
     Out o;
     std::vector<std::string> nm;     // current name of logical register i
     int tmp = 0;
-    // Lazy conditional X: an X on register bit T under a run-time predicate (control on a thread or
-    // tile bit) normally exchanges half of the thread's amplitudes with predicated moves.  When the
-    // next thing that looks at bit T in the stage is the stage's store, the exchange becomes a choice
-    // of store address (two base pointers); when it is an unconditional Hadamard on T, H X = Z H
-    // turns it into a sign flip of half the outputs.  flags[T] = the predicate variable.
-    std::map<int, std::string> flags;
-    int cur_stage_first = 0, cur_stage_nops = 0, cur_op = 0;
+    // Deferred conditional X.  An X on register bit T under a run-time predicate (controls on thread or
+    // tile bits) would exchange the selected amplitude pairs of the thread with predicated moves.
+    // Instead it is kept as a PENDING flip (predicate variable, register set) that later ops are
+    // commuted over:
+    //   * the stage's store consumes it as a choice between two store offsets,
+    //   * a Hadamard on T consumes it as a sign (H X = Z H: negate the "1" outputs where it holds),
+    //   * a diagonal on T swaps its two factors where it holds (D X = X D'),
+    //   * a renaming X on another bit whose register set depends on bit T (CNOT controlled by T)
+    //     spawns a second pending flip on its own target (X_t[T=1 xor f] = X_t[T=1] X_t^f),
+    //   * ops that neither read nor depend on bit T commute,
+    // and anything else makes the flip happen first (flush = the predicated exchange, later).
+    // Invariant: pending flips commute with each other, so the order in which they are consumed is free.
+    struct Pend { int T; std::string var; uint32_t sel; };
+    std::vector<Pend> pend;
     bool lazy_x = true;
+    // what the op being emitted has to do for the pending flips it consumes
+    std::vector<std::pair<std::string, uint32_t>> h_neg;      // after a butterfly: negate registers (mask) where var holds
+    std::map<int, std::string> phase_swap;                    // PHASE: register bit -> var: exchange d0 / d1 where it holds
+    std::string u2_swap;                                      // U2: exchange the matrix columns where it holds
+    std::string cdiag_swap;                                   // CDIAG on a register bit: exchange d0 / d1 where it holds
+    std::vector<std::string> post_stmts;                      // statements behind the op's (conditional) block
 
-    static bool symmetric_in(uint32_t regsel, int T, int NR) {
-        for (int i = 0; i < NR; i++) if (((regsel >> i) & 1u) != ((regsel >> (i ^ (1 << T))) & 1u)) return false;
+    static bool sig_partial(const std::vector<Pend>& pd, uint32_t sig, uint32_t all) {
+        for (size_t k = 0; k < pd.size(); k++) if (((sig >> k) & 1u) && pd[k].sel != all) return true;
+        return false;
+    }
+    uint32_t all_sel() const { return NR >= 32 ? 0xffffffffu : ((1u << NR) - 1u); }
+    uint32_t flip_sel(uint32_t sel, int T) const {
+        uint32_t r = 0;
+        for (int i = 0; i < NR; i++) if ((sel >> i) & 1u) r |= 1u << (i ^ (1 << T));
+        return r;
+    }
+    uint32_t asym(uint32_t sel, int T) const { return sel ^ flip_sel(sel, T); }
+    // do the pair exchanges X_Ta[sa] and X_Tb[sb] commute?  (sufficient conditions)
+    bool flips_commute(int Ta, uint32_t sa, int Tb, uint32_t sb) const {
+        if (Ta == Tb || !(sa & sb)) return true;
+        return !(asym(sa, Tb) & sb) && !(asym(sb, Ta) & sa);
+    }
+    std::string new_flag(const std::string& init) {
+        char nmf[32];
+        snprintf(nmf, sizeof(nmf), "fx%d", tmp++);
+        o.f("    bool %s = (%s);\n", nmf, init.c_str());
+        return nmf;
+    }
+    void flush(size_t k) {
+        const Pend p = pend[k];
+        pend.erase(pend.begin() + (long)k);
+        o.f("    if (%s) {    // [flip:flush]\n", p.var.c_str());
+        for (int i = 0; i < NR; i++) {
+            if ((i >> p.T) & 1 || !((p.sel >> i) & 1u)) continue;
+            const int j = i | (1 << p.T);
+            o.f("      { const QJ_C t_ = %s; %s = %s; %s = t_; }\n", nm[i].c_str(), nm[i].c_str(), nm[j].c_str(), nm[j].c_str());
+        }
+        o.f("    }\n");
+    }
+    // add a pending flip (T, value of `init`, sel).  Where it does not commute with a pending flip q, one of
+    // the two has to happen now: q (its exchange is emitted before everything pending), or the new one --
+    // it is then commuted over q like a renaming X (q's flag spawns a flip on T over the registers whose
+    // membership in sel depends on q's bit) and emitted as a predicated exchange.  The cheaper one is taken.
+    void add_pending(int T, const std::string& init, uint32_t sel) {
+        if (!sel) return;
+        int conflicts = 0, min_q = 64;
+        bool can_go_first = true;
+        for (size_t k = 0; k < pend.size(); k++) {
+            const Pend& q = pend[k];
+            if (flips_commute(T, sel, q.T, q.sel)) continue;
+            conflicts++;
+            min_q = std::min(min_q, __builtin_popcount(q.sel));
+            const uint32_t ns = asym(sel, q.T) & q.sel;
+            if (asym(q.sel, T) || !admissible(T, ns, pend.size())) can_go_first = false;
+        }
+        if (conflicts && can_go_first && __builtin_popcount(sel) < min_q) {
+            std::vector<std::pair<std::string, uint32_t>> spawned;
+            for (const Pend& q : pend)
+                if (!flips_commute(T, sel, q.T, q.sel)) spawned.push_back({"(" + q.var + ") && (" + init + ")", asym(sel, q.T) & q.sel});
+            o.f("    if (%s) {    // [flip:first]\n", init.c_str());
+            for (int i = 0; i < NR; i++) {
+                if ((i >> T) & 1 || !((sel >> i) & 1u)) continue;
+                const int j = i | (1 << T);
+                o.f("      { const QJ_C t_ = %s; %s = %s; %s = t_; }\n", nm[i].c_str(), nm[i].c_str(), nm[j].c_str(), nm[j].c_str());
+            }
+            o.f("    }\n");
+            for (const auto& sp : spawned) add_pending(T, sp.first, sp.second);
+            return;
+        }
+        for (size_t k = 0; k < pend.size();) {
+            if (!flips_commute(T, sel, pend[k].T, pend[k].sel)) flush(k); else k++;
+        }
+        for (Pend& q : pend)
+            if (q.T == T && q.sel == sel) { o.f("    %s ^= (%s);\n", q.var.c_str(), init.c_str()); return; }
+        pend.push_back({T, new_flag(init), sel});
+    }
+    // would a new flip commute with every pending one except index `skip`?
+    bool admissible(int T, uint32_t sel, size_t skip) const {
+        for (size_t k = 0; k < pend.size(); k++)
+            if (k != skip && !flips_commute(T, sel, pend[k].T, pend[k].sel)) return false;
         return true;
     }
-    bool touches(const QtOp& op2, int T) const {
-        switch (op2.type) {
-            case QT_OP_X: if (op2.t0 == T) return false; break;        // swaps of the same pairs commute with the flip
-            case QT_OP_H: case QT_OP_U2: if (op2.t0 == T) return true; break;
-            case QT_OP_U4: if (op2.t0 == T || op2.t1 == T) return true; break;
-            case QT_OP_CDIAG: if (op2.t1 == QT_LOC_REG && op2.t0 == T) return true; break;
-            case QT_OP_PHASE:
-                for (int e = 0; e < op2.nent; e++) {
-                    int64_t code;
-                    memcpy(&code, pool + op2.pool + 5 * e, sizeof(code));
-                    if ((code & 0xff) == QT_LOC_REG && (int)(code >> 8) == T) return true;
+
+    // Commute the op about to be emitted (it comes AFTER the pending flips in time, its code BEFORE theirs)
+    // over every pending flip: nothing to do, a consumption recorded for the op's emitter, or a flush.
+    void settle(const QtOp& op, const std::string& c) {
+        const bool conditional = !c.empty();
+        const uint32_t R2 = op.regsel;
+        h_neg.clear(); phase_swap.clear(); cdiag_swap.clear(); u2_swap.clear(); post_stmts.clear();
+        struct Spawn { int T; std::string init; uint32_t sel; };
+        std::vector<Spawn> spawns;
+        for (size_t k = 0; k < pend.size();) {
+            Pend& p = pend[k];
+            bool fl = false;
+            // generic test for an op that works on register pairs / quads over targets tg[]:
+            auto pairs_commute = [&](std::initializer_list<int> tg) {
+                uint32_t a1 = 0;
+                for (int t : tg) a1 |= asym(p.sel, t);
+                return !(a1 & R2) && !(asym(R2, p.T) & p.sel);
+            };
+            switch (op.type) {
+                case QT_OP_X:       // unconditional: a renaming
+                    if (op.t0 == p.T || !(p.sel & (R2 | flip_sel(R2, p.T)))) break;
+                    if (pairs_commute({(int)op.t0})) break;
+                    if (!asym(p.sel, op.t0)) {
+                        const uint32_t ns = asym(R2, p.T) & p.sel;
+                        if (admissible(op.t0, ns, k)) { spawns.push_back({(int)op.t0, p.var, ns}); break; }
+                    }
+                    fl = true;
+                    break;
+                case QT_OP_H:
+                    if (op.t0 == p.T) {
+                        const uint32_t ov = p.sel & R2;
+                        if (!ov) break;
+                        uint32_t ones = 0;
+                        for (int i = 0; i < NR; i++) if (((ov >> i) & 1u) && ((i >> p.T) & 1)) ones |= 1u << i;
+                        if (!conditional) {
+                            const uint32_t rest = p.sel & ~R2;
+                            if (rest && !admissible(p.T, rest, k)) { fl = true; break; }
+                            h_neg.push_back({p.var, ones});
+                            p.sel = rest;
+                            if (!rest) { pend.erase(pend.begin() + (long)k); continue; }
+                        } else fl = true;      // (the planner emits controlled Hadamards as U2)
+                        break;
+                    }
+                    fl = !pairs_commute({(int)op.t0});
+                    break;
+                case QT_OP_U2:
+                    if (op.t0 == p.T) {
+                        // U X = U' (columns exchanged): the flip is absorbed into the matrix where it holds
+                        const uint32_t ov = p.sel & R2;
+                        if (!ov) break;
+                        if (ov != R2 || !u2_swap.empty()) { fl = true; break; }
+                        if (!conditional) {
+                            const uint32_t rest = p.sel & ~R2;
+                            if (rest && !admissible(p.T, rest, k)) { fl = true; break; }
+                            u2_swap = p.var;
+                            p.sel = rest;
+                            if (!rest) { pend.erase(pend.begin() + (long)k); continue; }
+                        } else if (ov == p.sel) {
+                            // absorbed where the op's predicate holds, still pending where it does not
+                            u2_swap = new_flag(p.var);
+                            post_stmts.push_back("    " + p.var + " = " + p.var + " && !(" + c + ");    // [flip:u2cond]\n");
+                        } else fl = true;
+                        break;
+                    }
+                    fl = !pairs_commute({(int)op.t0});
+                    break;
+                case QT_OP_U4:
+                    if (op.t0 == p.T || op.t1 == p.T) fl = (p.sel & R2) != 0; else fl = !pairs_commute({(int)op.t0, (int)op.t1});
+                    break;
+                case QT_OP_CDIAG:
+                    if (op.t1 == QT_LOC_REG && op.t0 == p.T) {
+                        const uint32_t ov = p.sel & R2;
+                        if (!ov) break;
+                        if (ov == R2 && cdiag_swap.empty()) { cdiag_swap = p.var; break; }
+                        fl = true;
+                        break;
+                    }
+                    fl = (asym(R2, p.T) & p.sel) != 0;
+                    break;
+                case QT_OP_PHASE: {
+                    bool has = false;
+                    for (int e = 0; e < op.nent; e++) {
+                        int64_t code;
+                        memcpy(&code, pool + op.pool + 5 * e, sizeof(code));
+                        if ((code & 0xff) == QT_LOC_REG && (int)(code >> 8) == p.T) has = true;
+                    }
+                    if (!has) break;
+                    if (p.sel == all_sel() && !conditional && !phase_swap.count(p.T)) { phase_swap[p.T] = p.var; break; }
+                    fl = true;
+                    break;
                 }
-                break;
-            default: break;
+                default: fl = true; break;
+            }
+            if (fl) flush(k); else k++;
         }
-        return !symmetric_in(op2.regsel, T, NR);
-    }
-    // 0: nothing else looks at bit T in this stage, 1: an unconditional full Hadamard on T comes first, 2: anything else
-    int lookahead(int T) const {
-        for (int y = cur_op + 1; y < cur_stage_nops; y++) {
-            const QtOp& op2 = ops[cur_stage_first + y];
-            if (!touches(op2, T)) continue;
-            if (op2.type == QT_OP_H && op2.t0 == T && (op2.flags & QT_FLAG_ALLREG) && !op2.lmask && !op2.gmask) return 1;
-            return 2;
+        for (const Spawn& sp : spawns) {
+            o.f("    // [flip:spawn]\n");
+            add_pending(sp.T, sp.init, sp.sel);
         }
-        return 0;
     }
 
     std::string P(uint32_t i) const {
@@ -141,14 +299,13 @@ struct Gen {
             o.f("    { const double xr = %s.x, xi = %s.y; %s.x = xr + %s.x; %s.y = xi + %s.y; %s.x = xr - %s.x; %s.y = xi - %s.y; }\n",
                 A.c_str(), A.c_str(), A.c_str(), B.c_str(), A.c_str(), B.c_str(), B.c_str(), B.c_str(), B.c_str(), B.c_str());
         }
-        auto fl = flags.find(t);
-        if (fl != flags.end()) {
+        for (const auto& hn : h_neg) {
             // pending conditional X on this bit: H X = Z H -> flip the sign of the "1" outputs where it holds
-            o.f("    if (%s) {\n", fl->second.c_str());
-            for (int i = 0; i < NR; i++) if ((i >> t) & 1) negate(nm[i]);
+            o.f("    if (%s) {    // [flip:h]\n", hn.first.c_str());
+            for (int i = 0; i < NR; i++) if ((hn.second >> i) & 1u) negate(nm[i]);
             o.f("    }\n");
-            flags.erase(fl);
         }
+        h_neg.clear();
     }
 
     void op_x(const QtOp& op, bool conditional) {
@@ -166,8 +323,17 @@ struct Gen {
     void op_u2(const QtOp& op) {
         const int t = op.t0;
         const uint32_t p = op.pool;
-        o.f("    { const double m0 = %s, m1 = %s, m2 = %s, m3 = %s, m4 = %s, m5 = %s, m6 = %s, m7 = %s;\n", P(p).c_str(),
-            P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str(), P(p + 4).c_str(), P(p + 5).c_str(), P(p + 6).c_str(), P(p + 7).c_str());
+        if (u2_swap.empty())
+            o.f("    { const double m0 = %s, m1 = %s, m2 = %s, m3 = %s, m4 = %s, m5 = %s, m6 = %s, m7 = %s;\n", P(p).c_str(),
+                P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str(), P(p + 4).c_str(), P(p + 5).c_str(), P(p + 6).c_str(), P(p + 7).c_str());
+        else {
+            o.f("    { const bool f_ = %s;    // [flip:u2]\n", u2_swap.c_str());
+            for (int r = 0; r < 2; r++)
+                o.f("      const double m%d = f_ ? %s : %s, m%d = f_ ? %s : %s, m%d = f_ ? %s : %s, m%d = f_ ? %s : %s;\n", 4 * r, P(p + 4 * r + 2).c_str(),
+                    P(p + 4 * r).c_str(), 4 * r + 1, P(p + 4 * r + 3).c_str(), P(p + 4 * r + 1).c_str(), 4 * r + 2, P(p + 4 * r).c_str(),
+                    P(p + 4 * r + 2).c_str(), 4 * r + 3, P(p + 4 * r + 1).c_str(), P(p + 4 * r + 3).c_str());
+            u2_swap.clear();
+        }
         for (int i = 0; i < NR; i++) {
             if ((i >> t) & 1 || !((op.regsel >> i) & 1u)) continue;
             const std::string &A = nm[i], &B = nm[i | (1 << t)];
@@ -223,13 +389,25 @@ struct Gen {
         if (op.t1 == QT_LOC_REG) {
             const bool one0 = pool_is_one(p), one1 = pool_is_one(p + 2);
             o.f("    { const double d0r = %s, d0i = %s, d1r = %s, d1i = %s;\n", P(p).c_str(), P(p + 1).c_str(), P(p + 2).c_str(), P(p + 3).c_str());
-            for (int i = 0; i < NR; i++) {
-                if (!((op.regsel >> i) & 1u)) continue;
-                const bool hi = (i >> op.t0) & 1;
-                if (hi ? one1 : one0) continue;          // exact unit factor: structural, part of the source text
-                if (pool_is_minus_one(hi ? p + 2 : p)) { negate(nm[i]); continue; }
-                o.f("  ");
-                cmul_into(nm[i], hi ? "d1r" : "d0r", hi ? "d1i" : "d0i");
+            // inv: a pending conditional X on the target bit holds -> the two factors trade places (D X = X D')
+            auto body = [&](bool inv) {
+                for (int i = 0; i < NR; i++) {
+                    if (!((op.regsel >> i) & 1u)) continue;
+                    const bool hi = (((i >> op.t0) & 1) != 0) != inv;
+                    if (hi ? one1 : one0) continue;          // exact unit factor: structural, part of the source text
+                    if (pool_is_minus_one(hi ? p + 2 : p)) { negate(nm[i]); continue; }
+                    o.f("  ");
+                    cmul_into(nm[i], hi ? "d1r" : "d0r", hi ? "d1i" : "d0i");
+                }
+            };
+            if (cdiag_swap.empty()) body(false);
+            else {
+                o.f("      if (%s) {    // [flip:cdiag]\n", cdiag_swap.c_str());
+                body(true);
+                o.f("      } else {\n");
+                body(false);
+                o.f("      }\n");
+                cdiag_swap.clear();
             }
             o.f("    }\n");
         } else {
@@ -299,6 +477,13 @@ struct Gen {
             // is the (product) d0 of this bit exactly one?  (structural: single entries come in as (1, 0))
             bool d0_one = reg_entries[q].size() >= 1;
             for (int ex : reg_entries[q]) d0_one = d0_one && pool_is_one(p + 5 * ex + 1);
+            auto sw = phase_swap.find(q);
+            if (sw != phase_swap.end()) {
+                // pending conditional X on this bit: D X = X D' with the two factors exchanged where it holds
+                o.f("      if (%s) { double t_ = %s; %s = %s; %s = t_; t_ = %s; %s = %s; %s = t_; }    // [flip:phase]\n", sw->second.c_str(), d0r, d0r, d1r, d1r, d0i,
+                    d0i, d1i, d1i);
+                d0_one = false;
+            }
             std::vector<Ent> next;
             if (table.empty()) {
                 if (d0_one) next.push_back({0, "", ""}); else next.push_back({0, d0r, d0i});
@@ -336,18 +521,11 @@ struct Gen {
     void emit_op(const QtOp& op) {
         const std::string c = cond_of(op);
         const bool conditional = !c.empty();
-        if (op.type == QT_OP_X && !conditional) { op_x(op, false); return; }
-        if (op.type == QT_OP_X && lazy_x && (op.flags & QT_FLAG_ALLREG) && lookahead(op.t0) != 2) {
-            auto fl = flags.find(op.t0);
-            if (fl != flags.end()) o.f("    %s ^= (%s);\n", fl->second.c_str(), c.c_str());
-            else {
-                char nmf[32];
-                snprintf(nmf, sizeof(nmf), "fx%d", tmp++);
-                o.f("    bool %s = (%s);\n", nmf, c.c_str());
-                flags[op.t0] = nmf;
-            }
-            return;
+        if (lazy_x) {
+            if (op.type == QT_OP_X && conditional) { add_pending(op.t0, c, op.regsel); return; }
+            settle(op, c);
         }
+        if (op.type == QT_OP_X && !conditional) { op_x(op, false); return; }
         if (conditional) o.f("    if (%s) {\n", c.c_str());
         switch (op.type) {
             case QT_OP_H: op_h(op); break;
@@ -359,6 +537,8 @@ struct Gen {
             default: break;
         }
         if (conditional) o.f("    }\n");
+        for (const std::string& st : post_stmts) o.f("%s", st.c_str());
+        post_stmts.clear();
     }
 
     uint64_t hbm_reg_offset(const QtStage& st, int i) const {
@@ -461,34 +641,43 @@ struct Gen {
         // last stage: every thread of the CTA has read its amplitudes out of the buffer -> it is free
         // for the next tile's asynchronous copies (this barrier replaces the one before stage 0's stores)
         if (last) o.f("    QJ_ISSUE_NEXT(tid, nbase, psi, buf);\n");
-        flags.clear();
-        cur_stage_first = st.first_op;
-        cur_stage_nops = st.nops;
-        for (int x = 0; x < st.nops; x++) { cur_op = x; emit_op(ops[st.first_op + x]); }
-        // pending conditional X exchanges become a choice of store address: register i of a thread whose
-        // flag holds goes where register i ^ (1 << T) would have gone
-        int fmask = 0;
-        for (const auto& fl : flags) {
-            const int T = fl.first;
-            fmask |= 1 << T;
-            if (last) {
-                const unsigned long long hT = 1ull << h->hb[st.rb[T] - QT_L];
-                o.f("    const unsigned long long e%d_0 = %s ? 0x%llxull : 0ull, e%d_1 = %s ? 0ull : 0x%llxull;\n", T, fl.second.c_str(), hT, T,
-                    fl.second.c_str(), hT);
-            } else {
-                const unsigned sT = qt_slot(1u << st.rb[T]);
-                o.f("    const unsigned e%d_0 = %s ? %uu : 0u, e%d_1 = %s ? 0u : %uu;\n", T, fl.second.c_str(), sT, T, fl.second.c_str(), sT);
+        pend.clear();
+        for (int x = 0; x < st.nops; x++) emit_op(ops[st.first_op + x]);
+        // pending flips become a choice of store address: register i of a thread whose flag holds goes
+        // where register i ^ (1 << T) would have gone.  Per target bit, registers are grouped by the set of
+        // pending flips that select them (the XOR of those flags decides).
+        std::vector<int> fmask(NR, 0);
+        std::vector<std::string> fterms(NR);
+        for (int T = 0; T < R; T++) {
+            std::map<uint32_t, int> groups;         // signature (bit k <-> pend[k] selects the register) -> group id
+            for (int i = 0; i < NR; i++) {
+                uint32_t sig = 0;
+                for (size_t k = 0; k < pend.size(); k++) if (pend[k].T == T && ((pend[k].sel >> i) & 1u)) sig |= 1u << k;
+                if (!sig) continue;
+                auto it = groups.find(sig);
+                if (it == groups.end()) {
+                    const int g = (int)groups.size();
+                    it = groups.emplace(sig, g).first;
+                    std::string fe;
+                    for (size_t k = 0; k < pend.size(); k++) if ((sig >> k) & 1u) fe += (fe.empty() ? "" : " ^ ") + pend[k].var;
+                    o.f("    // [flip:store%s]\n", __builtin_popcount(sig) > 1 ? "-multi" : sig_partial(pend, sig, all_sel()) ? "-partial" : "");
+                    if (last) {
+                        const unsigned long long hT = 1ull << h->hb[st.rb[T] - QT_L];
+                        o.f("    const bool g%d_%d = %s; const unsigned long long e%d_%d_0 = g%d_%d ? 0x%llxull : 0ull, e%d_%d_1 = g%d_%d ? 0ull : 0x%llxull;\n",
+                            T, g, fe.c_str(), T, g, T, g, hT, T, g, T, g, hT);
+                    } else {
+                        const unsigned sT = qt_slot(1u << st.rb[T]);
+                        o.f("    const bool g%d_%d = %s; const unsigned e%d_%d_0 = g%d_%d ? %uu : 0u, e%d_%d_1 = g%d_%d ? 0u : %uu;\n", T, g, fe.c_str(), T,
+                            g, T, g, sT, T, g, T, g, sT);
+                    }
+                }
+                char b[48];
+                snprintf(b, sizeof(b), " + e%d_%d_%d", T, it->second, (i >> T) & 1);
+                fterms[i] += b;
+                fmask[i] |= 1 << T;
             }
         }
-        auto flag_terms = [&](int i) {
-            std::string t;
-            for (const auto& fl : flags) {
-                char b[32];
-                snprintf(b, sizeof(b), " + e%d_%d", fl.first, (i >> fl.first) & 1);
-                t += b;
-            }
-            return t;
-        };
+        auto flag_terms = [&](int i) { return fterms[i]; };
         if (last) {
             if (h->scale != 1.0) {
                 const uint32_t sidx = (uint32_t)npool_prog;      // the header scale rides behind the program's pool
@@ -497,13 +686,13 @@ struct Gen {
                 o.f("    }\n");
             }
             for (int i = 0; i < NR; i++)
-                o.f("    QJ_ST(gp + (0x%llxull%s), %s);\n", (unsigned long long)hbm_reg_offset(st, i & ~fmask), flag_terms(i).c_str(), nm[i].c_str());
+                o.f("    QJ_ST(gp + (0x%llxull%s), %s);\n", (unsigned long long)hbm_reg_offset(st, i & ~fmask[i]), flag_terms(i).c_str(), nm[i].c_str());
         } else {
             // stage 0 stores into the very slots this thread has just read (or, for the CTA's first tile,
             // into a buffer nobody has touched yet): no barrier needed before them
-            for (int i = 0; i < NR; i++) o.f("    sp[%uu%s] = %s;\n", smem_reg_offset(st, i & ~fmask), flag_terms(i).c_str(), nm[i].c_str());
+            for (int i = 0; i < NR; i++) o.f("    sp[%uu%s] = %s;\n", smem_reg_offset(st, i & ~fmask[i]), flag_terms(i).c_str(), nm[i].c_str());
         }
-        flags.clear();
+        pend.clear();
         o.f("}\n\n");
     }
 

@@ -12,7 +12,7 @@ import plan_emu
 from oracle import qbot_oracle as orc
 from qbot_b200.circuits import rc
 from conftest import close
-from test_planner import random_gate_list, oracle_apply_bits, rand_ket
+from test_planner import random_gate_list, oracle_apply_bits, rand_ket, rand_u
 
 
 def tileable(gl):
@@ -57,6 +57,99 @@ def test_generated_source_mixed(M, merge, plan_R):
         for m, tb, cm in gl:
             ref = oracle_apply_bits(ref, n, m, tb, cm)
         assert close(out, ref, 1e-12), (n, info)
+
+
+def _flip_heavy(rng, n, count):
+    """X / H / diagonal / 2x2 traffic under 0-2 controls: with n close to the tile size most controls are
+    thread bits, which is what the deferred-flip rules of the generator (qb_jitgen.cpp, `Pend`) see"""
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    H = np.array([[1, 1], [1, -1]], dtype=complex) * 2 ** -0.5
+    Z = np.diag([1, -1]).astype(complex)
+    out = []
+    for _ in range(count):
+        bits = [int(b) for b in rng.permutation(n)]
+        r = rng.random()
+        nc = int(rng.integers(0, 3))
+        if r < 0.40:
+            m = X
+            nc = max(nc, 1) if rng.random() < 0.8 else nc
+        elif r < 0.60:
+            m = H
+            nc = 0 if rng.random() < 0.8 else nc
+        elif r < 0.72:
+            m = np.diag(np.exp(1j * rng.uniform(0, 6.28, 2)))
+        elif r < 0.80:
+            m = Z
+        elif r < 0.88:
+            m = rand_u(rng, 1)
+            nc = min(nc, 1)
+        elif r < 0.94:
+            out.append((rand_u(rng, 2), bits[:2], 0))
+            continue
+        else:
+            out.append((np.diag(np.exp(1j * rng.uniform(0, 6.28, 4))), bits[:2], 0))
+            continue
+        cm = 0
+        for c in bits[1:1 + nc]:
+            cm |= 1 << c
+        out.append((m, bits[:1], cm))
+    return out
+
+
+def _cx_then_ch(rng, n, count):
+    """controlled X directly followed by a controlled Hadamard (a conditional 2x2) on the same target"""
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    H = np.array([[1, 1], [1, -1]], dtype=complex) * 2 ** -0.5
+    out = []
+    for _ in range(count):
+        b = [int(x) for x in rng.permutation(n)]
+        out.append((X, b[:1], 1 << b[1]))
+        out.append((H, b[:1], (1 << b[2]) if rng.random() < 0.7 else (1 << b[2]) | (1 << b[3])))
+        if rng.random() < 0.3:
+            out.append((H, [b[4]], 0))
+    return out
+
+
+def test_deferred_conditional_x(plan_R):
+    """A controlled X whose controls are thread / tile bits is not executed as a predicated exchange: it stays a
+    pending flip that the store (address choice), a Hadamard (sign), a diagonal (factor exchange), a 2x2
+    (column exchange) or a CNOT controlled by its bit (second flip) absorb.  Every rule must occur in the
+    generated text of these circuits and every result must match the oracle."""
+    import re
+    seen = set()
+    cases = [(_flip_heavy, seed, 60) for seed in (1, 3, 13, 21)] + [(_cx_then_ch, seed, 20) for seed in (0, 3)]
+    for make, seed, count in cases:
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(12, 15))
+        M = 12 if seed % 3 else 11
+        gl = make(rng, n, count)
+        psi = rand_ket(rng, n)
+        for fused, _, prog in jit_emu.plan(n, gl, M, True):
+            assert fused
+            seen.update(re.findall(r'\[flip:([a-z0-9-]+)\]', jit_emu.source_of(prog)))
+        out, info = jit_emu.run(n, gl, psi, M=M)
+        ref = psi
+        for m, tb, cm in gl:
+            ref = oracle_apply_bits(ref, n, m, tb, cm)
+        assert close(out, ref, 1e-12), (make.__name__, seed, n, info)
+    assert {'store', 'store-partial', 'h', 'phase', 'cdiag', 'u2', 'u2cond', 'spawn', 'first', 'flush'} <= seen, seen
+
+
+def test_eager_x_switch(monkeypatch):
+    """QBOT_B200_EAGER_X=1 restores the predicated exchanges (A/B timing): same results, no deferred flips"""
+    import re
+    monkeypatch.setenv('QBOT_B200_EAGER_X', '1')
+    rng = np.random.default_rng(13)
+    n = 13
+    gl = _flip_heavy(rng, n, 50)
+    psi = rand_ket(rng, n)
+    for _, _, prog in jit_emu.plan(n, gl, 12, True):
+        assert not re.findall(r'\[flip:', jit_emu.source_of(prog))
+    out, _ = jit_emu.run(n, gl, psi, M=12)
+    ref = psi
+    for m, tb, cm in gl:
+        ref = oracle_apply_bits(ref, n, m, tb, cm)
+    assert close(out, ref, 1e-12)
 
 
 def test_generated_source_matches_interpreter_semantics():
