@@ -77,7 +77,11 @@ struct Gen {
     //   * ops that neither read nor depend on bit T commute,
     // and anything else makes the flip happen first (flush = the predicated exchange, later).
     // Invariant: pending flips commute with each other, so the order in which they are consumed is free.
-    struct Pend { int T; std::string var; uint32_t sel; };
+    struct Pend {
+        int T; std::string var; uint32_t sel;
+        uint32_t lmask = 0, lval = 0;     // thread-bit part of the predicate (tile-local positions) ...
+        bool simple = false;              // ... exact only while the flag is a single op's predicate
+    };
     std::vector<Pend> pend;
     bool lazy_x = true;
     // what the op being emitted has to do for the pending flips it consumes
@@ -89,6 +93,25 @@ struct Gen {
 
     static bool sig_partial(const std::vector<Pend>& pd, uint32_t sig, uint32_t all) {
         for (size_t k = 0; k < pd.size(); k++) if (((sig >> k) & 1u) && pd[k].sel != all) return true;
+        return false;
+    }
+    bool bank_aware = false;
+    // would the store offsets chosen by pending flip p put two lanes of an 8-lane wavefront on one bank?
+    bool store_conflicts(const QtStage& st, const Pend& p) const {
+        uint32_t phase = 0;
+        for (int q = 0; q < 3 && q < M - R; q++) phase |= 1u << st.tpos[q];
+        if (!(p.lmask & phase)) return false;          // the same choice for all lanes of a wavefront
+        if (!p.simple) return true;
+        const uint32_t sT = qt_slot(1u << st.rb[p.T]);
+        int used = 0;
+        for (int j = 0; j < 8; j++) {
+            uint32_t lbj = 0;
+            for (int q = 0; q < 3 && q < M - R; q++) if ((j >> q) & 1) lbj |= 1u << st.tpos[q];
+            const bool f = ((lbj ^ p.lval) & p.lmask & phase) == 0;
+            const int bank = (int)((qt_slot(lbj) + (f ? sT : 0u)) & 7u);
+            if ((used >> bank) & 1) return true;
+            used |= 1 << bank;
+        }
         return false;
     }
     uint32_t all_sel() const { return NR >= 32 ? 0xffffffffu : ((1u << NR) - 1u); }
@@ -124,7 +147,7 @@ struct Gen {
     // the two has to happen now: q (its exchange is emitted before everything pending), or the new one --
     // it is then commuted over q like a renaming X (q's flag spawns a flip on T over the registers whose
     // membership in sel depends on q's bit) and emitted as a predicated exchange.  The cheaper one is taken.
-    void add_pending(int T, const std::string& init, uint32_t sel) {
+    void add_pending(int T, const std::string& init, uint32_t sel, uint32_t lmask, uint32_t lval, bool simple) {
         if (!sel) return;
         int conflicts = 0, min_q = 64;
         bool can_go_first = true;
@@ -138,8 +161,12 @@ struct Gen {
         }
         if (conflicts && can_go_first && __builtin_popcount(sel) < min_q) {
             std::vector<std::pair<std::string, uint32_t>> spawned;
+            uint32_t spawned_dep = lmask;
             for (const Pend& q : pend)
-                if (!flips_commute(T, sel, q.T, q.sel)) spawned.push_back({"(" + q.var + ") && (" + init + ")", asym(sel, q.T) & q.sel});
+                if (!flips_commute(T, sel, q.T, q.sel)) {
+                    spawned.push_back({"(" + q.var + ") && (" + init + ")", asym(sel, q.T) & q.sel});
+                    spawned_dep |= q.lmask;
+                }
             o.f("    if (%s) {    // [flip:first]\n", init.c_str());
             for (int i = 0; i < NR; i++) {
                 if ((i >> T) & 1 || !((sel >> i) & 1u)) continue;
@@ -147,15 +174,22 @@ struct Gen {
                 o.f("      { const QJ_C t_ = %s; %s = %s; %s = t_; }\n", nm[i].c_str(), nm[i].c_str(), nm[j].c_str(), nm[j].c_str());
             }
             o.f("    }\n");
-            for (const auto& sp : spawned) add_pending(T, sp.first, sp.second);
+            for (const auto& sp : spawned) add_pending(T, sp.first, sp.second, spawned_dep, 0, false);
             return;
         }
         for (size_t k = 0; k < pend.size();) {
             if (!flips_commute(T, sel, pend[k].T, pend[k].sel)) flush(k); else k++;
         }
         for (Pend& q : pend)
-            if (q.T == T && q.sel == sel) { o.f("    %s ^= (%s);\n", q.var.c_str(), init.c_str()); return; }
-        pend.push_back({T, new_flag(init), sel});
+            if (q.T == T && q.sel == sel) {
+                o.f("    %s ^= (%s);\n", q.var.c_str(), init.c_str());
+                q.lmask |= lmask;
+                q.simple = false;
+                return;
+            }
+        Pend np;
+        np.T = T; np.var = new_flag(init); np.sel = sel; np.lmask = lmask; np.lval = lval; np.simple = simple;
+        pend.push_back(np);
     }
     // would a new flip commute with every pending one except index `skip`?
     bool admissible(int T, uint32_t sel, size_t skip) const {
@@ -170,7 +204,7 @@ struct Gen {
         const bool conditional = !c.empty();
         const uint32_t R2 = op.regsel;
         h_neg.clear(); phase_swap.clear(); cdiag_swap.clear(); u2_swap.clear(); post_stmts.clear();
-        struct Spawn { int T; std::string init; uint32_t sel; };
+        struct Spawn { int T; std::string init; uint32_t sel; uint32_t dep; };
         std::vector<Spawn> spawns;
         for (size_t k = 0; k < pend.size();) {
             Pend& p = pend[k];
@@ -187,7 +221,7 @@ struct Gen {
                     if (pairs_commute({(int)op.t0})) break;
                     if (!asym(p.sel, op.t0)) {
                         const uint32_t ns = asym(R2, p.T) & p.sel;
-                        if (admissible(op.t0, ns, k)) { spawns.push_back({(int)op.t0, p.var, ns}); break; }
+                        if (admissible(op.t0, ns, k)) { spawns.push_back({(int)op.t0, p.var, ns, p.lmask}); break; }
                     }
                     fl = true;
                     break;
@@ -223,6 +257,8 @@ struct Gen {
                         } else if (ov == p.sel) {
                             // absorbed where the op's predicate holds, still pending where it does not
                             u2_swap = new_flag(p.var);
+                            pend[k].lmask |= op.lmask;
+                            pend[k].simple = false;
                             post_stmts.push_back("    " + p.var + " = " + p.var + " && !(" + c + ");    // [flip:u2cond]\n");
                         } else fl = true;
                         break;
@@ -260,7 +296,7 @@ struct Gen {
         }
         for (const Spawn& sp : spawns) {
             o.f("    // [flip:spawn]\n");
-            add_pending(sp.T, sp.init, sp.sel);
+            add_pending(sp.T, sp.init, sp.sel, sp.dep, 0, false);
         }
     }
 
@@ -522,7 +558,7 @@ struct Gen {
         const std::string c = cond_of(op);
         const bool conditional = !c.empty();
         if (lazy_x) {
-            if (op.type == QT_OP_X && conditional) { add_pending(op.t0, c, op.regsel); return; }
+            if (op.type == QT_OP_X && conditional) { add_pending(op.t0, c, op.regsel, op.lmask, op.lval, true); return; }
             settle(op, c);
         }
         if (op.type == QT_OP_X && !conditional) { op_x(op, false); return; }
@@ -646,6 +682,14 @@ struct Gen {
         // pending flips become a choice of store address: register i of a thread whose flag holds goes
         // where register i ^ (1 << T) would have gone.  Per target bit, registers are grouped by the set of
         // pending flips that select them (the XOR of those flags decides).
+        if (!last && bank_aware) {
+            // A flag that differs between the 8 lanes of one shared-memory wavefront moves some of them by
+            // qt_slot(1 << bit) units = 1, 2 or 4 banks (mod 8) onto banks other lanes still use: every STS.128
+            // of the stage would take two wavefronts, which costs more than the exchange.  Those flips happen now.
+            for (size_t k = 0; k < pend.size();) {
+                if (store_conflicts(st, pend[k])) { o.f("    // [flip:bank]\n"); flush(k); } else k++;
+            }
+        }
         std::vector<int> fmask(NR, 0);
         std::vector<std::string> fterms(NR);
         for (int T = 0; T < R; T++) {
@@ -737,6 +781,7 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     g.T = 1 << (g.M - g.R);
     g.npool_prog = (int)((g.h->total_bytes - g.h->pool_off) / sizeof(double));
     g.lazy_x = getenv("QBOT_B200_EAGER_X") == nullptr;
+    g.bank_aware = getenv("QBOT_B200_FLIP_BANK_AWARE") != nullptr;      // measured neutral (5 016 vs 5 023 gates/s): off by default
     const int npool = g.npool_prog + 1;      // + header scale
     Out& o = g.o;
     o.f("// generated by qbot_b200 qj_generate: M=%d R=%d stages=%d ops=%d gates=%d\n", g.M, g.R, (int)g.h->nstages, (int)g.h->nops, (int)g.h->ngates);
