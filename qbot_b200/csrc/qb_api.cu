@@ -631,7 +631,7 @@ int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, c
     if (const char* e = getenv("QBOT_B200_TILE_M")) { const int v = atoi(e); if (v == 11 || v == 12) opt.M = v; }
     opt.R = QT_MAXR;          // the specialiser's own plan shape (32 amplitudes per thread) unless overridden
     if (const char* e = getenv("QBOT_B200_JIT_R")) { const int v = atoi(e); if (v == 4 || v == 5) opt.R = v; }
-    opt.search_trials = nbits >= 27 ? 32 : nbits >= 23 ? 8 : 1;      // the engine's search effort (qb_tile.cu get_plan)
+    opt.search_trials = nbits >= 29 ? 128 : nbits >= 27 ? 32 : nbits >= 23 ? 8 : 1;      // the engine's search effort (qb_tile.cu get_plan)
     if (const char* e = getenv("QBOT_B200_PLAN_TRIALS")) opt.search_trials = atoi(e);
     std::vector<QGate> planned;
     std::vector<QtPlanStep> steps = qt_plan_best(gates, nbits, opt, &planned);

@@ -1055,20 +1055,27 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
 
     // ---- plan search: the greedy tile-bit choice is a local optimum per sweep.  Every sweep is a
     //      full pass over HBM, so on large states a beam search over the choices (deterministic
-    //      seed) is worth its fraction of a second: 14 -> 12 sweeps at 30 q, 9 -> 8 at 34 q.  The
+    //      seed) is worth its fraction of a second: 14 -> 12 (deepest level: 11) sweeps at 30 q, 9 -> 8 at 34 q.  The
     //      programs of the best few candidates are built and the cheapest plan wins (passes, then
     //      stages, then ops).
     std::vector<QtPlanStep> best = build_steps(gates, info, nbits, opt, nullptr);
     if (can_tile && opt.search_trials > 1 && gates.size() >= 8) {
-        const int width = opt.search_trials >= 128 ? 24 : opt.search_trials >= 32 ? 8 : 4;
-        const int branch = opt.search_trials >= 128 ? 10 : opt.search_trials >= 32 ? 6 : 4;
-        std::vector<std::vector<std::vector<int>>> guides;
-        beam_plan(info, nbits, NH, WINDOW, width, branch, &guides);
+        // search effort: (beam width, branching) per level; the top level also runs the one below it (the two
+        // explore different parts of the tree: the wider beam usually saves a sweep, sometimes only stages)
+        struct Level { int width, branch; };
+        std::vector<Level> levels;
+        if (opt.search_trials >= 128) { levels.push_back({24, 10}); levels.push_back({8, 6}); }
+        else if (opt.search_trials >= 32) levels.push_back({8, 6});
+        else levels.push_back({4, 4});
         PlanCost best_cost = cost_of(best);
-        for (const auto& g : guides) {
-            std::vector<QtPlanStep> cand = build_steps(gates, info, nbits, opt, &g);
-            const PlanCost c = cost_of(cand);
-            if (c < best_cost) { best_cost = c; best.swap(cand); }
+        for (const Level& lv : levels) {
+            std::vector<std::vector<std::vector<int>>> guides;
+            beam_plan(info, nbits, NH, WINDOW, lv.width, lv.branch, &guides);
+            for (const auto& g : guides) {
+                std::vector<QtPlanStep> cand = build_steps(gates, info, nbits, opt, &g);
+                const PlanCost c = cost_of(cand);
+                if (c < best_cost) { best_cost = c; best.swap(cand); }
+            }
         }
     }
     return best;

@@ -330,7 +330,9 @@ CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gat
     opt.R = R;
     // plan search effort grows with the cost of a sweep (env QBOT_B200_PLAN_TRIALS overrides)
     const int total_bits = s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0);
-    opt.search_trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);
+    // (the deepest level, ~0.2 s, only for plans of the specialiser's shape: those are made in the background or on
+    // request, and run many times; the generic first-sight plan must not wait for it)
+    opt.search_trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 29 && R == QT_MAXR ? 128 : total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);
     cp.steps = qt_plan_best(gates, s->nbits, opt, &cp.gates);
     size_t total = 0;
     cp.prog_off.resize(cp.steps.size(), 0);
@@ -390,7 +392,7 @@ void warm_in_background(const std::vector<QGate>& gates, int nbits, int total_bi
     if (std::find(g_warmers.started.begin(), g_warmers.started.end(), plan_hash) != g_warmers.started.end()) return;
     g_warmers.started.push_back(plan_hash);
     g_warmers.running++;
-    const int trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);   // as get_plan
+    const int trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 29 ? 128 : total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);   // as get_plan
     g_warmers.threads.emplace_back([gates, nbits, M, trials]() {
         try {
             QtPlanOptions opt;

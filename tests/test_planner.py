@@ -176,6 +176,35 @@ def test_plan_search_never_worse_and_still_correct(monkeypatch):
         assert b['fused_sweeps'] <= (12 if nn == 30 else 8)
 
 
+def test_deep_plan_search_is_correct_and_not_worse(monkeypatch):
+    """the deepest search level (QBOT_B200_PLAN_TRIALS >= 128: beam 24 x 10 plus the level below it), the engine's
+    setting for specialised plans on states of >= 29 index bits: executes to the same state as the greedy plan,
+    through the op interpreter and through the generated kernels, and never needs more sweeps than level 32"""
+    import jit_emu
+    for n, depth, seed in ((15, 16, 7), (14, 24, 8)):
+        gates = rc(n, depth, seed)
+        gl = plan_emu.circuit_to_bits(n, gates)
+        psi = rand_ket(np.random.default_rng(seed), n)
+        monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '1')
+        base, st1 = plan_emu.run(n, gl, psi)
+        monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '128')
+        out, st2 = plan_emu.run(n, gl, psi)
+        assert st2['steps'] <= st1['steps']
+        assert close(out, base, 1e-13)
+        monkeypatch.setenv('QBOT_B200_PLAN_R', '5')
+        out5, _ = jit_emu.run(n, gl, psi)
+        monkeypatch.delenv('QBOT_B200_PLAN_R')
+        assert close(out5, base, 1e-12)
+    for nn, d, s, most in ((30, 20, 30, 11), (31, 20, 7, 11), (34, 10, 34, 8)):
+        gl = plan_emu.circuit_to_bits(nn, rc(nn, d, s))
+        monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '32')
+        _, a = plan_emu.run(nn, gl, None, execute=False)
+        monkeypatch.setenv('QBOT_B200_PLAN_TRIALS', '128')
+        _, b = plan_emu.run(nn, gl, None, execute=False)
+        assert (b['fused_sweeps'], b.get('stages', 0)) <= (a['fused_sweeps'], a.get('stages', 0)), (a, b)
+        assert b['fused_sweeps'] <= most, b
+
+
 def test_peephole_rewrite_preserves_the_state(monkeypatch):
     """X (any controls) followed by H on its target is rewritten to H followed by a controlled Z
     (H X = Z H): same state, the diagonal gate needs no tile bit and costs a sign flip"""
