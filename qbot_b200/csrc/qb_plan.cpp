@@ -1067,6 +1067,7 @@ std::vector<QtPlanStep> qt_plan(const std::vector<QGate>& gates, int nbits, cons
         if (opt.search_trials >= 128) { levels.push_back({24, 10}); levels.push_back({8, 6}); }
         else if (opt.search_trials >= 32) levels.push_back({8, 6});
         else levels.push_back({4, 4});
+        if (const char* e = getenv("QBOT_B200_BEAM")) { int w = 0, b = 0; if (sscanf(e, "%dx%d", &w, &b) == 2 && w > 0 && b > 0) { levels.clear(); levels.push_back({w, b}); } }
         PlanCost best_cost = cost_of(best);
         for (const Level& lv : levels) {
             std::vector<std::vector<std::vector<int>>> guides;
