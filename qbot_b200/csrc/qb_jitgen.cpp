@@ -1,8 +1,11 @@
 // qbot_b200 -- sweep specialiser (see qb_jit.h).  Pure host code, no CUDA dependency.
 //
 // What is resolved at generation time
-//   * the 16 amplitudes of a thread are 16 named locals (a0..a15), so a Pauli-X / CNOT / Toffoli
+//   * the 16 or 32 amplitudes of a thread are named locals (a0..a31), so a Pauli-X / CNOT / Toffoli
 //     whose controls are register bits is a RENAMING and costs no instruction at all;
+//   * an X under a run-time predicate (controls on thread / tile bits) is deferred: it stays a pending
+//     flip that the stage's store offsets, the next Hadamard's signs, a diagonal's factor order or a
+//     2x2's column order absorb (see `Pend` below); only conflicts fall back to register exchanges;
 //   * every shared-memory and HBM offset is an immediate; the tile base and the thread's
 //     position are a few shifts with constant amounts;
 //   * predicates on thread bits / tile bits are tests of constant masks; ops whose predicate
