@@ -79,9 +79,10 @@ def is_state(x) -> bool:
 
 
 def hilbertSpaceNumQubits(state) -> int:
-    if len(state.shape) == 0 or state.size == 0:
+    shape = state.shape
+    if len(shape) == 0 or 0 in shape:
         return 0
-    return int(np.log2(state.shape[0]))
+    return int(shape[0]).bit_length() - 1          # = int(np.log2(shape[0])) (operators.py:14-17)
 
 
 def _unaliased(ns, key) -> bool:

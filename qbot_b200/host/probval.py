@@ -261,6 +261,8 @@ def funcWrapper(func: Callable, *args, **kwargs):
     branches (first ProbVal argument fastest) and collect ``ProbVal.fromUnzipped``."""
     lens = [len(a.probs) for a in args if isinstance(a, ProbVal)]
     lens += [len(v.probs) for v in kwargs.values() if isinstance(v, ProbVal)]
+    if not lens:
+        return func(*args, **kwargs)          # one certain branch: fromUnzipped([1], [v]) is v (probVal.py:89-95)
     total = 1
     for n in lens:
         total *= n
