@@ -212,9 +212,13 @@ def interweave(rho_a: np.ndarray, rho_b: np.ndarray, a_positions: Iterable[int])
 def replace_arbitrary(rho: np.ndarray, new_rho: np.ndarray, targets: Sequence[int]) -> np.ndarray:
     """Trace the target qubits out and put ``new_rho`` in their place -- density.py:195-227.
 
-    As in the reference the i-th qubit of ``new_rho`` goes to ``targets[i]`` *as listed*
-    (no sort), which the reference's state map only handles consistently for ascending
-    lists; ascending lists are what its tests and ops use."""
+    Defined for ASCENDING target lists, which is what the reference's tests use: the i-th qubit
+    of ``new_rho`` goes to ``targets[i]``.  For a descending / unsorted list the reference's state
+    map (density.py:207-220) is not injective -- it walks the qubits once and only ever matches
+    ``qubitsToReplace`` in listed order -- so `genArbitrarySwap` returns a non-unitary 0/1 matrix
+    and the result is not a density matrix (finding F13; found by
+    scripts/fuzz_dsl.py).  There the positions are taken as a set (sorted), like
+    `interweaveDensities` does: parity unpinned for unsorted lists."""
     n = ilog2(square_dim(rho))
     k = ilog2(square_dim(new_rho))
     if len(targets) != k:

@@ -38,6 +38,8 @@ class Golden:
         self.l1_arr = np.load(os.path.join(GOLDEN, 'l1_cases.npz'))
         self.scripts = json.load(open(os.path.join(GOLDEN, 'scripts.json')))
         self.scripts_arr = np.load(os.path.join(GOLDEN, 'scripts.npz'))
+        self.scripts_fuzz = json.load(open(os.path.join(GOLDEN, 'scripts_fuzz.json')))
+        self.scripts_fuzz_arr = np.load(os.path.join(GOLDEN, 'scripts_fuzz.npz'))
         self.probval = json.load(open(os.path.join(GOLDEN, 'probval.json')))
         self.rc = np.load(os.path.join(GOLDEN, 'rc_small.npz'))
 

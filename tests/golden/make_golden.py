@@ -9,6 +9,7 @@ travel to the GPU box):
 Outputs (small, committed):
     l1_cases.npz / l1_cases.json   -- qgates / density / measurement functions on seeded inputs
     scripts.json + scripts.npz     -- DSL programs run through the reference's executeTxt
+    scripts_fuzz.json + .npz       -- random DSL programs (scripts/fuzz_dsl.py --emit ...scripts_fuzz_src.json), same recording
     probval.json                   -- ProbVal normalise / funcWrapper ordering cases
     rc_small.npz                   -- rc(n, D, seed) circuits pushed through the reference's applyGate
 
@@ -70,6 +71,47 @@ def slot_aligned(n, t, controls):
     if t == 0:
         return list(controls) == list(range(n - c, n))
     return list(controls) == list(range(t - c, t))
+
+
+def record_scripts(src_name, out_stem):
+    """run every program of `src_name` through the reference's executeTxt and record stdout, exit
+    behaviour, the final register and the named results -> <out_stem>.json / .npz"""
+    scripts = json.load(open(os.path.join(HERE, src_name)))
+    sarrays = {}
+    sout = []
+    for i, sc in enumerate(scripts):
+        buf = io.StringIO()
+        exited = False
+        try:
+            with redirect_stdout(buf):
+                ns = executeTxt(sc['text'])
+        except SystemExit:
+            exited = True
+            ns = {}
+        rec = dict(name=sc['name'], text=sc['text'], stdout=buf.getvalue(), exited=exited, vars={})
+        if 'state' in ns and isinstance(ns['state'], np.ndarray):
+            sarrays[f's{i}'] = ns['state']
+            rec['state'] = f's{i}'
+        for v in ([] if exited else sc.get('vars', [])):
+            val = ns.get(v)
+            if isinstance(val, rm.MeasurementResult):
+                rec['vars'][v] = dict(type='meas', probs=[float(p) for p in val.probs], symbols=val.basisSymbols)
+                sarrays[f's{i}_{v}_un'] = val.unMeasuredDensity
+            elif isinstance(val, ProbVal):
+                rec['vars'][v] = dict(type='probval', probs=val.probs, values=json.loads(json.dumps(val.values, default=str)))
+            elif isinstance(val, np.ndarray):
+                sarrays[f's{i}_{v}'] = val
+                rec['vars'][v] = dict(type='array', key=f's{i}_{v}')
+            elif isinstance(val, (complex, np.complexfloating)):
+                sarrays[f's{i}_{v}'] = np.asarray(val)
+                rec['vars'][v] = dict(type='array', key=f's{i}_{v}')
+            else:
+                rec['vars'][v] = dict(type='py', value=json.loads(json.dumps(val, default=str)))
+        sout.append(rec)
+    np.savez_compressed(os.path.join(HERE, out_stem + '.npz'), **sarrays)
+    with open(os.path.join(HERE, out_stem + '.json'), 'w') as f:
+        json.dump(sout, f, indent=0)
+    return sout
 
 
 def main():
@@ -233,38 +275,9 @@ def main():
         json.dump(pv_cases, f, indent=0)
 
     # ---- DSL programs through the reference interpreter -------------------------------
-    scripts = json.load(open(os.path.join(HERE, 'scripts_src.json')))
-    sarrays = {}
-    sout = []
-    for i, sc in enumerate(scripts):
-        buf = io.StringIO()
-        exited = False
-        try:
-            with redirect_stdout(buf):
-                ns = executeTxt(sc['text'])
-        except SystemExit:
-            exited = True
-            ns = {}
-        rec = dict(name=sc['name'], text=sc['text'], stdout=buf.getvalue(), exited=exited, vars={})
-        if 'state' in ns and isinstance(ns['state'], np.ndarray):
-            sarrays[f's{i}'] = ns['state']
-            rec['state'] = f's{i}'
-        for v in sc.get('vars', []):
-            val = ns.get(v)
-            if isinstance(val, rm.MeasurementResult):
-                rec['vars'][v] = dict(type='meas', probs=[float(p) for p in val.probs], symbols=val.basisSymbols)
-                sarrays[f's{i}_{v}_un'] = val.unMeasuredDensity
-            elif isinstance(val, ProbVal):
-                rec['vars'][v] = dict(type='probval', probs=val.probs, values=json.loads(json.dumps(val.values, default=str)))
-            elif isinstance(val, np.ndarray):
-                sarrays[f's{i}_{v}'] = val
-                rec['vars'][v] = dict(type='array', key=f's{i}_{v}')
-            else:
-                rec['vars'][v] = dict(type='py', value=json.loads(json.dumps(val, default=str)))
-        sout.append(rec)
-    np.savez_compressed(os.path.join(HERE, 'scripts.npz'), **sarrays)
-    with open(os.path.join(HERE, 'scripts.json'), 'w') as f:
-        json.dump(sout, f, indent=0)
+    sout = record_scripts('scripts_src.json', 'scripts')
+    # ---- random DSL programs (scripts/fuzz_dsl.py --emit), recorded the same way ----------
+    fout = record_scripts('scripts_fuzz_src.json', 'scripts_fuzz')
 
     # ---- rc circuits through the reference's applyGate --------------------------------
     rarr = {}
@@ -286,7 +299,7 @@ def main():
         rarr[f'rc_{n}_{depth}_{seed}'] = rho
         rarr[f'rc_{n}_{depth}_{seed}_info'] = np.array([len(gates), ref_built])
     np.savez_compressed(os.path.join(HERE, 'rc_small.npz'), **rarr)
-    print('golden fixtures written:', len(meta), 'L1 cases,', len(sout), 'scripts')
+    print('golden fixtures written:', len(meta), 'L1 cases,', len(sout), 'scripts,', len(fout), 'fuzz scripts')
 
 
 if __name__ == '__main__':

@@ -28,7 +28,7 @@ def run_script(text, state_cls):
     return ns, buf.getvalue(), exited
 
 
-def check_script(rec, arrays, state_cls, rtol=1e-12):
+def check_script(rec, arrays, state_cls, rtol=1e-12, prob_tol=0.0):
     ns, out, exited = run_script(rec['text'], state_cls)
     assert exited == rec['exited'], rec['name']
     assert out == rec['stdout'], rec['name']
@@ -37,7 +37,10 @@ def check_script(rec, arrays, state_cls, rtol=1e-12):
     for name, exp in rec['vars'].items():
         got = ns[name]
         if exp['type'] == 'meas':
-            assert got.probs == exp['probs'], (rec['name'], got.probs)
+            if prob_tol:        # device arithmetic: same outcomes in the same order, weights to the fp64 tolerance
+                assert len(got.probs) == len(exp['probs']) and np.allclose(got.probs, exp['probs'], rtol=0, atol=prob_tol), (rec['name'], got.probs)
+            else:
+                assert got.probs == exp['probs'], (rec['name'], got.probs)
             assert list(got.basisSymbols) == exp['symbols']
             assert close(np.asarray(got.unMeasuredDensity), arrays[f"{rec['state']}_{name}_un"], rtol)
         elif exp['type'] == 'array':
@@ -50,6 +53,15 @@ def test_all_golden_scripts(golden):
     assert len(golden.scripts) >= 60
     for rec in golden.scripts:
         check_script(rec, golden.scripts_arr, FakeState)
+
+
+def test_fuzzed_scripts(golden):
+    """random programs (scripts/fuzz_dsl.py: every state op with plain and ProbVal arguments, conditions,
+    sub-register qset, disc, meas / peek in three bases, injected errors) recorded from the real reference"""
+    assert len(golden.scripts_fuzz) >= 150
+    assert sum(r['exited'] for r in golden.scripts_fuzz) >= 20
+    for rec in golden.scripts_fuzz:
+        check_script(rec, golden.scripts_fuzz_arr, FakeState)
 
 
 def test_probval_rules(golden):
