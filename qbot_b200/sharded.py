@@ -208,7 +208,11 @@ class QubitMap:
             if kk == 0:
                 s = complex(t)
                 # a per-rank scalar: diag(s, s) on a local bit outside the control mask
-                free = next(p for p in range(nl) if not (cmask >> p) & 1)
+                free = next((p for p in range(nl) if not (cmask >> p) & 1), None)
+                if free is None:
+                    # every local bit is a control: diag(1, s) on one of them, the others stay controls
+                    p = (cmask & -cmask).bit_length() - 1
+                    return np.array([[1, 0], [0, s]], dtype=np.complex128), [p], cmask & ~(1 << p)
                 return np.array([[s, 0], [0, s]], dtype=np.complex128), [free], cmask
             m = np.ascontiguousarray(t.reshape(1 << kk, 1 << kk))
             tbits = [self.pos[g.tb[ax]] for ax in keep_axes]

@@ -104,6 +104,22 @@ def test_virtual_ranks_match_oracle(n, world):
     assert res[0]['exchanges'] >= 1          # the circuit does need global qubits
 
 
+def test_rank_scalar_under_controls_on_every_local_bit():
+    """A diagonal gate whose target is a rank bit is a per-rank scalar on the amplitudes its controls select; with
+    only two local bits and both of them controls there is no free local bit to carry diag(s, s) -- it becomes
+    diag(1, s) on one of the controls."""
+    n, world = 4, 4
+    rz = circuits.z_rot(0.7)
+    H = circuits.HADAMARD
+    ops = [(H, q, []) for q in range(n)] + [(rz, 0, [2, 3]), (rz, 1, [3, 2]), (H, 3, []), (rz, 0, [3])]
+    want = expected_ket(n, ops)
+    for r in run_virtual(n, world, ops, [0, 3]):
+        assert np.max(np.abs(r['ket'] - want)) < 1e-12
+    mp = QubitMap(4, 2)
+    m, tb, cm = mp.localise(make_lgate(rz, [3], [0, 1]), 2)      # logical bit 3 = rank bit 1, set on rank 2
+    assert tb == [0] and cm == 0b10 and np.allclose(m, np.diag([1, rz[1, 1]]))
+
+
 def test_reset_zero_gives_a_fresh_register():
     """reset_zero: |0...0> and the identity qubit map again (used by the multi-GPU e2e loop)"""
     n, world = 8, 4
