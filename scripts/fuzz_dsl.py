@@ -60,8 +60,23 @@ def slot_aligned(n, t, cs):
     return cs == (list(range(t - c, t)) if t > 0 else list(range(n - c, n)))
 
 
-def line(rng, n, names):
+def line(rng, n, names, extra=False):
     r = rng.random()
+    if extra and rng.random() < 0.2:               # forms kept out of the recorded fixtures (they print floats / reuse results)
+        ms = [v for v in names if v.startswith('m')]
+        q = rng.random()
+        if ms and q < 0.35:
+            return 'cout %s' % ms[int(rng.integers(len(ms)))]
+        if ms and q < 0.6:
+            m = ms[int(rng.integers(len(ms)))]
+            return 'gate %s ; %d ; [] ; ProbVal(%s.probs, [k %% 2 == 0 for k in range(len(%s.probs))])' % (gate1(rng), rng.integers(n), m, m)
+        if q < 0.75:
+            return 'qset %s ; %d' % (pv(rng, ['comp[1]', 'hada[1]', 'comp[1]']), rng.integers(n))
+        if q < 0.9:
+            name = 'c%d' % len(names)
+            names.append(name)
+            return 'cdef %s ; %s * 2 + 1' % (name, pv(rng, ['1', '2', '1']))
+        return 'gate %s ; %s ; [] ; %s' % (pv(rng, [gate1(rng), gate1(rng)]), pv(rng, [str(int(rng.integers(n))), str(int(rng.integers(n)))]), pv(rng, ['True', 'False']))
     if r < 0.40:                                   # gate, 0-2 controls, optional ProbVal pieces / condition
         k = 2 if (n >= 2 and rng.random() < 0.15) else 1
         t = int(rng.integers(0, n - k + 1))
@@ -136,13 +151,13 @@ def line(rng, n, names):
     return 'cdef %s ; %s' % (name, rng.choice(['np_trace(state)', 'np_real(state[0][0])', 'state.shape[0]']))
 
 
-def program(seed):
+def program(seed, extra=False):
     rng = np.random.default_rng(50_000 + seed)
     n = int(rng.integers(1, 5))
     names = []
     lines = [initial(rng, n)]
     for _ in range(int(rng.integers(2, 12))):
-        ln = line(rng, n, names)
+        ln = line(rng, n, names, extra)
         if isinstance(ln, tuple):
             _, m, ln = ln
             n -= m
@@ -172,8 +187,8 @@ def run(execute, text, **kw):
     return ns, buf.getvalue(), exited
 
 
-def compare(seed, ref_exec, our_exec, FakeState):
-    text, names = program(seed)
+def compare(seed, ref_exec, our_exec, FakeState, extra=False):
+    text, names = program(seed, extra)
     rns, rout, rexit = run(ref_exec, text)
     ons, oout, oexit = run(our_exec, text, state_cls=FakeState)
     if rexit != oexit or rout != oout:
@@ -213,27 +228,28 @@ def main():
     ap.add_argument('--seeds', default='0:200')
     ap.add_argument('--emit')
     ap.add_argument('--show', type=int)
+    ap.add_argument('--extra', action='store_true', help='also result-dependent conditions, cout of results, ProbVal arithmetic')
     a = ap.parse_args()
     from qbot.interpreter import executeTxt as ref_exec
     import qbot_b200
     from fake_backend import FakeState
     if a.show is not None:
-        print(program(a.show)[0])
-        print(compare(a.show, ref_exec, qbot_b200.executeTxt, FakeState)[1])
+        print(program(a.show, a.extra)[0])
+        print(compare(a.show, ref_exec, qbot_b200.executeTxt, FakeState, a.extra)[1])
         return
     lo, hi = (int(x) for x in a.seeds.split(':'))
     bad = 0
     emitted = []
     for seed in range(lo, hi):
         try:
-            text, why = compare(seed, ref_exec, qbot_b200.executeTxt, FakeState)
+            text, why = compare(seed, ref_exec, qbot_b200.executeTxt, FakeState, a.extra)
         except Exception as e:  # noqa: BLE001
-            text, why = program(seed)[0], 'exception: %r' % e
+            text, why = program(seed, a.extra)[0], 'exception: %r' % e
         if why:
             bad += 1
             print('seed %d:\n%s\n=> %s\n' % (seed, text, why), flush=True)
         else:
-            emitted.append(dict(name='fuzz_%d' % seed, text=text, vars=program(seed)[1]))
+            emitted.append(dict(name='fuzz_%d' % seed, text=text, vars=program(seed, a.extra)[1]))
     print('seeds %d:%d: %d differences' % (lo, hi, bad))
     if a.emit:
         with open(a.emit, 'w') as f:
