@@ -39,6 +39,9 @@ const char* kPrelude = R"QJ(
 #define QJ_ST(p, v) __stcs(p, v)
 #endif
 #define QJ_RESTRICT __restrict__
+// conditional sign flip without a branch and off the FP64 pipe: XOR of the sign bits with s = 0 / 0x80000000
+#define QJ_XSIGN(a, s) do { (a).x = __hiloint2double(__double2hiint((a).x) ^ (int)(s), __double2loint((a).x)); \
+                            (a).y = __hiloint2double(__double2hiint((a).y) ^ (int)(s), __double2loint((a).y)); } while (0)
 #define QJ_SYNC() __syncthreads()
 // two mbarriers per CTA count the bytes of the next tile's bulk copies: [0] the early half (landing
 // buffer behind the transposition buffer), [1] the late half (transposition buffer)

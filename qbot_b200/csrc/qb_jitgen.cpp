@@ -87,11 +87,14 @@ struct Gen {
     };
     std::vector<Pend> pend;
     bool lazy_x = true;
+    bool xor_signs = true;     // conditional sign flips as XORs of the sign bit (op_zsign) instead of branches
     // what the op being emitted has to do for the pending flips it consumes
     std::vector<std::pair<std::string, uint32_t>> h_neg;      // after a butterfly: negate registers (mask) where var holds
     std::map<int, std::string> phase_swap;                    // PHASE: register bit -> var: exchange d0 / d1 where it holds
     std::string u2_swap;                                      // U2: exchange the matrix columns where it holds
     std::string cdiag_swap;                                   // CDIAG on a register bit: exchange d0 / d1 where it holds
+    struct ZCtl { std::string var; int T = 0; uint32_t sel = 0; } zsign_ctl;   // sign flip CONTROLLED by a register bit with a pending flip:
+                                                                             // where var holds the flip's pairs trade places in the register set
     std::vector<std::string> post_stmts;                      // statements behind the op's (conditional) block
 
     static bool sig_partial(const std::vector<Pend>& pd, uint32_t sig, uint32_t all) {
@@ -135,10 +138,10 @@ struct Gen {
         o.f("    bool %s = (%s);\n", nmf, init.c_str());
         return nmf;
     }
-    void flush(size_t k) {
+    void flush(size_t k, const char* why = "") {
         const Pend p = pend[k];
         pend.erase(pend.begin() + (long)k);
-        o.f("    if (%s) {    // [flip:flush]\n", p.var.c_str());
+        o.f("    if (%s) {    // [flip:flush] %s, %d pairs\n", p.var.c_str(), why, __builtin_popcount(p.sel) / 2);
         for (int i = 0; i < NR; i++) {
             if ((i >> p.T) & 1 || !((p.sel >> i) & 1u)) continue;
             const int j = i | (1 << p.T);
@@ -181,7 +184,7 @@ struct Gen {
             return;
         }
         for (size_t k = 0; k < pend.size();) {
-            if (!flips_commute(T, sel, pend[k].T, pend[k].sel)) flush(k); else k++;
+            if (!flips_commute(T, sel, pend[k].T, pend[k].sel)) flush(k, "before a conflicting flip"); else k++;
         }
         for (Pend& q : pend)
             if (q.T == T && q.sel == sel) {
@@ -207,6 +210,7 @@ struct Gen {
         const bool conditional = !c.empty();
         const uint32_t R2 = op.regsel;
         h_neg.clear(); phase_swap.clear(); cdiag_swap.clear(); u2_swap.clear(); post_stmts.clear();
+        zsign_ctl = ZCtl();
         struct Spawn { int T; std::string init; uint32_t sel; uint32_t dep; };
         std::vector<Spawn> spawns;
         for (size_t k = 0; k < pend.size();) {
@@ -275,11 +279,20 @@ struct Gen {
                     if (op.t1 == QT_LOC_REG && op.t0 == p.T) {
                         const uint32_t ov = p.sel & R2;
                         if (!ov) break;
-                        if (ov == R2 && cdiag_swap.empty()) { cdiag_swap = p.var; break; }
+                        if (ov == R2 && cdiag_swap.empty() && zsign_ctl.var.empty()) { cdiag_swap = p.var; break; }
                         fl = true;
                         break;
                     }
-                    fl = (asym(R2, p.T) & p.sel) != 0;
+                    if ((asym(R2, p.T) & p.sel) != 0) {
+                        // the diagonal is CONTROLLED by the flip's bit (its register set depends on bit T).  A sign
+                        // flip commutes over the pending exchange when it is applied to the registers that hold its
+                        // amplitudes right now: where the flag holds, the partner registers of the flip's pairs
+                        if (xor_signs && is_z_like(pool, op.pool) && zsign_ctl.var.empty() && cdiag_swap.empty()) {
+                            zsign_ctl.var = p.var; zsign_ctl.T = p.T; zsign_ctl.sel = p.sel;
+                            break;
+                        }
+                        fl = true;
+                    }
                     break;
                 case QT_OP_PHASE: {
                     bool has = false;
@@ -295,7 +308,12 @@ struct Gen {
                 }
                 default: fl = true; break;
             }
-            if (fl) flush(k); else k++;
+            if (fl) {
+                static const char* const kind[] = {"?", "H", "X", "U2", "U4", "CDIAG", "PHASE"};
+                char why[64];
+                snprintf(why, sizeof(why), "before %s on bit %d (flip on %d)", kind[op.type <= QT_OP_PHASE ? op.type : 0], (int)op.t0, p.T);
+                flush(k, why);
+            } else k++;
         }
         for (const Spawn& sp : spawns) {
             o.f("    // [flip:spawn]\n");
@@ -340,6 +358,12 @@ struct Gen {
         }
         for (const auto& hn : h_neg) {
             // pending conditional X on this bit: H X = Z H -> flip the sign of the "1" outputs where it holds
+            if (xor_signs) {
+                o.f("    if (%s) {    // [flip:h]\n", hn.first.c_str());
+                for (int i = 0; i < NR; i++) if ((hn.second >> i) & 1u) xsign(nm[i], "0x80000000u");
+                o.f("    }\n");
+                continue;
+            }
             o.f("    if (%s) {    // [flip:h]\n", hn.first.c_str());
             for (int i = 0; i < NR; i++) if ((hn.second >> i) & 1u) negate(nm[i]);
             o.f("    }\n");
@@ -412,6 +436,52 @@ struct Gen {
     bool pool_is_one(uint32_t p) const { return pool[p] == 1.0 && pool[p + 1] == 0.0; }
     bool pool_is_minus_one(uint32_t p) const { return pool[p] == -1.0 && pool[p + 1] == 0.0; }
     void negate(const std::string& a) { o.f("      %s.x = -%s.x; %s.y = -%s.y;\n", a.c_str(), a.c_str(), a.c_str(), a.c_str()); }
+    void xsign(const std::string& a, const char* mask) { o.f("      QJ_XSIGN(%s, %s);\n", a.c_str(), mask); }
+
+    static bool is_z_like(const double* pool, uint32_t p) {
+        return pool[p] == 1.0 && pool[p + 1] == 0.0 && pool[p + 2] == -1.0 && pool[p + 3] == 0.0;
+    }
+
+    // diag(1, -1) under a RUN-TIME predicate (controls on thread / tile bits, a target that is a thread / tile
+    // bit, or a pending flip on a register target): a sign flip where the predicate holds.  Written as an FP64
+    // negation it is a DADD per component on the busiest pipe (measured on the benchmark's sweeps: 8 % of the
+    // FP64 instructions); here it is one XOR of the sign bit per component on the integer pipe, still skipped
+    // as a whole where the predicate is false.
+    void op_zsign(const QtOp& op, const std::string& c) {
+        std::string pred = c.empty() ? std::string() : "(" + c + ")";
+        char b[96];
+        b[0] = 0;
+        if (op.t1 == QT_LOC_LOCAL) snprintf(b, sizeof(b), "((lb >> %d) & 1u)", (int)op.t0);
+        else if (op.t1 == QT_LOC_GLOBAL) snprintf(b, sizeof(b), "((tbase >> %d) & 1ull)", (int)op.t0);
+        if (b[0]) pred += (pred.empty() ? "" : " && ") + std::string(b);
+        if (pred.empty()) pred = "true";
+        if (!zsign_ctl.var.empty()) {
+            o.f("    if (%s) {    // [flip:zctl] [zsign]\n      if (%s) {\n", pred.c_str(), zsign_ctl.var.c_str());
+            for (int i = 0; i < NR; i++)
+                if (((op.regsel >> i) & 1u) && (op.t1 != QT_LOC_REG || ((i >> op.t0) & 1)))
+                    xsign(nm[((zsign_ctl.sel >> i) & 1u) ? i ^ (1 << zsign_ctl.T) : i], "0x80000000u");
+            o.f("      } else {\n");
+            for (int i = 0; i < NR; i++)
+                if (((op.regsel >> i) & 1u) && (op.t1 != QT_LOC_REG || ((i >> op.t0) & 1))) xsign(nm[i], "0x80000000u");
+            o.f("      }\n    }\n");
+            zsign_ctl = ZCtl();
+            return;
+        }
+        if (op.t1 != QT_LOC_REG || cdiag_swap.empty()) {
+            o.f("    if (%s) {    // [zsign]\n", pred.c_str());
+            for (int i = 0; i < NR; i++)
+                if (((op.regsel >> i) & 1u) && (op.t1 != QT_LOC_REG || ((i >> op.t0) & 1))) xsign(nm[i], "0x80000000u");
+            o.f("    }\n");
+            return;
+        }
+        // pending conditional X on the target bit: Z X = X (-Z), the minus sign sits on the "0" side where it holds
+        o.f("    if (%s) {    // [flip:cdiag] [zsign]\n      if (%s) {\n", pred.c_str(), cdiag_swap.c_str());
+        for (int i = 0; i < NR; i++) if (((op.regsel >> i) & 1u) && !((i >> op.t0) & 1)) xsign(nm[i], "0x80000000u");
+        o.f("      } else {\n");
+        for (int i = 0; i < NR; i++) if (((op.regsel >> i) & 1u) && ((i >> op.t0) & 1)) xsign(nm[i], "0x80000000u");
+        o.f("      }\n    }\n");
+        cdiag_swap.clear();
+    }
 
     void op_cdiag(const QtOp& op) {
         const uint32_t p = op.pool;
@@ -565,6 +635,13 @@ struct Gen {
             settle(op, c);
         }
         if (op.type == QT_OP_X && !conditional) { op_x(op, false); return; }
+        if (xor_signs && op.type == QT_OP_CDIAG && is_z_like(pool, op.pool) &&
+            (conditional || op.t1 != QT_LOC_REG || !cdiag_swap.empty() || !zsign_ctl.var.empty())) {
+            op_zsign(op, c);
+            for (const std::string& st : post_stmts) o.f("%s", st.c_str());
+            post_stmts.clear();
+            return;
+        }
         if (conditional) o.f("    if (%s) {\n", c.c_str());
         switch (op.type) {
             case QT_OP_H: op_h(op); break;
@@ -784,6 +861,7 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     g.T = 1 << (g.M - g.R);
     g.npool_prog = (int)((g.h->total_bytes - g.h->pool_off) / sizeof(double));
     g.lazy_x = getenv("QBOT_B200_EAGER_X") == nullptr;
+    g.xor_signs = getenv("QBOT_B200_BRANCHY_SIGNS") == nullptr;        // A/B switch: conditional sign flips as branches + FP64 negations
     g.bank_aware = getenv("QBOT_B200_FLIP_BANK_AWARE") != nullptr;      // measured neutral (5 016 vs 5 023 gates/s): off by default
     const int npool = g.npool_prog + 1;      // + header scale
     Out& o = g.o;

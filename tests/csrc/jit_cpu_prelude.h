@@ -13,6 +13,8 @@ struct QjC { double x, y; };
 #define QJ_P(i) (P[i])
 #define QJ_POOL_PARAM const double* P
 #define QJ_RESTRICT
+static inline double qj_xsign1(double v, unsigned s) { unsigned long long b; memcpy(&b, &v, 8); b ^= (unsigned long long)s << 32; memcpy(&v, &b, 8); return v; }
+#define QJ_XSIGN(a, s) do { (a).x = qj_xsign1((a).x, (s)); (a).y = qj_xsign1((a).y, (s)); } while (0)
 #define QJ_SYNC()
 #define QJ_BULK_COPY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
 #define QJ_BULK_COPY_EARLY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
