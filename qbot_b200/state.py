@@ -31,6 +31,45 @@ def _cmat(m, dim=None) -> np.ndarray:
     return a
 
 
+def marshal_batched(nq: int, nbranch: int, matrices, target_qubits, controls=None, enable=None):
+    """Host-side preparation of one batched launch (qb_apply_gate_batched): [nbranch, 2^k, 2^k] complex128
+    matrices, int32 target index bits [nbranch * k] (qubit q <-> bit nq-1-q, matrix msb first), uint64 control
+    masks, uint8 enable flags or None.  Vectorised: at 4096 branches the per-branch Python loops this replaces
+    cost more than the kernel (1.5 ms against 1.36 ms)."""
+    m = np.ascontiguousarray(np.asarray(matrices), dtype=np.complex128)
+    b = nbranch
+    if m.ndim != 3 or m.shape[0] != b or m.shape[1] != m.shape[2]:
+        raise ValueError("matrices must be [nbranch, 2^k, 2^k]")
+    k = int(m.shape[1]).bit_length() - 1
+    try:
+        tq = np.asarray(target_qubits, dtype=np.int64)
+    except (ValueError, TypeError):
+        tq = None                                    # ragged
+    if tq is None or tq.ndim != 2 or tq.shape[1] != k:
+        raise ValueError("every branch needs k target qubits")
+    if tq.shape[0] != b:
+        raise ValueError("one target list per branch")
+    tb = np.ascontiguousarray(nq - 1 - tq, dtype=np.int32).reshape(-1)
+    masks = np.zeros(max(b, 1), dtype=np.uint64)
+    if controls is not None:
+        cs = None
+        try:
+            cs = np.asarray(controls, dtype=np.int64)
+        except (ValueError, TypeError):
+            pass
+        if cs is not None and cs.ndim == 2 and cs.shape[0] == b:
+            if cs.shape[1]:
+                masks[:b] = np.bitwise_or.reduce(np.uint64(1) << (nq - 1 - cs).astype(np.uint64), axis=1)
+        else:                                        # ragged control lists
+            for i, c in enumerate(controls):
+                cm = 0
+                for q in c:
+                    cm |= 1 << (nq - 1 - int(q))
+                masks[i] = cm
+    en = None if enable is None else np.ascontiguousarray(np.asarray(enable, dtype=np.uint8))
+    return m, k, tb, masks, en
+
+
 class DeviceState:
     """A ket (n qubits -> 2^n amplitudes) or density matrix (2^n x 2^n) in HBM, optionally
     with a leading branch axis (``nbranch`` independent copies: the ProbVal batch)."""
@@ -261,39 +300,20 @@ class DeviceState:
         """Branch b applies matrices[b] on qubits first_targets[b].. with controls[b] (one launch)."""
         m = np.asarray(matrices)
         k = int(m.shape[1]).bit_length() - 1
-        qubits = []
-        for t in first_targets:
-            if t < 0 or t + k - 1 >= self.nq:
-                raise IndexError(f"{k} qubit gate does not fit the {self.nq} qubit hilbertspace when started on qubit {t}")
-            qubits.append([t + j for j in range(k)])
-        return self.apply_gate_batched_qubits(m, qubits, controls, enable)
+        ft = np.asarray(first_targets, dtype=np.int64).reshape(-1)
+        bad = (ft < 0) | (ft + k - 1 >= self.nq)
+        if bad.any():
+            t = int(ft[bad][0])
+            raise IndexError(f"{k} qubit gate does not fit the {self.nq} qubit hilbertspace when started on qubit {t}")
+        return self.apply_gate_batched_qubits(m, ft[:, None] + np.arange(k, dtype=np.int64)[None, :], controls, enable)
 
     def apply_gate_batched_qubits(self, matrices, target_qubits: Sequence[Sequence[int]],
                                   controls: Sequence[Iterable[int]] = None, enable: Sequence[bool] = None) -> "DeviceState":
         """Same, with an explicit (possibly non-contiguous) qubit list per branch;
         target_qubits[b][0] carries the matrix's most significant index bit."""
-        m = np.ascontiguousarray(np.asarray(matrices), dtype=np.complex128)
-        b = self.nbranch
-        if m.ndim != 3 or m.shape[0] != b or m.shape[1] != m.shape[2]:
-            raise ValueError("matrices must be [nbranch, 2^k, 2^k]")
-        k = int(m.shape[1]).bit_length() - 1
-        tb = []
-        for qs in target_qubits:
-            if len(qs) != k:
-                raise ValueError("every branch needs k target qubits")
-            tb += [self._bit(q) for q in qs]
-        masks = (C.c_uint64 * b)()
-        if controls is not None:
-            for i, cs in enumerate(controls):
-                cm = 0
-                for c in cs:
-                    cm |= 1 << self._bit(c)
-                masks[i] = cm
-        en = None
-        if enable is not None:
-            en_arr = np.ascontiguousarray(np.asarray(enable, dtype=np.uint8))
-            en = _cptr(en_arr)
-        _lib.call('qb_apply_gate_batched', self._h, _cptr(m), k, _lib.int_array(tb), masks, en)
+        m, k, tb, masks, en_arr = marshal_batched(self.nq, self.nbranch, matrices, target_qubits, controls, enable)
+        _lib.call('qb_apply_gate_batched', self._h, _cptr(m), k, tb.ctypes.data_as(C.POINTER(C.c_int)),
+                  masks.ctypes.data_as(C.POINTER(C.c_uint64)), None if en_arr is None else _cptr(en_arr))
         self._dirty()
         return self
 
