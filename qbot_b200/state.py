@@ -414,9 +414,11 @@ class DeviceState:
         return DeviceState(h, s0.kind, s0.nq, s0.nbranch)
 
     def mix_branches(self, probs: Sequence[float]) -> "DeviceState":
-        p = (C.c_double * self.nbranch)(*[float(x) for x in probs])
+        p = np.ascontiguousarray(np.asarray(probs, dtype=np.float64).reshape(-1))
+        if p.size != self.nbranch:
+            raise ValueError("one weight per branch")
         h = C.c_void_p()
-        _lib.call('qb_mix_branches', self._h, p, C.byref(h))
+        _lib.call('qb_mix_branches', self._h, p.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h))
         return DeviceState(h, self.kind, self.nq, 1)
 
     def broadcast(self, nbranch: int) -> "DeviceState":
