@@ -90,7 +90,8 @@ struct Gen {
     bool xor_signs = true;     // conditional sign flips as XORs of the sign bit (op_zsign) instead of branches
     // what the op being emitted has to do for the pending flips it consumes
     std::vector<std::pair<std::string, uint32_t>> h_neg;      // after a butterfly: negate registers (mask) where var holds
-    std::map<int, std::string> phase_swap;                    // PHASE: register bit -> var: exchange d0 / d1 where it holds
+    struct PSwap { std::string var; uint32_t sel; };
+    std::map<int, PSwap> phase_swap;                          // PHASE: register bit -> (var, register set): d0 / d1 trade places where it holds
     std::string u2_swap;                                      // U2: exchange the matrix columns where it holds
     std::string cdiag_swap;                                   // CDIAG on a register bit: exchange d0 / d1 where it holds
     struct ZCtl { std::string var; int T = 0; uint32_t sel = 0; } zsign_ctl;   // sign flip CONTROLLED by a register bit with a pending flip:
@@ -302,7 +303,13 @@ struct Gen {
                         if ((code & 0xff) == QT_LOC_REG && (int)(code >> 8) == p.T) has = true;
                     }
                     if (!has) break;
-                    if (p.sel == all_sel() && !conditional && !phase_swap.count(p.T)) { phase_swap[p.T] = p.var; break; }
+                    if (!conditional && !phase_swap.count(p.T)) {
+                        // one flip (any register set): the op is emitted in two variants; several: only full register
+                        // sets, as a run-time exchange of the bit's two factors
+                        bool all_full = p.sel == all_sel();
+                        for (const auto& e : phase_swap) all_full = all_full && e.second.sel == all_sel();
+                        if (phase_swap.empty() ? (all_full || xor_signs) : all_full) { phase_swap[p.T] = PSwap{p.var, p.sel}; break; }
+                    }
                     fl = true;
                     break;
                 }
@@ -534,6 +541,7 @@ struct Gen {
 
     void op_phase(const QtOp& op) {
         const uint32_t p = op.pool;
+        bool variant = false;      // decided below, once the entries are known
         const int u = tmp++;
         o.f("    {\n");
         bool have = false;
@@ -562,6 +570,14 @@ struct Gen {
         }
         // factor table over the register bits that carry entries; an entry with an empty name is
         // exactly 1 (register-bit diagonals arrive as diag(1, d1/d0)): nothing to multiply
+        if (xor_signs && phase_swap.size() == 1) {
+            // the two-variant form pays when some registers keep an exact unit factor (no thread-uniform factor,
+            // every register bit's d0 exactly one), and it is the only form that handles a partial register set
+            bool unit_possible = !have;
+            for (int q = 0; q < R; q++)
+                for (int ex : reg_entries[q]) unit_possible = unit_possible && pool_is_one(p + 5 * ex + 1);
+            variant = unit_possible || phase_swap.begin()->second.sel != all_sel();
+        }
         struct Ent { int mask; std::string r, i; };
         std::vector<Ent> table;
         if (have) table.push_back({0, "cr", "ci"});
@@ -587,9 +603,9 @@ struct Gen {
             bool d0_one = reg_entries[q].size() >= 1;
             for (int ex : reg_entries[q]) d0_one = d0_one && pool_is_one(p + 5 * ex + 1);
             auto sw = phase_swap.find(q);
-            if (sw != phase_swap.end()) {
+            if (sw != phase_swap.end() && !variant) {
                 // pending conditional X on this bit: D X = X D' with the two factors exchanged where it holds
-                o.f("      if (%s) { double t_ = %s; %s = %s; %s = t_; t_ = %s; %s = %s; %s = t_; }    // [flip:phase]\n", sw->second.c_str(), d0r, d0r, d1r, d1r, d0i,
+                o.f("      if (%s) { double t_ = %s; %s = %s; %s = t_; t_ = %s; %s = %s; %s = t_; }    // [flip:phase]\n", sw->second.var.c_str(), d0r, d0r, d1r, d1r, d0i,
                     d0i, d1i, d1i);
                 d0_one = false;
             }
@@ -614,15 +630,30 @@ struct Gen {
             }
             table.swap(next);
         }
-        if (!table.empty()) {
+        auto apply_table = [&](int flip_bit, uint32_t flip_sel) {
             for (int i = 0; i < NR; i++) {
-                const int mk = i & regbits;
+                const int src = (flip_bit >= 0 && ((flip_sel >> i) & 1u)) ? i ^ (1 << flip_bit) : i;
+                const int mk = src & regbits;
                 for (const Ent& t : table)
                     if (t.mask == mk) {
                         if (!t.r.empty()) { o.f("  "); cmul_into(nm[i], t.r, t.i); }
                         break;
                     }
             }
+        };
+        if (!table.empty()) {
+            if (variant) {
+                // one pending conditional X on a bit that carries entries: where it holds, the registers of its set
+                // take the factor of their partner (D X = X D').  Two variants of the multiplies instead of a
+                // run-time exchange of the factors: exact unit factors stay skipped in both, and a flip over a
+                // partial register set needs no exchange of amplitudes first
+                const auto& sw = *phase_swap.begin();
+                o.f("      if (%s) {    // [flip:phase]\n", sw.second.var.c_str());
+                apply_table(sw.first, sw.second.sel);
+                o.f("      } else {\n");
+                apply_table(-1, 0);
+                o.f("      }\n");
+            } else apply_table(-1, 0);
         }
         o.f("    }\n");
     }
