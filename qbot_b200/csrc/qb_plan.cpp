@@ -468,7 +468,55 @@ void place_diagonals(SweepBuild& sw) {
         win[x] = {ps < 0 ? 0 : ps, nsx - 1};
         if (e.stage >= ns) win[x].lo = std::min(win[x].lo, ns - 1);
     }
-    // second pass: sandwiched entries stay, the others go to a stage tail
+    // second pass: sandwiched entries stay, the others go to a stage tail.  The tails that carry a PHASE op are
+    // chosen first as a MINIMUM set of stages that meets every window (intervals on a line: sort by right end,
+    // take the right end of every window that is not met yet) -- every PHASE op is a complex multiply per
+    // amplitude, so their number is what counts; each entry then picks, among the chosen stages of its window,
+    // one where its bit is not a register bit if there is one (no factor table), the latest on ties.
+    static const bool pierce = getenv("QBOT_B200_PHASE_GREEDY") == nullptr;
+    std::vector<char> chosen(ns, pierce ? 0 : 1);
+    if (pierce) {
+        std::vector<size_t> order;
+        for (size_t x = 0; x < sw.pending.size(); x++) if (win[x].lo <= win[x].hi) order.push_back(x);
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return win[a].hi != win[b].hi ? win[a].hi < win[b].hi : win[a].lo < win[b].lo; });
+        // groups of windows met by one point each: the point may sit anywhere in the intersection of its
+        // group's windows -- take the stage where the group's PHASE op is cheapest (all entries on register
+        // bits: only 32 - 32 / 2^bits amplitudes are multiplied; any other entry: all 32), the latest on ties
+        std::vector<char> done(sw.pending.size(), 0);
+        for (size_t oi = 0; oi < order.size(); oi++) {
+            const size_t x = order[oi];
+            if (done[x]) continue;
+            bool met = false;
+            for (int s = win[x].lo; s <= win[x].hi && !met; s++) met = chosen[s] != 0;
+            if (met) { done[x] = 1; continue; }
+            const int h = win[x].hi;
+            int glo = 0;
+            std::vector<size_t> group;
+            for (size_t oj = oi; oj < order.size(); oj++) {
+                const size_t y = order[oj];
+                if (done[y] || win[y].lo > h) continue;
+                bool my = false;
+                for (int s = win[y].lo; s <= win[y].hi && !my; s++) my = chosen[s] != 0;
+                if (my) continue;
+                group.push_back(y);
+                glo = std::max(glo, win[y].lo);
+            }
+            int best = h, best_cost = 1 << 30;
+            for (int s = h; s >= glo; s--) {
+                uint32_t regbits = 0;
+                bool other = false;
+                for (size_t y : group) {
+                    const int lp = sw.local_of[sw.pending[y].bit];
+                    const int ri = lp >= 0 ? reg_index(sw.stages[s].st, lp, sw.R) : -1;
+                    if (ri >= 0) regbits |= 1u << ri; else other = true;
+                }
+                const int cost = other ? 32 : 32 - (32 >> __builtin_popcount(regbits));
+                if (cost < best_cost) { best_cost = cost; best = s; }
+            }
+            chosen[best] = 1;
+            for (size_t y : group) done[y] = 1;
+        }
+    }
     std::vector<int> tail_count(ns, 0);
     for (size_t x = 0; x < sw.pending.size(); x++) {
         const auto& e = sw.pending[x];
@@ -476,6 +524,7 @@ void place_diagonals(SweepBuild& sw) {
         const int lp = sw.local_of[e.bit];
         int best = -1, best_score = -1;
         for (int s = win[x].lo; s <= win[x].hi; s++) {
+            if (!chosen[s]) continue;
             const bool is_reg = lp >= 0 && reg_index(sw.stages[s].st, lp, sw.R) >= 0;
             const int score = (is_reg ? 0 : 2) + (tail_count[s] > 0 ? 1 : 0);
             if (score > best_score || (score == best_score && s > best)) { best_score = score; best = s; }
