@@ -166,11 +166,13 @@ def program(seed, extra=False):
             break
     if n >= 1 and rng.random() < 0.25:              # one invalid line: the error text and the exit must match too
         bad = ['gate hadamardGate ; %d' % n, 'gate hadamardGate ; -1', 'gate pauliXGate ; 0 ; [%d]' % n, 'gate pauliXGate ; 0 ; [0]',
-               'gate qftGate(2) ; %d' % (n - 1), 'swap 0 ; %d' % n, 'swap 0', 'disc [%d]' % n, 'disc %s' % list(range(n)),
+               'gate qftGate(2) ; %d' % (n - 1), 'swap 0 ; %d' % n, 'swap 0', 'disc [%d]' % n, 'disc [0, %d]' % n,
                'qset bell[0] ; [0]', 'qset comp[0] ; [%d]' % n, 'meas mm ; comp ; [%d]' % n, 'meas mm ; bell ; [0]',
                "gate hadamardGate ; 'a'", 'gate np_ones((3, 3)) ; 0', 'cdef zz ; 1/0', 'cdef zz ; undefined_name', 'frob 1',
                'gate', 'meas mm', 'jump nowhere', 'qset tensorProd(comp[0], comp[0], comp[0], comp[0], comp[0]) ; [0]',
                'gate hadamardGate ; 0 ; [] ; []', 'gate hadamardGate ; 0.5', 'swap 0 ; 0']
+        if extra:
+            bad.append('disc %s' % list(range(n)))      # a 0-qubit register: legal in the reference, kept out of the fixtures
         lines.insert(int(rng.integers(1, len(lines) + 1)), bad[int(rng.integers(len(bad)))])
     return '\n'.join(lines), names
 
