@@ -473,7 +473,7 @@ void place_diagonals(SweepBuild& sw) {
     // take the right end of every window that is not met yet) -- every PHASE op is a complex multiply per
     // amplitude, so their number is what counts; each entry then picks, among the chosen stages of its window,
     // one where its bit is not a register bit if there is one (no factor table), the latest on ties.
-    static const bool pierce = getenv("QBOT_B200_PHASE_GREEDY") == nullptr;
+    const bool pierce = getenv("QBOT_B200_PHASE_GREEDY") == nullptr;
     std::vector<char> chosen(ns, pierce ? 0 : 1);
     if (pierce) {
         std::vector<size_t> order;

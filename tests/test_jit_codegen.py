@@ -152,6 +152,57 @@ def test_eager_x_switch(monkeypatch):
     assert close(out, ref, 1e-12)
 
 
+def _sign_heavy(rng, n, count):
+    """CZ / CCZ / CNOT / H / RZ traffic: conditional sign flips on thread and tile bits, signs controlled by
+    register bits that have a pending exchange, merged phases on the bit of a pending exchange"""
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    H = np.array([[1, 1], [1, -1]], dtype=complex) * 2 ** -0.5
+    Z = np.diag([1, -1]).astype(complex)
+    out = []
+    for _ in range(count):
+        b = [int(x) for x in rng.permutation(n)]
+        r = rng.random()
+        if r < 0.30:
+            out.append((Z, b[:1], (1 << b[1]) | ((1 << b[2]) if rng.random() < 0.4 else 0)))
+        elif r < 0.60:
+            out.append((X, b[:1], (1 << b[1]) | ((1 << b[2]) if rng.random() < 0.3 else 0)))
+        elif r < 0.80:
+            out.append((H, b[:1], 0))
+        else:
+            th = rng.uniform(0, 6.28)
+            out.append((np.diag([np.exp(-0.5j * th), np.exp(0.5j * th)]), b[:1], 0))
+    return out
+
+
+def test_sign_rules_and_their_switch(monkeypatch, plan_R):
+    """Conditional sign flips are XORs of the sign bit ([zsign]); a sign controlled by a register bit with a pending
+    exchange ([flip:zctl]) and a merged phase on the bit of one ([flip:phase] in two variants) commute over it.
+    QBOT_B200_BRANCHY_SIGNS=1 restores FP64 negations under branches: same results, no XOR in the text."""
+    import re
+    seen = set()
+    for seed in (2, 5, 8, 11):
+        rng = np.random.default_rng(seed)
+        n = int(rng.integers(12, 15))
+        gl = _sign_heavy(rng, n, 70)
+        psi = rand_ket(rng, n)
+        ref = psi
+        for m, tb, cm in gl:
+            ref = oracle_apply_bits(ref, n, m, tb, cm)
+        for branchy in (False, True):
+            if branchy:
+                monkeypatch.setenv('QBOT_B200_BRANCHY_SIGNS', '1')
+            else:
+                monkeypatch.delenv('QBOT_B200_BRANCHY_SIGNS', raising=False)
+            text = ''.join(jit_emu.source_of(p) for f, _, p in jit_emu.plan(n, gl) if f)
+            if branchy:
+                assert 'QJ_XSIGN' not in text and '[flip:zctl]' not in text
+            else:
+                seen.update(re.findall(r'\[(zsign|flip:zctl|flip:phase)\]', text))
+            out, _ = jit_emu.run(n, gl, psi)
+            assert close(out, ref, 1e-12), (seed, n, branchy)
+    assert {'zsign', 'flip:zctl', 'flip:phase'} <= seen, seen
+
+
 def test_generated_source_matches_interpreter_semantics():
     """same plan, two executors: the op interpreter shared with the generic kernel
     (qb_tile_ops.h) and the generated straight-line code"""

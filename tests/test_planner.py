@@ -242,3 +242,30 @@ def test_peephole_rewrite_preserves_the_state(monkeypatch):
     out2, st2 = plan_emu.run(n, gl, psi)
     assert close(out2, ref, 1e-12)
     assert st['fused_gates'] == st2['fused_gates'] == len(gl)
+
+
+def test_phase_ops_are_placed_on_a_minimum_set_of_stage_tails(monkeypatch):
+    """Merged phase ops: the stage tails that carry one are a minimum set meeting every entry's commutation
+    window (qb_plan.cpp place_diagonals); QBOT_B200_PHASE_GREEDY=1 restores the entry-by-entry placement.
+    Both execute correctly and the minimum set never needs more ops."""
+    from qbot_b200.circuits import rc
+    fewer = 0
+    for n, depth, seed in ((14, 10, 1), (15, 12, 2), (13, 20, 3), (16, 8, 4)):
+        gl = plan_emu.circuit_to_bits(n, rc(n, depth, seed))
+        psi = rand_ket(np.random.default_rng(seed), n)
+        ref = psi
+        for m, tb, cm in gl:
+            ref = oracle_apply_bits(ref, n, m, tb, cm)
+        ops = {}
+        for greedy in (False, True):
+            if greedy:
+                monkeypatch.setenv('QBOT_B200_PHASE_GREEDY', '1')
+            else:
+                monkeypatch.delenv('QBOT_B200_PHASE_GREEDY', raising=False)
+            out, st = plan_emu.run(n, gl, psi)
+            assert close(out, ref, 1e-12), (n, greedy)
+            ops[greedy] = (st['fused_sweeps'], st['stages'], st['ops'])
+        if ops[False][:2] == ops[True][:2]:            # same sweeps and stages: only the phase ops differ
+            assert ops[False][2] <= ops[True][2], ops
+            fewer += ops[False][2] < ops[True][2]
+    assert fewer >= 1
