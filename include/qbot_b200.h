@@ -78,6 +78,9 @@ int qb_set_stream(qb_state* s, void* cuda_stream);
 int qb_init_basis(qb_state* s, uint64_t index);                       /* |index><index| or |index> in every branch */
 /* per-qubit 2-vectors, qubit 0 first: vecs[(b*nq + q)*2 + {0,1}] complex; per_branch=0 shares one set */
 int qb_init_product(qb_state* s, const double* vecs, int per_branch);
+/* density matrix <- diag(values) (2^nqubits real weights): the collapsed measured system in the
+ * computational frame, measurement.py:160-161, before it is rotated into the basis */
+int qb_init_diag(qb_state* s, const double* values);
 int qb_upload(qb_state* s, const void* host, size_t bytes);            /* qset with a host array (operators.py:143-153) */
 int qb_download(qb_state* s, void* host, size_t bytes);                /* what a user expression reading `state` sees */
 int qb_download_range(qb_state* s, uint64_t first_amp, uint64_t count, void* host);
@@ -102,6 +105,13 @@ int qb_apply_swap(qb_state* s, int bit_a, int bit_b);
  * control_masks[b], enable[b] (0 = leave branch b untouched; NULL = all enabled). */
 int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int* target_bits,
                           const uint64_t* control_masks, const uint8_t* enable);
+/* density matrices only: rho <- R rho C^T with R applied to the row copy and C to the column copy
+ * of target_bits (either may be NULL = identity).  qb_apply_gate is the case R = U, C = conj(U).
+ * Used for the reference's non-conjugating forms: projector weights phi^T rho phi of
+ * basis.density = outer(ket, ket) (qbot/basis.py:24-26, qbot/measurement.py:147-155: R = C = W,
+ * rows of W = the basis kets) and the collapsed system sum_i p_i phi_i phi_i^T
+ * (qbot/measurement.py:160-161: R = C = W^T on diag(p)). */
+int qb_apply_gate_rc(qb_state* s, const double* row_matrix, const double* col_matrix, int k, const int* target_bits);
 int qb_flush(qb_state* s);
 int qb_sync(qb_state* s);
 int qb_set_fusion(qb_state* s, int enabled);
@@ -127,6 +137,17 @@ int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, c
  * This is the abs(trace(rho_A P_j)) loop of measurement.measureArbitraryMultiState
  * (measurement.py:147-155) for the computational basis; other bases rotate first. */
 int qb_probs(qb_state* s, const int* bits, int m, double* out);
+/* Outcome weights in a product of measurement bases (measurement.permuteBasis + the outcome loop,
+ * qbot/measurement.py:88-101, 147-155): the m listed bits are cut into m/b groups of b bits
+ * (bits[0..b-1] = the first group, most significant digit of the outcome index; inside a group the
+ * first bit is the most significant index bit of the basis kets); `basis` holds the 2^b basis kets
+ * as the rows of a 2^b x 2^b complex matrix W.  out[branch * L^(m/b) + i], L = 2^b:
+ *   density matrix  |tr(rho_A P_i)|, P_i = (x)_f outer(ket_{d_f(i)}, ket_{d_f(i)}) -- computed as the
+ *                   diagonal of (W..W) rho (W..W)^T on a scratch copy (two gate sweeps + the binned read);
+ *   ket             sum |(W..W) psi|^2 over the other bits (identical for real bases, the only kind
+ *                   the DSL can name; the reference has no ket path).
+ * basis == NULL is qb_probs. The state itself is not modified. */
+int qb_probs_basis(qb_state* s, const int* bits, int m, const double* basis, int b, double* out);
 int qb_norm2(qb_state* s, double* out);                                /* per branch: <psi|psi> or tr rho */
 /* ket only: project the listed bits on `outcome` and renormalise (textbook collapse) */
 int qb_project_renorm(qb_state* s, const int* bits, int m, uint64_t outcome);

@@ -44,6 +44,7 @@ PROTOTYPES = {
     'qb_set_stream': (C.c_int, [c_state_p, C.c_void_p]),
     'qb_init_basis': (C.c_int, [c_state_p, C.c_uint64]),
     'qb_init_product': (C.c_int, [c_state_p, C.c_void_p, C.c_int]),
+    'qb_init_diag': (C.c_int, [c_state_p, C.c_void_p]),
     'qb_upload': (C.c_int, [c_state_p, C.c_void_p, C.c_size_t]),
     'qb_download': (C.c_int, [c_state_p, C.c_void_p, C.c_size_t]),
     'qb_download_range': (C.c_int, [c_state_p, C.c_uint64, C.c_uint64, C.c_void_p]),
@@ -51,6 +52,7 @@ PROTOTYPES = {
     'qb_apply_gates': (C.c_int, [c_state_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.c_void_p]),
     'qb_apply_swap': (C.c_int, [c_state_p, C.c_int, C.c_int]),
     'qb_apply_gate_batched': (C.c_int, [c_state_p, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.c_void_p]),
+    'qb_apply_gate_rc': (C.c_int, [c_state_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     'qb_flush': (C.c_int, [c_state_p]),
     'qb_sync': (C.c_int, [c_state_p]),
     'qb_set_fusion': (C.c_int, [c_state_p, C.c_int]),
@@ -59,6 +61,7 @@ PROTOTYPES = {
     'qb_jit_check': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.c_void_p,
                                C.POINTER(C.c_int), C.c_char_p]),
     'qb_probs': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
+    'qb_probs_basis': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'qb_norm2': (C.c_int, [c_state_p, C.c_void_p]),
     'qb_project_renorm': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_uint64]),
     'qb_ptrace': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.POINTER(c_state_p)]),

@@ -422,6 +422,22 @@ int qb_init_product(qb_state* s, const double* vecs, int per_branch) {
     QB_API_END
 }
 
+int qb_init_diag(qb_state* s, const double* values) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && values, "NULL argument");
+    QB_REQUIRE(s->kind == QB_DM && s->nbranch == 1, "init_diag: needs a single-branch density matrix");
+    s->queue.clear();
+    DevGuard g(s->device);
+    const size_t vb = sizeof(double) << s->nq;
+    double* dv = (double*)work_alloc(s->device, vb);
+    QB_CUDA(cudaMemcpyAsync(dv, values, vb, cudaMemcpyHostToDevice, s->stream));
+    qb_launch_fill_diag(s->ctx(), s->d, s->nq, dv);
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    work_free(s->device, vb, dv);
+    s->stats.bytes_moved += s->bytes();
+    QB_API_END
+}
+
 int qb_upload(qb_state* s, const void* host, size_t bytes) {
     QB_API_BEGIN
     QB_REQUIRE(s && host, "NULL argument");
@@ -497,6 +513,24 @@ int qb_apply_gates(qb_state* s, int ngates, const int* ks, const int* target_bit
     return QB_OK;
 }
 
+int qb_apply_gate_rc(qb_state* s, const double* row_matrix, const double* col_matrix, int k, const int* target_bits) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && target_bits, "NULL argument");
+    QB_REQUIRE(s->kind == QB_DM, "apply_gate_rc is defined for density matrices");
+    QB_REQUIRE(k >= 1 && k <= QB_BIG_MAXK && k <= s->nq, "gate size out of range");
+    uint64_t tmask = 0;
+    int tb_row[QB_BIG_MAXK];
+    for (int i = 0; i < k; i++) {
+        QB_REQUIRE(target_bits[i] >= 0 && target_bits[i] < s->nq, "target bit out of range");
+        QB_REQUIRE(!((tmask >> target_bits[i]) & 1ull), "duplicate target bit");
+        tmask |= 1ull << target_bits[i];
+        tb_row[i] = target_bits[i] + s->nq;
+    }
+    if (row_matrix) s->enqueue(qb_classify((const cplx*)row_matrix, k, tb_row, 0));
+    if (col_matrix) s->enqueue(qb_classify((const cplx*)col_matrix, k, target_bits, 0));
+    QB_API_END
+}
+
 int qb_apply_swap(qb_state* s, int bit_a, int bit_b) {
     QB_API_BEGIN
     QB_REQUIRE(s, "NULL state");
@@ -523,6 +557,7 @@ int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int*
     QB_REQUIRE(s && matrices && target_bits, "NULL argument");
     QB_REQUIRE(k >= 1 && k <= QB_REG_MAXK, "batched gate: k must be 1..5");
     QB_REQUIRE(k <= s->nq, "gate has more qubits than the register");
+    QB_REQUIRE(s->nbranch <= 65535, "batched gate: more than 65535 branches per launch");   // before anything is allocated
     s->flush();
     DevGuard g(s->device);
     const int64_t B = s->nbranch;
@@ -729,6 +764,41 @@ int qb_probs(qb_state* s, const int* bits, int m, double* out) {
     QB_API_END
 }
 
+int qb_probs_basis(qb_state* s, const int* bits, int m, const double* basis, int b, double* out) {
+    if (!basis) return qb_probs(s, bits, m, out);
+    QB_API_BEGIN
+    QB_REQUIRE(s && out && bits, "NULL argument");
+    QB_REQUIRE(b >= 1 && b <= 5 && m >= b && m % b == 0, "probs_basis: the basis size must divide the number of bits");
+    QB_REQUIRE(m <= s->nq && m <= 26, "probs_basis: too many outcome bits");
+    s->flush();
+    DevGuard g(s->device);
+    // rotate a scratch copy so that basis ket j of every group sits at group index j, then read the
+    // computational-frame weights; the register itself stays as it is (peek must not change it)
+    std::unique_ptr<qb_state> tmp(new_state(s->kind, s->nq, s->nbranch, s->device, nullptr, nullptr));
+    tmp->fusion = s->fusion;
+    tmp->jit_mode = 0;                 // one-off gate list: never worth a specialised kernel
+    QB_CUDA(cudaStreamSynchronize(s->stream));
+    QB_CUDA(cudaMemcpyAsync(tmp->d, s->d, s->bytes(), cudaMemcpyDeviceToDevice, tmp->stream));
+    const cplx* W = (const cplx*)basis;
+    for (int f = 0; f < m / b; f++) {
+        const int* tb = bits + f * b;
+        if (s->kind == QB_KET) {
+            tmp->enqueue(qb_classify(W, b, tb, 0));
+        } else {
+            int tb_row[8];
+            for (int i = 0; i < b; i++) tb_row[i] = tb[i] + s->nq;
+            tmp->enqueue(qb_classify(W, b, tb_row, 0));
+            tmp->enqueue(qb_classify(W, b, tb, 0));
+        }
+    }
+    std::vector<cplx> h;
+    run_bins(tmp.get(), bits, m, h);
+    s->stats.kernel_launches += tmp->stats.kernel_launches;
+    s->stats.bytes_moved += tmp->stats.bytes_moved + 2 * s->bytes();
+    for (size_t i = 0; i < h.size(); i++) out[i] = s->kind == QB_KET ? h[i].x : std::hypot(h[i].x, h[i].y);
+    QB_API_END
+}
+
 int qb_norm2(qb_state* s, double* out) {
     QB_API_BEGIN
     QB_REQUIRE(s && out, "NULL argument");
@@ -842,6 +912,8 @@ int qb_mix(qb_state* const* states, const double* probs, int count, qb_state** o
     QB_REQUIRE(states && probs && out && count >= 1, "bad argument");
     qb_state* s0 = states[0];
     QB_REQUIRE(s0, "NULL state");
+    // an ensemble sum_i p_i rho_i is a density-matrix notion (density.py:49-58); sum_i p_i psi_i is not a state
+    if (s0->kind != QB_DM) throw qb_error(QB_ERR_STATE, "mix: needs density matrices (qb_outer turns a ket into one)");
     for (int i = 0; i < count; i++) {
         QB_REQUIRE(states[i] && states[i]->kind == s0->kind && states[i]->nq == s0->nq &&
                    states[i]->nbranch == s0->nbranch && states[i]->device == s0->device, "mix: states differ in shape");
@@ -868,16 +940,16 @@ int qb_mix(qb_state* const* states, const double* probs, int count, qb_state** o
 int qb_mix_branches(qb_state* s, const double* probs, qb_state** out) {
     QB_API_BEGIN
     QB_REQUIRE(s && probs && out, "NULL argument");
+    if (s->kind != QB_DM) throw qb_error(QB_ERR_STATE, "mix_branches: needs a batch of density matrices");
     s->flush();
     DevGuard g(s->device);
     qb_state* o = new_state(s->kind, s->nq, 1, s->device, nullptr, s->owns_stream ? nullptr : (void*)s->stream);
     o->fusion = s->fusion;
-    double* dp = nullptr;
-    QB_CUDA(cudaMalloc((void**)&dp, sizeof(double) * s->nbranch));
+    double* dp = (double*)work_alloc(s->device, sizeof(double) * s->nbranch);
     QB_CUDA(cudaMemcpyAsync(dp, probs, sizeof(double) * s->nbranch, cudaMemcpyHostToDevice, s->stream));
     qb_launch_mix_branches(s->ctx(), s->d, dp, s->nbranch, s->per_branch(), o->d);
     QB_CUDA(cudaStreamSynchronize(s->stream));
-    cudaFree(dp);
+    work_free(s->device, sizeof(double) * s->nbranch, dp);
     s->stats.bytes_moved += s->bytes() + o->bytes();
     *out = o;
     QB_API_END
@@ -908,9 +980,11 @@ int qb_broadcast(qb_state* src, qb_state* dst) {
     dst->queue.clear();
     DevGuard g(src->device);
     QB_CUDA(cudaStreamSynchronize(src->stream));
-    for (int64_t b = 0; b < dst->nbranch; b++)
-        QB_CUDA(cudaMemcpyAsync(dst->d + (uint64_t)b * dst->per_branch(), src->d, src->bytes(), cudaMemcpyDeviceToDevice, dst->stream));
-    dst->stats.bytes_moved += dst->bytes() * 2;
+    qb_launch_broadcast(dst->ctx(), src->d, dst->d, src->per_branch(), dst->nbranch);
+    // single-branch views of dst (qb_create_external) run on streams of their own: the copy must have
+    // landed before any of them touches its branch
+    QB_CUDA(cudaStreamSynchronize(dst->stream));
+    dst->stats.bytes_moved += dst->bytes() + src->bytes();
     QB_API_END
 }
 

@@ -163,6 +163,8 @@ struct LaunchCtx {
 };
 
 void qb_launch_fill_basis(const LaunchCtx&, cplx* d, uint64_t per_branch, int64_t nbranch, uint64_t index);
+void qb_launch_fill_diag(const LaunchCtx&, cplx* d, int nq, const double* values_dev);
+void qb_launch_broadcast(const LaunchCtx&, const cplx* src, cplx* dst, uint64_t per_branch, int64_t nbranch);
 void qb_launch_init_product(const LaunchCtx&, cplx* d, int kind, int nq, int64_t nbranch, const cplx* vecs_dev, int per_branch);
 void qb_launch_dense(const LaunchCtx&, int K, const DenseArgs& a);
 void qb_launch_diag(const LaunchCtx&, const DiagArgs& a);

@@ -221,7 +221,16 @@ std::string cu_err(CUresult e) {
     return s ? s : "unknown driver error";
 }
 
+// second, independent fingerprint of a generated source: the cache is keyed by a 64-bit FNV-1a hash,
+// and a hit whose length or second hash differs must never launch the other structure's kernel
+static uint64_t src_hash2(const std::string& src) {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)src.size();
+    for (unsigned char ch : src) { h ^= ch; h *= 0xff51afd7ed558ccdull; h ^= h >> 29; }
+    return h;
+}
+
 struct Compiled {
+    uint64_t src_len = 0, hash2 = 0;
     std::vector<char> cubin;
     QjSourceInfo info;
     bool pool_global = false;
@@ -354,6 +363,7 @@ void qb_jit_precompile(const std::vector<const uint8_t*>& programs) {
         if (!j.ok || g_cache.count(j.key)) continue;
         Compiled c;
         c.cubin = std::move(j.cubin);
+        c.src_len = j.src.size(); c.hash2 = src_hash2(j.src);
         c.info = j.info;
         c.pool_global = j.pg;
         c.compile_ms = j.ms;
@@ -376,6 +386,7 @@ void qb_jit_compile_cached(const uint8_t* program) {
     const auto t0 = std::chrono::steady_clock::now();
     Compiled c;
     c.cubin = qb_jit_compile(src, nullptr);
+    c.src_len = src.size(); c.hash2 = src_hash2(src);
     c.info = info;
     c.pool_global = pg;
     c.compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -398,6 +409,7 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
         const auto t0 = std::chrono::steady_clock::now();
         Compiled c;
         c.cubin = qb_jit_compile(src, nullptr);
+        c.src_len = src.size(); c.hash2 = src_hash2(src);
         c.info = info;
         c.pool_global = pg;
         c.compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -405,6 +417,8 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
         g_stats.compile_ms += c.compile_ms;
         it = g_cache.emplace(key, std::move(c)).first;
     } else {
+        if (it->second.src_len != src.size() || it->second.hash2 != src_hash2(src))
+            throw qb_error(-2, "sweep specialiser: source-hash collision in the kernel cache");
         g_stats.cache_hits++;
     }
     Compiled& c = it->second;

@@ -34,6 +34,35 @@ void qb_launch_fill_basis(const LaunchCtx& c, cplx* d, uint64_t per_branch, int6
     COUNT_LAUNCH(c);
 }
 
+// rho = diag(values): one write of the density matrix
+__global__ void __launch_bounds__(256) k_fill_diag(cplx* d, int nq, const double* __restrict__ values) {
+    const uint64_t N = 1ull << nq, total = N * N;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint64_t r = i >> nq, c = i & (N - 1);
+        __stcs(d + i, make_double2(r == c ? values[r] : 0.0, 0.0));
+    }
+}
+
+void qb_launch_fill_diag(const LaunchCtx& c, cplx* d, int nq, const double* values_dev) {
+    k_fill_diag<<<grid_for(c, 1ull << (2 * nq), 256), 256, 0, c.stream>>>(d, nq, values_dev);
+    COUNT_LAUNCH(c);
+}
+
+// every branch of dst <- src (fan-out before a batched gate): src is read once from HBM and then from
+// L2, the write is the traffic; one launch instead of nbranch device-to-device copies
+__global__ void __launch_bounds__(256) k_broadcast(const cplx* __restrict__ src, cplx* dst, uint64_t per, uint64_t total) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+        __stcs(dst + i, src[i & (per - 1)]);
+}
+
+void qb_launch_broadcast(const LaunchCtx& c, const cplx* src, cplx* dst, uint64_t per, int64_t nbranch) {
+    const uint64_t total = per * (uint64_t)nbranch;
+    k_broadcast<<<grid_for(c, total, 256), 256, 0, c.stream>>>(src, dst, per, total);
+    COUNT_LAUNCH(c);
+}
+
 // ket: psi[i] = prod_q v_q[bit_q(i)]   dm: rho[r][c] = prod_q D_q[r_q][c_q]   (qubit 0 first; the
 // reference builds these with a kron chain on the host, density.py:7-24).
 // The qubits are cut into groups of up to 8 (ket) / 4 (density matrix) consecutive qubits; a

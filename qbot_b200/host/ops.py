@@ -17,7 +17,7 @@ The module is written against a *binding* (``Host``) so that the same functions 
 """
 from __future__ import annotations
 
-import sys
+import re
 from typing import List, Sequence
 
 import numpy as np
@@ -85,11 +85,40 @@ def hilbertSpaceNumQubits(state) -> int:
     return int(shape[0]).bit_length() - 1          # = int(np.log2(shape[0])) (operators.py:14-17)
 
 
-def _unaliased(ns, key) -> bool:
-    """True when the namespace holds the only reference to ns[key], so an op may update the
-    device buffer in place instead of cloning it (the reference's ops never mutate the
-    register, they rebind it, so an aliased register must stay untouched)."""
-    return sys.getrefcount(ns[key]) <= 2        # the dict slot + the call argument
+_STATE_NAME = re.compile(r'\bstate\b')
+
+
+def _program_names_state(ns, lines) -> bool:
+    """True when some expression of the program can read the register by its name (`cdef x ; state`,
+    `pydo l.append(state)`, ...).  That is the only way DSL code can create a second reference to the
+    register object: expressions are evaluated with the namespace as locals and no builtins
+    (qbot/evaluation.py:573-580), and the register is the local called `state`.  Decided once per
+    program from its text (comment lines excluded); any mention counts, so the answer errs towards
+    True."""
+    cached = ns.get('__qb_names_state')
+    if cached is not None and cached[0] is lines:
+        return cached[1]
+    named = any(_STATE_NAME.search(ln) is not None for ln in lines if not ln.lstrip().startswith('note'))
+    ns['__qb_names_state'] = (lines, named)
+    return named
+
+
+def _exclusively_owned(ns, lines) -> bool:
+    """Explicit ownership of the register instead of reference counting: an op may update the device
+    buffer in place only when (i) the register object was created by an op and handed to nothing but
+    ``ns['state']`` (``_shared`` is False -- the ops clear it on values they make themselves; values that
+    come out of user expressions or are also stored in a measurement result keep the default True),
+    and (ii) no expression of the program names `state`.  Otherwise the op works on a device-side
+    copy, as the reference's ops do (they never mutate the register, they rebind it)."""
+    return not getattr(ns['state'], '_shared', True) and not _program_names_state(ns, lines)
+
+
+def _mark_fresh(st):
+    try:
+        st._shared = False
+    except AttributeError:
+        pass
+    return st
 
 
 class GateDesc:
@@ -257,8 +286,18 @@ def make_ops(host: Host) -> dict:
             err.raiseFormattedError(err.customTypeError(lines, lineNum, ['np.ndarray', 'ProbVal<np.ndarray>'], type(val).__name__))
         return val
 
-    def setState(ns, lines, lineNum, value):
-        ns['state'] = to_device(convertToDensity(lines, lineNum, value))
+    def setState(ns, lines, lineNum, value, fresh=False):
+        """Rebind the register.  `fresh`: the op made `value` itself and keeps no other reference to
+        it.  A host array / product descriptor is uploaded into a new device object, fresh by
+        construction; a device object that came out of a user expression stays shared."""
+        val = convertToDensity(lines, lineNum, value)
+        dev = to_device(val)
+        if is_state(dev):
+            try:
+                dev._shared = not (fresh or dev is not val)
+            except AttributeError:
+                pass
+        ns['state'] = dev
         ns['__is_q_state'] = True
         ns['__updated_state'] = True
 
@@ -266,19 +305,33 @@ def make_ops(host: Host) -> dict:
         """The register as a DeviceState (uploads it if a foreign op left a host array there)."""
         st = ns['state']
         if not is_state(st) and isinstance(st, np.ndarray) and st.ndim in (1, 2) and st.size:
-            ns['state'] = State.from_host(st)
+            ns['state'] = _mark_fresh(State.from_host(st))
         return ns['state']
 
     def current_dm(ns):
         return current(ns).as_density()
 
-    def writable(ns):
-        """A DeviceState the op may update in place: the register itself when nothing else
-        references it, otherwise a device-side copy."""
+    def ensemble_base(ns):
+        """The register as something an ensemble sum may be taken of.  A ProbVal-valued gate /
+        condition leaves a MIXED state sum_i p_i U_i rho U_i^dagger (operators.py:313-327 +
+        probVal.py:99-111), which only a density matrix can hold: a ket-mode register (the new
+        representation) becomes psi psi^dagger first; summing p_i U_i psi would be an
+        unnormalised pure state."""
+        st = current(ns)
+        if is_state(st) and st.kind == 0:
+            if st.nq > KET_AS_DENSITY_MAX:
+                raise ValueError(f"a ProbVal-valued gate leaves a mixed state; the {st.nq}-qubit ket-mode register "
+                                 f"cannot become a density matrix (limit {KET_AS_DENSITY_MAX} qubits)")
+            st = _mark_fresh(st.as_density())
+            ns['state'] = st
+        return st
+
+    def writable(ns, lines):
+        """A DeviceState the op may update in place: the register itself when the ops own it
+        exclusively (_exclusively_owned), otherwise a device-side copy."""
         current(ns)
-        own = _unaliased(ns, 'state')
         st = ns['state']
-        return st if own else st.clone()
+        return st if _exclusively_owned(ns, lines) else st.clone()
 
     # ---- gate (operators.py:255-329) ------------------------------------------------------------
     def _gate(lines, lineNum, numQubits, controls, firstTarget, gate):
@@ -296,11 +349,11 @@ def make_ops(host: Host) -> dict:
             raise Exception("gate size must be power of 2")
         return GateDesc(gate, firstTarget, list(controls))
 
-    def apply_descs(ns, g):
+    def apply_descs(ns, lines, g):
         """Apply one descriptor in place, or a ProbVal of descriptors as ONE batched launch
         followed by the weighted branch reduction (piece 5)."""
         if isinstance(g, ProbVal):
-            base = current(ns)
+            base = ensemble_base(ns)
             descs: List[GateDesc] = g.values
             batch = base.broadcast(len(descs))
             if all(isinstance(d, SwapDesc) for d in descs):
@@ -309,7 +362,7 @@ def make_ops(host: Host) -> dict:
             else:
                 _apply_batched_generic(batch, [(d.matrix, tuple(range(d.target, d.target + d.k)), d.controls) for d in descs])
             return batch.mix_branches(g.probs)
-        st = writable(ns)
+        st = writable(ns, lines)
         if isinstance(g, SwapDesc):
             st.apply_swap(g.a, g.b)
         elif isinstance(g, GateDesc):
@@ -359,13 +412,19 @@ def make_ops(host: Host) -> dict:
         if not isinstance(desc, (ProbVal, GateDesc)):
             raise Exception("gate is not array or ProbVal")
         if isinstance(cond, ProbVal):
-            before = current(ns).clone()
-            val = apply_descs(ns, desc)
+            try:
+                before = ensemble_base(ns).clone()
+            except ValueError as e:
+                err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+            val = apply_descs(ns, lines, desc)
             pair = [val, before] if cond.values[0] else [before, val]
             val = State.mix(cond.probs, pair)
         else:
-            val = apply_descs(ns, desc)
-        setState(ns, lines, lineNum, val)
+            try:
+                val = apply_descs(ns, lines, desc)
+            except ValueError as e:
+                err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+        setState(ns, lines, lineNum, val, fresh=True)
 
     # ---- swap (operators.py:364-393) -------------------------------------------------------------
     def _swap(lines, lineNum, numQubits, qubitA, qubitB):
@@ -385,7 +444,11 @@ def make_ops(host: Host) -> dict:
             desc = funcWrapper(_swap, lines, lineNum, numQubits, a, b)
         except Exception as e:
             err.raiseFormattedError(err.pythonError(lines, lineNum, e))
-        setState(ns, lines, lineNum, apply_descs(ns, desc))
+        try:
+            val = apply_descs(ns, lines, desc)
+        except ValueError as e:
+            err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+        setState(ns, lines, lineNum, val, fresh=True)
 
     # ---- qset (operators.py:133-166) / density.replaceArbitrary (density.py:195-227) -----------
     def replace_arbitrary(st, new_dm, targets):
@@ -397,6 +460,11 @@ def make_ops(host: Host) -> dict:
         tset = sorted(set(int(t) for t in targets))
         if tset[0] < 0 or tset[-1] > n - 1:
             raise IndexError()
+        if len(tset) != k:
+            # repeated targets: the reference traces out the distinct ones, krons all k new qubits on
+            # and fails in the permutation matmul (density.py:203-225) -- same exception, same text
+            raise ValueError("matmul: Input operand 1 has a mismatch in its core dimension 0, with gufunc signature "
+                             f"(n?,k),(k,m?)->(n?,m?) (size {1 << (n - len(tset) + k)} is different from {1 << n})")
         rest = [q for q in range(n) if q not in tset]
         new_dev = to_device(new_dm)
         b = st.ptrace_keep(rest)                  # (for n == k this is the 1x1 [[tr rho]] factor)
@@ -416,18 +484,17 @@ def make_ops(host: Host) -> dict:
         x = evaluateWrapper(lines, lineNum, tokens[1], ns)
         val = convertToDensity(lines, lineNum, x)
         if len(tokens) == 2:
-            if is_state(val) and val is ns.get('state'):
-                val = val.clone()
-            setState(ns, lines, lineNum, val)
+            same = is_state(val) and val is ns.get('state')
+            setState(ns, lines, lineNum, val.clone() if same else val, fresh=same)
             return
         targets = ensureContainer(lines, lineNum, evaluateWrapper(lines, lineNum, tokens[2], ns))
         if isinstance(targets, ProbVal):
             dens = funcWrapper(_qset, val, ns, lines, lineNum, numQubits, targets)
             if isinstance(dens, ProbVal):
                 dens = dens.toDensityMatrix()
-            setState(ns, lines, lineNum, dens)
+            setState(ns, lines, lineNum, dens, fresh=True)
             return
-        setState(ns, lines, lineNum, _qset(val, ns, lines, lineNum, numQubits, targets))
+        setState(ns, lines, lineNum, _qset(val, ns, lines, lineNum, numQubits, targets), fresh=True)
 
     # ---- disc (operators.py:169-188) / density.partialTraceArbitrary (density.py:122-148) ------
     def _disc(ns, lines, lineNum, numQubits, targets):
@@ -445,10 +512,51 @@ def make_ops(host: Host) -> dict:
             val = funcWrapper(_disc, ns, lines, lineNum, numQubits, targets)
         else:
             val = _disc(ns, lines, lineNum, numQubits, targets)
-        setState(ns, lines, lineNum, convertToDensity(lines, lineNum, val))
+        setState(ns, lines, lineNum, convertToDensity(lines, lineNum, val), fresh=True)
 
     # ---- meas / peek (operators.py:396-428; measurement.py:107-165) ---------------------------
-    HOST_MEAS_QUBITS = 7       # rho_A up to 128x128 is handled with the reference's host arithmetic
+    EAGER_OUTCOMES = 1 << 10   # projector / symbol lists are built up to this many outcomes, on demand above
+    HOST_COPY_QUBITS = 7       # rho_A up to 128 x 128 is handed out as a host array (what callers index and print)
+
+    def _basis_matrix(basis, basisQubitSize):
+        """rows = the basis kets; None for the computational basis (no rotation needed)"""
+        if len(basis.kets) != 1 << basisQubitSize:
+            raise ValueError(f"a measurement basis of {basisQubitSize} qubits needs {1 << basisQubitSize} kets, got {len(basis.kets)}")
+        if _is_computational(basis):
+            return None
+        return np.stack([np.asarray(k, dtype=complex).reshape(-1) for k in basis.kets])
+
+    def _outcome_weights(dev, qubits, W):
+        """|tr(rho_A P_i)| for every outcome i (measurement.py:147-155) -- on the device: the listed
+        qubits are rotated by the basis kets on a scratch copy and the diagonal is binned (qb_probs /
+        qb_probs_basis); what is left for the host is the normalisation, in the reference's order."""
+        w = dev.probs(qubits) if W is None else dev.probs_basis(qubits, W)
+        s = 0
+        probs = []
+        for x in np.asarray(w, dtype=np.float64).reshape(-1):
+            probs.append(x)            # stays np.float64, as abs(np.trace(..)) is in the reference: the later
+            s += probs[-1]             # round(p, 15) must be numpy's rounding, not Python's (they differ in the last digit)
+        return [p / s for p in probs]
+
+    def _outcome_labels(numTensProd, basis, nOutcomes):
+        if nOutcomes > EAGER_OUTCOMES:
+            return _LazyProjectors(numTensProd, basis), _LazySymbols(numTensProd, basis)
+        basisStates, basisSymbols = [], []
+        for i in range(nOutcomes):
+            proj, sym = hm.permute_basis(numTensProd, i, basis)
+            basisStates.append(proj)
+            basisSymbols.append(sym)
+        return basisStates, basisSymbols
+
+    def _collapsed_system(probs, numTensProd, basisQubitSize, W):
+        """sum_i p_i P_i (measurement.py:160-161) built on the device: diag(p) in the frame of the
+        basis, then W^T (.) W on every factor (P_i = (x)_f outer(ket, ket), no conjugation: F2)."""
+        measured = State.diagonal(probs)
+        if W is not None:
+            wt = np.ascontiguousarray(W.T)
+            for f in range(numTensProd):
+                measured.apply_gate_rc(wt, wt, f * basisQubitSize)
+        return measured
 
     def measure(st, basis, toMeasure=None, returnState=True):
         numQubits = st.nq
@@ -466,6 +574,8 @@ def make_ops(host: Host) -> dict:
             raise ValueError("measurement must have targets")
         if numTargets % basisQubitSize != 0:
             raise ValueError(f"number of qubits to measure {numTargets} must be divisable by the number of qubits in the basis states {basisQubitSize}")
+        if numTargets > 26:
+            raise ValueError(f"{numTargets} measured qubits give more outcomes than a result list can hold")
         full = toMeasure is None or len(toMeasure) == numQubits
         targets_sorted = list(range(numQubits)) if full else sorted(toMeasure)
         rest = [q for q in range(numQubits) if q not in targets_sorted]
@@ -473,57 +583,24 @@ def make_ops(host: Host) -> dict:
         sysB_dev = None if full else st.ptrace_keep(rest)
         numTensProd = numTargets // basisQubitSize
         nOutcomes = len(basis.density) ** numTensProd
+        W = _basis_matrix(basis, basisQubitSize)
 
-        if numTargets <= HOST_MEAS_QUBITS:
-            # small rho_A: the outcome loop of the reference, on the host copy of rho_A
-            sysA = np.asarray(sysA_dev)
-            probs, basisStates, basisSymbols = [], [], []
-            s = 0
-            for i in range(nOutcomes):
-                proj, sym = hm.permute_basis(numTensProd, i, basis)
-                probs.append(abs(np.trace(np.matmul(sysA, proj))))
-                basisStates.append(proj)
-                basisSymbols.append(sym)
-                s += probs[-1]
-            for i in range(len(probs)):
-                probs[i] /= s
-            measured = None
-            if returnState:
-                acc = np.zeros(basisStates[0].shape, dtype=complex)
-                for p, d in zip(probs, basisStates):
-                    acc += p * d
-                measured = State.from_host(acc)
-            unmeasured = sysA
-        else:
-            if basis.numQubits != 1 or not _is_computational(basis):
-                raise NotImplementedError(f"measuring {numTargets} qubits at once is only supported in the computational basis")
-            w = sysA_dev.probs(list(range(numTargets)))
-            s = 0
-            probs = []
-            for x in w:
-                probs.append(float(x))
-                s += probs[-1]
-            probs = [p / s for p in probs]
-            basisStates = _LazyProjectors(numTensProd, basis)
-            basisSymbols = _LazySymbols(numTensProd, basis)
-            measured = State.from_host(np.diag(np.array(probs, dtype=complex))) if returnState else None
-            unmeasured = sysA_dev
+        probs = _outcome_weights(sysA_dev, list(range(numTargets)), W)
+        basisStates, basisSymbols = _outcome_labels(numTensProd, basis, nOutcomes)
+        unmeasured = np.asarray(sysA_dev) if numTargets <= HOST_COPY_QUBITS else sysA_dev
 
         newState = None
         if returnState:
-            if full:
-                newState = measured
-            else:
-                newState = State.scatter_product(measured, sysB_dev, targets_sorted, rest)
+            measured = _collapsed_system(probs, numTensProd, basisQubitSize, W)
+            newState = measured if full else State.scatter_product(measured, sysB_dev, targets_sorted, rest)
         return Result(unmeasured, probs, basisStates, basisSymbols, newState)
 
     KET_AS_DENSITY_MAX = 13    # larger ket-mode registers are never expanded to 4^n density matrices
 
     def measure_ket(st, basis, toMeasure):
         """`peek` on a large ket-mode register (new representation): outcome weights
-        straight from the amplitudes (qb_probs); rho_A is computed only if somebody reads it.  The
-        reference's collapse (F7) yields a mixed product state, which a ket cannot hold -- `meas`
-        on such a register is refused."""
+        straight from the amplitudes, in any basis (the rotation runs on a scratch copy of the ket);
+        rho_A is computed only if somebody reads it."""
         numQubits = st.nq
         if toMeasure is None:
             toMeasure = list(range(numQubits))
@@ -533,22 +610,19 @@ def make_ops(host: Host) -> dict:
                 raise MeasurementIndexError(f"measurement target {target} outside of valid range [{0}, {numQubits - 1}]",
                                             target, 0, numQubits - 1)
         numTargets = len(toMeasure)
+        basisQubitSize = hm.ilog2(hm.ensure_square(basis.density[0]))
         if numTargets == 0:
             raise ValueError("measurement must have targets")
-        if basis.numQubits != 1 or not _is_computational(basis):
-            raise NotImplementedError("a ket-mode register is measured in the computational basis")
+        if numTargets % basisQubitSize != 0:
+            raise ValueError(f"number of qubits to measure {numTargets} must be divisable by the number of qubits in the basis states {basisQubitSize}")
         if numTargets > 26:
-            raise NotImplementedError("too many outcome qubits")
+            raise ValueError(f"{numTargets} measured qubits give more outcomes than a result list can hold")
         targets_sorted = sorted(toMeasure)
-        w = st.probs(targets_sorted)
-        s = 0
-        probs = []
-        for x in w.reshape(-1):
-            probs.append(float(x))
-            s += probs[-1]
-        probs = [p / s for p in probs]
-        return Result(_LazyReducedDensity(st, targets_sorted), probs, _LazyProjectors(numTargets, basis),
-                      _LazySymbols(numTargets, basis), None)
+        numTensProd = numTargets // basisQubitSize
+        W = _basis_matrix(basis, basisQubitSize)
+        probs = _outcome_weights(st, targets_sorted, W)
+        basisStates, basisSymbols = _outcome_labels(numTensProd, basis, len(basis.density) ** numTensProd)
+        return Result(_LazyReducedDensity(st, targets_sorted), probs, basisStates, basisSymbols, None)
 
     def meas(ns, lines, lineNum, tokens, changeState=True):
         varName = tokens[1]

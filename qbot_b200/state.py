@@ -75,6 +75,7 @@ class DeviceState:
     with a leading branch axis (``nbranch`` independent copies: the ProbVal batch)."""
     _qb_device_state = True
     __array_priority__ = 1000
+    _shared = True        # ownership flag of the DSL ops (host/ops.py _exclusively_owned): conservative default
 
     def __init__(self, handle, kind: int, nq: int, nbranch: int = 1):
         self._h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
@@ -366,6 +367,45 @@ class DeviceState:
         _lib.call('qb_probs', self._h, _lib.int_array([self._bit(q) for q in qubits]), m, _cptr(out))
         return out[0] if self.nbranch == 1 else out
 
+    def probs_basis(self, qubits: Sequence[int], basis_kets) -> np.ndarray:
+        """Outcome weights of the listed qubits in a product of measurement bases
+        (measurement.permuteBasis + the outcome loop, qbot/measurement.py:88-101, 147-155): the
+        qubits are taken in groups of b = log2(len(kets[0])) as listed, outcome index = base-2^b number
+        whose most significant digit belongs to the first group.  Runs on the device (two gate sweeps on
+        a scratch copy + the binned read); the register is not modified."""
+        w = np.ascontiguousarray(np.stack([np.asarray(k, dtype=np.complex128).reshape(-1) for k in basis_kets]))
+        b = int(w.shape[1]).bit_length() - 1
+        if w.shape != (1 << b, 1 << b):
+            raise ValueError("a measurement basis needs 2^b kets of 2^b amplitudes")
+        m = len(qubits)
+        out = np.empty((self.nbranch, 1 << m), dtype=np.float64)
+        _lib.call('qb_probs_basis', self._h, _lib.int_array([self._bit(q) for q in qubits]), m, _cptr(w), b, _cptr(out))
+        return out[0] if self.nbranch == 1 else out
+
+    def apply_gate_rc(self, row_matrix, col_matrix, first_target: int = 0) -> "DeviceState":
+        """Density matrices: rho <- R rho C^T on the contiguous qubits starting at first_target
+        (either matrix may be None).  The non-conjugating forms of the reference live here, see
+        qb_apply_gate_rc in the header."""
+        r = None if row_matrix is None else _cmat(row_matrix)
+        c = None if col_matrix is None else _cmat(col_matrix)
+        ref = r if r is not None else c
+        k = int(ref.shape[0]).bit_length() - 1
+        bits = _lib.int_array([self._bit(first_target + j) for j in range(k)])
+        _lib.call('qb_apply_gate_rc', self._h, None if r is None else _cptr(r), None if c is None else _cptr(c), k, bits)
+        self._dirty()
+        return self
+
+    @classmethod
+    def diagonal(cls, weights: Sequence[float], device: int = 0) -> "DeviceState":
+        """Density matrix diag(weights), built on the device."""
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64).reshape(-1))
+        nq = int(w.shape[0]).bit_length() - 1
+        if w.shape[0] != 1 << nq:
+            raise ValueError("diagonal: needs 2^n weights")
+        s = cls.create(DM, nq, 1, device)
+        _lib.call('qb_init_diag', s._h, _cptr(w))
+        return s
+
     def norm2(self) -> np.ndarray:
         out = np.empty(self.nbranch, dtype=np.float64)
         _lib.call('qb_norm2', self._h, _cptr(out))
@@ -407,6 +447,13 @@ class DeviceState:
         for s in states:
             if s.shape != s0.shape or s.kind != s0.kind:
                 raise ValueError(f"operands could not be broadcast together with shapes {s0.shape} {s.shape}")
+        if s0.kind == KET:
+            # an ensemble of kets is the density matrix sum_i p_i psi_i psi_i^T (ProbVal.toDensityMatrix,
+            # qbot/probVal.py:99-111 -- np.outer without conjugation), never sum_i p_i psi_i
+            if s0.nq > 13:
+                raise ValueError(f"an ensemble of {s0.nq}-qubit kets needs a 4^{s0.nq}-entry density matrix")
+            states = [s.outer(False) for s in states]
+            s0 = states[0]
         arr = (C.c_void_p * len(states))(*[s._h for s in states])
         p = (C.c_double * len(probs))(*[float(x) for x in probs])
         h = C.c_void_p()

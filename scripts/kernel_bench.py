@@ -76,10 +76,15 @@ rec('k_dense_batched per-branch RZ', timed(bs, lambda: bs.apply_gate_batched(mat
 xm = np.broadcast_to(PAULI_X, (B, 2, 2)).copy()
 rec('k_dense_batched per-branch X', timed(bs, lambda: bs.apply_gate_batched(xm, tg)), 2 * SB)
 rec('k_bins probs 4096 x 2^4', wall(lambda: bs.probs([1, 6, 11, 15])), SB, 'wall clock')
-pr = rng.uniform(size=B)
-pr /= pr.sum()
-rec('k_mix_branches 4096 -> 1', wall(lambda: bs.mix_branches(pr)), SB, 'wall clock')
 del bs
+# the weighted branch reduction is a density-matrix notion (sum_b p_b rho_b): 256 branches of a 10-qubit rho = 4 GiB
+Bm, nm = 256, 10
+bm = DeviceState.zero_state(nm, kind=DM).broadcast(Bm)
+pr = rng.uniform(size=Bm)
+pr /= pr.sum()
+rec('k_mix_branches 256 x 10q DM -> 1', wall(lambda: bm.mix_branches(pr)), 16 * (Bm + 1) * (1 << (2 * nm)), 'wall clock')
+rec('k_broadcast 10q DM -> 256', wall(lambda: bm.broadcast(Bm) if False else DeviceState.zero_state(nm, kind=DM).broadcast(Bm)), 16 * Bm * (1 << (2 * nm)), 'wall clock incl. allocation')
+del bm
 
 # ---- config 3: 12-qubit density matrix (256 MiB) --------------------------------------------------
 nd = 12

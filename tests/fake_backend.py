@@ -148,6 +148,34 @@ class FakeState:
         asc = sorted(qubits)
         return np.abs(np.transpose(d, [asc.index(q) for q in qubits]).reshape(-1))
 
+    def probs_basis(self, qubits, basis_kets):
+        """the reference's outcome loop (measurement.py:147-155) on the listed qubits of this state"""
+        kets = [np.asarray(k, dtype=complex).reshape(-1) for k in basis_kets]
+        dens = [np.outer(k, k) for k in kets]
+        b = orc.ilog2(kets[0].shape[0])
+        qubits = list(qubits)
+        rho = self.data if self.kind == DM else np.outer(self.data, self.data.conj())
+        if qubits != list(range(self.nq)):
+            assert qubits == sorted(qubits)
+            rho, _ = orc.ptrace_arbitrary(rho, self.nq, qubits)
+        f = len(qubits) // b
+        return np.array([abs(np.trace(np.matmul(rho, orc.basis_projector(f, i, dens)[0]))) for i in range(len(dens) ** f)])
+
+    def apply_gate_rc(self, row_matrix, col_matrix, first_target=0):
+        assert self.kind == DM
+        ref = row_matrix if row_matrix is not None else col_matrix
+        k = orc.ilog2(np.asarray(ref).shape[0])
+        if row_matrix is not None:
+            self.data = orc.embed_gate(self.nq, first_target, np.asarray(row_matrix, dtype=complex)) @ self.data
+        if col_matrix is not None:
+            self.data = self.data @ orc.embed_gate(self.nq, first_target, np.asarray(col_matrix, dtype=complex)).T
+        return self
+
+    @classmethod
+    def diagonal(cls, weights, device=0):
+        w = np.asarray(weights, dtype=float)
+        return cls(np.diag(w).astype(complex), DM, orc.ilog2(w.shape[0]))
+
     def as_density(self):
         return self if self.kind == DM else self.outer(True)
 

@@ -119,6 +119,46 @@ def test_inplace_only_when_unaliased():
     assert np.asarray(ns['x'].newState)[0, 0] == 1 and np.asarray(ns['state'])[1, 1] == 1
 
 
+def test_ownership_is_explicit_not_refcounted():
+    """in place only when the ops made the register themselves AND no expression names `state`"""
+    from qbot_b200.host import ops as ops_mod
+    lines_plain = ["qset comp[0]", "gate pauliXGate ; 0"]
+    lines_named = ["qset comp[0]", "note state is only mentioned in a comment", "pydo l.append(state)"]
+    assert not ops_mod._program_names_state({}, lines_plain)
+    assert not ops_mod._program_names_state({}, lines_plain + ["note a comment about the state"])
+    assert ops_mod._program_names_state({}, lines_named)
+    # a register that came out of a user expression (here: the measurement result's newState) is shared
+    ns, _, _ = run_script("qset tensorExp(comp[0], 2)\npeek x ; comp ; 0\nmeas y ; comp ; 0\nqset y.newState\ngate pauliXGate ; 1\n", FakeState)
+    assert np.asarray(ns['y'].newState)[0, 0] == 1 and np.asarray(ns['state'])[1, 1] == 1
+    # extra Python references held by somebody else (what broke the getrefcount rule) change nothing
+    ns, _, _ = run_script("qset comp[0]\ngate pauliXGate ; 0\ngate hadamardGate ; 0\n", FakeState)
+    assert not ns['state']._shared
+
+
+def test_probval_gate_on_a_ket_register_gives_the_mixed_state():
+    """a ProbVal-valued gate / condition / target on a ket-mode register must give
+    sum_i p_i U_i rho U_i^dagger, i.e. the same as on the density register -- never sum_i p_i U_i psi"""
+    ket = "qset np_array([1, 0, 0, 0]) * (1+0j)\n"
+    dm = "qset tensorExp(comp[0], 2)\n"
+    for body in ("gate pauliXGate ; 0 ; [] ; ProbVal([.5, .5], [True, False])\n",
+                 "gate hadamardGate ; ProbVal([.25, .75], [0, 1])\n",
+                 "gate hadamardGate ; 0\ngate pauliXGate ; 1 ; ProbVal([.5, .5], [[0], []])\n",
+                 "gate ProbVal([.3, .7], [pauliXGate, hadamardGate]) ; 1\n",
+                 "gate hadamardGate ; 0\nswap ProbVal([.5, .5], [0, 1]) ; 1\n"):
+        a, _, _ = run_script(ket + body, FakeState)
+        b, _, _ = run_script(dm + body, FakeState)
+        ra, rb = np.asarray(a['state']), np.asarray(b['state'])
+        assert ra.shape == (4, 4) and close(ra, rb), body
+        assert abs(np.trace(ra) - 1) < 1e-14
+
+
+def test_qset_with_repeated_targets_fails_like_the_reference():
+    """`qset rho2 ; [1, 1]` passes the count check, then the reference dies in its
+    permutation matmul with a ValueError (density.py:203-225)"""
+    ns, out, exited = run_script("qset tensorExp(comp[0], 3)\nqset tensorExp(comp[1], 2) ; [1, 1]\n", FakeState)
+    assert exited and "matmul: Input operand 1 has a mismatch in its core dimension 0" in out and "(size 16 is different from 8)" in out
+
+
 def test_ket_register_new_representation():
     # a 1-D qset starts a ket-mode register (the reference has no working ket path, SURVEY F1)
     ns, _, _ = run_script("qset np_array([1, 0, 0, 0]) * (1+0j)\ngate hadamardGate ; 0\ngate pauliXGate ; 1 ; [0]\n", FakeState)

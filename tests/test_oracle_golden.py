@@ -119,3 +119,32 @@ def test_measure_collapse_is_product_state():
     r = orc.measure(bs['bell'][0], bs['comp'], [0], True)
     assert r['probs'] == [0.5, 0.5]
     assert close(r['newState'], np.eye(4) / 4)
+
+
+def test_basis_weights_equals_the_literal_outcome_loop():
+    """oracle.basis_weights (rotation form, used as the checker at 9-13 measured qubits) against the
+    literal restatement of measurement.py:147-155 (abs(trace(rho_A @ P_i)) per outcome), all three
+    DSL bases, full / partial / non-contiguous targets, density matrices and kets"""
+    rng = np.random.default_rng(5)
+    r2 = 2 ** -0.5
+    bases = {'comp': [np.array([1, 0]), np.array([0, 1])], 'hada': [r2 * np.array([1, 1]), r2 * np.array([1, -1])],
+             'bell': [r2 * np.array([1, 0, 0, 1]), r2 * np.array([0, 1, 1, 0]), r2 * np.array([1, 0, 0, -1]), r2 * np.array([0, 1, -1, 0])]}
+    for n, t in ((1, [0]), (4, [0, 1, 2, 3]), (5, [1, 3]), (6, [0, 2, 3, 5]), (5, [0, 1, 2, 4]), (7, [1, 2, 4, 6])):
+        d = 1 << n
+        rho = np.zeros((d, d), dtype=complex)
+        for _ in range(3):
+            v = rng.normal(size=d) + 1j * rng.normal(size=d)
+            v /= np.linalg.norm(v)
+            rho += np.outer(v, v.conj()) / 3
+        psi = rng.normal(size=d) + 1j * rng.normal(size=d)
+        psi /= np.linalg.norm(psi)
+        for name, kets in bases.items():
+            b = orc.ilog2(len(kets[0]))
+            if len(t) % b:
+                continue
+            dens = [np.outer(k, k).astype(complex) for k in kets]
+            sys_a = rho if len(t) == n else orc.ptrace_arbitrary(rho, n, t)[0]
+            f = len(t) // b
+            lit = np.array([abs(np.trace(np.matmul(sys_a, orc.basis_projector(f, i, dens)[0]))) for i in range(len(dens) ** f)])
+            assert np.max(np.abs(orc.basis_weights(rho, n, t, kets) - lit)) < 1e-14, (n, t, name)
+            assert np.max(np.abs(orc.basis_weights(psi, n, t, kets) - orc.basis_weights(np.outer(psi, psi.conj()), n, t, kets))) < 1e-14
