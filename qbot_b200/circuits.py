@@ -90,3 +90,76 @@ def rc_script(n: int, depth: int, seed: int) -> str:
 
 def total_algorithmic_bytes(gates: List[Gate], n: int) -> int:
     return sum(g.algorithmic_bytes(n) for g in gates)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE config 3 and 4 workloads
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class C3Op:
+    """One state operation of the config-3 program: kind 'gate' (a circuit gate), 'meas' (two
+    qubits, computational basis, product-state collapse), 'pgate' (Hadamard on a ProbVal target)
+    or 'disc' (final partial trace)."""
+    kind: str
+    gate: Gate = None
+    qubits: Tuple[int, ...] = ()
+    name: str = ''
+
+    def dsl(self) -> str:
+        if self.kind == 'gate':
+            return self.gate.dsl()
+        if self.kind == 'meas':
+            return f"meas {self.name} ; comp ; {list(self.qubits)}"
+        if self.kind == 'pgate':
+            return f"gate hadamardGate ; ProbVal([.5,.5],[{self.qubits[0]},{self.qubits[1]}])"
+        return f"disc {list(self.qubits)}"
+
+
+def c3_ops(n: int = 12, depth: int = 50, seed: int = 12, every: int = 10) -> List[C3Op]:
+    """Config 3: rho_0 = |0..0><0..0| on n qubits, rc(n, depth, seed) with, after every `every`
+    layers, `meas m_i ; comp ; [two random qubits]` followed by one ProbVal-target gate
+    `gate hadamardGate ; ProbVal([.5,.5],[a,b])`, and a final `disc` of min(4, n-1) random qubits.
+    The extra choices come from their own generator (seed, 3), so the gate list is exactly rc()'s."""
+    gates = rc(n, depth, seed)
+    rng = np.random.default_rng([seed, 3])
+    # rc() emits whole layers: cut the flat list back into layers by replaying its qubit budget
+    ops: List[C3Op] = []
+    used, layer, mi = 0, 0, 0
+    for g in gates:
+        ops.append(C3Op('gate', gate=g))
+        used += 1 + len(g.controls)
+        if used == n:
+            used = 0
+            layer += 1
+            if layer % every == 0 and layer < depth:
+                q = [int(x) for x in rng.choice(n, size=2, replace=False)]
+                ops.append(C3Op('meas', qubits=tuple(q), name=f"m{mi}"))
+                mi += 1
+                ab = [int(x) for x in rng.choice(n, size=2, replace=False)]
+                ops.append(C3Op('pgate', qubits=tuple(ab)))
+    drop = sorted(int(x) for x in rng.choice(n, size=min(4, n - 1), replace=False))
+    ops.append(C3Op('disc', qubits=tuple(drop)))
+    return ops
+
+
+def c3_program(n: int = 12, depth: int = 50, seed: int = 12, every: int = 10) -> str:
+    """Config 3 as a qbot program (what a user of the reference would run through executeTxt)."""
+    return "\n".join([f"qset tensorExp(comp[0], {n})"] + [op.dsl() for op in c3_ops(n, depth, seed, every)])
+
+
+def c4_inputs(nbranch: int = 4096, n: int = 16, seed: int = 16):
+    """Config 4: `nbranch` random product kets (per-qubit angles theta ~ U[0, pi), phi ~ U[0, 2 pi)),
+    branch weights ~ U(0, 1] normalised, the shared circuit rc(n, 10, seed), a per-branch RZ(theta_b)
+    on a per-branch target t_b, and 4 fixed measured qubits.
+    Returns (factors [B, n, 2], weights [B], gates, rz_angles [B], rz_targets [B], measured qubits)."""
+    rng = np.random.default_rng(seed)
+    th = rng.uniform(0, np.pi, size=(nbranch, n))
+    ph = rng.uniform(0, 2 * np.pi, size=(nbranch, n))
+    factors = np.stack([np.cos(th / 2), np.exp(1j * ph) * np.sin(th / 2)], axis=-1)
+    w = 1.0 - rng.uniform(0, 1, size=nbranch)          # (0, 1]
+    w /= w.sum()
+    gates = rc(n, 10, seed)
+    ang = rng.uniform(0, 2 * np.pi, size=nbranch)
+    tgt = rng.integers(0, n, size=nbranch)
+    measured = sorted({1 % n, (3 * n) // 8, (11 * n) // 16, n - 1})
+    return factors, w, gates, ang, tgt, measured

@@ -1,0 +1,131 @@
+"""The BASELINE configs at the parity sizes SURVEY.md 8(d) names, against fixtures recorded from the
+REAL reference (tests/golden/make_golden_configs.py -> configs.npz / configs.json):
+
+    rc(10, 200, 20) density matrix     (config 2's parity run)
+    config 3 at n = 6 and 8            (mid-circuit meas with the reference's collapse, ProbVal-target gate, disc)
+    config 4 at B = 64, n = 6          (per-branch circuit + per-branch RZ + measurement weights)
+
+CPU: the oracle against the fixtures (pins the oracle at these sizes).  GPU (-m gpu): the CUDA path,
+through the DSL / the C ABI, against the same fixtures directly."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import qbot_oracle as orc
+from qbot_b200 import circuits
+from conftest import close, GOLDEN
+
+
+@pytest.fixture(scope='module')
+def cfg():
+    return json.load(open(os.path.join(GOLDEN, 'configs.json'))), np.load(os.path.join(GOLDEN, 'configs.npz'))
+
+
+def _rows(meta):
+    return meta['rc_10_200_20']['rows']
+
+
+def test_oracle_rc_10_200_20(cfg):
+    meta, arr = cfg
+    n = 10
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[0] = 1
+    for g in circuits.rc(n, 200, 20):
+        psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+    rho_rows = np.outer(psi[_rows(meta)], psi.conj())
+    assert close(rho_rows, arr['rc_10_200_20_rows'], 1e-11)          # 1 660 reference zgemm pairs accumulate ~1e-13
+    assert close(np.abs(psi) ** 2, arr['rc_10_200_20_diag'].real, 1e-11)
+    assert abs(meta['rc_10_200_20']['trace'][0] - 1) < 1e-11 and abs(meta['rc_10_200_20']['purity'] - 1) < 1e-11
+
+
+def _oracle_c3(n, depth):
+    rho = np.zeros((1 << n, 1 << n), dtype=complex)
+    rho[0, 0] = 1
+    comp = [np.diag([1, 0]).astype(complex), np.diag([0, 1]).astype(complex)]
+    probs = {}
+    for op in circuits.c3_ops(n, depth, n):
+        if op.kind == 'gate':
+            rho = orc.dm_apply(rho, n, op.gate.target, op.gate.matrix(), op.gate.controls)
+        elif op.kind == 'meas':
+            r = orc.measure(rho, comp, list(op.qubits), True)
+            probs[op.name] = r['probs']
+            rho = r['newState']
+        elif op.kind == 'pgate':
+            rho = orc.ensemble([.5, .5], [orc.dm_apply(rho, n, t, circuits.HADAMARD, []) for t in op.qubits])
+        else:
+            rho = orc.ptrace_arbitrary(rho, n, list(op.qubits))[1]
+    return rho, probs
+
+
+@pytest.mark.parametrize('n,depth', [(6, 20), (8, 30)])
+def test_oracle_config3(cfg, n, depth):
+    meta, arr = cfg
+    rho, probs = _oracle_c3(n, depth)
+    assert close(rho, arr[f'c3_{n}_state'], 1e-12)
+    for name, p in meta[f'c3_{n}']['probs'].items():
+        assert np.allclose(probs[name], p, rtol=0, atol=1e-12), name
+
+
+def test_oracle_config4(cfg):
+    meta, arr = cfg
+    B, n = 64, 6
+    factors, w, gates, ang, tgt, measured = circuits.c4_inputs(B, n, 16)
+    assert measured == meta['c4_64_6']['measured']
+    for b in range(B):
+        psi = np.array([1.0 + 0j])
+        for q in range(n):
+            psi = np.kron(psi, factors[b, q])
+        for g in gates:
+            psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+        psi = orc.ket_apply(psi, n, int(tgt[b]), circuits.z_rot(float(ang[b])))
+        p = orc.ket_probs(psi, n, measured)
+        assert np.allclose(p / p.sum(), arr['c4_64_6_probs'][b], rtol=0, atol=1e-12), b
+
+
+# ---- the CUDA path against the same fixtures -----------------------------------------------------
+@pytest.mark.gpu
+def test_device_rc_10_200_20_density_matrix(cfg):
+    """config 2's parity run as the reference does it: U rho U^dagger on the 1024 x 1024 density matrix"""
+    import qbot_b200
+    meta, arr = cfg
+    n = 10
+    prog = "\n".join([f"qset tensorExp(comp[0], {n})"] + [g.dsl() for g in circuits.rc(n, 200, 20)])
+    ns = qbot_b200.executeTxt(prog)
+    rho = np.asarray(ns['state'])
+    assert rho.shape == (1 << n, 1 << n)
+    assert close(rho[_rows(meta)], arr['rc_10_200_20_rows'], 1e-11)
+    assert close(np.diag(rho), arr['rc_10_200_20_diag'], 1e-11)
+    # and the ket representation of the same circuit: outer(psi, conj psi) == the reference's rho
+    st = qbot_b200.DeviceState.zero_state(n)
+    for g in circuits.rc(n, 200, 20):
+        st.apply_gate(g.matrix(), g.target, g.controls)
+    psi = np.asarray(st)
+    assert close(np.outer(psi[_rows(meta)], psi.conj()), arr['rc_10_200_20_rows'], 1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,depth', [(6, 20), (8, 30)])
+def test_device_config3(cfg, n, depth):
+    import qbot_b200
+    meta, arr = cfg
+    ns = qbot_b200.executeTxt(circuits.c3_program(n, depth, n))
+    assert close(np.asarray(ns['state']), arr[f'c3_{n}_state'], 1e-12)
+    for name, p in meta[f'c3_{n}']['probs'].items():
+        assert np.allclose(ns[name].probs, p, rtol=0, atol=1e-12), name
+
+
+@pytest.mark.gpu
+def test_device_config4(cfg):
+    from qbot_b200 import DeviceState
+    meta, arr = cfg
+    B, n = 64, 6
+    factors, w, gates, ang, tgt, measured = circuits.c4_inputs(B, n, 16)
+    st = DeviceState.product_batch(factors)
+    for g in gates:
+        st.apply_gate(g.matrix(), g.target, g.controls)
+    st.apply_gate_batched(np.stack([circuits.z_rot(float(a)) for a in ang]), [int(t) for t in tgt])
+    p = st.probs(measured)
+    p = p / p.sum(axis=1, keepdims=True)
+    assert np.allclose(p, arr['c4_64_6_probs'], rtol=0, atol=1e-12)
