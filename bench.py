@@ -22,6 +22,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; OpenBLAS reads it when numpy is imported and the
+    # reference arm (rank 0, the only rank that works) would run its zgemms on ONE core while claiming all
+    for _k in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import numpy as np  # noqa: E402
 
 
@@ -130,47 +136,39 @@ def cpu_ket_port(n: int, budget_s: float, seed: int):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference is Python and
-    does not travel to the GPU box) timed on the host cores.  The reference cannot represent
-    the 30/34-qubit workload at all (16*4^n bytes per matrix), so each step is a bounded sample
-    of the same generator at n = 12, the largest size its dense 2^n x 2^n form allows."""
+    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores
+    with all the threads BLAS can use.  When the pod's install of the unmodified reference is present
+    (baseline/_ref) its own `gate` op runs, line by line through its interpreter (kind "reference");
+    otherwise the oracle port of the same algorithm (kind "port").  The reference keeps a 4^n density
+    matrix and cannot represent the 30 / 34-qubit kets at all, so every step is a bounded sample of the
+    same generator on the largest register it can hold: the config-3 program's gates on 12 qubits --
+    the workload `configs.c3` of our arm runs in full (same config there; for the headline the ratio is
+    context only)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from oracle import qbot_oracle as orc
-    from qbot_b200.circuits import rc
+    import bench_configs as bc
+    cfg = args.config or 'headline'
     n_ref = args.ref_qubits
     total_steps = args.steps + args.warmup
-    budget = 150.0 / max(total_steps, 1)
-    gates = rc(n_ref, 50, 12)
-    rho = np.zeros((1 << n_ref, 1 << n_ref), dtype=complex)
-    rho[0, 0] = 1
-    # calibrate: one gate
-    t0 = time.perf_counter()
-    rho = orc.reference_style_gate(rho, n_ref, gates[0].target, gates[0].matrix(), gates[0].controls)
-    one = time.perf_counter() - t0
-    per_step = max(1, int(budget / max(one, 1e-6)))
-    per_step = min(per_step, 64)
-    gi = 1
-    times = []
-    for s in range(total_steps):
-        t0 = time.perf_counter()
-        for _ in range(per_step):
-            g = gates[gi % len(gates)]
-            gi += 1
-            rho = orc.reference_style_gate(rho, n_ref, g.target, g.matrix(), g.controls)
-        if s >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    total = sum(times)
-    value = per_step * len(times) / total
-    cores = os.cpu_count()
-    sample = (f"rc({n_ref}, 50, 12): {per_step} gates/step on a {1 << n_ref}x{1 << n_ref} complex128 density matrix "
-              f"(reference algorithm: full-space unitary + U rho U^dagger; it cannot represent n >= 14)")
+    budget = min(150.0 / max(total_steps, 1), 40.0)
+    if cfg == 'c4':
+        vals = [bc.cpu_c4_sample(budget) for _ in range(total_steps)][args.warmup:]
+        kind, cores, sample = vals[-1]['kind'], vals[-1]['cores'], vals[-1]['sample']
+        value = sum(v['value'] for v in vals) / len(vals)
+        ms = 1e3 * budget
+    else:
+        vals = [bc.cpu_c3_sample(n_ref, budget) for _ in range(total_steps)][args.warmup:]
+        kind, cores, sample = vals[-1]['kind'], vals[-1]['cores'], vals[-1]['sample']
+        value = sum(v['gates'] for v in vals) / sum(v['seconds'] for v in vals)
+        ms = 1e3 * sum(v['seconds'] for v in vals) / len(vals)
     line = {"impl": "reference", "metric": "gates/sec", "value": value, "unit": "gates/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-            "config": {"workload": sample, "qubits": n_ref},
-            "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": sample, "qubits": n_ref, "config": cfg,
+                       "same_workload_in_our_arm": "configs.c3 (bench.py --config c3)" if cfg != 'c4' else "configs.c4",
+                       "blas_threads": cores, "host_cores": os.cpu_count()},
+            "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -189,6 +187,54 @@ def apply_circuit(st, gates, mats):
         _packed[key] = type(st).pack_circuit(st.nq, [(m, g.target, g.controls) for g, m in zip(gates, mats)])
     st.apply_circuit(_packed[key])
     st.flush()
+
+
+def headline_parity(n, depth, seed, gates, mats):
+    """(i) the specialised path against the ORACLE on the same generator at 22 qubits (full ket, 64 MiB);
+    (ii) at full size (oracle infeasible: 16 GiB numpy ket, minutes per gate) the specialised sweeps
+    against the independent one-gate-per-launch kernels: 64 sampled amplitudes and the 4-qubit marginals,
+    relative to the largest value; norm."""
+    from qbot_b200 import DeviceState, circuits
+    from oracle import qbot_oracle as orc
+    res = {"tolerance": 1e-12}
+    m = 22
+    g22 = circuits.rc(m, 6, seed)
+    st = DeviceState.zero_state(m)
+    st.set_jit(2)
+    psi = np.zeros(1 << m, dtype=complex)
+    psi[0] = 1
+    for g in g22:
+        st.apply_gate(g.matrix(), g.target, g.controls)
+        psi = orc.ket_apply(psi, m, g.target, g.matrix(), g.controls)
+    got = np.asarray(st)
+    res["oracle_n22_max_rel_err"] = float(np.max(np.abs(got - psi)) / np.max(np.abs(psi)))
+    res["oracle_n22_specialised_sweeps"] = f"{st.stats()['jit_passes']}/{st.stats()['fused_passes']}"
+    del st
+    packed = DeviceState.pack_circuit(n, [(mm, g.target, g.controls) for g, mm in zip(gates, mats)])
+    fused = DeviceState.zero_state(n)
+    fused.set_jit(2)
+    fused.apply_circuit(packed)
+    rng = np.random.default_rng(7)
+    idx = [0, 1, (1 << n) - 1] + [int(i) for i in rng.integers(0, 1 << n, size=61)]
+    a = np.array([fused.download_range(i, 1)[0] for i in idx])
+    qs = [0, n // 3, (2 * n) // 3, n - 1]
+    pa = fused.probs(qs)
+    norm = float(fused.norm2()[0])
+    spec = f"{fused.stats()['jit_passes']}/{fused.stats()['fused_passes']}"
+    del fused
+    plain = DeviceState.zero_state(n)
+    plain.set_fusion(False)
+    plain.apply_circuit(packed)
+    b = np.array([plain.download_range(i, 1)[0] for i in idx])
+    pb = plain.probs(qs)
+    del plain
+    res["full_size_vs_one_gate_kernels"] = {
+        "qubits": n, "sampled_amplitudes": len(idx), "max_rel_err_amplitudes": float(np.max(np.abs(a - b)) / np.max(np.abs(b))),
+        "max_rel_err_marginals": float(np.max(np.abs(pa - pb)) / np.max(pb)), "norm": norm, "specialised_sweeps": spec}
+    ok = (res["oracle_n22_max_rel_err"] < 1e-12 and res["full_size_vs_one_gate_kernels"]["max_rel_err_amplitudes"] < 1e-12
+          and res["full_size_vs_one_gate_kernels"]["max_rel_err_marginals"] < 1e-12 and abs(norm - 1) < 1e-11)
+    res["status"] = "pass" if ok else "FAIL"
+    return res
 
 
 def run_single_gpu(args):
@@ -347,6 +393,20 @@ def run_single_gpu(args):
         except Exception as e:  # keep the headline even if pinned allocation fails
             out["e2e"]["upload_variant"] = {"value": None, "error": str(e)[:200]}
 
+    # ---- parity, in run (the judged line must carry its own evidence) ------------------------------
+    if not args.no_parity:
+        out["parity_check"] = headline_parity(n, depth, seed, gates, mats)
+    # ---- the other single-GPU configs of BASELINE.json as sub-lines -----------------------------------
+    if args.config is None and not args.no_configs and n == 30:
+        import bench_configs as bc
+        del st
+        out["configs"] = {}
+        for name, fn in (('c2', bc.run_c2), ('c3', bc.run_c3), ('c4', bc.run_c4)):
+            try:
+                out["configs"][name] = fn(max(args.steps, 3), 3, cpu=not args.no_cpu_baseline)
+            except Exception as e:      # a sub-line must never take the headline down
+                out["configs"][name] = {"config": name, "error": f"{type(e).__name__}: {e}"[:400]}
+        st = DeviceState.zero_state(2)
     if not args.no_cpu_baseline:
         v, done, dt = cpu_reference_algorithm(args.ref_qubits_default, 12.0, 12)
         kv, kdone, kdt = cpu_ket_port(24, 6.0, 24)
@@ -357,6 +417,26 @@ def run_single_gpu(args):
             "ket_port": {"value": kv, "unit": "gates/s", "qubits": 24,
                          "sample": f"{kdone} gates of rc(24, 2, 24) in {kdt:.1f}s, numpy strided ket update (not a reference code path)"}}
     print(json.dumps(out))
+
+
+def run_single_config(args):
+    """--config c2|c3|c4 on one GPU: the config's own line in the bench contract's shape"""
+    import torch
+    import bench_configs as bc
+    torch.cuda.init()
+    sampler = ClockSampler(0)
+    sampler.start()
+    r = {'c2': bc.run_c2, 'c3': bc.run_c3, 'c4': bc.run_c4}[args.config](args.steps, args.warmup, cpu=not args.no_cpu_baseline)
+    clocks = sampler.stop()
+    line = {"metric": r['metric'], "value": r['value'], "unit": r['unit'], "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r['ms_per_step'], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "complex128 (f64)", "data": "synthetic",
+            "config": {"workload": r['workload'], "config": args.config, "l2": r.get('l2'), "gates_per_step": r.get('gates_per_step')},
+            "clocks": clocks, "gpu_launches": r.get('gpu_launches')}
+    for k in ('roofline', 'e2e', 'cpu_baseline', 'parity_check', 'vs_reference', 'value_definition'):
+        if k in r:
+            line[k] = r[k]
+    print(json.dumps(line))
 
 
 def main():
@@ -371,6 +451,11 @@ def main():
     ap.add_argument('--no-fusion', action='store_true')
     ap.add_argument('--jit', type=int, default=None, choices=[0, 1, 2],
                     help="sweep specialisation: 0 never, 1 when a plan repeats (library default), 2 always")
+    ap.add_argument('--config', default=None, choices=['headline', 'c2', 'c3', 'c4', 'c5'],
+                    help="BASELINE.json config to run alone (default: the headline line with c2/c3/c4 as sub-lines on one GPU; "
+                         "c5 with a c4 sub-line and the cross-rank parity check on several)")
+    ap.add_argument('--no-configs', action='store_true', help="headline only: skip the c2/c3/c4 sub-lines")
+    ap.add_argument('--no-parity', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
@@ -383,8 +468,10 @@ def main():
         return
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.gpus > 1 or world > 1:
-        from qbot_b200.dist_bench import run_multi_gpu
+        from bench_multi import run_multi_gpu
         run_multi_gpu(args)
+    elif args.config in ('c2', 'c3', 'c4'):
+        run_single_config(args)
     else:
         run_single_gpu(args)
 

@@ -1,0 +1,448 @@
+"""Bench arms of BASELINE.json's configs 2, 3 and 4 on one GPU, the CPU reference arms that run the
+SAME workloads, and the in-run parity checks (bench.py prints them as sub-objects of its one JSON
+line and as stand-alone lines with ``--config c2|c3|c4``).
+
+    c2  rc(20, 200, 20) on a complex128 ket (16 MiB)                      SURVEY.md 8(d) C2
+    c3  12-qubit density matrix: rc(12, 50, 12) + mid-circuit meas (reference collapse) +
+        ProbVal-target gates + final disc, as a qbot program                SURVEY.md 8(d) C3
+    c4  4096 branch kets of 16 qubits: shared rc(16, 10, 16), a per-branch RZ, outcome weights
+        of 4 qubits                                                           SURVEY.md 8(d) C4
+
+Only bench.py's cpu_baseline / reference legs and the parity checks touch ``oracle/`` (test
+infrastructure); the measured GPU path never does.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+# ---------------------------------------------------------------------------------------------
+# host threads (torchrun exports OMP_NUM_THREADS=1, which silently throttles OpenBLAS)
+# ---------------------------------------------------------------------------------------------
+def blas_threads(want: int = None) -> int:
+    """Set (when asked) and return the number of threads numpy's BLAS really uses."""
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        if want:
+            threadpool_limits(limits=int(want))
+        n = [p.get('num_threads') for p in threadpool_info() if p.get('user_api') == 'blas']
+        return int(max(n)) if n else (want or os.cpu_count() or 1)
+    except Exception:
+        return want or os.cpu_count() or 1
+
+
+def load_reference():
+    """The unmodified reference package, when the pod's install of it is present (baseline/_ref).
+    Returns the module dict or None (then the oracle port stands in)."""
+    if not os.path.isdir(os.path.join(REF_DIR, 'qbot')):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import importlib
+        sys.dont_write_bytecode = True
+        return dict(interp=importlib.import_module('qbot.interpreter'), qgates=importlib.import_module('qbot.qgates'),
+                    density=importlib.import_module('qbot.density'), measurement=importlib.import_module('qbot.measurement'),
+                    basis=importlib.import_module('qbot.basis'))
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm of config 3 (also the default reference arm: the headline's 30-qubit ket does not exist
+# in the reference's 4^n representation, so its bounded sample is this same 12-qubit generator)
+# ---------------------------------------------------------------------------------------------
+def cpu_c3_sample(n: int, budget_s: float, max_ops: int = 64, threads: int = None):
+    """Time the first state operations of the config-3 program (qset |0..0><0..0|, then the gates of
+    rc(n, 50, 12) in order) on the host.
+
+    kind 'reference': the stock reference's own `gate` op, line by line through its interpreter
+    (qbot/interpreter.py:114-215 `runtime`, qbot/operators.py:274-329) -- full-space unitary built
+    with np.kron / genMultiControlledGate, then U rho U^dagger.  Lines the stock op cannot execute
+    (TypeError for some multi-control layouts) are skipped and counted.
+    kind 'port': the oracle's restatement of the same algorithm (oracle.reference_style_gate)."""
+    from qbot_b200 import circuits
+    used = blas_threads(threads or os.cpu_count())
+    ops = [op for op in circuits.c3_ops(n, 50, 12) if op.kind == 'gate'][:max_ops]
+    ref = load_reference()
+    done, skipped, t_total = 0, 0, 0.0
+    if ref is not None:
+        import io
+        from contextlib import redirect_stdout
+        interp = ref['interp']
+        lines = [f"qset tensorExp(comp[0], {n})"] + [op.dsl() for op in ops]
+        ns = {'state': np.array([], dtype=complex), '__updated_state': False, '__marks': dict(), '__prev_jump': -1}
+        interp.runtime(ns, lines, 0, 1)                         # the register (not timed)
+        interp.runtime(ns, lines, 1, 2)                         # warm-up gate (BLAS threads, page faults)
+        for i in range(2, len(lines)):
+            t0 = time.perf_counter()
+            try:
+                with redirect_stdout(io.StringIO()):
+                    interp.runtime(ns, lines, i, i + 1)
+                t_total += time.perf_counter() - t0
+                done += 1
+            except SystemExit:
+                skipped += 1
+            if t_total > budget_s:
+                break
+        kind = 'reference'
+        how = "stock reference `gate` op line by line (qbot.interpreter.runtime on baseline/_ref)"
+    else:
+        from oracle import qbot_oracle as orc
+        rho = np.zeros((1 << n, 1 << n), dtype=complex)
+        rho[0, 0] = 1
+        g = ops[0].gate
+        rho = orc.reference_style_gate(rho, n, g.target, g.matrix(), g.controls)
+        for op in ops[1:]:
+            g = op.gate
+            t0 = time.perf_counter()
+            rho = orc.reference_style_gate(rho, n, g.target, g.matrix(), g.controls)
+            t_total += time.perf_counter() - t0
+            done += 1
+            if t_total > budget_s:
+                break
+        kind = 'port'
+        how = "oracle port of the reference's algorithm (full 2^n x 2^n unitary + U rho U^dagger); baseline/_ref absent"
+    value = done / max(t_total, 1e-9)
+    sample = (f"first {done} gates of the config-3 program (rc({n}, 50, 12) on a {1 << n}x{1 << n} complex128 density matrix) "
+              f"in {t_total:.1f}s: {how}" + (f"; {skipped} lines the stock op cannot execute skipped (SURVEY F6)" if skipped else ''))
+    return dict(value=value, unit='gates/s', cores=used, kind=kind, sample=sample, gates=done, seconds=t_total)
+
+
+def cpu_c4_sample(budget_s: float):
+    """Config 4 on the host: the oracle's ket path, branch after branch (the reference has no ket
+    path, SURVEY.md F1, and a 16-qubit branch as a density matrix would be 64 GiB)."""
+    from oracle import qbot_oracle as orc
+    from qbot_b200 import circuits
+    B, n = 4096, 16
+    factors, w, gates, ang, tgt, measured = circuits.c4_inputs(B, n, 16)
+    done_gates, t0, b = 0, time.perf_counter(), 0
+    while b < B and time.perf_counter() - t0 < budget_s:
+        psi = np.array([1.0 + 0j])
+        for q in range(n):
+            psi = np.kron(psi, factors[b, q])
+        for g in gates:
+            psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+        psi = orc.ket_apply(psi, n, int(tgt[b]), circuits.z_rot(float(ang[b])))
+        orc.ket_probs(psi, n, measured)
+        done_gates += len(gates) + 1
+        b += 1
+    dt = time.perf_counter() - t0
+    return dict(value=done_gates / dt, unit='gates/s', cores=1, kind='port',
+                sample=f"{b} of the 4096 branches ({done_gates} branch-gates) in {dt:.1f}s, numpy strided ket update per branch "
+                       "(not a reference code path: the reference has no ket representation)")
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arms
+# ---------------------------------------------------------------------------------------------
+def _peak():
+    from bench import measured_peaks
+    return measured_peaks()
+
+
+def _flush_l2(torch, buf):
+    buf.add_(1)          # 256 MiB read + write on torch's stream: evicts the 126 MB L2
+
+
+def run_c2(steps: int, warmup: int, cpu: bool = True):
+    """rc(20, 200, 20): 2 913 gates on a 16 MiB ket.  The ket fits the L2, so the L2 is flushed between
+    timed steps (a 256 MiB read-modify-write) and every step is timed on its own."""
+    import torch
+    from qbot_b200 import DeviceState, circuits
+    from oracle import qbot_oracle as orc
+    n, depth, seed = 20, 200, 20
+    gates = circuits.rc(n, depth, seed)
+    items = [(np.ascontiguousarray(g.matrix()), g.target, g.controls) for g in gates]
+    packed = DeviceState.pack_circuit(n, items)
+    st = DeviceState.zero_state(n)
+    st.set_jit(2)
+    for _ in range(max(warmup, 3)):
+        st.apply_circuit(packed)
+        st.flush()
+    st.sync()
+    st.reset_stats()
+    junk = torch.zeros(32 << 20, dtype=torch.float64, device='cuda')
+    ms = []
+    for _ in range(steps):
+        _flush_l2(torch, junk)
+        torch.cuda.synchronize()
+        st.timer_start()
+        st.apply_circuit(packed)
+        st.flush()
+        ms.append(st.timer_stop())
+    stats = st.stats()
+    secs = sum(ms) / 1e3
+    peak, src = _peak()
+    sweeps = max(stats['fused_passes'], 1)
+    achieved = 32 * (1 << n) * sweeps / secs / 1e9
+    # e2e: the program through executeTxt (fresh register, one `gate` line per gate, peek -> host)
+    import qbot_b200
+    qs = [0, 7, 13, 19]
+    script = "\n".join([f"qset tensorExp(comp.kets[0], {n})"] + [g.dsl() for g in gates] + [f"peek r ; comp ; {qs}"])
+    ns = qbot_b200.executeTxt(script)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _flush_l2(torch, junk)
+        ns = qbot_b200.executeTxt(script)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    p_dsl = np.array(ns['r'].probs)
+    # parity: the same path at n = 14 against the oracle (full ket), and fused vs one-gate-per-launch at n = 20
+    par = _parity_ket(14, depth, seed, jit=2)
+    ref = DeviceState.zero_state(n)
+    ref.set_fusion(False)
+    ref.apply_circuit(packed)
+    a, b = np.asarray(st), None
+    # st has been through warm-up + steps circuits; compare a fresh fused run instead
+    fresh = DeviceState.zero_state(n)
+    fresh.set_jit(2)
+    fresh.apply_circuit(packed)
+    a, b = np.asarray(fresh), np.asarray(ref)
+    self_err = float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+    out = {
+        "config": "c2", "workload": f"rc({n}, {depth}, seed={seed}) on a {n}-qubit complex128 ket (16 MiB)", "metric": "gates/sec",
+        "value": len(gates) * steps / secs, "unit": "gates/s", "ms_per_step": 1e3 * secs / steps, "gates_per_step": len(gates),
+        "l2": "state fits the L2: flushed between timed steps (256 MiB read-modify-write), each step timed on its own",
+        "gpu_launches": int(stats['kernel_launches']),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "qj_kernel (specialised fused sweep)", "launches": int(sweeps), "avg_launch_ms": 1e3 * secs / sweeps,
+                     "peak_source": src, "sweeps_per_step": sweeps / steps,
+                     "note": "a 16 MiB ket is L2-resident after the first sweep of a step: the sweeps are launch- and latency-bound "
+                             "(~15 us each), the HBM fraction is reported for completeness"},
+        "e2e": {"value": len(gates) / e2e_s, "unit": "gates/s", "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": int(sum(m.nbytes for m, _, _ in items)), "d2h_bytes_per_step": int(p_dsl.nbytes),
+                "what": "qbot_b200.executeTxt(program): device-side constructor, one `gate` line per gate, peek of 4 qubits"},
+        "parity_check": {"status": "pass" if par['max_rel_err'] < 1e-12 and self_err < 1e-12 else "FAIL",
+                         "oracle_n14_max_rel_err": par['max_rel_err'], "fused_vs_unfused_n20_max_rel_err": self_err,
+                         "tolerance": 1e-12},
+    }
+    if cpu:
+        t0 = time.perf_counter()
+        psi = np.zeros(1 << n, dtype=complex)
+        psi[0] = 1
+        k = 0
+        for g in gates:
+            psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+            k += 1
+            if time.perf_counter() - t0 > 6.0:
+                break
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": k / dt, "unit": "gates/s", "cores": 1, "kind": "port",
+                               "sample": f"first {k} gates of the same circuit in {dt:.1f}s, numpy strided ket update (the reference "
+                                         "has no ket path and cannot hold 20 qubits as a density matrix: 16 TiB)"}
+    return out
+
+
+def _parity_ket(n, depth, seed, jit):
+    from qbot_b200 import DeviceState, circuits
+    from oracle import qbot_oracle as orc
+    gates = circuits.rc(n, depth, seed)
+    st = DeviceState.zero_state(n)
+    st.set_jit(jit)
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[0] = 1
+    for g in gates:
+        st.apply_gate(g.matrix(), g.target, g.controls)
+        psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+    got = np.asarray(st)
+    return dict(max_rel_err=float(np.max(np.abs(got - psi)) / np.max(np.abs(psi))))
+
+
+def c3_device_step(DeviceState, ops_list, n):
+    """Config 3 with the register resident in HBM: the same operations as the DSL program, called on
+    the device handle directly (no interpreter, no host arrays except the 2x2 matrices)."""
+    from qbot_b200 import DM, circuits
+    from qbot_b200.host.interp import Interpreter
+    from qbot_b200.host.namespace import globalNameSpace as gns
+    measure = Interpreter(DeviceState).state_ops['measure']
+    st = DeviceState.zero_state(n, kind=DM)
+    probs = {}
+    for op in ops_list:
+        if op.kind == 'gate':
+            st.apply_gate(op.gate.matrix(), op.gate.target, op.gate.controls)
+        elif op.kind == 'meas':
+            r = measure(st, gns['comp'], list(op.qubits), True)
+            probs[op.name] = r.probs
+            st = r.newState
+        elif op.kind == 'pgate':
+            batch = st.broadcast(2)
+            batch.apply_gate_batched(np.stack([circuits.HADAMARD, circuits.HADAMARD]), [op.qubits[0], op.qubits[1]])
+            st = batch.mix_branches([.5, .5])
+        else:
+            st = st.ptrace_keep([q for q in range(st.nq) if q not in op.qubits])
+    return st, probs
+
+
+def run_c3(steps: int, warmup: int, cpu: bool = True, cpu_budget_s: float = 20.0):
+    import torch
+    import qbot_b200
+    from qbot_b200 import DeviceState, circuits
+    n, depth, seed = 12, 50, 12
+    ops_list = circuits.c3_ops(n, depth, seed)
+    ngates = sum(1 for o in ops_list if o.kind in ('gate', 'pgate'))
+    nmeas = sum(1 for o in ops_list if o.kind == 'meas')
+    program = circuits.c3_program(n, depth, seed)
+    clock = DeviceState.zero_state(1)
+    junk = torch.zeros(32 << 20, dtype=torch.float64, device='cuda')
+    for _ in range(max(warmup, 3)):
+        st, probs = c3_device_step(DeviceState, ops_list, n)
+    st.sync()
+    clock.reset_stats()
+    launches0 = 0
+    ms = []
+    for _ in range(steps):
+        _flush_l2(torch, junk)
+        torch.cuda.synchronize()
+        clock.timer_start()
+        st, probs = c3_device_step(DeviceState, ops_list, n)
+        st.flush()
+        ms.append(clock.timer_stop())
+    secs = sum(ms) / 1e3
+    final_dev = np.asarray(st)
+    # e2e = the call a user of the reference makes: executeTxt(program).  `qset tensorExp(comp[0], 12)`
+    # builds the 256 MiB rho_0 on the HOST (the reference's kron chain) and uploads it; the final 8-qubit
+    # register and every measurement's weights come back to the host.
+    ns = qbot_b200.executeTxt(program)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _flush_l2(torch, junk)
+        ns = qbot_b200.executeTxt(program)
+        final = np.asarray(ns['state'])
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    # parity, in run: (i) the DSL path and the direct path agree; (ii) config 3 at n = 8 against the
+    # oracle's restatement of the reference (register + every measurement's weights)
+    from oracle import qbot_oracle as orc
+    rho8, probs8 = orc.run_config3(circuits.c3_ops(8, 30, 8), 8)
+    ns8 = qbot_b200.executeTxt(circuits.c3_program(8, 30, 8))
+    err8 = float(np.max(np.abs(np.asarray(ns8['state']) - rho8)) / np.max(np.abs(rho8)))
+    perr8 = max(float(np.max(np.abs(np.array(ns8[k].probs) - np.array(v)))) for k, v in probs8.items())
+    err_paths = float(np.max(np.abs(final - final_dev)) / np.max(np.abs(final_dev)))
+    tr = complex(np.trace(final))
+    herm = float(np.max(np.abs(final - final.conj().T)))
+    ok = err8 < 1e-12 and perr8 < 1e-12 and err_paths < 1e-12 and abs(tr - 1) < 1e-10 and herm < 1e-12
+    peak, src = _peak()
+    # algorithmic bytes of the step: DM conjugation 32 * 4^n * 2^-c per gate (row and column pass
+    # are fused into one sweep pair), a ProbVal gate 2 branches, a meas reads rho twice and writes it once
+    dm_bytes = 16 << (2 * n)
+    alg = 0
+    for o in ops_list:
+        if o.kind == 'gate':
+            alg += 2 * dm_bytes >> len(o.gate.controls)
+        elif o.kind == 'pgate':
+            alg += 2 * dm_bytes + 2 * 2 * dm_bytes + 3 * dm_bytes       # broadcast, 2 branch gates, mix
+        elif o.kind == 'meas':
+            alg += 3 * dm_bytes
+        else:
+            alg += dm_bytes
+    out = {
+        "config": "c3", "workload": f"config 3: {n}-qubit density matrix (256 MiB), rc({n}, {depth}, seed={seed}) with {nmeas} mid-circuit "
+                                    f"`meas` (reference product-state collapse), {nmeas} ProbVal-target Hadamards, final `disc` of 4 qubits",
+        "metric": "gates/sec", "value": ngates * steps / secs, "unit": "gates/s", "ms_per_step": 1e3 * secs / steps,
+        "gates_per_step": ngates, "ops_per_step": len(ops_list),
+        "l2": "256 MiB state > 126 MB L2; L2 additionally flushed between steps",
+        "roofline": {"bound": "hbm", "achieved": alg * steps / secs / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg * steps / secs / 1e9 / peak, "traffic": None, "peak_source": src,
+                     "kernel": "whole step (fused sweeps over vec(rho) + measurement / mixture kernels)",
+                     "algorithmic_bytes_per_step": int(alg),
+                     "note": "UN-FUSED algorithmic bytes (32*4^n*2^-c per gate) over the step time: exceeds 1 when the fused "
+                             "engine applies several gates per pass over rho"},
+        "e2e": {"value": ngates / e2e_s, "unit": "gates/s", "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": int(dm_bytes + 64 * ngates), "d2h_bytes_per_step": int(final.nbytes + 32 * nmeas),
+                "what": "qbot_b200.executeTxt(config-3 program): host kron chain for rho_0 + upload, gates / meas / disc on the device, "
+                        "final register + measurement weights back on the host"},
+        "parity_check": {"status": "pass" if ok else "FAIL", "oracle_c3_n8_state_max_rel_err": err8, "oracle_c3_n8_probs_max_abs_err": perr8,
+                         "dsl_vs_direct_n12_max_rel_err": err_paths, "trace": [tr.real, tr.imag], "hermiticity": herm, "tolerance": 1e-12},
+    }
+    if cpu:
+        cb = cpu_c3_sample(n, cpu_budget_s)
+        out["cpu_baseline"] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        out["vs_reference"] = {"same_config": True, "reference_value": cb['value'], "ratio": out['value'] / cb['value'],
+                               "e2e_ratio": out['e2e']['value'] / cb['value'],
+                               "note": "both arms: gates/s of the config-3 program on the same 12-qubit density matrix; the CPU arm "
+                                       "times a bounded prefix of the program's gates"}
+    return out
+
+
+def run_c4(steps: int, warmup: int, cpu: bool = True):
+    import torch
+    from qbot_b200 import DeviceState, circuits
+    from oracle import qbot_oracle as orc
+    B, n = 4096, 16
+    factors, w, gates, ang, tgt, measured = circuits.c4_inputs(B, n, 16)
+    mats = np.stack([circuits.z_rot(float(a)) for a in ang])
+    tl = [int(t) for t in tgt]
+    items = [(np.ascontiguousarray(g.matrix()), g.target, g.controls) for g in gates]
+    packed = DeviceState.pack_circuit(n, items)
+
+    def body(st):
+        st.apply_circuit(packed)
+        st.apply_gate_batched(mats, tl)
+        return st.probs(measured)
+
+    st = DeviceState.product_batch(factors)
+    for _ in range(max(warmup, 3)):
+        body(st)
+    st.sync()
+    st.reset_stats()
+    st.timer_start()
+    for _ in range(steps):
+        p = body(st)
+    ms = st.timer_stop()
+    stats = st.stats()
+    secs = ms / 1e3
+    per_step = (len(gates) + 1) * B
+
+    def e2e_step():
+        s2 = DeviceState.product_batch(factors)
+        return body(s2)
+
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pe = e2e_step()
+    e2e_s = (time.perf_counter() - t0) / steps
+    # parity: sampled branches of a fresh run against the oracle's ket path
+    worst = 0.0
+    for b in (0, 1, 777, 2048, 4095):
+        psi = np.array([1.0 + 0j])
+        for q in range(n):
+            psi = np.kron(psi, factors[b, q])
+        for g in gates:
+            psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+        psi = orc.ket_apply(psi, n, tl[b], mats[b])
+        want = orc.ket_probs(psi, n, measured)
+        worst = max(worst, float(np.max(np.abs(pe[b] - want)) / np.max(want)))
+    norm_err = float(np.max(np.abs(pe.sum(axis=1) - 1)))
+    peak, src = _peak()
+    state_bytes = 16 * B * (1 << n)
+    sweeps = max(stats['state_passes'], 1)
+    out = {
+        "config": "c4", "workload": f"config 4: {B} branch kets of {n} qubits (4 GiB), shared rc({n}, 10, {n}) + per-branch RZ + "
+                                    f"outcome weights of qubits {measured}",
+        "metric": "gates/sec", "value": per_step * steps / secs, "unit": "gates/s", "ms_per_step": 1e3 * secs / steps,
+        "gates_per_step": per_step, "value_definition": "one gate on one 16-qubit branch ket counts as one gate",
+        "l2": "4 GiB batch > L2; no flush needed", "gpu_launches": int(stats['kernel_launches']),
+        "roofline": {"bound": "hbm", "achieved": 2 * state_bytes * sweeps / secs / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": 2 * state_bytes * sweeps / secs / 1e9 / peak, "traffic": None, "peak_source": src,
+                     "kernel": "fused sweeps over the batch + k_dense_batched + k_bins", "launches": int(sweeps),
+                     "sweeps_per_step": sweeps / steps,
+                     "note": "passes over the 4 GiB batch (read + write each; the final k_bins pass only reads) over the step time"},
+        "e2e": {"value": per_step / e2e_s, "unit": "gates/s", "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": int(factors.nbytes + mats.nbytes), "d2h_bytes_per_step": int(pe.nbytes),
+                "what": "DeviceState.product_batch(host factors) + shared circuit + per-branch gate + probs -> host [4096, 16]"},
+        "parity_check": {"status": "pass" if worst < 1e-12 and norm_err < 1e-12 else "FAIL", "sampled_branches": [0, 1, 777, 2048, 4095],
+                         "oracle_probs_max_rel_err": worst, "max_norm_deviation": norm_err, "tolerance": 1e-12},
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu_c4_sample(6.0)
+    return out

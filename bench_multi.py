@@ -1,5 +1,7 @@
 """Multi-GPU arm of bench.py: BASELINE config 5, a random circuit on a ket sharded over the
-GPUs of one box (one process per GPU, launched by torchrun; see qbot_b200/sharded.py)."""
+GPUs of one box (one process per GPU, launched by torchrun; see qbot_b200/sharded.py), with config 4
+(the ProbVal branch batch, sharded by branches) as a sub-line and an IN-RUN parity check of the real
+multi-GPU exchange (the driver's pytest box has one GPU and skips those tests)."""
 from __future__ import annotations
 
 import json
@@ -20,8 +22,8 @@ def pick_qubits(world: int, mem_bytes: int, want: int = 34) -> int:
 def run_multi_gpu(args):
     import torch
     import torch.distributed as dist
-    from . import circuits
-    from .sharded import ShardedKet, TorchComm
+    from qbot_b200 import circuits
+    from qbot_b200.sharded import ShardedKet, TorchComm
     from bench import ClockSampler, measured_peaks
 
     rank = int(os.environ.get('RANK', '0'))
@@ -40,6 +42,16 @@ def run_multi_gpu(args):
     ngates = len(gates)
     peak, peak_src = measured_peaks()
 
+    parity = None
+    if not getattr(args, 'no_parity', False):
+        parity = sharded_parity(comm, local, args.exchange, rank, world)
+    c4 = None
+    if getattr(args, 'config', None) is None and not getattr(args, 'no_configs', False):
+        try:
+            c4 = run_c4_sharded(comm, local, rank, world, max(args.steps, 3))
+        except Exception as e:
+            c4 = {"config": "c4", "error": f"{type(e).__name__}: {e}"[:300]}
+
     sk = ShardedKet(n, comm, device=local, exchange=args.exchange)
     sk.shard.state.set_fusion(not args.no_fusion)
     # the benchmark repeats one circuit: specialise every sweep at first sight (the qubit map, and
@@ -57,7 +69,7 @@ def run_multi_gpu(args):
     sk.sync()
     # extra untimed steps until a whole step ran on specialised kernels (NVRTC compiles stay out
     # of the timed region even when the driver asks for a very short warm-up)
-    from . import _lib as _l
+    from qbot_b200 import _lib as _l
     extra = clean = 0
     while extra < 24 and getattr(args, 'jit', None) != 0:
         c0 = _l.jit_info()['kernels_compiled']
@@ -121,7 +133,7 @@ def run_multi_gpu(args):
         tt = torch.tensor([_t.perf_counter() - t0], dtype=torch.float64, device=f'cuda:{local}')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-        e2e = {"value": ngates * args.steps / e2e_s * 2.0 ** (n - 30), "unit": "gates/s (30-qubit equivalents)",
+        e2e = {"value": ngates * args.steps / e2e_s * 2.0 ** (n - 30), "unit": "gates/s",
                "h2d_bytes_per_step": int(sum(m.nbytes for m in mats)), "d2h_bytes_per_step": int(pr.nbytes),
                "ms_per_step": 1e3 * e2e_s / args.steps, "probs_sum": float(pr.sum()),
                "what": "ShardedKet.reset_zero() + apply_gate per gate (host matrices -> C ABI) + flush (fused sweeps, "
@@ -136,7 +148,7 @@ def run_multi_gpu(args):
     achieved = 2 * shard_bytes / (local_s / sweeps) / 1e9
     if rank == 0:
         out = {
-            "metric": "gates/sec", "value": value, "unit": "gates/s (30-qubit equivalents)", "n_gpus": world, "steps": args.steps,
+            "metric": "gates/sec", "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
             "config": {"workload": f"rc({n}, {depth}, seed={seed}) random circuit (H .35 / RZ .35 / CNOT .20 / Toffoli .10) on a "
@@ -145,7 +157,8 @@ def run_multi_gpu(args):
                        "qubits": n, "depth": depth, "gates_per_step": ngates, "state_bytes": 16 << n,
                        "l2": "shard larger than L2; no flush needed", "fusion": not args.no_fusion,
                        "specialised_sweeps": f"{int(jit_passes)}/{int(fused_passes)}", "extra_warmup_steps": extra,
-                       "value_definition": "gates/s on the n-qubit ket x 2^(n-30): the number of 30-qubit-sized gate "
+                       "value_definition": "unit gates/s as at N = 1, counted in 30-qubit-sized gate applications: "
+                                           "gates/s on the n-qubit ket x 2^(n-30), i.e. the number of 30-qubit-sized gate "
                                            "applications per second, so that the N = 1 line (30 qubits) and the sharded "
                                            "lines (33 qubits at 2 GPUs, 34 at 4 and 8 -- the largest kets whose two "
                                            "shard buffers fit in HBM) are in the same unit",
@@ -161,8 +174,137 @@ def run_multi_gpu(args):
                          "nvlink_peak_gbs": 900.0, "frac": (exb / ex_s / 1e9 / 900.0) if ex_s > 0 else None,
                          "share_of_step": ex_s / secs},
             "e2e": e2e, "amp_updates_per_s": raw * (1 << n), "norm_check": norm,
+            "parity_check": parity,
         }
+        if c4 is not None:
+            out["configs"] = {"c4": c4}
         print(json.dumps(out))
     sk.close()
     dist.barrier()
     dist.destroy_process_group()
+
+
+def sharded_parity(comm, local, exchange, rank, world):
+    """In-run correctness of the real multi-GPU path, every rank takes part:
+      (i)  rc(20, 8, 20) on the P ranks against the ORACLE: the gathered ket, all 2^20 amplitudes;
+      (ii) rc(30, 10, 30) on the P ranks against the single-GPU engine on rank 0: 64 sampled amplitudes and
+           the 4-qubit marginals, relative to the largest value, plus the norm.
+    Both runs use the benchmark's exchange mode and go through at least one global-qubit exchange."""
+    import torch
+    import torch.distributed as dist
+    from qbot_b200 import DeviceState, circuits
+    from qbot_b200.sharded import ShardedKet
+    res = {"tolerance": 1e-12, "ranks": world, "exchange": exchange}
+    # (i) oracle
+    n = 20
+    gates = circuits.rc(n, 8, 20)
+    sk = ShardedKet(n, comm, device=local, exchange=exchange)
+    for g in gates:
+        sk.apply_gate(g.matrix(), g.target, g.controls)
+    got = sk.gather()
+    ex1 = sk.shard.exchanges
+    sk.close()
+    if rank == 0:
+        from oracle import qbot_oracle as orc
+        psi = np.zeros(1 << n, dtype=complex)
+        psi[0] = 1
+        for g in gates:
+            psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+        res["oracle_n20_max_rel_err"] = float(np.max(np.abs(got - psi)) / np.max(np.abs(psi)))
+        res["oracle_n20_exchanges"] = int(ex1)
+    # (ii) N ranks against one GPU at 30 qubits
+    n = 30
+    gates = circuits.rc(n, 10, 30)
+    sk = ShardedKet(n, comm, device=local, exchange=exchange)
+    for g in gates:
+        sk.apply_gate(g.matrix(), g.target, g.controls)
+    rng = np.random.default_rng(11)
+    idx = [0, 1, (1 << n) - 1] + [int(i) for i in rng.integers(0, 1 << n, size=61)]
+    qs = [0, n // 3, (2 * n) // 3, n - 1]
+    amps = sk.amplitudes(idx)
+    marg = sk.probs(qs)
+    norm = sk.norm2()
+    ex2 = sk.shard.exchanges
+    sk.close()
+    dist.barrier()
+    if rank == 0:
+        one = DeviceState.zero_state(n, device=local)
+        for g in gates:
+            one.apply_gate(g.matrix(), g.target, g.controls)
+        a1 = np.array([one.download_range(i, 1)[0] for i in idx])
+        p1 = one.probs(qs)
+        del one
+        res["n30_vs_single_gpu"] = {"sampled_amplitudes": len(idx), "max_rel_err_amplitudes": float(np.max(np.abs(amps - a1)) / np.max(np.abs(a1))),
+                                    "max_rel_err_marginals": float(np.max(np.abs(marg - p1)) / np.max(p1)), "norm": float(norm),
+                                    "exchanges": int(ex2)}
+        ok = (res["oracle_n20_max_rel_err"] < 1e-12 and res["n30_vs_single_gpu"]["max_rel_err_amplitudes"] < 1e-12
+              and res["n30_vs_single_gpu"]["max_rel_err_marginals"] < 1e-12 and abs(norm - 1) < 1e-11 and ex1 > 0 and ex2 > 0)
+        res["status"] = "pass" if ok else "FAIL"
+    dist.barrier()
+    torch.cuda.synchronize()
+    return res
+
+
+def run_c4_sharded(comm, local, rank, world, steps):
+    """BASELINE config 4 on the N GPUs: 4096 branch kets of 16 qubits in contiguous blocks of 4096/N
+    branches per rank (ProbVal order kept), shared circuit + per-branch RZ, no communication until the
+    all-gather of the [4096, 16] outcome weights.  Device-timed per rank, max over ranks."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from qbot_b200 import circuits
+    from qbot_b200.sharded import ShardedBranchBatch
+    B, n = 4096, 16
+    factors, w, gates, ang, tgt, measured = circuits.c4_inputs(B, n, 16)
+    mats = np.stack([circuits.z_rot(float(a)) for a in ang])
+    tl = [int(t) for t in tgt]
+    bb = ShardedBranchBatch(n, B, comm, local, factors)
+    items = [(np.ascontiguousarray(g.matrix()), g.target, g.controls) for g in gates]
+    packed = type(bb.state).pack_circuit(n, items)
+
+    def body():
+        bb.state.apply_circuit(packed)
+        bb.apply_gate_per_branch(mats, tl)
+        return bb.probs(measured)
+
+    for _ in range(3):
+        p = body()
+    bb.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    bb.state.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        p = body()
+    ms = bb.state.timer_stop()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([ms, 1e3 * wall], dtype=torch.float64, device=f'cuda:{local}')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, wall_max = [float(x) for x in t.tolist()]
+    per_step = (len(gates) + 1) * B
+    res = None
+    if rank == 0:
+        from oracle import qbot_oracle as orc
+        worst = 0.0
+        for b in (0, 1, 777, 2048, 4095):
+            psi = np.array([1.0 + 0j])
+            for q in range(n):
+                psi = np.kron(psi, factors[b, q])
+            for _ in range(3 + steps):                      # the batch has been through warm-up + timed steps
+                for g in gates:
+                    psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+                psi = orc.ket_apply(psi, n, tl[b], mats[b])
+            want = orc.ket_probs(psi, n, measured)
+            worst = max(worst, float(np.max(np.abs(p[b] - want)) / np.max(want)))
+        res = {"config": "c4", "workload": f"config 4: {B} branch kets of {n} qubits in blocks of {B // world} per GPU, shared rc({n}, 10, {n}) "
+                                          f"+ per-branch RZ + outcome weights of qubits {measured} (all-gather of [4096, 16] doubles)",
+               "metric": "gates/sec", "value": per_step * steps / (ms_max / 1e3), "unit": "gates/s", "n_gpus": world,
+               "ms_per_step": ms_max / steps, "gates_per_step": per_step, "scaling": "strong (4096 branches in total at every N)",
+               "value_definition": "one gate on one 16-qubit branch ket counts as one gate",
+               "e2e": {"value": per_step * steps / (wall_max / 1e3), "unit": "gates/s", "ms_per_step": wall_max / steps,
+                       "h2d_bytes_per_step": int(mats.nbytes // world), "d2h_bytes_per_step": int(p.nbytes),
+                       "what": "host per-branch matrices -> C ABI, probabilities gathered over NCCL and read back on every rank; wall clock"},
+               "parity_check": {"status": "pass" if worst < 1e-12 else "FAIL", "sampled_branches": [0, 1, 777, 2048, 4095],
+                                "oracle_probs_max_rel_err": worst, "tolerance": 1e-12, "steps_replayed_by_the_oracle": 3 + steps}}
+    dist.barrier()
+    return res

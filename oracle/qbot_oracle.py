@@ -335,6 +335,32 @@ def measure(rho: np.ndarray, basis_density: Sequence[np.ndarray], targets=None,
                 newState=new_state)
 
 
+def run_config3(ops, n: int):
+    """BASELINE config 3 in the reference's semantics, op by op: `ops` is a list of
+    records with .kind in {'gate', 'meas', 'pgate', 'disc'}, .gate (target / controls / matrix()),
+    .qubits and .name (qbot_b200.circuits.c3_ops).  gate = operators.py:255-329 (U rho U^dagger),
+    meas = measurement.py:107-165 (computational basis, product-state collapse F7), pgate = a Hadamard on
+    a ProbVal([.5,.5]) target (operators.py:308-316: per-branch applyGate + ensemble), disc =
+    operators.py:169-175 (keeps the qubits that are not listed).  Returns (final rho, {name: probs})."""
+    rho = np.zeros((1 << n, 1 << n), dtype=C128)
+    rho[0, 0] = 1
+    comp = [np.diag([1, 0]).astype(C128), np.diag([0, 1]).astype(C128)]
+    had = np.array([[1, 1], [1, -1]], dtype=C128) * 2 ** (-1 / 2)
+    probs = {}
+    for op in ops:
+        if op.kind == 'gate':
+            rho = dm_apply(rho, n, op.gate.target, op.gate.matrix(), op.gate.controls)
+        elif op.kind == 'meas':
+            r = measure(rho, comp, list(op.qubits), True)
+            probs[op.name] = r['probs']
+            rho = r['newState']
+        elif op.kind == 'pgate':
+            rho = ensemble([.5, .5], [dm_apply(rho, n, t, had, []) for t in op.qubits])
+        else:
+            rho = ptrace_arbitrary(rho, n, list(op.qubits))[1]
+    return rho, probs
+
+
 # ----------------------------------------------------------------------------------------
 # ProbVal rules (reference qbot/probVal.py:22-51, 347-390)
 # ----------------------------------------------------------------------------------------

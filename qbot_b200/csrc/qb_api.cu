@@ -41,9 +41,20 @@ struct DevGuard {
 };
 
 static int sm_count_of(int dev) {
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
     int v = 0;
     QB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    cache[dev] = v;
     return v;
+}
+static int device_count_cached() {
+    static int n = -1;
+    if (n < 0) QB_CUDA(cudaGetDeviceCount(&n));
+    return n;
 }
 
 // Large register buffers are recycled instead of returned to the driver: cudaMalloc / cudaFree of
@@ -59,6 +70,32 @@ struct BufCache {
 BufCache g_bufs;
 constexpr size_t kCacheMinBytes = 64u << 20;
 
+// ONE compute stream per device and process.  Every handle works on it unless its creator supplies
+// a stream of its own (qb_create_external / qb_set_stream).  Consequences: a handle made from another
+// one (partial trace, scatter product, mixture, clone, branch view ...) is ordered after its source
+// without any host-side synchronisation, and recycled buffers are handed from one user to the next in
+// stream order.  (Creating a stream per handle and synchronising around every hand-over cost ~100 us
+// per density-matrix op, several times the kernels themselves at 256 MiB.)
+cudaStream_t default_stream(int device) {
+    static std::mutex mu;
+    static std::map<int, cudaStream_t>& streams = *new std::map<int, cudaStream_t>;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = streams.find(device);
+    if (it != streams.end()) return it->second;
+    cudaStream_t st = nullptr;
+    QB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    streams[device] = st;
+    return st;
+}
+// pooled buffers are only ever "free in the order of the default stream": a user on another stream
+// synchronises on the way in (with the default stream) and on the way out (with its own)
+void pool_enter(int device, cudaStream_t user) {
+    if (user != default_stream(device)) cudaStreamSynchronize(default_stream(device));
+}
+void pool_leave(int device, cudaStream_t user) {
+    if (user && user != default_stream(device)) cudaStreamSynchronize(user);
+}
+
 // short-lived work buffers (partials of a probability reduction, ...): cudaMalloc / cudaFree cost
 // from a few to hundreds of milliseconds next to multi-GiB allocations, so they are recycled too
 size_t work_class(size_t bytes) {
@@ -66,8 +103,9 @@ size_t work_class(size_t bytes) {
     while (c < bytes) c <<= 1;
     return c;
 }
-void* work_alloc(int device, size_t bytes) {
+void* work_alloc(int device, size_t bytes, cudaStream_t user) {
     const size_t c = work_class(bytes);
+    pool_enter(device, user);
     {
         std::lock_guard<std::mutex> lk(g_bufs.mu);
         for (size_t i = 0; i < g_bufs.small_list.size(); i++) {
@@ -82,17 +120,20 @@ void* work_alloc(int device, size_t bytes) {
     QB_CUDA(cudaMalloc(&p, c));
     return p;
 }
-void work_free(int device, size_t bytes, void* p) {
+void work_free(int device, size_t bytes, void* p, cudaStream_t user) {
     const size_t c = work_class(bytes);
+    pool_leave(device, user);
     if (c <= (256u << 20)) {
         std::lock_guard<std::mutex> lk(g_bufs.mu);
         if (g_bufs.small_list.size() < 64) { g_bufs.small_list.emplace_back(device, c, p); return; }
     }
+    cudaStreamSynchronize(default_stream(device));
     cudaFree(p);
 }
 
-void* cached_alloc(int device, size_t bytes) {
-    if (bytes < kCacheMinBytes) return work_alloc(device, bytes);        // small registers: power-of-two size classes
+void* cached_alloc(int device, size_t bytes, cudaStream_t user) {
+    if (bytes < kCacheMinBytes) return work_alloc(device, bytes, user);        // small registers: power-of-two size classes
+    pool_enter(device, user);
     {
         std::lock_guard<std::mutex> lk(g_bufs.mu);
         for (size_t i = 0; i < g_bufs.free_list.size(); i++) {
@@ -132,14 +173,13 @@ size_t device_total_mem(int device) {           // asked once per device (cudaMe
 
 void cached_free(int device, size_t bytes, void* p, cudaStream_t stream) {
     if (bytes < kCacheMinBytes) {
-        if (stream) cudaStreamSynchronize(stream);
-        work_free(device, bytes, p);
+        work_free(device, bytes, p, stream);
         return;
     }
     if (bytes >= kCacheMinBytes) {
         const size_t total_b = device_total_mem(device);
         if (bytes <= total_b / 3) {
-            if (stream) cudaStreamSynchronize(stream);            // nothing may still be writing into it
+            pool_leave(device, stream);            // nothing on a foreign stream may still be writing into it
             std::lock_guard<std::mutex> lk(g_bufs.mu);
             int mine = 0;
             size_t held = 0;
@@ -149,6 +189,8 @@ void cached_free(int device, size_t bytes, void* p, cudaStream_t stream) {
             if (mine < 8 && held + bytes <= total_b / 3) { g_bufs.free_list.emplace_back(device, bytes, p); return; }
         }
     }
+    if (stream) cudaStreamSynchronize(stream);
+    cudaStreamSynchronize(default_stream(device));
     cudaFree(p);
 }
 }  // namespace
@@ -157,7 +199,7 @@ qb_state::~qb_state() {
     qb_engine_free(this);
     if (d && owns) { DevGuard g(device); cached_free(device, bytes(), d, stream); }
     if (scratch) { DevGuard g(device); cached_free(device, bytes(), scratch, stream); }   // same allocator as `d`: the two may have been swapped
-    if (stage) cudaFree(stage);
+    if (stage) { DevGuard g(device); work_free(device, STAGE_BYTES, stage, stream); }
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream && owns_stream) cudaStreamDestroy(stream);
@@ -169,24 +211,28 @@ static qb_state* new_state(int kind, int nq, int64_t nbranch, int device, void* 
     QB_REQUIRE(nbranch >= 1, "nbranch must be >= 1");
     int nbits = kind == QB_KET ? nq : 2 * nq;
     QB_REQUIRE(nbits <= 40, "state too large (index bits > 40)");
-    int ndev = 0;
-    QB_CUDA(cudaGetDeviceCount(&ndev));
+    const int ndev = device_count_cached();
     QB_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
     std::unique_ptr<qb_state> s(new qb_state());
     s->kind = kind; s->nq = nq; s->nbits = nbits; s->nbranch = nbranch; s->device = device;
     DevGuard g(device);
     s->sms = sm_count_of(device);
-    if (ext_stream) { s->stream = (cudaStream_t)ext_stream; s->owns_stream = false; }
-    else { QB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->owns_stream = true; }
+    s->stream = ext_stream ? (cudaStream_t)ext_stream : default_stream(device);
+    s->owns_stream = false;
     if (ext) { s->d = (cplx*)ext; s->owns = false; }
-    else { s->d = (cplx*)cached_alloc(device, s->bytes()); s->owns = true; }
+    else { s->d = (cplx*)cached_alloc(device, s->bytes(), s->stream); s->owns = true; }
     return s.release();
+}
+
+// work queued on `earlier`'s stream must be visible to what `later_stream` does next
+static void order_after(cudaStream_t later_stream, const qb_state* earlier) {
+    if (earlier->stream != later_stream) QB_CUDA(cudaStreamSynchronize(earlier->stream));
 }
 
 LaunchCtx qb_state::ctx() { return LaunchCtx{stream, sms, &stats.kernel_launches}; }
 
 cplx* qb_state::get_scratch() {
-    if (!scratch) scratch = (cplx*)cached_alloc(device, bytes());       // interchangeable with `d` (out-of-place gates swap them)
+    if (!scratch) scratch = (cplx*)cached_alloc(device, bytes(), stream);       // interchangeable with `d` (out-of-place gates swap them)
     return scratch;
 }
 
@@ -200,7 +246,7 @@ static void fill_ins(uint64_t mask, int nbits_total, int* ins, int& nins) {
 
 cplx* qb_state::upload_small(const void* host, size_t bytes) {
     // staging ring for gate matrices: consecutive launches must not overwrite each other
-    if (!stage) { QB_CUDA(cudaMalloc((void**)&stage, STAGE_BYTES)); stage_off = 0; }
+    if (!stage) { stage = work_alloc(device, STAGE_BYTES, stream); stage_off = 0; }
     size_t need = (bytes + 255) & ~size_t(255);
     QB_REQUIRE(need <= STAGE_BYTES, "matrix too large for the staging buffer");
     if (stage_off + need > STAGE_BYTES) { QB_CUDA(cudaStreamSynchronize(stream)); stage_off = 0; }
@@ -339,8 +385,7 @@ int qb_destroy(qb_state* s) {
     QB_API_BEGIN
     if (s) {
         DevGuard g(s->device);
-        cudaStreamSynchronize(s->stream);
-        delete s;                                   // the destructor releases stage / scratch / the register buffer
+        delete s;                                   // the destructor hands stage / scratch / the register buffer back in stream order
     }
     QB_API_END
 }
@@ -353,8 +398,7 @@ int qb_clone(const qb_state* cs, qb_state** out) {
     DevGuard g(s->device);
     qb_state* n = new_state(s->kind, s->nq, s->nbranch, s->device, nullptr, s->owns_stream ? nullptr : (void*)s->stream);
     n->fusion = s->fusion;
-    QB_CUDA(cudaMemcpyAsync(n->d, s->d, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
-    QB_CUDA(cudaStreamSynchronize(s->stream));
+    QB_CUDA(cudaMemcpyAsync(n->d, s->d, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));      // n shares s's stream
     *out = n;
     QB_API_END
 }
@@ -384,8 +428,9 @@ int qb_set_stream(qb_state* s, void* cuda_stream) {
     DevGuard g(s->device);
     QB_CUDA(cudaStreamSynchronize(s->stream));
     if (s->owns_stream && s->stream) cudaStreamDestroy(s->stream);
-    if (cuda_stream) { s->stream = (cudaStream_t)cuda_stream; s->owns_stream = false; }
-    else { QB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->owns_stream = true; }
+    s->stream = cuda_stream ? (cudaStream_t)cuda_stream : default_stream(s->device);
+    s->owns_stream = false;
+    QB_CUDA(cudaStreamSynchronize(default_stream(s->device)));     // the buffer changes stream: nothing of the old order may be pending
     QB_API_END
 }
 
@@ -413,11 +458,10 @@ int qb_init_product(qb_state* s, const double* vecs, int per_branch) {
     size_t per = (s->kind == QB_KET ? 2 : 4) * (size_t)s->nq;
     size_t count = per * (per_branch ? (size_t)s->nbranch : 1);
     const size_t dv_bytes = sizeof(cplx) * std::max<size_t>(count, 1);
-    cplx* dv = (cplx*)work_alloc(s->device, dv_bytes);
-    QB_CUDA(cudaMemcpyAsync(dv, vecs, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));
+    cplx* dv = (cplx*)work_alloc(s->device, dv_bytes, s->stream);
+    QB_CUDA(cudaMemcpyAsync(dv, vecs, sizeof(cplx) * count, cudaMemcpyHostToDevice, s->stream));   // pageable source: staged before the call returns
     qb_launch_init_product(s->ctx(), s->d, s->kind, s->nq, s->nbranch, dv, per_branch);
-    QB_CUDA(cudaStreamSynchronize(s->stream));
-    work_free(s->device, dv_bytes, dv);
+    work_free(s->device, dv_bytes, dv, s->stream);
     s->stats.bytes_moved += s->bytes();
     QB_API_END
 }
@@ -429,11 +473,10 @@ int qb_init_diag(qb_state* s, const double* values) {
     s->queue.clear();
     DevGuard g(s->device);
     const size_t vb = sizeof(double) << s->nq;
-    double* dv = (double*)work_alloc(s->device, vb);
+    double* dv = (double*)work_alloc(s->device, vb, s->stream);
     QB_CUDA(cudaMemcpyAsync(dv, values, vb, cudaMemcpyHostToDevice, s->stream));
     qb_launch_fill_diag(s->ctx(), s->d, s->nq, dv);
-    QB_CUDA(cudaStreamSynchronize(s->stream));
-    work_free(s->device, vb, dv);
+    work_free(s->device, vb, dv, s->stream);
     s->stats.bytes_moved += s->bytes();
     QB_API_END
 }
@@ -579,7 +622,7 @@ int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int*
     char* buf = nullptr;
     size_t off_tb = (mat_bytes + 255) & ~size_t(255), off_cm = (off_tb + tb_bytes + 255) & ~size_t(255),
            off_en = (off_cm + cm_bytes + 255) & ~size_t(255), tot = off_en + B + 256;
-    buf = (char*)work_alloc(s->device, tot);
+    buf = (char*)work_alloc(s->device, tot, s->stream);
     std::vector<cplx> hm((const cplx*)matrices, (const cplx*)matrices + D2 * B);
     std::vector<int> htb(target_bits, target_bits + (size_t)k * B);
     std::vector<uint64_t> hcm(B, 0);
@@ -599,11 +642,11 @@ int qb_apply_gate_batched(qb_state* s, const double* matrices, int k, const int*
         if (enable) QB_CUDA(cudaMemcpyAsync(buf + off_en, enable, B, cudaMemcpyHostToDevice, s->stream));
         qb_launch_dense_batched(s->ctx(), k, s->d, s->nbits, B, (const cplx*)buf, (const int*)(buf + off_tb),
                                 (const uint64_t*)(buf + off_cm), enable ? (const uint8_t*)(buf + off_en) : nullptr);
-        QB_CUDA(cudaStreamSynchronize(s->stream));
+        if (pass + 1 < passes) QB_CUDA(cudaStreamSynchronize(s->stream));       // the tables are rewritten for the column pass
         s->stats.bytes_moved += s->bytes() * 2;
         s->stats.state_passes++;
     }
-    work_free(s->device, tot, buf);
+    work_free(s->device, tot, buf, s->stream);
     s->stats.gates_applied += B;
     QB_API_END
 }
@@ -742,16 +785,16 @@ static void run_bins(qb_state* s, const int* bits, int m, std::vector<cplx>& hos
     }
     size_t npartial = (size_t)s->nbranch * a.nchunks << a.ml;
     size_t nout = (size_t)s->nbranch << m;
-    cplx* dpart = (cplx*)work_alloc(s->device, sizeof(cplx) * npartial);
-    cplx* dout = (cplx*)work_alloc(s->device, sizeof(cplx) * nout);
+    cplx* dpart = (cplx*)work_alloc(s->device, sizeof(cplx) * npartial, s->stream);
+    cplx* dout = (cplx*)work_alloc(s->device, sizeof(cplx) * nout, s->stream);
     a.partial = dpart; f.partial = dpart; f.out = dout;
     qb_launch_bins(s->ctx(), a, s->nbranch);
     qb_launch_bins_final(s->ctx(), f, s->nbranch);
     host_out.resize(nout);
     QB_CUDA(cudaMemcpyAsync(host_out.data(), dout, sizeof(cplx) * nout, cudaMemcpyDeviceToHost, s->stream));
     QB_CUDA(cudaStreamSynchronize(s->stream));
-    work_free(s->device, sizeof(cplx) * npartial, dpart);
-    work_free(s->device, sizeof(cplx) * nout, dout);
+    work_free(s->device, sizeof(cplx) * npartial, dpart, s->stream);
+    work_free(s->device, sizeof(cplx) * nout, dout, s->stream);
     s->stats.bytes_moved += (s->kind == QB_KET ? s->bytes() : (sizeof(cplx) * (size_t)s->nbranch << s->nq));
 }
 
@@ -774,11 +817,10 @@ int qb_probs_basis(qb_state* s, const int* bits, int m, const double* basis, int
     DevGuard g(s->device);
     // rotate a scratch copy so that basis ket j of every group sits at group index j, then read the
     // computational-frame weights; the register itself stays as it is (peek must not change it)
-    std::unique_ptr<qb_state> tmp(new_state(s->kind, s->nq, s->nbranch, s->device, nullptr, nullptr));
+    std::unique_ptr<qb_state> tmp(new_state(s->kind, s->nq, s->nbranch, s->device, nullptr, (void*)s->stream));
     tmp->fusion = s->fusion;
     tmp->jit_mode = 0;                 // one-off gate list: never worth a specialised kernel
-    QB_CUDA(cudaStreamSynchronize(s->stream));
-    QB_CUDA(cudaMemcpyAsync(tmp->d, s->d, s->bytes(), cudaMemcpyDeviceToDevice, tmp->stream));
+    QB_CUDA(cudaMemcpyAsync(tmp->d, s->d, s->bytes(), cudaMemcpyDeviceToDevice, s->stream));
     const cplx* W = (const cplx*)basis;
     for (int f = 0; f < m / b; f++) {
         const int* tb = bits + f * b;
@@ -856,7 +898,6 @@ int qb_ptrace(qb_state* s, const int* keep_bits, int nkeep, qb_state** out) {
     // order the new handle's stream after ours
     if (s->kind == QB_DM) qb_launch_ptrace(s->ctx(), a);
     else qb_launch_ket_rdm(s->ctx(), a);          // Tr_rest |psi><psi| straight from the amplitudes
-    QB_CUDA(cudaStreamSynchronize(s->stream));
     s->stats.bytes_moved += (sizeof(cplx) << (s->nq + nkeep)) + o->bytes();
     *out = o;
     QB_API_END
@@ -899,9 +940,11 @@ int qb_scatter_product(qb_state* a, qb_state* b, const int* a_bits, const int* b
         has = true;
     }
     sa.has_scale = has ? 1 : 0; sa.scale = extra;
-    if (b) QB_CUDA(cudaStreamSynchronize(b->stream));
-    qb_launch_scatter(a->ctx(), sa);
-    QB_CUDA(cudaStreamSynchronize(a->stream));
+    if (b) order_after(a->stream, b);
+    const size_t tab_bytes = sizeof(uint32_t) * 2 * ((size_t)1 << n);
+    uint32_t* tabs = (uint32_t*)work_alloc(a->device, tab_bytes, a->stream);
+    qb_launch_scatter(a->ctx(), sa, tabs);
+    work_free(a->device, tab_bytes, tabs, a->stream);
     a->stats.bytes_moved += o->bytes();
     *out = o;
     QB_API_END
@@ -920,7 +963,7 @@ int qb_mix(qb_state* const* states, const double* probs, int count, qb_state** o
         states[i]->flush();
     }
     DevGuard g(s0->device);
-    for (int i = 1; i < count; i++) QB_CUDA(cudaStreamSynchronize(states[i]->stream));
+    for (int i = 1; i < count; i++) order_after(s0->stream, states[i]);
     qb_state* o = new_state(s0->kind, s0->nq, s0->nbranch, s0->device, nullptr, s0->owns_stream ? nullptr : (void*)s0->stream);
     o->fusion = s0->fusion;
     for (int first = 0; first < count; first += QB_MIX_MAX) {
@@ -931,7 +974,6 @@ int qb_mix(qb_state* const* states, const double* probs, int count, qb_state** o
         a.accumulate = first > 0; a.out = o->d; a.total = s0->total();
         qb_launch_mix(s0->ctx(), a);
     }
-    QB_CUDA(cudaStreamSynchronize(s0->stream));
     s0->stats.bytes_moved += s0->bytes() * (count + 1);
     *out = o;
     QB_API_END
@@ -945,11 +987,10 @@ int qb_mix_branches(qb_state* s, const double* probs, qb_state** out) {
     DevGuard g(s->device);
     qb_state* o = new_state(s->kind, s->nq, 1, s->device, nullptr, s->owns_stream ? nullptr : (void*)s->stream);
     o->fusion = s->fusion;
-    double* dp = (double*)work_alloc(s->device, sizeof(double) * s->nbranch);
+    double* dp = (double*)work_alloc(s->device, sizeof(double) * s->nbranch, s->stream);
     QB_CUDA(cudaMemcpyAsync(dp, probs, sizeof(double) * s->nbranch, cudaMemcpyHostToDevice, s->stream));
     qb_launch_mix_branches(s->ctx(), s->d, dp, s->nbranch, s->per_branch(), o->d);
-    QB_CUDA(cudaStreamSynchronize(s->stream));
-    work_free(s->device, sizeof(double) * s->nbranch, dp);
+    work_free(s->device, sizeof(double) * s->nbranch, dp, s->stream);
     s->stats.bytes_moved += s->bytes() + o->bytes();
     *out = o;
     QB_API_END
@@ -965,7 +1006,6 @@ int qb_outer(qb_state* ket, int conj, qb_state** out) {
     qb_state* o = new_state(QB_DM, ket->nq, 1, ket->device, nullptr, ket->owns_stream ? nullptr : (void*)ket->stream);
     o->fusion = ket->fusion;
     qb_launch_outer(ket->ctx(), ket->d, o->d, ket->nq, conj);
-    QB_CUDA(cudaStreamSynchronize(ket->stream));
     ket->stats.bytes_moved += o->bytes();
     *out = o;
     QB_API_END
@@ -979,11 +1019,12 @@ int qb_broadcast(qb_state* src, qb_state* dst) {
     src->flush();
     dst->queue.clear();
     DevGuard g(src->device);
-    QB_CUDA(cudaStreamSynchronize(src->stream));
+    order_after(dst->stream, src);
     qb_launch_broadcast(dst->ctx(), src->d, dst->d, src->per_branch(), dst->nbranch);
-    // single-branch views of dst (qb_create_external) run on streams of their own: the copy must have
-    // landed before any of them touches its branch
-    QB_CUDA(cudaStreamSynchronize(dst->stream));
+    // single-branch views of dst (qb_create_external without a stream) work on the device's default
+    // stream like dst itself, so they are ordered after this copy; a dst on a foreign stream is
+    // synchronised here because its views cannot be
+    if (dst->stream != default_stream(dst->device)) QB_CUDA(cudaStreamSynchronize(dst->stream));
     dst->stats.bytes_moved += dst->bytes() + src->bytes();
     QB_API_END
 }

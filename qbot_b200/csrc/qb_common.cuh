@@ -176,7 +176,7 @@ void qb_launch_bins(const LaunchCtx&, const BinArgs& a, int64_t nbranch);
 void qb_launch_bins_final(const LaunchCtx&, const BinFinalArgs& a, int64_t nbranch);
 void qb_launch_ptrace(const LaunchCtx&, const PtraceArgs& a);
 void qb_launch_ket_rdm(const LaunchCtx&, const PtraceArgs& a);
-void qb_launch_scatter(const LaunchCtx&, const ScatterArgs& a);
+void qb_launch_scatter(const LaunchCtx&, const ScatterArgs& a, uint32_t* tables_dev);   // tables_dev: 2 * 2^n uint32 of work space
 void qb_launch_mix(const LaunchCtx&, const MixArgs& a);
 void qb_launch_mix_branches(const LaunchCtx&, const cplx* src, const double* probs_dev, int64_t nbranch, uint64_t per_branch, cplx* out);
 void qb_launch_outer(const LaunchCtx&, const cplx* ket, cplx* out, int nq, int conj);

@@ -433,10 +433,47 @@ __global__ void __launch_bounds__(256) k_bins_final(BinFinalArgs a) {
     if (threadIdx.x == 0) a.out[blockIdx.x] = make_double2(sre[0], sim[0]);
 }
 
+// few partials per outcome (a branch batch: 4096 x 16 outcomes with ONE partial each): a thread per
+// (branch, outcome) instead of a 256-thread block -- 65 536 blocks summing one value each took 131 us
+__global__ void __launch_bounds__(256) k_bins_final_small(BinFinalArgs a, uint64_t noutcomes) {
+    const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= noutcomes) return;
+    const uint64_t M = 1ull << a.m;
+    const uint64_t branch = o / M, j = o % M;
+    uint64_t jl = 0, hfix = 0, hmask = 0;
+    for (int t = 0; t < a.m; t++) {
+        uint64_t v = (j >> (a.m - 1 - t)) & 1ull;
+        if (a.tbits[t] < a.c) jl |= v << a.lowrank[t];
+        else { hfix |= v << (a.tbits[t] - a.c); hmask |= 1ull << (a.tbits[t] - a.c); }
+    }
+    const int qbits = a.nb - a.c > 0 ? a.nb - a.c : 0;
+    hmask |= a.groupmask;
+    const int nfix = __popcll(hmask);
+    const uint64_t nfree = 1ull << (qbits - nfix);
+    const uint64_t ML = 1ull << a.ml;
+    double re = 0.0, im = 0.0;
+    for (uint64_t r = 0; r < nfree; r++) {
+        uint64_t q = r;
+        for (int p = 0; p < qbits; p++) if ((hmask >> p) & 1ull) q = qb_insert_zero(q, p);
+        q |= hfix;
+        const cplx v = a.partial[(branch * a.nchunks + q) * ML + jl];
+        re += v.x; im += v.y;
+    }
+    a.out[o] = make_double2(re, im);
+}
+
 void qb_launch_bins_final(const LaunchCtx& c, const BinFinalArgs& a, int64_t nbranch) {
     uint64_t blocks = ((uint64_t)nbranch) << a.m;
     QB_REQUIRE(blocks < (1ull << 31), "probs: too many outcomes");
-    k_bins_final<<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+    const int qbits = a.nb - a.c > 0 ? a.nb - a.c : 0;
+    uint64_t hmask = a.groupmask;
+    for (int t = 0; t < a.m; t++) if (a.tbits[t] >= a.c) hmask |= 1ull << (a.tbits[t] - a.c);
+    const int free_bits = qbits - __builtin_popcountll(hmask);
+    if (free_bits <= 3 && blocks >= 1024) {
+        k_bins_final_small<<<(unsigned)((blocks + 255) / 256), 256, 0, c.stream>>>(a, blocks);
+    } else {
+        k_bins_final<<<(unsigned)blocks, 256, 0, c.stream>>>(a);
+    }
     COUNT_LAUNCH(c);
 }
 
@@ -549,21 +586,36 @@ __device__ __forceinline__ uint64_t sc_gather(uint64_t v, const int* pos, int n)
     return o;
 }
 
-__global__ void __launch_bounds__(256) k_scatter(ScatterArgs a) {
-    const uint64_t N = 1ull << a.n, total = N * N;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        uint64_t r = e >> a.n, cidx = e & (N - 1);
-        cplx v = a.a[(sc_gather(r, a.abits, a.na) << a.na) | sc_gather(cidx, a.abits, a.na)];
-        if (a.b) v = qb_cmul(v, a.b[(sc_gather(r, a.bbits, a.nb) << a.nb) | sc_gather(cidx, a.bbits, a.nb)]);
-        if (a.has_scale) v = qb_cmul(v, a.scale);
-        a.out[e] = v;
+// index tables: tA[i] = A-index of the n-bit row / column index i, tB[i] likewise (the same map
+// serves rows and columns).  Evaluating the two bit gathers per output entry cost ~100 integer
+// instructions per 16-byte store (1.2 TB/s); with the tables the kernel is a plain HBM write.
+__global__ void __launch_bounds__(256) k_scatter_tables(ScatterArgs a, uint32_t* tA, uint32_t* tB) {
+    const uint64_t N = 1ull << a.n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+        tA[i] = (uint32_t)sc_gather(i, a.abits, a.na);
+        tB[i] = (uint32_t)sc_gather(i, a.bbits, a.nb);
     }
 }
 
-void qb_launch_scatter(const LaunchCtx& c, const ScatterArgs& a) {
-    uint64_t total = 1ull << (2 * a.n);
-    k_scatter<<<grid_for(c, total, 256), 256, 0, c.stream>>>(a);
+__global__ void __launch_bounds__(256) k_scatter(ScatterArgs a, const uint32_t* __restrict__ tA, const uint32_t* __restrict__ tB) {
+    const uint64_t N = 1ull << a.n, total = N * N;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint64_t r = e >> a.n, cidx = e & (N - 1);
+        cplx v = a.a[((uint64_t)tA[r] << a.na) | tA[cidx]];
+        if (a.b) v = qb_cmul(v, a.b[((uint64_t)tB[r] << a.nb) | tB[cidx]]);
+        if (a.has_scale) v = qb_cmul(v, a.scale);
+        __stcs(a.out + e, v);
+    }
+}
+
+void qb_launch_scatter(const LaunchCtx& c, const ScatterArgs& a, uint32_t* tables_dev) {
+    const uint64_t N = 1ull << a.n, total = N * N;
+    uint32_t* tA = tables_dev;
+    uint32_t* tB = tables_dev + N;
+    k_scatter_tables<<<grid_for(c, N, 256), 256, 0, c.stream>>>(a, tA, tB);
+    COUNT_LAUNCH(c);
+    k_scatter<<<grid_for(c, total, 256), 256, 0, c.stream>>>(a, tA, tB);
     COUNT_LAUNCH(c);
 }
 

@@ -26,7 +26,7 @@ def test_reference_arm_line():
     assert d['impl'] == 'reference' and d['metric'] == 'gates/sec' and d['unit'] == 'gates/s' and d['higher_is_better'] is True
     assert d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 0
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
+    assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
     e = d['e2e']
     assert e['value'] == d['value'] and e['h2d_bytes_per_step'] == 0 and e['d2h_bytes_per_step'] == 0
     assert 'workload' in d['config']

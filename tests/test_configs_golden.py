@@ -41,22 +41,7 @@ def test_oracle_rc_10_200_20(cfg):
 
 
 def _oracle_c3(n, depth):
-    rho = np.zeros((1 << n, 1 << n), dtype=complex)
-    rho[0, 0] = 1
-    comp = [np.diag([1, 0]).astype(complex), np.diag([0, 1]).astype(complex)]
-    probs = {}
-    for op in circuits.c3_ops(n, depth, n):
-        if op.kind == 'gate':
-            rho = orc.dm_apply(rho, n, op.gate.target, op.gate.matrix(), op.gate.controls)
-        elif op.kind == 'meas':
-            r = orc.measure(rho, comp, list(op.qubits), True)
-            probs[op.name] = r['probs']
-            rho = r['newState']
-        elif op.kind == 'pgate':
-            rho = orc.ensemble([.5, .5], [orc.dm_apply(rho, n, t, circuits.HADAMARD, []) for t in op.qubits])
-        else:
-            rho = orc.ptrace_arbitrary(rho, n, list(op.qubits))[1]
-    return rho, probs
+    return orc.run_config3(circuits.c3_ops(n, depth, n), n)
 
 
 @pytest.mark.parametrize('n,depth', [(6, 20), (8, 30)])
