@@ -407,7 +407,14 @@ def run_single_gpu(args):
             except Exception as e:      # a sub-line must never take the headline down
                 out["configs"][name] = {"config": name, "error": f"{type(e).__name__}: {e}"[:400]}
         st = DeviceState.zero_state(2)
-    if not args.no_cpu_baseline:
+    c3cb = (out.get("configs", {}).get("c3") or {}).get("cpu_baseline")
+    if not args.no_cpu_baseline and c3cb:
+        # the reference's own path on the largest register it can hold was timed for the c3 sub-line a moment ago:
+        # the same number serves the headline (the 30-qubit ket does not exist in its 4^n representation)
+        kv, kdone, kdt = cpu_ket_port(24, 6.0, 24)
+        out["cpu_baseline"] = dict(c3cb, ket_port={"value": kv, "unit": "gates/s", "qubits": 24,
+                                                   "sample": f"{kdone} gates of rc(24, 2, 24) in {kdt:.1f}s, numpy strided ket update (not a reference code path)"})
+    elif not args.no_cpu_baseline:
         v, done, dt = cpu_reference_algorithm(args.ref_qubits_default, 12.0, 12)
         kv, kdone, kdt = cpu_ket_port(24, 6.0, 24)
         out["cpu_baseline"] = {

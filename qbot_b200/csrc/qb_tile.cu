@@ -279,7 +279,10 @@ bool step_jit(qb_state* s, CachedPlan* plan, size_t i, int jit_mode) {
     CachedPlan::StepJit& j = plan->jit[i];
     if (j.ready) return true;
     if (j.failed) return false;
-    if (jit_mode == 1 && s->nbits + (s->nbranch > 1 ? 4 : 0) < engine_jit_min_bits()) return false;
+    // size that decides whether specialising pays: index bits of a branch plus the branch axis (a 4096 x 16-qubit
+    // batch is a 28-bit sweep; counting it as 20 bits kept config 4 on the generic kernel at 0.25 of HBM peak)
+    const int total_bits = s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0);
+    if (jit_mode == 1 && total_bits < engine_jit_min_bits()) return false;
     const uint8_t* program = plan->steps[i].program.data();
     try {
         if (!j.key) j.key = qj_hash(qb_jit_full_source(program, nullptr, nullptr));

@@ -92,6 +92,8 @@ def shift_matrix(num_qubits: int, up: bool = True, shifts: int = 1):
 
 # ---- tensor helpers -----------------------------------------------------------------------------
 LAZY_MIN_QUBITS = 14      # smaller products are built on the host exactly as the reference does
+LAZY_MIN_QUBITS_DM = 8    # ... density matrices from 8 qubits on (1 MiB): the 12-qubit |0..0><0..0| of BASELINE config 3
+                          # costs ~0.25 s as a host kron chain + 256 MiB upload and ~0.05 ms as a device fill
 
 
 class LazyProduct:
@@ -147,6 +149,37 @@ class LazyProduct:
     def __repr__(self):
         return f"LazyProduct({len(self.factors)} factors, {self.num_qubits} qubits, {'ket' if self.ndim == 1 else 'density'})"
 
+    def __getattr__(self, name):
+        # anything else a user expression asks of the product is answered by the array it stands for
+        if name.startswith('_'):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+    __hash__ = None
+    __array_priority__ = 1000
+
+
+def _lazy_binop(name):
+    def f(self, other):
+        return getattr(self.materialize(), name)(np.asarray(other) if is_lazy(other) else other)
+    f.__name__ = name
+    return f
+
+
+for _n in ('__add__', '__radd__', '__sub__', '__rsub__', '__mul__', '__rmul__', '__truediv__', '__rtruediv__',
+           '__matmul__', '__rmatmul__', '__eq__', '__ne__', '__pow__', '__neg__', '__abs__'):
+    setattr(LazyProduct, _n, _lazy_binop(_n) if _n not in ('__neg__', '__abs__') else
+            (lambda nm: (lambda self: getattr(self.materialize(), nm)()))(_n))
+
 
 def is_lazy(x) -> bool:
     return getattr(x, '_qb_lazy_product', False)
@@ -157,7 +190,7 @@ def tensor_prod(*parts):
     if not parts:
         return np.array([], dtype=complex)
     if len({p.ndim for p in parts}) == 1 and parts[0].ndim in (1, 2) and \
-            sum(ilog2(p.shape[0]) for p in parts) >= LAZY_MIN_QUBITS:
+            sum(ilog2(p.shape[0]) for p in parts) >= (LAZY_MIN_QUBITS if parts[0].ndim == 1 else LAZY_MIN_QUBITS_DM):
         return LazyProduct(parts)
     out = None
     for p in parts:
