@@ -74,6 +74,13 @@ class MeasurementResult:
 # ---------------------------------------------------------------------------------------------
 # helpers shared by the ops
 # ---------------------------------------------------------------------------------------------
+def probval_meas_enabled() -> bool:
+    """ProbVal-valued measurement targets: off by default (the reference's behaviour -- a crash -- is
+    reproduced), on with QBOT_B200_PROBVAL_MEAS=1 (definitional semantics, see measure_probval)."""
+    import os
+    return os.environ.get('QBOT_B200_PROBVAL_MEAS', '0') == '1'
+
+
 def is_state(x) -> bool:
     return getattr(x, '_qb_device_state', False)
 
@@ -624,6 +631,37 @@ def make_ops(host: Host) -> dict:
         basisStates, basisSymbols = _outcome_labels(numTensProd, basis, len(basis.density) ** numTensProd)
         return Result(_LazyReducedDensity(st, targets_sorted), probs, basisStates, basisSymbols, None)
 
+    def measure_probval(st, basis, targets_pv, returnState):
+        """`meas x ; basis ; ProbVal(targets)` -- SURVEY.md row f4 / F8.  The reference fans the measurement
+        out over the target sets (funcWrapper, operators.py:411) and then dies in
+        MeasurementResult.fromProbVal (measurement.py:41-69: an assert on a class attribute that does not
+        exist; its accumulation loop also indexes with the wrong variable), so there is no reference
+        behaviour to match.  What that function is evidently meant to compute -- and what this does when
+        QBOT_B200_PROBVAL_MEAS=1 -- is the mixture over the target sets:
+            probs[j]          = sum_i p_i probs_i[j]            (same number of outcomes in every branch)
+            unMeasuredDensity = sum_i p_i rho_A,i
+            newState          = sum_i p_i newState_i
+        with the basis projectors / symbols of the last branch, as fromProbVal takes them."""
+        results = [measure(st, basis, t, returnState) for t in targets_pv.values]
+        nout = len(results[0].probs)
+        if any(len(r.probs) != nout for r in results):
+            raise ValueError("every target set of a ProbVal measurement must give the same number of outcomes")
+        probs = [0.0 * results[0].probs[0]] * nout
+        for p, r in zip(targets_pv.probs, results):
+            for j in range(nout):
+                probs[j] = probs[j] + p * r.probs[j]
+        s = sum(probs)
+        probs = [x / s for x in probs]
+        un = [np.asarray(r.unMeasuredDensity) for r in results]
+        if any(u.shape != un[0].shape for u in un):
+            raise ValueError("every target set of a ProbVal measurement must have the same number of qubits")
+        unmeasured = np.zeros(un[0].shape, dtype=complex)
+        for p, u in zip(targets_pv.probs, un):
+            unmeasured += p * u
+        newState = State.mix(list(targets_pv.probs), [r.newState for r in results]) if returnState else None
+        last = results[-1]
+        return Result(unmeasured, probs, last.basisDensity, last.basisSymbols, newState)
+
     def meas(ns, lines, lineNum, tokens, changeState=True):
         varName = tokens[1]
         if not varName.isidentifier():
@@ -643,8 +681,16 @@ def make_ops(host: Host) -> dict:
             else:
                 targets = ensureContainer(lines, lineNum, evaluateWrapper(lines, lineNum, tokens[3], ns))
                 if isinstance(targets, ProbVal):
-                    # the reference crashes here (MeasurementResult.fromProbVal)
-                    raise AttributeError("type object 'ProbVal' has no attribute 'probs'")
+                    if not probval_meas_enabled():
+                        # the reference crashes here (MeasurementResult.fromProbVal)
+                        raise AttributeError("type object 'ProbVal' has no attribute 'probs'")
+                    if big_ket:
+                        raise ValueError("ProbVal measurement targets need a density-matrix register")
+                    result = measure_probval(st, measBasis, targets, changeState)
+                    ns[varName] = result
+                    if changeState:
+                        setState(ns, lines, lineNum, result.newState)
+                    return
                 result = measure_ket(st, measBasis, targets) if big_ket else measure(st, measBasis, targets, changeState)
         except MeasurementIndexError as e:
             err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', e.args[1], e.args[3]))

@@ -36,7 +36,7 @@ def install(qbot_module=None, state_cls=None):
     gns = getattr(ev_mod, 'globalNameSpace', None)
     _saved = dict(table={k: table[k] for k in ('qset', 'gate', 'disc', 'swap', 'meas', 'peek')},
                   valsClose=pv_mod.valsClose, toDensityMatrix=pv_mod.ProbVal.toDensityMatrix,
-                  convert=ops_mod.convertToDensity, mods=(ops_mod, pv_mod), gns=gns,
+                  convert=ops_mod.convertToDensity, mods=(ops_mod, pv_mod), gns=gns, normalize=pv_mod.ProbVal.normalize,
                   tensor={k: gns[k] for k in ('tensorProd', 'tensorExp') if gns is not None and k in gns})
     if _saved['tensor']:
         # state constructors of >= 14 qubits stay descriptors and are built on the device
@@ -65,8 +65,36 @@ def install(qbot_module=None, state_cls=None):
     def convertToDensity(lines, lineNum, val):      # used by the reference's qdef
         return val if is_state(val) else ref_convert(lines, lineNum, val)
 
+    ref_normalize = _saved['normalize']
+    from .host.probval import ProbVal as _MirrorProbVal
+
+    def normalize(self):
+        """the reference's de-duplication is a pairwise loop, O(B^2) value comparisons
+        (qbot/probVal.py:22-51) -- 8 million gate-descriptor comparisons for the 4096-branch ProbVal of
+        BASELINE config 4.  For value kinds whose equality is exact (same-shape arrays, gate descriptors,
+        ints / bools / strings) a hash set keeps exactly what that loop keeps (first occurrence wins, later
+        duplicates are dropped without adding their probability, entries below smallVal go when reached);
+        everything else -- floats compare with a tolerance -- takes the reference's own loop."""
+        keys = _MirrorProbVal._exact_keys(self.values)
+        if keys is None:
+            return ref_normalize(self)
+        seen, np_, nv = set(), [], []
+        for pi, vi, ki in zip(self.probs, self.values, keys):
+            if pi < pv_mod.smallVal or ki in seen:
+                continue
+            seen.add(ki)
+            np_.append(pi)
+            nv.append(vi)
+        self.probs[:] = np_
+        self.values[:] = nv
+        total = sum(self.probs)
+        for i in range(len(self.probs)):
+            self.probs[i] /= total
+            self.probs[i] = round(self.probs[i], pv_mod.probRounding)
+
     pv_mod.valsClose = valsClose
     pv_mod.ProbVal.toDensityMatrix = toDensityMatrix
+    pv_mod.ProbVal.normalize = normalize
     ops_mod.convertToDensity = convertToDensity
 
 
@@ -81,5 +109,6 @@ def uninstall():
         _saved['gns'][k] = v
     pv_mod.valsClose = _saved['valsClose']
     pv_mod.ProbVal.toDensityMatrix = _saved['toDensityMatrix']
+    pv_mod.ProbVal.normalize = _saved['normalize']
     ops_mod.convertToDensity = _saved['convert']
     _saved = None

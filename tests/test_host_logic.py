@@ -243,3 +243,26 @@ def test_probval_normalize_fast_path_equals_pairwise_loop():
     r = pv.ProbVal([1.0 / 4096] * 4096, vals)
     assert len(r.values) == 64 * 16 // np.gcd(64, 16) or len(r.values) <= 1024
     assert time.perf_counter() - t0 < 5.0
+
+
+def test_probval_measurement_targets_behind_the_flag(monkeypatch):
+    """row f4 / F8: off -> the reference's crash text; on -> the mixture over the target sets, checked
+    against the oracle's measurement on each branch"""
+    from oracle import qbot_oracle as orc
+    prog = ("qset tensorProd(hada[0], comp[1], comp[0])\ngate pauliXGate ; 2 ; [0]\n"
+            "meas m ; comp ; ProbVal([.25, .75], [[0], [1]])\n")
+    monkeypatch.delenv('QBOT_B200_PROBVAL_MEAS', raising=False)
+    ns, out, exited = run_script(prog, FakeState)
+    assert exited and "has no attribute 'probs'" in out
+    monkeypatch.setenv('QBOT_B200_PROBVAL_MEAS', '1')
+    ns, out, exited = run_script(prog, FakeState)
+    assert not exited
+    plus = np.array([1, 1]) / np.sqrt(2)
+    psi = np.kron(np.kron(plus, [0, 1]), [1, 0]).astype(complex)
+    rho = orc.dm_apply(np.outer(psi, psi.conj()), 3, 2, np.array([[0, 1], [1, 0]], dtype=complex), [0])
+    comp = [np.diag([1, 0]).astype(complex), np.diag([0, 1]).astype(complex)]
+    r0, r1 = orc.measure(rho, comp, [0], True), orc.measure(rho, comp, [1], True)
+    want_p = [.25 * a + .75 * b for a, b in zip(r0['probs'], r1['probs'])]
+    assert np.allclose(ns['m'].probs, want_p, atol=1e-15)
+    assert close(np.asarray(ns['state']), .25 * r0['newState'] + .75 * r1['newState'])
+    assert close(np.asarray(ns['m'].unMeasuredDensity), .25 * r0['unMeasuredDensity'] + .75 * r1['unMeasuredDensity'])

@@ -31,3 +31,43 @@ sys.exit(0 if res.wasSuccessful() and res.testsRun >= 78 else 1)
     p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert 'RAN 78 FAIL 0 ERR 0' in p.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_installed_normalize_equals_the_stock_pairwise_loop():
+    """row f4: install() swaps the O(B^2) de-duplication of the REAL qbot.probVal.ProbVal for a hashed one
+    on exact-equality values; results identical to the stock class, 4096 gate arrays in well under a second"""
+    code = r'''
+import sys, time
+sys.dont_write_bytecode = True
+sys.path[:0] = [%r, %r, %r]
+import numpy as np
+from fake_backend import FakeState
+import qbot.probVal as pv
+rng = np.random.default_rng(4)
+cases = {
+  'ints': [int(x) for x in rng.integers(0, 9, 300)],
+  'arrays': [np.array([[1, 0], [0, np.exp(1j * float(k))]]) for k in rng.integers(0, 7, 200)],
+  'strs': [str(int(x)) for x in rng.integers(0, 5, 100)],
+  'floats': [float(x) for x in rng.integers(0, 5, 100)],
+}
+probs = {k: list(rng.uniform(0.01, 1, len(v))) for k, v in cases.items()}
+for k in probs: probs[k][3] = 1e-7
+stock = {k: pv.ProbVal(list(probs[k]), list(v)) for k, v in cases.items()}
+import qbot_b200.integration as integ
+integ.install(state_cls=FakeState)
+for k, v in cases.items():
+    got = pv.ProbVal(list(probs[k]), list(v))
+    assert got.probs == stock[k].probs, k
+    assert len(got.values) == len(stock[k].values) and all(pv.valsClose(a, b) for a, b in zip(got.values, stock[k].values)), k
+big = [np.diag([1, np.exp(1j * (i %% 64))]) for i in range(4096)]
+t0 = time.perf_counter()
+r = pv.ProbVal([1 / 4096] * 4096, big)
+dt = time.perf_counter() - t0
+assert len(r.values) == 64 and dt < 2.0, (len(r.values), dt)
+integ.uninstall()
+assert pv.ProbVal.normalize is not None and pv.ProbVal([.5, .5], [1, 1]).probs == [1.0]
+print("OK", dt)
+''' % (REF, ROOT, os.path.join(ROOT, 'tests'))
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
