@@ -289,6 +289,36 @@ void qb_state::run_gate_unfused(const QGate& g) {
         else a.mat = upload_small(m.data(), sizeof(cplx) << (2 * K));
         qb_launch_dense(c, K, a);
         stats.bytes_moved += touched * 32;
+    } else if (K >= QB_MMA_MINK && K <= QB_MMA_MAXK && !getenv("QBOT_B200_NO_DMMA") &&
+               nbits - K - ncontrols >= QB_MMA_TILE_BITS - K) {
+        // dense 6..8-qubit block (qftGate(k), user unitaries): complex GEMM on the FP64 tensor cores, in place
+        std::vector<cplx> m = qb_dense_of(g);
+        const int D = 1 << K, ncb = QB_MMA_TILE_BITS - K, ldx = (1 << ncb) + 4;
+        std::vector<double> planes((size_t)2 * D * D);
+        for (size_t i = 0; i < (size_t)D * D; i++) { planes[i] = m[i].x; planes[(size_t)D * D + i] = m[i].y; }
+        const size_t pbytes = planes.size() * sizeof(double);
+        double* dp = (double*)work_alloc(device, pbytes, stream);
+        QB_CUDA(cudaMemcpyAsync(dp, planes.data(), pbytes, cudaMemcpyHostToDevice, stream));     // pageable: staged before returning
+        DenseMmaArgs a;
+        memset(&a, 0, sizeof(a));
+        a.psi = d; a.ur = dp; a.ui = dp + (size_t)D * D; a.cmask = g.cmask;
+        uint64_t colmask = 0;
+        for (int p = 0, left = ncb; p < nbits && left; p++)
+            if (!(((g.tmask() | g.cmask) >> p) & 1ull)) { colmask |= 1ull << p; left--; }
+        int nb = 0, ncol = 0;
+        for (int p = 0; p < nbits; p++) {
+            if ((colmask >> p) & 1ull) { a.apos[nb] = p; a.sw[nb] = 1 << ncol++; nb++; }
+            else if ((g.tmask() >> p) & 1ull) {
+                int b = 0;
+                while (g.tb[b] != p) b++;
+                a.apos[nb] = p; a.sw[nb] = (1 << (K - 1 - b)) * ldx; nb++;
+            }
+        }
+        fill_ins(g.cmask | g.tmask() | colmask, nbits, a.ins, a.nins);
+        a.ntiles = touched >> QB_MMA_TILE_BITS;
+        qb_launch_dense_mma(c, K, a);
+        work_free(device, pbytes, dp, stream);
+        stats.bytes_moved += touched * 32;
     } else {
         QB_REQUIRE(K <= QB_BIG_MAXK, "gate acts on too many qubits");
         std::vector<cplx> m = qb_dense_of(g);

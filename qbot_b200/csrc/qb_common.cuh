@@ -12,6 +12,9 @@
 #define QB_MAX_INS    48      // zero-insert positions (targets + controls)
 #define QB_REG_MAXK   5       // dense gates up to 5 target bits run out of registers
 #define QB_DIAG_MAXK  12
+#define QB_MMA_MINK   6       // dense gates of 6..8 target bits run on the FP64 tensor cores (qb_dense_mma.cu)
+#define QB_MMA_MAXK   8
+#define QB_MMA_TILE_BITS 12   // targets + column bits of one CTA tile
 
 struct qb_error : public std::runtime_error {
     int code;
@@ -76,6 +79,18 @@ struct BigArgs {
     uint64_t tmask;
     int k;
     int tb[QB_BIG_MAXK];
+};
+
+struct DenseMmaArgs {
+    cplx* psi;
+    const double* ur;             // device matrix, real plane, row-major 2^k x 2^k
+    const double* ui;             // imaginary plane
+    uint64_t ntiles;
+    uint64_t cmask;
+    int nins;
+    int ins[QB_MAX_INS];          // targets + column bits + controls, ascending
+    int apos[QB_MMA_TILE_BITS];   // index bit of tile-local bit b (ascending)
+    int sw[QB_MMA_TILE_BITS];     // its contribution to the shared-memory word offset (row * LDX + column)
 };
 
 struct BinArgs {
@@ -170,6 +185,7 @@ void qb_launch_dense(const LaunchCtx&, int K, const DenseArgs& a);
 void qb_launch_diag(const LaunchCtx&, const DiagArgs& a);
 void qb_launch_swap(const LaunchCtx&, cplx* d, uint64_t total, int lo, int hi);
 void qb_launch_big(const LaunchCtx&, const BigArgs& a);
+void qb_launch_dense_mma(const LaunchCtx&, int K, const DenseMmaArgs& a);     // qb_dense_mma.cu
 void qb_launch_dense_batched(const LaunchCtx&, int K, cplx* psi, int nbits, int64_t nbranch, const cplx* mats,
                              const int* tb, const uint64_t* cmasks, const uint8_t* enable);
 void qb_launch_bins(const LaunchCtx&, const BinArgs& a, int64_t nbranch);

@@ -277,6 +277,12 @@ def make_ops(host: Host) -> dict:
             from ..state import KET, DM
             fs = val.single_qubit_factors()
             if fs is not None:
+                if val.ndim == 1:
+                    # one process per GPU (torchrun) and a large ket: the register is sharded over the ranks
+                    from .. import sharded_register as sr
+                    ctx = sr.context()
+                    if ctx is not None and len(fs) >= ctx.min_qubits:
+                        return sr.ShardedRegister.product(fs, ctx)
                 return State.product(fs, KET if val.ndim == 1 else DM)
             return State.from_host(val.materialize())
         if val.size == 0 or val.ndim not in (1, 2):
@@ -733,7 +739,8 @@ class _LazyReducedDensity:
     """rho_A of a ket-mode register, computed on the device when somebody looks at it."""
 
     def __init__(self, ket_state, keep):
-        self._snapshot = ket_state.clone() if ket_state.nq <= 24 else ket_state   # large kets: a view of the live register
+        big = ket_state.nq > 24 or getattr(ket_state, '_qb_sharded', False)
+        self._snapshot = ket_state if big else ket_state.clone()                  # large / sharded kets: a view of the live register
         self._keep = list(keep)
         self._val = None
         d = 1 << len(self._keep)

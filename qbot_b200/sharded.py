@@ -319,6 +319,19 @@ class CudaShard:
             torch.cuda.synchronize(self.device)
         self.state.sync()
 
+    def init_product(self, local_factors: Sequence[np.ndarray], coeff: complex):
+        """coeff * kron(local_factors) (first factor = highest local position) built on the device."""
+        v = np.ascontiguousarray(np.stack([np.asarray(f, dtype=np.complex128).reshape(2) for f in local_factors]))
+        v[0] = v[0] * coeff
+        self._lib.call('qb_init_product', self.state._h, v.ctypes.data_as(C.c_void_p), 0)
+        self.state._dirty()
+        self.state.sync()
+
+    def rdm_local(self, positions: Sequence[int]) -> np.ndarray:
+        """sum over the other local bits of psi psi^dagger on the listed local positions (first = MSB)."""
+        nl = self.nl
+        return np.asarray(self.state.ptrace_keep([nl - 1 - p for p in positions]))
+
     def apply(self, m: np.ndarray, target_positions: Sequence[int], cmask: int):
         self.state.apply_gate_bits(m, list(target_positions), cmask)
 
@@ -443,11 +456,43 @@ class ShardedKet:
         self.shard = shard_factory(nq - g, comm)
         self.queue: List[LGate] = []
         self.gates_applied = 0
+        self.label = list(range(nq))     # qubit of the caller -> qubit of the stored ket (`swap` only relabels)
         self.shard.init_basis(self.rank == 0, 0)
+
+    def init_product(self, factors: Sequence[np.ndarray]):
+        """The product ket kron(factors[0], factors[1], ...) (one 2-vector per qubit, qubit 0 first;
+        density.tensorProd, qbot/density.py:7-24) with the identity qubit map: the rank bits are
+        qubits 0 .. g-1, so this rank holds kron(local factors) times the product of the rank qubits'
+        entries selected by its rank bits."""
+        if len(factors) != self.nq:
+            raise ValueError("one factor per qubit")
+        g = self.map.g
+        self.queue = []
+        self.shard.sync()
+        self.comm.barrier()
+        self.map = QubitMap(self.nq, g)
+        self.label = list(range(self.nq))
+        coeff = 1.0 + 0.0j
+        for q in range(g):
+            coeff *= complex(np.asarray(factors[q]).reshape(2)[(self.rank >> (g - 1 - q)) & 1])
+        self.shard.init_product([np.asarray(f, dtype=np.complex128).reshape(2) for f in factors[g:]], coeff)
 
     # -- gates ---------------------------------------------------------------------------------
     def _bit(self, q: int) -> int:
-        return self.nq - 1 - int(q)
+        return self.nq - 1 - self.label[int(q)]
+
+    def swap_qubits(self, a: int, b: int):
+        """genSwapGate (qbot/qgates.py:77-133) as a relabelling: later gates on qubit a act on what was b."""
+        self.label[a], self.label[b] = self.label[b], self.label[a]
+        return self
+
+    def apply_gate_qubits(self, matrix, qubits: Sequence[int], controls: Iterable[int] = ()):
+        """A gate on an arbitrary (not necessarily contiguous) list of qubits, qubits[0] = matrix MSB."""
+        m = np.asarray(matrix)
+        if m.shape != (1 << len(qubits), 1 << len(qubits)):
+            raise ValueError("matrix does not match the number of qubits")
+        self.queue.append(make_lgate(m, [self._bit(q) for q in qubits], [self._bit(c) for c in controls]))
+        return self
 
     def apply_gate(self, matrix, first_target: int = 0, controls: Iterable[int] = ()):
         m = np.asarray(matrix)
@@ -491,6 +536,7 @@ class ShardedKet:
         self.shard.sync()
         self.comm.barrier()
         self.map = QubitMap(self.nq, self.map.g)
+        self.label = list(range(self.nq))
         self.shard.init_basis(self.rank == 0, 0)
 
     # -- read-outs -----------------------------------------------------------------------------
@@ -525,8 +571,8 @@ class ShardedKet:
         out = np.zeros(2 * len(indices), dtype=np.float64)
         for x, idx in enumerate(indices):
             phys = 0
-            for b in range(self.nq):
-                phys |= ((idx >> b) & 1) << mp.pos[b]
+            for q in range(self.nq):
+                phys |= ((idx >> (self.nq - 1 - q)) & 1) << mp.pos[self._bit(q)]
             if (phys >> nl) == self.rank:
                 v = self.shard.download_range(phys & ((1 << nl) - 1), 1)[0]
                 out[2 * x], out[2 * x + 1] = v.real, v.imag
@@ -542,8 +588,34 @@ class ShardedKet:
         phys = np.concatenate([np.frombuffer(p, dtype=np.complex128) for p in parts])
         # phys index bit p holds logical bit at[p]
         t = phys.reshape([2] * n)                      # axis a <-> physical bit n-1-a
-        axes = [n - 1 - mp.pos[n - 1 - a] for a in range(n)]    # logical axis a takes physical axis
+        axes = [n - 1 - mp.pos[self._bit(q)] for q in range(n)]    # the caller's qubit q takes this physical axis
         return np.ascontiguousarray(t.transpose(axes)).reshape(-1)
+
+    def make_local(self, qubits: Sequence[int]):
+        """Exchange so that none of the listed qubits selects the rank (read-outs that need them local)."""
+        self.flush()
+        bits = [self._bit(q) for q in qubits]
+        if all(self.map.is_local(b) for b in bits):
+            return
+        w = 0
+        for b in bits:
+            w |= 1 << b
+        touch = LGate(np.eye(1 << len(bits), dtype=np.complex128), tuple(bits), (), w, 0)   # writes nothing, pins the bits
+        ex = self.map.plan_exchange([touch])
+        self.shard.flush()
+        self.shard.do_exchange(ex)
+
+    def reduced_density(self, qubits: Sequence[int]) -> np.ndarray:
+        """Tr_rest psi psi^dagger on the listed qubits (first listed = most significant): the qubits are
+        made local, every rank sums over its shard, one all-reduce adds the ranks."""
+        if len(qubits) > 10:
+            raise ValueError("reduced density of a sharded ket: at most 10 qubits")
+        self.make_local(qubits)
+        local = self.shard.rdm_local([self.map.pos[self._bit(q)] for q in qubits])
+        d = 1 << len(qubits)
+        flat = np.ascontiguousarray(np.asarray(local, dtype=np.complex128).reshape(-1)).view(np.float64)
+        out = self.comm.allreduce_sum(flat, self.shard.reduce_device())
+        return np.ascontiguousarray(out).view(np.complex128).reshape(d, d)
 
     def close(self):
         self.shard.close()

@@ -78,6 +78,20 @@ class NumpyShard:
         if has_one:
             self.psi[local_index] = 1
 
+    def init_product(self, local_factors, coeff):
+        v = np.array([coeff], dtype=complex)
+        for f in local_factors:
+            v = np.kron(v, np.asarray(f, dtype=complex).reshape(2))
+        self.psi = v
+
+    def rdm_local(self, positions):
+        nl = self.nl
+        t = self.psi.reshape([2] * nl)                       # axis a <-> local bit nl-1-a
+        keep = [nl - 1 - p for p in positions]
+        rest = [a for a in range(nl) if a not in keep]
+        m = np.ascontiguousarray(t.transpose(keep + rest)).reshape(1 << len(keep), -1)
+        return m @ m.conj().T
+
     def apply(self, m, tpos, cmask):
         self.psi = np_apply_bits(self.psi, self.nl, np.asarray(m), list(tpos), cmask)
         self.applied += 1

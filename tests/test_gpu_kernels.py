@@ -100,6 +100,48 @@ def test_large_gates_fallback(DS):
         assert close(np.asarray(st), orc.ket_apply(psi, n, t, g, [n - 1] if t + k < n else [])), (n, k)
 
 
+@pytest.mark.parametrize('fusion', [False, True])
+def test_dense_blocks_on_the_tensor_cores(DS, fusion):
+    """Row f3: dense 6..8-qubit blocks (qftGate(k), user unitaries; qbot/qgates.py:63-74, 161-182) run as a
+    complex GEMM on the FP64 tensor cores (k_dense_mma) once the register has 12 free index bits."""
+    from qbot_b200.host import hostmath as hm
+    rng = np.random.default_rng(33)
+    used = 0
+    for n, k in ((12, 6), (13, 6), (14, 7), (15, 8), (16, 6), (16, 8)):
+        for t in sorted(set([0, (n - k) // 2, n - k])):
+            for g in (rand_u(rng, k), hm.qft(k)):
+                psi = rand_ket(rng, n)
+                free = [q for q in range(n) if q < t or q >= t + k]
+                nc = int(rng.integers(0, 3))
+                controls = [int(c) for c in rng.choice(free, size=nc, replace=False)] if nc and n - k - nc >= 12 - k else []
+                st = DS.from_host(psi)
+                st.set_fusion(fusion)
+                st.reset_stats()
+                st.apply_gate(g, t, controls)
+                got = np.asarray(st)
+                assert close(got, orc.ket_apply(psi, n, t, g, controls)), (n, k, t, controls)
+                used += 1
+    assert used
+    # density matrix: U on the row bits, conj(U) on the column bits of vec(rho)
+    n, k, t = 8, 6, 1
+    rho = rand_dm(rng, n)
+    g = rand_u(rng, k)
+    sd = DS.from_host(rho)
+    sd.set_fusion(fusion)
+    sd.apply_gate(g, t, [])
+    assert close(np.asarray(sd), orc.dm_apply(rho, n, t, g, []))
+    # branch batch: the same block on every branch ket
+    nb, n, k, t = 3, 13, 7, 2
+    kets = np.stack([rand_ket(rng, n) for _ in range(nb)])
+    sb = DS.from_kets(kets)
+    sb.set_fusion(fusion)
+    g = rand_u(rng, k)
+    sb.apply_gate(g, t, [0])
+    out = np.asarray(sb).reshape(nb, -1)
+    for b in range(nb):
+        assert close(out[b], orc.ket_apply(kets[b], n, t, g, [0])), b
+
+
 def test_swap(DS):
     rng = np.random.default_rng(4)
     for n in (2, 5, 9):

@@ -220,3 +220,115 @@ def test_gloo_world_size_2():
         assert np.max(np.abs(ket - want)) < 1e-12
         assert np.max(np.abs(pr - orc.ket_probs(want, n, [0, n - 1]))) < 1e-12
         assert exch >= 1
+
+
+# ---------------------------------------------------------------------------------------------
+# the sharded ket behind the DSL ops (qbot_b200/sharded_register.py): `qset` of a large product ket
+# under one-process-per-rank gives a sharded register that gate / swap / peek drive
+# ---------------------------------------------------------------------------------------------
+SHARDED_PROGRAM_N = 16      # tensorExp(.., 14) is the smallest product the DSL keeps as a descriptor (hostmath.LAZY_MIN_QUBITS)
+
+
+def sharded_program(n):
+    gates = circuits.rc(n, 3, 5)
+    lines = [f"qset tensorProd(hadamard.kets[0], tensorExp(comp.kets[0], {n - 2}), comp.kets[1])"]
+    ops = []
+    for i, g in enumerate(gates):
+        lines.append(g.dsl())
+        ops.append((g.matrix(), g.target, list(g.controls)))
+        if i == len(gates) // 2:
+            lines.append("swap 1 ; 9")
+            ops.append(('swap', 1, 9))
+    lines.append(f"peek r ; comp ; [0, 5, {n - 1}]")
+    lines.append("peek b ; bell ; [3, 0]")
+    lines.append(f"peek h ; hadamard ; [{n - 2}]")
+    lines.append("cdef rho_a ; r.unMeasuredDensity")
+    return "\n".join(lines) + "\n", ops
+
+
+def expected_sharded_program(n, ops):
+    plus = np.array([1, 1], dtype=complex) / np.sqrt(2)
+    psi = np.array([1], dtype=complex)
+    for f in [plus] + [np.array([1, 0], dtype=complex)] * (n - 2) + [np.array([0, 1], dtype=complex)]:
+        psi = np.kron(psi, f)
+    for op in ops:
+        psi = orc.ket_swap(psi, n, op[1], op[2]) if isinstance(op[0], str) else orc.ket_apply(psi, n, op[1], op[0], op[2])
+    return psi
+
+
+def _register_worker(rank, world, n, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+    import qbot_b200
+    from qbot_b200 import sharded_register as sr
+    from qbot_b200.sharded import TorchComm
+    from np_shard import NumpyShard
+    from fake_backend import FakeState
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        sr.enable(TorchComm(), shard_factory=NumpyShard, min_qubits=n)
+        text, _ = sharded_program(n)
+        ns = qbot_b200.executeTxt(text, state_cls=FakeState)
+        reg = ns['state']
+        out = dict(kind=type(reg).__name__, r=list(ns['r'].probs), b=list(ns['b'].probs), h=list(ns['h'].probs),
+                   rho_a=np.asarray(ns['rho_a']), ket=np.asarray(reg), exchanges=reg.stats()['exchanges'])
+        # a second program on a fresh interpreter reuses the shards of the dropped register
+        del ns, reg
+        ns2 = qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\ngate hadamardGate ; 0\ngate pauliXGate ; {n - 1} ; [0]\npeek p ; comp ; [0, {n - 1}]\n",
+                                   state_cls=FakeState)
+        out['p2'] = list(ns2['p'].probs)
+        out['err'] = None
+        try:
+            qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\ngate hadamardGate ; 0 ; [] ; ProbVal([.5, .5], [True, False])\n", state_cls=FakeState)
+        except SystemExit:
+            out['err'] = 'exit'
+        q.put((rank, out))
+    except BaseException as e:      # noqa: BLE001  (a formatted DSL error ends in sys.exit(): report it instead of hanging the parent)
+        q.put((rank, dict(failed=f"{type(e).__name__}: {e}")))
+        raise
+    finally:
+        sr.disable()
+        dist.destroy_process_group()
+
+
+def test_sharded_register_behind_the_dsl_ops_gloo():
+    import torch.multiprocessing as mp
+    n, world = SHARDED_PROGRAM_N, 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_register_worker, args=(r, world, n, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _, ops = sharded_program(n)
+    psi = expected_sharded_program(n, ops)
+    from qbot_b200.host import hostmath as hm
+
+    def weights(targets, basis):
+        w = orc.basis_weights(psi, n, sorted(targets), basis.kets)
+        w = w / w.sum()
+        return [round(float(x / w.sum()), 15) for x in w]
+
+    want_r = dict(probs=weights([0, 5, n - 1], hm.computation))
+    want_b = dict(probs=weights([3, 0], hm.bell))
+    want_h = dict(probs=weights([n - 2], hm.hadamard))
+    t = psi.reshape([2] * n)
+    keep = [0, 5, n - 1]
+    mm = np.ascontiguousarray(t.transpose(keep + [a for a in range(n) if a not in keep])).reshape(8, -1)
+    want_r['rho_a'] = mm @ mm.conj().T
+    for rank, out in got:
+        assert 'failed' not in out, out
+        assert out['kind'] == 'ShardedRegister'
+        assert np.max(np.abs(out['ket'] - psi)) < 1e-12
+        for key, want in (('r', want_r), ('b', want_b), ('h', want_h)):
+            assert np.max(np.abs(np.array(out[key]) - np.array(want['probs']))) < 1e-12, key
+        assert np.max(np.abs(out['rho_a'] - want_r['rho_a'])) < 1e-12
+        assert out['p2'] == [0.5, 0.0, 0.0, 0.5]
+        assert out['err'] == 'exit'          # a ProbVal condition leaves a mixed state: refused on a sharded ket, formatted error
