@@ -296,13 +296,25 @@ def run_single_gpu(args):
     achieved = dom_bytes / avg_launch_s / 1e9
     unfused_equiv = alg_bytes * args.steps / secs / 1e9
 
-    traffic = None
-    try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
-        if stats['jit_passes'] > 0 and str(n) in tj.get('qj_kernel', {}):
-            traffic = tj['qj_kernel'][str(n)]['dram_bytes_per_launch']
-    except Exception:
-        pass
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of THIS kernel set:
+    # the capture is looked up by the hash of the specialised sweeps' generated sources (one step's launches,
+    # qb_stats.jit_kernel_hash); a capture of another generator version is refused (traffic = null, reason stated)
+    traffic, traffic_src, kernel_set = None, None, None
+    if stats['jit_passes'] > 0:
+        st.reset_stats()
+        apply_circuit(st, gates, mats)
+        st.sync()
+        kernel_set = f"{st.stats()['jit_kernel_hash']:016x}"
+        try:
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
+            rec = tj.get('qj_kernel', {}).get(kernel_set)
+            if rec is not None and rec.get('qubits') == n:
+                traffic, traffic_src = rec['dram_bytes_per_launch'], rec.get('source')
+            else:
+                traffic_src = "no committed ncu capture of this kernel set (profiles/r02_traffic.json holds: " + \
+                    ", ".join(sorted(tj.get('qj_kernel', {}))) + ")"
+        except Exception as e:       # noqa: BLE001
+            traffic_src = f"profiles/r02_traffic.json unreadable: {e}"
 
     out = {
         "metric": "gates/sec", "value": value, "unit": "gates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -319,6 +331,7 @@ def run_single_gpu(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                     "traffic_source": traffic_src, "kernel_set": kernel_set,
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "kernel": dom_kernel, "per_launch": dom_unit, "launches": dom_launches,
                      "avg_launch_ms": 1e3 * avg_launch_s, "peak_source": peak_src,

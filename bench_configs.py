@@ -187,7 +187,9 @@ def run_c2(steps: int, warmup: int, cpu: bool = True):
     import qbot_b200
     qs = [0, 7, 13, 19]
     script = "\n".join([f"qset tensorExp(comp.kets[0], {n})"] + [g.dsl() for g in gates] + [f"peek r ; comp ; {qs}"])
-    ns = qbot_b200.executeTxt(script)
+    for _ in range(3):
+        ns = qbot_b200.executeTxt(script)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
         _flush_l2(torch, junk)
@@ -307,17 +309,27 @@ def run_c3(steps: int, warmup: int, cpu: bool = True, cpu_budget_s: float = 20.0
         ms.append(clock.timer_stop())
     secs = sum(ms) / 1e3
     final_dev = np.asarray(st)
-    # e2e = the call a user of the reference makes: executeTxt(program).  `qset tensorExp(comp[0], 12)`
-    # builds the 256 MiB rho_0 on the HOST (the reference's kron chain) and uploads it; the final 8-qubit
-    # register and every measurement's weights come back to the host.
-    ns = qbot_b200.executeTxt(program)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        _flush_l2(torch, junk)
+    # e2e = the call a user of the reference makes: executeTxt(program).  `qset tensorExp(comp[0], 12)` is a
+    # product descriptor built on the device (host -> device: the per-qubit factors and every gate matrix); the
+    # final 8-qubit register and every measurement's weights / rho_A come back to the host.
+    from qbot_b200 import _lib as _l
+    for i in range(8):          # warm-up: the program's sweeps are specialised (NVRTC) when it is seen again; none of that is timed
+        c0 = _l.jit_info()['kernels_compiled']
         ns = qbot_b200.executeTxt(program)
         final = np.asarray(ns['state'])
+        if i >= 2 and _l.jit_info()['kernels_compiled'] == c0:
+            break
     torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / steps
+    e2e_s = 0.0
+    for _ in range(steps):
+        _flush_l2(torch, junk)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ns = qbot_b200.executeTxt(program)
+        final = np.asarray(ns['state'])
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+    e2e_s /= steps
     # parity, in run: (i) the DSL path and the direct path agree; (ii) config 3 at n = 8 against the
     # oracle's restatement of the reference (register + every measurement's weights)
     from oracle import qbot_oracle as orc
@@ -356,9 +368,11 @@ def run_c3(steps: int, warmup: int, cpu: bool = True, cpu_budget_s: float = 20.0
                      "note": "UN-FUSED algorithmic bytes (32*4^n*2^-c per gate) over the step time: exceeds 1 when the fused "
                              "engine applies several gates per pass over rho"},
         "e2e": {"value": ngates / e2e_s, "unit": "gates/s", "ms_per_step": 1e3 * e2e_s,
-                "h2d_bytes_per_step": int(dm_bytes + 64 * ngates), "d2h_bytes_per_step": int(final.nbytes + 32 * nmeas),
-                "what": "qbot_b200.executeTxt(config-3 program): host kron chain for rho_0 + upload, gates / meas / disc on the device, "
-                        "final register + measurement weights back on the host"},
+                "h2d_bytes_per_step": int(64 * n + 64 * ngates + 32 * nmeas), "d2h_bytes_per_step": int(final.nbytes + (32 + 256) * nmeas),
+                "what": "qbot_b200.executeTxt(config-3 program) on a fresh interpreter: rho_0 from its per-qubit factors (device-side "
+                        "constructor), one line per gate / meas / ProbVal gate / disc (host matrices -> C ABI), every measurement's weights "
+                        "and rho_A and the final 8-qubit register back on the host; wall clock per call, L2 flushed between calls, "
+                        "specialised sweeps compiled during warm-up"},
         "parity_check": {"status": "pass" if ok else "FAIL", "oracle_c3_n8_state_max_rel_err": err8, "oracle_c3_n8_probs_max_abs_err": perr8,
                          "dsl_vs_direct_n12_max_rel_err": err_paths, "trace": [tr.real, tr.imag], "hermiticity": herm, "tolerance": 1e-12},
     }
@@ -405,11 +419,17 @@ def run_c4(steps: int, warmup: int, cpu: bool = True):
         s2 = DeviceState.product_batch(factors)
         return body(s2)
 
-    e2e_step()
+    from qbot_b200 import _lib as _l
+    for i in range(8):          # specialised sweeps of the fresh-register variant are compiled here, not in the timed calls
+        c0 = _l.jit_info()['kernels_compiled']
+        e2e_step()
+        if i >= 1 and _l.jit_info()['kernels_compiled'] == c0:
+            break
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
         pe = e2e_step()
+    torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / steps
     # parity: sampled branches of a fresh run against the oracle's ket path
     worst = 0.0

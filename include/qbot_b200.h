@@ -53,6 +53,8 @@ typedef struct {
     uint64_t fused_gates;       /* gates executed inside fused sweeps */
     uint64_t bytes_moved;       /* bytes the launched kernels were asked to read + write */
     uint64_t jit_passes;        /* fused sweeps run by a structure-specialised (NVRTC) kernel */
+    uint64_t jit_kernel_hash;   /* sum (mod 2^64) of the source hashes of those kernels, one term per launch:
+                                   identifies the kernel set a measurement (ncu capture, bench line) was taken on */
 } qb_stats;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -200,6 +202,28 @@ int qb_ipc_close(int device, void* dev);
  * chunk number, which makes concurrent ranks follow a pairwise-exchange schedule -- no two of
  * them store to the same peer at the same time. */
 int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst, int first_chunk);
+/* The same pass over a SUB-BLOCK of the source, on a stream of the caller's: the source index bits of
+ * `src_fixed_mask` are held at `src_fixed_value`, the other ndst_bits = nbits - popcount(mask) bits are
+ * permuted as above (src_bit_of_dst_bit has ndst_bits entries; chunks are 2^(ndst_bits - chunk_bits)
+ * amplitudes).  Lets a global-qubit exchange be issued in pieces that overlap with the sweeps of the
+ * pieces already delivered (qbot_b200/sharded.py).  cuda_stream NULL = the handle's stream; otherwise the
+ * caller orders that stream against the handle's work with events (qb_compute_stream). */
+int qb_permute_scatter_sub(qb_state* s, const int* src_bit_of_dst_bit, int ndst_bits, uint64_t src_fixed_mask, uint64_t src_fixed_value,
+                           int chunk_bits, void* const* chunk_dst, int first_chunk, void* cuda_stream, int max_ctas);
+/* max_ctas > 0 caps the grid (256-thread CTAs), so that the kernel leaves SM slots to sweeps running beside it.
+ * qb_set_sm_limit is the other half: the handle's sweeps size their persistent grids for nsms SMs (0 = all). */
+int qb_set_sm_limit(qb_state* s, int nsms);
+/* Stream-ordered signals between the GPUs of a box.  `flags` are 8-byte counters in device memory, local or
+ * peer-mapped (qb_buffer_alloc + qb_ipc_export / qb_ipc_open; zero them once).  qb_signal_flags stores `value`
+ * into each of them after everything queued earlier on `cuda_stream` (NULL = the compute stream) has completed;
+ * qb_wait_flags holds `cuda_stream` until every listed counter is >= value (bounded: after ~10 s the wait gives
+ * up and qb_flag_timeouts counts it -- a lost peer must not hang the GPU). */
+int qb_signal_flags(int device, void* cuda_stream, void* const* flags, int n, uint64_t value);
+int qb_wait_flags(int device, void* cuda_stream, void* const* flags, int n, uint64_t value);
+int qb_flag_timeouts(int device, uint64_t* count);
+/* The CUDA stream every handle of `device` works on unless it was given one of its own
+ * (qb_create_external / qb_set_stream): for event-ordering foreign streams against the library's work. */
+int qb_compute_stream(int device, void** cuda_stream_out);
 
 /* ---- instrumentation ------------------------------------------------------------------- */
 int qb_get_stats(const qb_state* s, qb_stats* out);

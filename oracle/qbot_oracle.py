@@ -438,6 +438,38 @@ def ket_apply(psi: np.ndarray, n: int, t: int, g: np.ndarray, controls: Sequence
     return out.reshape(-1)
 
 
+def ket_apply_inplace(psi: np.ndarray, n: int, t: int, g: np.ndarray, controls: Sequence[int] = ()) -> np.ndarray:
+    """ket_apply for registers of 2^26 and more amplitudes: the same two products and one sum per output
+    amplitude, on strided views of `psi` itself (a complex128 array that is overwritten) -- no full-size
+    temporaries.  1-qubit gates only; larger blocks go through ket_apply.  Checked against ket_apply in the
+    CPU tests."""
+    g = np.asarray(g, dtype=C128)
+    if g.shape != (2, 2):
+        psi[...] = ket_apply(psi, n, t, g, controls)
+        return psi
+    if t < 0 or t >= n:
+        raise IndexError("gate does not fit")
+    T = psi.reshape((2,) * n)
+    sl = [slice(None)] * n
+    for c in controls:
+        sl[c] = 1
+    s0, s1 = list(sl), list(sl)
+    s0[t], s1[t] = 0, 1
+    a0, a1 = T[tuple(s0)], T[tuple(s1)]
+    if g[0, 1] == 0 and g[1, 0] == 0:
+        if g[0, 0] != 1:
+            a0 *= g[0, 0]
+        if g[1, 1] != 1:
+            a1 *= g[1, 1]
+        return psi
+    n0 = g[0, 0] * a0
+    n0 += g[0, 1] * a1
+    a1 *= g[1, 1]
+    a1 += g[1, 0] * a0
+    a0[...] = n0
+    return psi
+
+
 def ket_swap(psi: np.ndarray, n: int, a: int, b: int) -> np.ndarray:
     return np.array(psi, dtype=C128).reshape((2,) * n).swapaxes(a, b).reshape(-1).copy()
 

@@ -10,7 +10,8 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'lts__t_sector_hit_rate.pct', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores', 'sass__inst_executed_shared_loads', 'sass__inst_executed_shared_stores',
         'sass__inst_executed_global_loads', 'sass__inst_executed_global_stores']
-rows = list(csv.reader(subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout.splitlines()))
+text = open(sys.argv[1]).read() if sys.argv[1].endswith('.csv') else subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(text.splitlines()))
 hdr = rows[0]
 for i, h in enumerate(hdr):
     if h in KEYS or h == 'Kernel Name' or ('issue_stalled' in h and 'per_issue_active' in h and 'pcsamp' not in h):

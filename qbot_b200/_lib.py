@@ -19,7 +19,7 @@ c_state_p = C.c_void_p
 class QbStats(C.Structure):
     _fields_ = [('kernel_launches', C.c_uint64), ('gates_applied', C.c_uint64), ('state_passes', C.c_uint64),
                 ('fused_passes', C.c_uint64), ('fused_gates', C.c_uint64), ('bytes_moved', C.c_uint64),
-                ('jit_passes', C.c_uint64)]
+                ('jit_passes', C.c_uint64), ('jit_kernel_hash', C.c_uint64)]
 
 
 class QbotB200Error(RuntimeError):
@@ -77,6 +77,12 @@ PROTOTYPES = {
     'qb_ipc_open': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     'qb_ipc_close': (C.c_int, [C.c_int, C.c_void_p]),
     'qb_permute_scatter': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p), C.c_int]),
+    'qb_permute_scatter_sub': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int]),
+    'qb_set_sm_limit': (C.c_int, [c_state_p, C.c_int]),
+    'qb_signal_flags': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint64]),
+    'qb_wait_flags': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint64]),
+    'qb_flag_timeouts': (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
+    'qb_compute_stream': (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     'qb_get_stats': (C.c_int, [c_state_p, C.POINTER(QbStats)]),
     'qb_reset_stats': (C.c_int, [c_state_p]),
     'qb_timer_start': (C.c_int, [c_state_p]),

@@ -1117,19 +1117,23 @@ int qb_ipc_close(int device, void* dev) {
     QB_API_END
 }
 
-int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst, int first_chunk) {
+int qb_permute_scatter_sub(qb_state* s, const int* src_bit_of_dst_bit, int ndst_bits, uint64_t src_fixed_mask, uint64_t src_fixed_value,
+                           int chunk_bits, void* const* chunk_dst, int first_chunk, void* cuda_stream, int max_ctas) {
     QB_API_BEGIN
     QB_REQUIRE(s && src_bit_of_dst_bit && chunk_dst, "NULL argument");
     QB_REQUIRE(first_chunk >= 0 && first_chunk < (1 << chunk_bits), "permute_scatter: first_chunk out of range");
-    QB_REQUIRE(s->nbits - chunk_bits >= 8, "permute_scatter: chunks must hold at least 256 amplitudes");
+    QB_REQUIRE(ndst_bits >= 0 && ndst_bits <= s->nbits, "permute_scatter: bad number of destination bits");
+    QB_REQUIRE(ndst_bits - chunk_bits >= 8, "permute_scatter: chunks must hold at least 256 amplitudes");
     QB_REQUIRE(s->kind == QB_KET && s->nbranch == 1, "permute_scatter: single-branch kets only");
-    QB_REQUIRE(chunk_bits >= 0 && chunk_bits <= 4 && chunk_bits <= s->nbits, "permute_scatter: chunk_bits must be 0..4");
+    QB_REQUIRE(chunk_bits >= 0 && chunk_bits <= 4 && chunk_bits <= ndst_bits, "permute_scatter: chunk_bits must be 0..4");
+    QB_REQUIRE(__builtin_popcountll(src_fixed_mask) == s->nbits - ndst_bits && (src_fixed_value & ~src_fixed_mask) == 0 &&
+               (s->nbits >= 64 || (src_fixed_mask >> s->nbits) == 0), "permute_scatter: the fixed source bits do not complete the destination bits");
     s->flush();
     DevGuard g(s->device);
     PermArgs a;
     memset(&a, 0, sizeof(a));
-    uint64_t seen = 0;
-    for (int d = 0; d < s->nbits; d++) {
+    uint64_t seen = src_fixed_mask;
+    for (int d = 0; d < ndst_bits; d++) {
         const int f = src_bit_of_dst_bit[d];
         QB_REQUIRE(f >= 0 && f < s->nbits && !((seen >> f) & 1ull), "permute_scatter: not a permutation of the index bits");
         seen |= 1ull << f;
@@ -1140,8 +1144,9 @@ int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bit
         }
     }
     a.in = s->d;
-    a.total = s->per_branch();
-    a.chunk_shift = s->nbits - chunk_bits;
+    a.src_or = src_fixed_value;
+    a.total = 1ull << ndst_bits;
+    a.chunk_shift = ndst_bits - chunk_bits;
     a.chunk_bits = chunk_bits;
     a.unit_bits = std::min(12, a.chunk_shift);
     a.first_chunk = first_chunk;
@@ -1150,10 +1155,84 @@ int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bit
         QB_REQUIRE(chunk_dst[c] != (void*)s->d, "permute_scatter: destination aliases the source");
         a.dst[c] = (cplx*)chunk_dst[c];
     }
-    qb_launch_permute_scatter(s->ctx(), a);
+    LaunchCtx ctx = s->ctx();
+    if (cuda_stream) ctx.stream = (cudaStream_t)cuda_stream;      // the caller orders this stream against the handle's (events)
+    qb_launch_permute_scatter(ctx, a, max_ctas);
     QB_CUDA(cudaGetLastError());
-    s->stats.bytes_moved += s->bytes() * 2;
-    s->stats.state_passes++;
+    s->stats.bytes_moved += (16ull << ndst_bits) * 2;
+    if (ndst_bits == s->nbits) s->stats.state_passes++;
+    QB_API_END
+}
+
+int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst, int first_chunk) {
+    if (!s) { g_err = "NULL argument"; return QB_ERR_ARG; }
+    return qb_permute_scatter_sub(s, src_bit_of_dst_bit, s->nbits, 0, 0, chunk_bits, chunk_dst, first_chunk, nullptr, 0);
+}
+
+int qb_set_sm_limit(qb_state* s, int nsms) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    s->flush();
+    const int all = sm_count_of(s->device);
+    s->sms = (nsms > 0 && nsms < all) ? nsms : all;
+    QB_API_END
+}
+
+static unsigned long long* flag_timeouts(int device) {
+    static std::mutex mu;
+    static std::map<int, unsigned long long*>& m = *new std::map<int, unsigned long long*>;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = m.find(device);
+    if (it != m.end()) return it->second;
+    unsigned long long* p = nullptr;
+    QB_CUDA(cudaMalloc((void**)&p, sizeof(unsigned long long)));
+    QB_CUDA(cudaMemset(p, 0, sizeof(unsigned long long)));
+    m[device] = p;
+    return p;
+}
+
+int qb_signal_flags(int device, void* cuda_stream, void* const* flags, int n, uint64_t value) {
+    QB_API_BEGIN
+    QB_REQUIRE(flags && n >= 0 && n <= QB_FLAG_MAXPEERS, "signal_flags: 0..16 flag pointers");
+    DevGuard g(device);
+    FlagPtrs f;
+    memset(&f, 0, sizeof(f));
+    f.n = n;
+    for (int i = 0; i < n; i++) { QB_REQUIRE(flags[i], "signal_flags: NULL flag"); f.p[i] = (unsigned long long*)flags[i]; }
+    if (n) qb_launch_signal_flags(cuda_stream ? (cudaStream_t)cuda_stream : default_stream(device), f, value);
+    QB_CUDA(cudaGetLastError());
+    QB_API_END
+}
+
+int qb_wait_flags(int device, void* cuda_stream, void* const* flags, int n, uint64_t value) {
+    QB_API_BEGIN
+    QB_REQUIRE(flags && n >= 0 && n <= QB_FLAG_MAXPEERS, "wait_flags: 0..16 flag pointers");
+    DevGuard g(device);
+    FlagPtrs f;
+    memset(&f, 0, sizeof(f));
+    f.n = n;
+    for (int i = 0; i < n; i++) { QB_REQUIRE(flags[i], "wait_flags: NULL flag"); f.p[i] = (unsigned long long*)flags[i]; }
+    if (n) qb_launch_wait_flags(cuda_stream ? (cudaStream_t)cuda_stream : default_stream(device), f, value, flag_timeouts(device));
+    QB_CUDA(cudaGetLastError());
+    QB_API_END
+}
+
+int qb_flag_timeouts(int device, uint64_t* count) {
+    QB_API_BEGIN
+    QB_REQUIRE(count, "NULL argument");
+    DevGuard g(device);
+    unsigned long long v = 0;
+    QB_CUDA(cudaMemcpy(&v, flag_timeouts(device), sizeof(v), cudaMemcpyDeviceToHost));
+    *count = v;
+    QB_API_END
+}
+
+int qb_compute_stream(int device, void** cuda_stream_out) {
+    QB_API_BEGIN
+    QB_REQUIRE(cuda_stream_out, "NULL argument");
+    QB_REQUIRE(device >= 0 && device < device_count_cached(), "no such CUDA device");
+    DevGuard g(device);
+    *cuda_stream_out = (void*)default_stream(device);
     QB_API_END
 }
 

@@ -161,6 +161,7 @@ struct PermArgs {
     cplx* dst[QB_PERM_MAXCHUNK];  // destination of chunk c (local buffer or a peer mapping)
     uint64_t total;               // amplitudes of the shard
     uint64_t fixed_mask;          // index bits that keep their position
+    uint64_t src_or;              // source index bits that are constant for this launch (a sub-block of the source)
     int chunk_shift;              // nbits - chunk_bits
     int chunk_bits;
     int unit_bits;                // 2^unit_bits consecutive destination amplitudes per work unit (8..12)
@@ -196,5 +197,9 @@ void qb_launch_scatter(const LaunchCtx&, const ScatterArgs& a, uint32_t* tables_
 void qb_launch_mix(const LaunchCtx&, const MixArgs& a);
 void qb_launch_mix_branches(const LaunchCtx&, const cplx* src, const double* probs_dev, int64_t nbranch, uint64_t per_branch, cplx* out);
 void qb_launch_outer(const LaunchCtx&, const cplx* ket, cplx* out, int nq, int conj);
-void qb_launch_permute_scatter(const LaunchCtx&, const PermArgs& a);
+void qb_launch_permute_scatter(const LaunchCtx&, const PermArgs& a, int max_ctas = 0);
+#define QB_FLAG_MAXPEERS 16
+struct FlagPtrs { unsigned long long* p[QB_FLAG_MAXPEERS]; int n; };
+void qb_launch_signal_flags(cudaStream_t stream, const FlagPtrs& f, unsigned long long value);
+void qb_launch_wait_flags(cudaStream_t stream, const FlagPtrs& f, unsigned long long value, unsigned long long* timeouts);
 void qb_launch_project(const LaunchCtx&, cplx* psi, uint64_t total, uint64_t mask, uint64_t want, double scale);

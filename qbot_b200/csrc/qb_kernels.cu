@@ -740,7 +740,7 @@ __global__ void __launch_bounds__(256) k_permute_scatter(PermArgs a) {
     for (uint64_t w = blockIdx.x; w < nunits; w += gridDim.x) {
         const uint64_t c = (w & cmask) ^ (uint64_t)a.first_chunk;
         const uint64_t o = (w >> k) << ub;                      // offset of the unit inside its chunk
-        const uint64_t ubase = perm_bits(a, (c << a.chunk_shift) | o);
+        const uint64_t ubase = perm_bits(a, (c << a.chunk_shift) | o) | a.src_or;
         cplx* __restrict__ out = a.dst[c] + o + threadIdx.x;
         cplx v[16];
 #pragma unroll
@@ -750,7 +750,48 @@ __global__ void __launch_bounds__(256) k_permute_scatter(PermArgs a) {
     }
 }
 
-void qb_launch_permute_scatter(const LaunchCtx& c, const PermArgs& a) {
-    k_permute_scatter<<<grid_for(c, a.total >> 4, 256, 4), 256, 0, c.stream>>>(a);
+void qb_launch_permute_scatter(const LaunchCtx& c, const PermArgs& a, int max_ctas) {
+    int grid = grid_for(c, a.total >> 4, 256, 4);
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;      // leave the other SM slots to the sweeps this exchange overlaps with
+    k_permute_scatter<<<grid, 256, 0, c.stream>>>(a);
     COUNT_LAUNCH(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stream-ordered signals between the GPUs of a box (pieces of a pipelined global-qubit exchange):
+// after a piece's stores to the peers have completed (stream order: the scatter kernel has ended, so
+// its writes are acknowledged), the sender raises a counter in every receiver's flag block; the
+// receiver's compute stream waits (one polling warp, bounded) until all its sources have raised
+// theirs, and only then runs the sweeps that read the piece.  The flag blocks are peer-mapped device
+// memory (CUDA IPC), like the shard buffers.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_signal_flags(FlagPtrs f, unsigned long long value) {
+    const int i = threadIdx.x;
+    if (i < f.n) {
+        __threadfence_system();
+        *(volatile unsigned long long*)f.p[i] = value;
+        __threadfence_system();
+    }
+}
+
+__global__ void k_wait_flags(FlagPtrs f, unsigned long long value, unsigned long long* timeouts) {
+    const int i = threadIdx.x;
+    if (i < f.n) {
+        const long long t0 = clock64();
+        volatile unsigned long long* p = (volatile unsigned long long*)f.p[i];
+        bool ok = false;
+        while (!(ok = *p >= value)) {
+            if (clock64() - t0 > 20000000000ll) break;        // ~10 s: a peer died; fail (counted) instead of hanging the GPU
+            __nanosleep(500);
+        }
+        __threadfence_system();
+        if (!ok && timeouts) atomicAdd(timeouts, 1ull);
+    }
+}
+
+void qb_launch_signal_flags(cudaStream_t stream, const FlagPtrs& f, unsigned long long value) {
+    k_signal_flags<<<1, 32, 0, stream>>>(f, value);
+}
+void qb_launch_wait_flags(cudaStream_t stream, const FlagPtrs& f, unsigned long long value, unsigned long long* timeouts) {
+    k_wait_flags<<<1, 32, 0, stream>>>(f, value, timeouts);
 }

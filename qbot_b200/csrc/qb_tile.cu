@@ -481,6 +481,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
             if (plan->R != QT_R && !j.ready) throw qb_error(-2, "no specialised kernel for a 32-amplitudes-per-thread sweep");
             qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_jit_prefetch(), j.pool.data(), j.pool_dev);
             s->stats.jit_passes++;
+            s->stats.jit_kernel_hash += j.key;
         } else {
             if (plan->R != QT_R) throw qb_error(-2, "the generic sweep kernel cannot run a 32-amplitudes-per-thread plan");
             const uint8_t* prog = plan->dev + plan->prog_off[i];

@@ -25,6 +25,7 @@ reference cannot represent.  Everything in this file is host logic; device work 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from dataclasses import dataclass
 from typing import Iterable, List, Optional, Sequence, Tuple
@@ -102,10 +103,16 @@ class Exchange:
     rank_bits[i]."""
     src_bit_of_dst_bit: List[int]
     rank_bits: List[int]
+    hbits: Tuple[int, ...] = ()     # logical bits parked at the top local positions: the sub-blocks of a pipelined exchange
 
     @property
     def k(self) -> int:
         return len(self.rank_bits)
+
+    @property
+    def split(self) -> int:
+        """v: the shard is exchanged in 2^v pieces (packed layout [v piece bits][k chunk bits][rest]); 0 = in one go"""
+        return len(self.hbits)
 
 
 class QubitMap:
@@ -126,8 +133,15 @@ class QubitMap:
                 m |= 1 << b
         return m
 
-    def plan_exchange(self, rem: Sequence[LGate]) -> Exchange:
-        """Choose the new rank bits (farthest next non-diagonal use) and update the map."""
+    def plan_exchange(self, rem: Sequence[LGate], split: int = 0, min_first_phase: int = 40) -> Exchange:
+        """Choose the new rank bits (farthest next non-diagonal use) and update the map.
+
+        split = v > 0 asks for a PIPELINED exchange: v further local bits -- the ones written last among the
+        gates that follow -- are parked at the top v local positions, so that the shard is 2^v contiguous
+        sub-blocks that (i) can be exchanged one after the other and (ii) can each run the gates that do not
+        write those v bits (for which they are predicates / scalars, like rank bits) as soon as their piece has
+        arrived, while the later pieces are still on the wire.  Declined (hbits = ()) when fewer than
+        min_first_phase gates could run that way."""
         n, nl, g = self.n, self.nl, self.g
         nxt = [INF] * n
         for i, gt in enumerate(rem):
@@ -155,33 +169,53 @@ class QubitMap:
         rank_bits = sorted(r for r in range(g) if self.at[nl + r] not in new_global)
         k = len(victims)
         assert k == len(rank_bits)
+        hbits: List[int] = []
+        if split > 0 and k and nl - k - split >= max(LOW_KEEP, 8):
+            for b in order:                     # farthest next write first
+                if b in new_global or self.pos[b] >= nl or self.pos[b] < LOW_KEEP or (head_w >> b) & 1:
+                    continue
+                hbits.append(b)
+                if len(hbits) == split:
+                    break
+            if len(hbits) == split:
+                allowed = 0
+                for b in range(n):
+                    if b not in new_global and b not in hbits:
+                        allowed |= 1 << b
+                if len(select_pass(rem, allowed)) < min_first_phase:
+                    hbits = []
+            else:
+                hbits = []
+        v = len(hbits)
         perm = list(range(nl))
         if k:
-            top = list(range(nl - k, nl))
-            vpos = [self.pos[b] for b in victims]
-            displaced = [p for p in top if p not in vpos]          # non-victims sitting in the top-k slots
-            vacated = [p for p in vpos if p not in top]            # victim slots outside the top-k
-            for i, p in enumerate(vpos):
-                perm[nl - k + i] = p
+            # packed layout, top down: [v parked bits][k outgoing bits][the rest]
+            top = list(range(nl - v - k, nl))
+            want = [self.pos[b] for b in victims] + [self.pos[b] for b in hbits]
+            displaced = [p for p in top if p not in want]          # others sitting in the top slots
+            vacated = [p for p in want if p not in top]            # wanted bits' slots outside the top
+            for i, p in enumerate(want):
+                perm[nl - v - k + i] = p
             for d, s in zip(vacated, displaced):
                 perm[d] = s
             # new map: pack first ...
             new_at = list(self.at)
             for d in range(nl):
                 new_at[d] = self.at[perm[d]]
-            # ... then the exchange swaps top-k local position i with rank bit rank_bits[i]
+            # ... then the exchange swaps chunk-index position i with rank bit rank_bits[i]
             for i, r in enumerate(rank_bits):
-                new_at[nl - k + i], new_at[nl + r] = new_at[nl + r], new_at[nl - k + i]
+                new_at[nl - v - k + i], new_at[nl + r] = new_at[nl + r], new_at[nl - v - k + i]
             self.at = new_at
             for p, b in enumerate(self.at):
                 self.pos[b] = p
-        return Exchange(perm, rank_bits)
+        return Exchange(perm, rank_bits, tuple(hbits))
 
-    def localise(self, g: LGate, rank: int):
+    def localise(self, g: LGate, rank: int, nl: Optional[int] = None):
         """The gate as this rank sees it: (matrix, local target positions, local control mask),
         or None when a rank-bit control is 0 here.  Block-diagonal target axes that sit on rank
-        bits are sliced by the rank's bit value."""
-        nl = self.nl
+        bits are sliced by the rank's bit value.  With nl < self.nl the top local positions count as
+        rank bits too (sub-blocks of a pipelined exchange: rank = (rank << v) | sub-block number)."""
+        nl = self.nl if nl is None else nl
         cmask = 0
         for c in g.controls:
             p = self.pos[c]
@@ -281,33 +315,192 @@ class CudaShard:
         self.state = DeviceState(h, KET, nl, 1)
         self.exchange_mode = exchange
         self.peer = None                      # peer[r][i] = mapping of rank r's buffer i
+        self.peer_flags = None                # peer_flags[r] = mapping of rank r's flag block (one 8-byte counter per source rank)
+        self.flags = C.c_void_p()
         self.exchanged_bytes = 0
         self.exchanges = 0
-        self.exchange_seconds = 0.0           # pack + transfer, measured between the two barriers
+        self.split_exchanges = 0
+        self.exchange_seconds = 0.0           # pack + transfer: between the two barriers, or (pipelined) first piece start -> last piece done on the exchange stream
+        self._pending_times = []              # (start event, end event) of pipelined exchanges not yet read
+        self._subs = {}                       # (buffer index, v, j) -> DeviceState of sub-block j
+        self._jit = None
+        self._xseq = 0                        # pieces signalled so far (same on every rank)
+        self._streams = None
+        # SM slots a pipelined exchange's scatter kernels may take (256-thread CTAs); the sweeps that run beside them
+        # size their persistent grids for the rest
+        self.exchange_ctas = int(os.environ.get('QBOT_B200_EXCHANGE_CTAS', '48'))
         if exchange == 'p2p' and comm.world > 1:
+            _lib.call('qb_buffer_alloc', device, 4096, C.byref(self.flags))
+            import torch
+            torch.as_tensor(_CudaArray(self.flags.value, 512), device=f'cuda:{device}').zero_()
+            torch.cuda.synchronize(device)
             self._open_peers()
         elif exchange not in ('p2p', 'nccl'):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
 
+    @property
+    def supports_split(self) -> bool:
+        return self.peer is not None
+
+    def timer_start(self):
+        self.state.timer_start()
+
+    def timer_stop(self) -> float:
+        return self.state.timer_stop()       # the compute stream: sub-block sweeps and the waits for the exchange pieces are on it
+
+    def reset_stats(self):
+        self.state.reset_stats()
+        for sub in self._subs.values():
+            sub.reset_stats()
+
+    def stats(self) -> dict:
+        """Counters of the shard handle plus those of the sub-block handles of pipelined exchanges; a sweep over
+        one of 2^v sub-blocks counts as 2^-v of a pass."""
+        out = {k: float(x) for k, x in self.state.stats().items()}
+        for (_, v, _), sub in self._subs.items():
+            st = sub.stats()
+            for key in ('state_passes', 'fused_passes', 'jit_passes'):
+                out[key] += st[key] / (1 << v)
+            for key in ('kernel_launches', 'gates_applied', 'fused_gates', 'bytes_moved'):
+                out[key] += st[key]
+        return out
+
+    def set_jit(self, mode: int):
+        self._jit = mode
+        self.state.set_jit(mode)
+        for sub in self._subs.values():
+            sub.set_jit(mode)
+
     def _open_peers(self):
         lib = self._lib
         handles = b''
-        for b in self.buf:
+        for b in self.buf + [self.flags]:
             hb = C.create_string_buffer(64)
             lib.call('qb_ipc_export', self.device, b, hb)
             handles += hb.raw
         allh = self.comm.allgather_bytes(handles)
-        self.peer = []
+        self.peer, self.peer_flags = [], []
         for r, hs in enumerate(allh):
             if r == self.comm.rank:
                 self.peer.append([self.buf[0].value, self.buf[1].value])
+                self.peer_flags.append(self.flags.value)
                 continue
             ptrs = []
-            for i in range(2):
+            for i in range(3):
                 p = C.c_void_p()
                 lib.call('qb_ipc_open', self.device, C.create_string_buffer(hs[64 * i:64 * i + 64], 64), C.byref(p))
                 ptrs.append(p.value)
-            self.peer.append(ptrs)
+            self.peer.append(ptrs[:2])
+            self.peer_flags.append(ptrs[2])
+
+    def _stream_pair(self):
+        """(compute stream of the library as a torch stream, high-priority exchange stream)"""
+        if self._streams is None:
+            import torch
+            p = C.c_void_p()
+            self._lib.call('qb_compute_stream', self.device, C.byref(p))
+            cs = torch.cuda.ExternalStream(p.value, device=f'cuda:{self.device}')
+            xs = torch.cuda.Stream(device=f'cuda:{self.device}', priority=-1)
+            tok = torch.zeros(1, dtype=torch.float32, device=f'cuda:{self.device}')
+            self._streams = (cs, xs, tok)
+        return self._streams
+
+    def _sub(self, buf_index: int, v: int, j: int):
+        key = (buf_index, v, j)
+        sub = self._subs.get(key)
+        if sub is None:
+            from .state import DeviceState, KET
+            h = C.c_void_p()
+            ptr = C.c_void_p(self.buf[buf_index].value + j * (self.bytes >> v))
+            self._lib.call('qb_create_external', C.byref(h), KET, self.nl - v, 1, self.device, ptr, None)
+            sub = DeviceState(h, KET, self.nl - v, 1)
+            if self._jit is not None:
+                sub.set_jit(self._jit)
+            sms = C.c_int(0)
+            self._lib.call('qb_device_info', self.device, None, 0, C.byref(sms), None, None, None)
+            self._lib.call('qb_set_sm_limit', sub._h, max(sms.value - (self.exchange_ctas + 1) // 2, 8))
+            self._subs[key] = sub
+        return sub
+
+    def do_exchange_split(self, ex: "Exchange", per_sub):
+        """The exchange in 2^v pieces on a stream of its own, each piece followed on the compute stream by the
+        sweeps of the gates `per_sub[j]` (localised for sub-block j) on that piece.  No host synchronisation:
+        pieces are ordered by events (local) and by flag counters in the receivers' memory (between GPUs)."""
+        import torch
+        lib, comm = self._lib, self.comm
+        k, v, nl = ex.k, ex.split, self.nl
+        Q, sub_bits = 1 << v, nl - v
+        rank = comm.rank
+        my_s = 0
+        for i, r in enumerate(ex.rank_bits):
+            my_s |= ((rank >> r) & 1) << i
+        sub_bytes = self.bytes >> v
+        chunk_bytes = sub_bytes >> k
+        other = 1 - self.cur
+
+        def peer_rank(c):
+            pr = rank
+            for i, r in enumerate(ex.rank_bits):
+                pr = (pr & ~(1 << r)) | (((c >> i) & 1) << r)
+            return pr
+
+        group = [peer_rank(c) for c in range(1 << k) if peer_rank(c) != rank]
+        cs, xs, tok = self._stream_pair()
+        perm = ex.src_bit_of_dst_bit
+        perm_sub = lib.int_array(perm[:sub_bits])
+        fixed_mask = 0
+        for i in range(v):
+            fixed_mask |= 1 << perm[sub_bits + i]
+        self.state.flush()
+        ready = torch.cuda.Event()
+        ready.record(cs)                       # the sweeps of the pass before the exchange
+        xs.wait_event(ready)
+        with torch.cuda.stream(xs):
+            # every rank is past everything that read or wrote the buffers about to be overwritten remotely
+            comm.dist.all_reduce(tok, group=comm.group)
+        t0 = torch.cuda.Event(enable_timing=True)
+        t0.record(xs)
+        dst = (C.c_void_p * (1 << k))()
+        sig = (C.c_void_p * max(len(group), 1))(*[self.peer_flags[p] + 8 * rank for p in group])
+        wait = (C.c_void_p * max(len(group), 1))(*[self.flags.value + 8 * p for p in group])
+        arrived = []
+        for j in range(Q):
+            fixed_val = 0
+            for i in range(v):
+                fixed_val |= ((j >> i) & 1) << perm[sub_bits + i]
+            for c in range(1 << k):
+                dst[c] = self.peer[peer_rank(c)][other] + j * sub_bytes + my_s * chunk_bytes
+            lib.call('qb_permute_scatter_sub', self.state._h, perm_sub, sub_bits, fixed_mask, fixed_val, k, dst, my_s,
+                     C.c_void_p(xs.cuda_stream), self.exchange_ctas)
+            self._xseq += 1
+            lib.call('qb_signal_flags', self.device, C.c_void_p(xs.cuda_stream), sig, len(group), self._xseq)
+            # my own piece is complete when my kernel is (event) and the sources' counters say so (flags)
+            ev = torch.cuda.Event()
+            ev.record(xs)
+            arrived.append((ev, self._xseq))
+        t1 = torch.cuda.Event(enable_timing=True)
+        t1.record(xs)
+        self._pending_times.append((t0, t1))
+        lib.call('qb_rebind', self.state._h, self.buf[other])
+        self.cur = other
+        for j in range(Q):
+            ev, seq = arrived[j]
+            cs.wait_event(ev)
+            lib.call('qb_wait_flags', self.device, None, wait, len(group), seq)
+            sub = self._sub(other, v, j)
+            for loc in per_sub[j]:
+                if loc is not None:
+                    sub.apply_gate_bits(loc[0], list(loc[1]), loc[2])
+            sub.flush()
+        self.exchanged_bytes += (self.bytes >> k) * ((1 << k) - 1)
+        self.exchanges += 1
+        self.split_exchanges += 1
+
+    def _collect_times(self):
+        for t0, t1 in self._pending_times:
+            t1.synchronize()
+            self.exchange_seconds += t0.elapsed_time(t1) / 1e3
+        self._pending_times = []
 
     def init_basis(self, has_one: bool, local_index: int = 0):
         import torch
@@ -340,6 +533,12 @@ class CudaShard:
 
     def sync(self):
         self.state.sync()
+        if self._pending_times:
+            self._collect_times()
+            n = C.c_uint64(0)
+            self._lib.call('qb_flag_timeouts', self.device, C.byref(n))
+            if n.value:
+                raise RuntimeError(f"pipelined exchange: {n.value} wait(s) for a peer's piece timed out")
 
     def do_exchange(self, ex: Exchange):
         import torch
@@ -418,14 +617,21 @@ class CudaShard:
     def close(self):
         lib = self._lib
         self.state.sync()
+        self._subs = {}
         if self.peer:
+            import torch
+            torch.cuda.synchronize(self.device)
             self.comm.barrier()
             for r, ptrs in enumerate(self.peer):
                 if r != self.comm.rank:
-                    for p in ptrs:
+                    for p in ptrs + [self.peer_flags[r]]:
                         lib.call('qb_ipc_close', self.device, C.c_void_p(p))
             self.peer = None
+            self.peer_flags = None
             self.comm.barrier()
+        if self.flags.value:
+            lib.call('qb_buffer_free', self.device, self.flags)
+            self.flags.value = None
         self.state = None
         for b in self.buf:
             if b.value:
@@ -440,8 +646,12 @@ class ShardedKet:
     """n-qubit ket over comm.world = 2^g ranks.  Qubit arguments use the reference's numbering
     (qubit 0 = most significant index bit, qbot/qgates.py:161-182)."""
 
-    def __init__(self, nq: int, comm, shard_factory=None, device: Optional[int] = None, exchange: str = 'p2p'):
+    def __init__(self, nq: int, comm, shard_factory=None, device: Optional[int] = None, exchange: str = 'p2p',
+                 split: Optional[int] = None):
         world = comm.world
+        # pieces (2^split) of a pipelined exchange; QBOT_B200_EXCHANGE_SPLIT=0 exchanges in one go
+        self.split = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT', '2')) if split is None else int(split)
+        self.min_first_phase = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT_MIN_GATES', '40'))   # fewer gates in the overlapped phase: not worth a split
         g = world.bit_length() - 1
         if 1 << g != world:
             raise ValueError("the number of ranks must be a power of two")
@@ -519,11 +729,26 @@ class ShardedKet:
                 rem = [g for i, g in enumerate(rem) if i not in ps]
                 if not rem:
                     break
-            ex = mp.plan_exchange(rem)
+            ex = mp.plan_exchange(rem, self.split if getattr(self.shard, 'supports_split', False) else 0, self.min_first_phase)
             if ex.k == 0 and not picked:
                 raise RuntimeError("sharded planner made no progress")
             self.shard.flush()
-            self.shard.do_exchange(ex)
+            if ex.split:
+                # pipelined exchange: the gates that leave the parked bits alone run sub-block by sub-block,
+                # each as soon as its piece of the exchange has arrived (the parked bits and the rank bits
+                # are predicates / scalars there); the others follow on the whole shard
+                v = ex.split
+                hmask = 0
+                for b in ex.hbits:
+                    hmask |= 1 << b
+                first = select_pass(rem, mp.local_mask() & ~hmask)
+                fs = set(first)
+                per_sub = [[mp.localise(rem[i], (self.rank << v) | j, mp.nl - v) for i in first] for j in range(1 << v)]
+                self.shard.do_exchange_split(ex, per_sub)
+                self.gates_applied += len(first)
+                rem = [g for i, g in enumerate(rem) if i not in fs]
+            else:
+                self.shard.do_exchange(ex)
         self.shard.flush()
 
     def sync(self):

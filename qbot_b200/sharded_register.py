@@ -54,8 +54,8 @@ class ShardingContext:
             for sk in self._idle.pop(other):
                 sk.close()
         sk = ShardedKet(nq, self.comm, shard_factory=self.shard_factory, device=self.device, exchange=self.exchange)
-        if self.jit is not None and hasattr(sk.shard, 'state'):
-            sk.shard.state.set_jit(self.jit)
+        if self.jit is not None and hasattr(sk.shard, 'set_jit'):
+            sk.shard.set_jit(self.jit)
         return sk
 
     def release(self, sk: ShardedKet):

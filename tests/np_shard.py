@@ -118,25 +118,53 @@ class NumpyShard:
             for i, r in enumerate(ex.rank_bits):
                 pr = (pr & ~(1 << r)) | (((c >> i) & 1) << r)
             return pr
-        chunks = packed.reshape(1 << k, -1)
+        # packed layout, top down: [v parked bits][k chunk bits][rest] (v = ex.split; 0 = the plain exchange)
+        v = getattr(ex, 'split', 0)
+        chunks = packed.reshape(1 << v, 1 << k, -1)
         if getattr(self.comm, 'dist', None) is not None:
             import torch
-            t_in = torch.from_numpy(np.ascontiguousarray(packed).view(np.float64))
+            send = np.ascontiguousarray(chunks.transpose(1, 0, 2))         # [chunk][piece][rest]
+            t_in = torch.from_numpy(send.reshape(-1).view(np.float64))
             t_out = torch.zeros_like(t_in)
             splits = [0] * self.comm.world
             for c in range(1 << k):
                 splits[peer_rank(c)] = t_in.numel() >> k
             self.comm.all_to_all(t_out, t_in, splits, splits)
-            self.psi = t_out.numpy().view(np.complex128).copy()
+            # arrives ordered by source RANK; chunk s of the new shard comes from peer_rank(s)
+            got = t_out.numpy().view(np.complex128).reshape(1 << k, 1 << v, -1)
+            by_rank = sorted(range(1 << k), key=peer_rank)
+            new = np.empty_like(chunks)
+            for slot, s_ in enumerate(by_rank):
+                new[:, s_, :] = got[slot]
+            self.psi = new.reshape(-1).copy()
         else:
             send = [None] * self.comm.world
             for c in range(1 << k):
-                send[peer_rank(c)] = chunks[c].copy()
+                send[peer_rank(c)] = chunks[:, c, :].copy()
             got = self.comm.all_to_all_np(send)
-            parts = [got[peer_rank(s)] for s in range(1 << k)]
-            self.psi = np.concatenate(parts)
+            new = np.empty_like(chunks)
+            for s_ in range(1 << k):
+                new[:, s_, :] = got[peer_rank(s_)]
+            self.psi = new.reshape(-1)
         self.exchanges += 1
         self.exchanged_bytes += (16 << nl) * ((1 << k) - 1) >> k
+
+    supports_split = True      # (tests switch it off to compare with the plain exchange)
+
+    def do_exchange_split(self, ex, per_sub):
+        """The data movement of a pipelined exchange in one go, then the first-phase gates sub-block by
+        sub-block (what CudaShard overlaps with the later pieces)."""
+        self.do_exchange(ex)
+        v = ex.split
+        sub = 1 << (self.nl - v)
+        for j, gates in enumerate(per_sub):
+            blk = self.psi[j * sub:(j + 1) * sub]
+            for loc in gates:
+                if loc is not None:
+                    blk = np_apply_bits(blk, self.nl - v, np.asarray(loc[0]), list(loc[1]), loc[2])
+                    self.applied += 1
+            self.psi[j * sub:(j + 1) * sub] = blk
+        self.split_exchanges = getattr(self, 'split_exchanges', 0) + 1
 
     def probs_local(self, positions):
         m = len(positions)

@@ -62,7 +62,9 @@ dev = int(os.environ.get('LOCAL_RANK', '0')) if backend == 'nccl' else 0
 torch.cuda.set_device(dev)
 dist.init_process_group(backend)
 ops = circuit_ops(n, 6, 11)
-sk = ShardedKet(n, TorchComm(), device=dev, exchange=mode)
+split = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+sk = ShardedKet(n, TorchComm(), device=dev, exchange=mode, split=split)
+sk.min_first_phase = 6
 for m, t, cs in ops:
     sk.apply_gate(m, t, cs)
 ket = sk.gather()
@@ -72,7 +74,7 @@ err = float(np.max(np.abs(ket - want)))
 perr = float(np.max(np.abs(pr - orc.ket_probs(want, n, [1, n - 1, 0]))))
 amp = sk.amplitudes([3, (1 << n) - 2])
 aerr = float(np.max(np.abs(amp - want[[3, (1 << n) - 2]])))
-print(json.dumps(dict(rank=rank, err=err, perr=perr, aerr=aerr, exchanges=sk.shard.exchanges,
+print(json.dumps(dict(rank=rank, err=err, perr=perr, aerr=aerr, exchanges=sk.shard.exchanges, split_exchanges=sk.shard.split_exchanges,
                       launches=sk.shard.state.stats()['kernel_launches'])))
 sk.close()
 dist.barrier()
@@ -81,12 +83,12 @@ assert err < 1e-12 and perr < 1e-12 and aerr < 1e-12 and sk.shard.exchanges >= 1
 '''
 
 
-def _run_ranks(nproc, mode, backend, n, tmp_path):
+def _run_ranks(nproc, mode, backend, n, tmp_path, split=0):
     script = tmp_path / 'worker.py'
     script.write_text(WORKER.format(root=ROOT))
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={nproc}',
-           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script), mode, backend, str(n)]
+           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script), mode, backend, str(n), str(split)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
@@ -102,6 +104,17 @@ def test_p2p_exchange_four_processes_one_gpu(tmp_path):
     assert out.count('"err"') == 4
 
 
+@pytest.mark.parametrize('nproc,n,split', [(2, 17, 2), (4, 18, 1)])
+def test_pipelined_exchange_processes_sharing_one_gpu(tmp_path, nproc, n, split):
+    """The exchange in 2^split pieces on its own stream (qb_permute_scatter_sub), pieces announced by flag
+    counters in the receivers' memory (qb_signal_flags / qb_wait_flags), first-phase sweeps per sub-block on
+    sub-ket handles with a reduced grid: same ket as the oracle, and the pipelined path was taken."""
+    import json
+    out = _run_ranks(nproc, 'p2p', 'gloo', n, tmp_path, split)
+    recs = [json.loads(ln) for ln in out.splitlines() if ln.startswith('{')]
+    assert len(recs) == nproc and all(r['split_exchanges'] >= 1 for r in recs), recs
+
+
 @pytest.mark.parametrize('mode', ['p2p', 'nccl'])
 def test_exchange_one_rank_per_gpu(tmp_path, mode):
     import torch
@@ -111,6 +124,18 @@ def test_exchange_one_rank_per_gpu(tmp_path, mode):
     nproc = 1 << (ng.bit_length() - 1)
     out = _run_ranks(nproc, mode, 'nccl', 16, tmp_path)
     assert out.count('"err"') == nproc
+
+
+def test_pipelined_exchange_one_rank_per_gpu(tmp_path):
+    import json
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    nproc = 1 << (ng.bit_length() - 1)
+    out = _run_ranks(nproc, 'p2p', 'nccl', 20, tmp_path, 2)
+    recs = [json.loads(ln) for ln in out.splitlines() if ln.startswith('{')]
+    assert len(recs) == nproc and all(r['split_exchanges'] >= 1 for r in recs), recs
 
 
 BATCH_WORKER = r'''
@@ -164,3 +189,59 @@ def test_branch_batch_sharded_over_ranks(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count('"worst"') == 4
+
+
+REGISTER_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, 'tests'))
+import numpy as np, torch, torch.distributed as dist
+import qbot_b200
+from qbot_b200 import sharded_register as sr
+from qbot_b200.sharded import TorchComm
+from test_sharded_host import sharded_program, expected_sharded_program
+from oracle import qbot_oracle as orc
+from qbot_b200.host import hostmath as hm
+rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE'])
+n = int(sys.argv[1])
+torch.cuda.set_device(0)
+dist.init_process_group('gloo')
+sr.enable(TorchComm(), device=0, min_qubits=n, exchange='p2p')
+text, ops = sharded_program(n)
+ns = qbot_b200.executeTxt(text)
+reg = ns['state']
+psi = expected_sharded_program(n, ops)
+def weights(targets, basis):
+    w = orc.basis_weights(psi, n, sorted(targets), basis.kets)
+    return w / w.sum()
+errs = dict(ket=float(np.max(np.abs(np.asarray(reg) - psi))),
+            r=float(np.max(np.abs(np.array(ns['r'].probs) - weights([0, 5, n - 1], hm.computation)))),
+            b=float(np.max(np.abs(np.array(ns['b'].probs) - weights([3, 0], hm.bell)))),
+            h=float(np.max(np.abs(np.array(ns['h'].probs) - weights([n - 2], hm.hadamard)))))
+t = psi.reshape([2] * n)
+keep = [0, 5, n - 1]
+mm = np.ascontiguousarray(t.transpose(keep + [a for a in range(n) if a not in keep])).reshape(8, -1)
+errs['rho_a'] = float(np.max(np.abs(np.asarray(ns['rho_a']) - mm @ mm.conj().T)))
+st = reg.stats()
+print(json.dumps(dict(rank=rank, kind=type(reg).__name__, errs=errs, exchanges=st['exchanges'], launches=st['kernel_launches'])))
+del ns, reg
+sr.disable()
+dist.barrier()
+dist.destroy_process_group()
+assert all(v < 1e-12 for v in errs.values()), errs
+'''
+
+
+def test_sharded_register_through_the_dsl_two_processes_one_gpu(tmp_path):
+    """`qset` of a product ket under one process per rank -> ShardedRegister on CUDA shards (peer stores
+    through CUDA IPC), driven by gate / swap / peek of a .qb program (qbot/operators.py:133-166, 255-329,
+    364-428); ket, outcome weights in three bases and rho_A against the oracle on every rank."""
+    import json
+    script = tmp_path / 'register_worker.py'
+    script.write_text(REGISTER_WORKER.format(root=ROOT))
+    port = 29650 + (os.getpid() % 300)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2',
+           '--master-addr', '127.0.0.1', '--master-port', str(port), str(script), '16']
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    recs = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith('{')]
+    assert len(recs) == 2 and all(x['kind'] == 'ShardedRegister' and x['launches'] > 0 for x in recs)

@@ -148,3 +148,21 @@ def test_basis_weights_equals_the_literal_outcome_loop():
             lit = np.array([abs(np.trace(np.matmul(sys_a, orc.basis_projector(f, i, dens)[0]))) for i in range(len(dens) ** f)])
             assert np.max(np.abs(orc.basis_weights(rho, n, t, kets) - lit)) < 1e-14, (n, t, name)
             assert np.max(np.abs(orc.basis_weights(psi, n, t, kets) - orc.basis_weights(np.outer(psi, psi.conj()), n, t, kets))) < 1e-14
+
+
+def test_inplace_ket_update_is_the_ket_update():
+    """oracle.ket_apply_inplace (used by the GPU tests at 26 qubits) against oracle.ket_apply."""
+    import numpy as np
+    from oracle import qbot_oracle as orc
+    from qbot_b200 import circuits
+    n = 9
+    rng = np.random.default_rng(5)
+    psi = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    a, b = psi.copy(), psi.copy()
+    for g in circuits.rc(n, 6, 9):
+        a = orc.ket_apply(a, n, g.target, g.matrix(), g.controls)
+        b = orc.ket_apply_inplace(b, n, g.target, g.matrix(), g.controls)
+    u = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))[0]
+    a = orc.ket_apply(a, n, 3, u, [0])
+    b = orc.ket_apply_inplace(b, n, 3, u, [0])
+    assert np.max(np.abs(a - b)) <= 4e-16 * np.max(np.abs(a))

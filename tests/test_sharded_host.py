@@ -104,6 +104,48 @@ def test_virtual_ranks_match_oracle(n, world):
     assert res[0]['exchanges'] >= 1          # the circuit does need global qubits
 
 
+@pytest.mark.parametrize('n,world,split', [(15, 2, 2), (16, 4, 2), (16, 8, 1), (16, 4, 3)])
+def test_pipelined_exchange_plan_matches_oracle(n, world, split):
+    """Exchanges planned in 2^split pieces: parked bits on top of the shard, the first-phase gates localised
+    per sub-block (parked bits as predicates / scalars), the rest on the whole shard -- same ket as the oracle,
+    same ket as the plain exchange, and the pipelined path is actually taken."""
+    ops = circuit_ops(n, 8, 300 + n)
+    want = expected_ket(n, ops)
+    shared = VirtualComm.Shared(world)
+    out = [None] * world
+    errors = []
+
+    def work(rank):
+        try:
+            sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard, split=split)
+            sk.min_first_phase = 6
+            for rep in range(2):                 # the second pass starts from a permuted qubit map
+                for m, t, cs in ops:
+                    sk.apply_gate(m, t, cs)
+                sk.flush()
+                if rep == 0:
+                    first = sk.gather()
+            out[rank] = dict(first=first, second=sk.gather(), split_exchanges=getattr(sk.shard, 'split_exchanges', 0),
+                             exchanges=sk.shard.exchanges, probs=sk.probs([0, n - 1]))
+        except Exception as e:     # pragma: no cover
+            errors.append(e)
+            shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errors:
+        raise errors[0]
+    want2 = want
+    for m, t, cs in ops:
+        want2 = orc.ket_apply(want2, n, t, m, cs)
+    for r in range(world):
+        assert np.max(np.abs(out[r]['first'] - want)) < 1e-12
+        assert np.max(np.abs(out[r]['second'] - want2)) < 1e-12
+        assert np.max(np.abs(out[r]['probs'] - orc.ket_probs(want2, n, [0, n - 1]))) < 1e-12
+        assert out[r]['split_exchanges'] >= 1, out[r]
+
+
 def test_rank_scalar_under_controls_on_every_local_bit():
     """A diagonal gate whose target is a rank bit is a per-rank scalar on the amplitudes its controls select; with
     only two local bits and both of them controls there is no free local bit to carry diag(s, s) -- it becomes
