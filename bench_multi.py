@@ -87,6 +87,7 @@ def run_multi_gpu(args):
     st.reset_stats()
     sk.shard.sync()
     ex0, eb0, es0, sx0 = sk.shard.exchanges, sk.shard.exchanged_bytes, sk.shard.exchange_seconds, sk.shard.split_exchanges
+    ov0 = sk.shard.overlapped_steps
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -193,6 +194,7 @@ def run_multi_gpu(args):
                          "nvlink_peak_gbs": 900.0, "frac": (exb / ex_s / 1e9 / 900.0) if ex_s > 0 else None,
                          "share_of_step": ex_s / secs,
                          "pipelined_per_step": nsplit / args.steps, "pieces": 1 << sk.split if nsplit else 1,
+                         "sweeps_run_per_sub_block_per_step": (sk.shard.overlapped_steps - ov0) / args.steps,
                          "note": ("pipelined exchanges run on their own stream in pieces; the sweeps of the gates that do not write the "
                                   "parked bits run on each piece as it arrives, so seconds_per_step (first piece start -> last piece "
                                   "delivered) OVERLAPS with sweep time and share_of_step is not a serial share") if nsplit else
@@ -203,11 +205,16 @@ def run_multi_gpu(args):
         if c4 is not None:
             out["configs"] = {"c4": c4}
         print(json.dumps(out))
+    from qbot_b200.sharded import _trace
+    _trace("bench: closing the shards")
     sk.close()
     from qbot_b200 import sharded_register as _sr
     _sr.disable()
+    _trace("bench: final barrier")
     dist.barrier()
+    _trace("bench: destroy_process_group")
     dist.destroy_process_group()
+    _trace("bench: done")
 
 
 def sharded_parity(comm, local, exchange, rank, world):

@@ -210,6 +210,20 @@ int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bit
  * caller orders that stream against the handle's work with events (qb_compute_stream). */
 int qb_permute_scatter_sub(qb_state* s, const int* src_bit_of_dst_bit, int ndst_bits, uint64_t src_fixed_mask, uint64_t src_fixed_value,
                            int chunk_bits, void* const* chunk_dst, int first_chunk, void* cuda_stream, int max_ctas);
+/* The queued gates as a plan whose steps (fused sweeps, one-gate kernels) the CALLER runs, in order, each either over
+ * the whole state or sub-block by sub-block -- what lets the pieces of a global-qubit exchange leave (arrive) between the
+ * sub-block runs of the last (first) sweeps of a pass:
+ *   qb_plan_queue   plans the queue (it is empty afterwards); *nsteps steps; the first *head and the last *tail of them
+ *                   may run on 2^park_bits contiguous sub-blocks one at a time: they are specialised sweeps whose tiles
+ *                   do not contain the top park_bits index bits (controls / diagonals there are fine: the kernel runs a
+ *                   tile range and still sees the true index bits)
+ *   qb_run_steps    steps [from, to) on part `part` of `nparts` (nparts = 1: the whole state); sm_limit > 0 sizes the
+ *                   persistent grids for that many SMs (the rest is left to an exchange kernel running beside them)
+ *   qb_finish_queue checks that every step has run on every part, releases the plan
+ * Every step must run exactly once on every amplitude, steps in ascending order per amplitude. */
+int qb_plan_queue(qb_state* s, int park_bits, int* nsteps, int* head, int* tail);
+int qb_run_steps(qb_state* s, int from, int to, int part, int nparts, int sm_limit);
+int qb_finish_queue(qb_state* s);
 /* max_ctas > 0 caps the grid (256-thread CTAs), so that the kernel leaves SM slots to sweeps running beside it.
  * qb_set_sm_limit is the other half: the handle's sweeps size their persistent grids for nsms SMs (0 = all). */
 int qb_set_sm_limit(qb_state* s, int nsms);

@@ -79,6 +79,9 @@ PROTOTYPES = {
     'qb_permute_scatter': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p), C.c_int]),
     'qb_permute_scatter_sub': (C.c_int, [c_state_p, C.POINTER(C.c_int), C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int]),
     'qb_set_sm_limit': (C.c_int, [c_state_p, C.c_int]),
+    'qb_plan_queue': (C.c_int, [c_state_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    'qb_run_steps': (C.c_int, [c_state_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'qb_finish_queue': (C.c_int, [c_state_p]),
     'qb_signal_flags': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint64]),
     'qb_wait_flags': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint64]),
     'qb_flag_timeouts': (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),

@@ -359,6 +359,7 @@ void qb_state::enqueue(QGate&& g) {
 
 void qb_state::flush() {
     if (queue.empty()) return;
+    if (pending_plan) throw qb_error(-4, "gates were queued while a planned queue is being run step by step (qb_finish_queue first)");
     DevGuard gd(device);
     std::vector<QGate> q;
     q.swap(queue);
@@ -1167,6 +1168,35 @@ int qb_permute_scatter_sub(qb_state* s, const int* src_bit_of_dst_bit, int ndst_
 int qb_permute_scatter(qb_state* s, const int* src_bit_of_dst_bit, int chunk_bits, void* const* chunk_dst, int first_chunk) {
     if (!s) { g_err = "NULL argument"; return QB_ERR_ARG; }
     return qb_permute_scatter_sub(s, src_bit_of_dst_bit, s->nbits, 0, 0, chunk_bits, chunk_dst, first_chunk, nullptr, 0);
+}
+
+int qb_plan_queue(qb_state* s, int park_bits, int* nsteps, int* head, int* tail) {
+    QB_API_BEGIN
+    QB_REQUIRE(s && nsteps && head && tail, "NULL argument");
+    QB_REQUIRE(!s->pending_plan, "plan_queue: the previous plan has not been finished (qb_finish_queue)");
+    *nsteps = *head = *tail = 0;
+    if (s->queue.empty()) return QB_OK;
+    if (!s->fusion || !qb_engine_available()) { s->flush(); return QB_OK; }
+    DevGuard gd(s->device);
+    std::vector<QGate> q;
+    q.swap(s->queue);
+    *nsteps = qb_engine_plan_pending(s, q, park_bits, head, tail);
+    QB_API_END
+}
+
+int qb_run_steps(qb_state* s, int from, int to, int part, int nparts, int sm_limit) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    DevGuard gd(s->device);
+    qb_engine_run_pending(s, from, to, part, nparts, sm_limit);
+    QB_API_END
+}
+
+int qb_finish_queue(qb_state* s) {
+    QB_API_BEGIN
+    QB_REQUIRE(s, "NULL state");
+    qb_engine_finish_pending(s);
+    QB_API_END
 }
 
 int qb_set_sm_limit(qb_state* s, int nsms) {

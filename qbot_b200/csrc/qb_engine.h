@@ -26,6 +26,11 @@ struct qb_state {
     size_t stage_off = 0;
     // fused engine state (plan cache, device copies of the sweep programs)
     void* engine = nullptr;
+    // a planned gate list whose steps the caller runs range by range (qb_plan_queue / qb_run_steps / qb_finish_queue)
+    void* pending_plan = nullptr;
+    int pending_jit = 0;
+    std::vector<uint32_t> pending_done;       // per step: parts that have run
+    std::vector<int> pending_parts_of;        // per step: number of parts it was run in
 
     ~qb_state();
     uint64_t per_branch() const { return 1ull << nbits; }
@@ -43,3 +48,6 @@ struct qb_state {
 bool qb_engine_available();
 void qb_engine_run(qb_state* s, const std::vector<QGate>& gates);
 void qb_engine_free(qb_state* s);
+int qb_engine_plan_pending(qb_state* s, const std::vector<QGate>& gates, int park_bits, int* head, int* tail);
+void qb_engine_run_pending(qb_state* s, int from, int to, int part, int nparts, int sms);
+void qb_engine_finish_pending(qb_state* s);

@@ -129,14 +129,15 @@ __device__ __forceinline__ unsigned qj_mbar(const int which) {
 // issued in the last stage); only a CTA's first tile is loaded with LDG.
 const char* kPostlude = R"QJ(
 extern "C" __global__ void __launch_bounds__(QJ_T, QJ_CTAS)
-qj_kernel(double2* __restrict__ psi, const unsigned long long ntiles, const int prefetch, QJ_POOL_KPARAM) {
+qj_kernel(double2* __restrict__ psi, const unsigned long long tile0, const unsigned long long ntiles, const int prefetch, QJ_POOL_KPARAM) {
     extern __shared__ __align__(16) double2 buf[];
     const unsigned tid = threadIdx.x;
     // prefetch bit 0: L2 prefetch of the CTA's next tile at the start of a tile; bit 1: asynchronous
     // copy of the next tile into the transposition buffer during the last stage
     unsigned pre = 0, phase = 0;
     QJ_MBAR_INIT();
-    for (unsigned long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // tiles [tile0, ntiles): the whole state, or one sub-block of it (a piece of a pipelined exchange)
+    for (unsigned long long tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const unsigned long long tbase = qj_tile_base(tile);
         const unsigned long long nt = tile + gridDim.x;
         const unsigned long long next = nt < ntiles ? qj_tile_base(nt) : ~0ull;
@@ -450,15 +451,15 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
 }
 
 // launch: `pool` = qj_pool(program) on the host (parameter variant) or its device copy
-void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
+void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t tile_begin, uint64_t tile_end, int prefetch,
                    const double* pool_host, const double* pool_dev) {
     Driver& d = driver();
-    unsigned long long nt = ntiles;
+    unsigned long long t0 = tile_begin, nt = tile_end;
     int pf = prefetch;
     void* psi_arg = (void*)psi;
     const void* pool_ptr = pool_dev;
-    void* args[4] = {&psi_arg, &nt, &pf, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
-    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * k.ctas_per_sm);
+    void* args[5] = {&psi_arg, &t0, &nt, &pf, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
+    const unsigned grid = (unsigned)std::min<uint64_t>(tile_end - tile_begin, (uint64_t)sms * k.ctas_per_sm);
     CUresult e = d.LaunchKernel((CUfunction)k.fn, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem_bytes, (CUstream)stream, args, nullptr);
     if (e != CUDA_SUCCESS) throw qb_error(-2, "cuLaunchKernel(sweep): " + cu_err(e));
 }

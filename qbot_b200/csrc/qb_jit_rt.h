@@ -25,7 +25,7 @@ std::vector<char> qb_jit_compile(const std::string& src, std::string* log_out);
 void qb_jit_precompile(const std::vector<const uint8_t*>& programs);
 void qb_jit_compile_cached(const uint8_t* program);
 QbJitKernel qb_jit_get(const uint8_t* program, int device);
-void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t ntiles, int prefetch,
+void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t tile_begin, uint64_t tile_end, int prefetch,
                    const double* pool_host, const double* pool_dev);
 QbJitStats qb_jit_stats();
 // record one sighting of a specialised source (by hash): returns the number of sightings so far,

@@ -355,29 +355,62 @@ __global__ void __launch_bounds__(256) k_bins(BinArgs a) {
         goff[gi] = (qq << a.c) * a.elem_stride;
     }
     __syncthreads();
-    for (int l = threadIdx.x; l < C; l += blockDim.x) {
+    // a thread holds the 2^(BIN_C-8) values l = tid + 256 i of the chunk in registers; non-target ("fold") bits are
+    // summed away where they live: bits >= 8 inside the thread, bits 0..4 across the lanes with warp shuffles,
+    // bits 5..7 (the warp number) through shared memory -- at most 3 barrier rounds instead of one per fold bit.
+    // Fixed order, no atomics: the result is deterministic.
+    constexpr int PER = (1 << BIN_C) / 256;
+    double vre[PER], vim[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int l = (int)threadIdx.x + 256 * i;
         double re = 0.0, im = 0.0;
-        const cplx* p = src + (uint64_t)l * a.elem_stride;
-        if (a.mode == 0) {
+        if (l < C) {
+            const cplx* p = src + (uint64_t)l * a.elem_stride;
+            if (a.mode == 0) {
 #pragma unroll 8
-            for (int gi = 0; gi < G; gi++) {
-                const cplx v = __ldcs(p + goff[gi]);
-                re += v.x * v.x + v.y * v.y;
-            }
-        } else {
+                for (int gi = 0; gi < G; gi++) {
+                    const cplx v = __ldcs(p + goff[gi]);
+                    re += v.x * v.x + v.y * v.y;
+                }
+            } else {
 #pragma unroll 8
-            for (int gi = 0; gi < G; gi++) {
-                const cplx v = __ldcs(p + goff[gi]);
-                re += v.x; im += v.y;
+                for (int gi = 0; gi < G; gi++) {
+                    const cplx v = __ldcs(p + goff[gi]);
+                    re += v.x; im += v.y;
+                }
             }
         }
-        sre[l] = re; sim[l] = im;
+        vre[i] = re; vim[i] = im;
     }
+    unsigned foldmask = 0;
+    for (int f = 0; f < a.nfold; f++) foldmask |= 1u << a.foldbits[f];
+#pragma unroll
+    for (int b = 0; (1 << b) < PER; b++) {
+        if ((foldmask >> (8 + b)) & 1u) {
+#pragma unroll
+            for (int i = 0; i < PER; i++)
+                if (!(i & (1 << b))) { vre[i] += vre[i | (1 << b)]; vim[i] += vim[i | (1 << b)]; }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+        if ((foldmask >> b) & 1u) {
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                vre[i] += __shfl_xor_sync(0xffffffffu, vre[i], 1 << b);
+                if (a.mode != 0) vim[i] += __shfl_xor_sync(0xffffffffu, vim[i], 1 << b);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; i++) { sre[threadIdx.x + 256 * i] = vre[i]; sim[threadIdx.x + 256 * i] = vim[i]; }
     __syncthreads();
-    unsigned folded = 0;
-    for (int f = 0; f < a.nfold; f++) {
-        unsigned bit = 1u << a.foldbits[f];
-        unsigned dead = folded | bit;
+    unsigned folded = foldmask & ~0xe0u;        // the entries with a folded bit set are dead from here on
+    for (int bpos = 5; bpos < 8; bpos++) {
+        const unsigned bit = 1u << bpos;
+        if (!(foldmask & bit)) continue;
+        const unsigned dead = folded | bit;
         for (int l = threadIdx.x; l < C; l += blockDim.x) {
             if ((l & dead) == 0) { sre[l] += sre[l | bit]; sim[l] += sim[l | bit]; }
         }

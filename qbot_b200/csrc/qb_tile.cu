@@ -429,8 +429,8 @@ bool qb_engine_available() { return qb_engine_available_impl(); }
 
 void qb_engine_free(qb_state* s) { s->engine = nullptr; }      // plans belong to the device, not to the handle
 
-void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
-    std::lock_guard<std::mutex> lk(g_engine_mu);
+// plan (or find the cached plan of) `gates` and decide which executor runs it
+static CachedPlan* engine_prepare(qb_state* s, const std::vector<QGate>& gates, int* jit_mode_out) {
     EngineState* es = &g_engines[s->device];
     const int M = engine_M();
     int jit_mode = s->jit_mode >= 0 ? s->jit_mode : engine_jit_default();
@@ -468,21 +468,33 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
         }
     }
     if (plan->R != QT_R) jit_mode = 2;          // only specialised kernels can run this plan shape
+    *jit_mode_out = jit_mode;
+    return plan;
+}
 
+// steps [from, to) of a prepared plan on part `part` of `nparts` equal, contiguous sub-blocks of the state (nparts = 1: all
+// of it).  Only specialised sweeps can run on a sub-block (the kernel takes a tile range; its predicates still see the true
+// index bits) and only when the bits that select the sub-block -- the top log2(nparts) index bits -- are not tile bits.
+static void engine_run_steps(qb_state* s, CachedPlan* plan, int jit_mode, size_t from, size_t to, int part, int nparts, int sms) {
+    EngineState* es = &g_engines[s->device];
+    const int M = engine_M();
     const uint64_t ntiles = s->total() >> M;
-    for (size_t i = 0; i < plan->steps.size(); i++) {
+    const uint64_t t0 = ntiles / (uint64_t)nparts * (uint64_t)part, t1 = ntiles / (uint64_t)nparts * (uint64_t)(part + 1);
+    const bool counts = part == nparts - 1;          // a pass over the state is complete with its last part
+    for (size_t i = from; i < to && i < plan->steps.size(); i++) {
         const QtPlanStep& st = plan->steps[i];
         if (!st.fused) {
+            if (nparts != 1) throw qb_error(-1, "a one-gate step cannot run on a sub-block");
             s->run_gate_unfused(plan->gates[st.gate_index]);
             continue;
         }
         if (jit_mode != 0 && step_jit(s, plan, i, jit_mode)) {
             const CachedPlan::StepJit& j = plan->jit[i];
             if (plan->R != QT_R && !j.ready) throw qb_error(-2, "no specialised kernel for a 32-amplitudes-per-thread sweep");
-            qb_jit_launch(j.k, s->stream, s->sms, s->d, ntiles, engine_jit_prefetch(), j.pool.data(), j.pool_dev);
-            s->stats.jit_passes++;
-            s->stats.jit_kernel_hash += j.key;
+            qb_jit_launch(j.k, s->stream, sms, s->d, t0, t1, engine_jit_prefetch(), j.pool.data(), j.pool_dev);
+            if (counts) { s->stats.jit_passes++; s->stats.jit_kernel_hash += j.key; }
         } else {
+            if (nparts != 1) throw qb_error(-1, "the generic sweep kernel cannot run on a sub-block");
             if (plan->R != QT_R) throw qb_error(-2, "the generic sweep kernel cannot run a 32-amplitudes-per-thread plan");
             const uint8_t* prog = plan->dev + plan->prog_off[i];
             {   // a stale error of an earlier unchecked runtime call must not be blamed on this launch
@@ -494,10 +506,81 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
             QB_CUDA(cudaGetLastError());
         }
         s->stats.kernel_launches++;
-        s->stats.fused_passes++;
-        s->stats.state_passes++;
-        s->stats.fused_gates += st.ngates;
-        s->stats.gates_applied += st.ngates;
-        s->stats.bytes_moved += (uint64_t)s->bytes() * 2;
+        if (counts) {
+            s->stats.fused_passes++;
+            s->stats.state_passes++;
+            s->stats.fused_gates += st.ngates;
+            s->stats.gates_applied += st.ngates;
+            s->stats.bytes_moved += (uint64_t)s->bytes() * 2;
+        }
     }
+}
+
+void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    int jit_mode = 0;
+    CachedPlan* plan = engine_prepare(s, gates, &jit_mode);
+    engine_run_steps(s, plan, jit_mode, 0, plan->steps.size(), 0, 1, s->sms);
+}
+
+// ---- a plan kept pending on the handle, its steps run by the caller range by range (pipelined exchanges) ----------
+int qb_engine_plan_pending(qb_state* s, const std::vector<QGate>& gates, int park_bits, int* head, int* tail) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    int jit_mode = 0;
+    CachedPlan* plan = engine_prepare(s, gates, &jit_mode);
+    s->pending_plan = plan;
+    s->pending_jit = jit_mode;
+    const size_t n = plan->steps.size();
+    s->pending_done.assign(n, 0u);
+    const int M = engine_M();
+    // a step can run sub-block by sub-block when it is a specialised sweep whose tile leaves the parked (top) bits alone
+    std::vector<char> ok(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        const QtPlanStep& st = plan->steps[i];
+        if (!st.fused || s->nbranch != 1 || park_bits <= 0 || s->nbits - park_bits < M) continue;
+        if (jit_mode == 0 || !step_jit(s, plan, i, jit_mode)) continue;
+        const QtHeader* h = (const QtHeader*)st.program.data();
+        bool clear = true;
+        for (int x = 0; x < (int)h->M - QT_L; x++) if (h->hb[x] >= s->nbits - park_bits) clear = false;
+        ok[i] = clear;
+    }
+    int hd = 0, tl = 0;
+    while ((size_t)hd < n && ok[hd]) hd++;
+    while ((size_t)tl < n && ok[n - 1 - tl]) tl++;
+    if (head) *head = hd;
+    if (tail) *tail = tl;
+    return (int)n;
+}
+
+void qb_engine_run_pending(qb_state* s, int from, int to, int part, int nparts, int sms) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    CachedPlan* plan = (CachedPlan*)s->pending_plan;
+    if (!plan) throw qb_error(-1, "no pending plan (qb_plan_queue first)");
+    if (from < 0 || to < from || (size_t)to > plan->steps.size() || nparts < 1 || nparts > 16 || part < 0 || part >= nparts)
+        throw qb_error(-1, "run_steps: bad step or part range");
+    for (int i = from; i < to; i++) {
+        const uint32_t bits = nparts == 1 ? 0xffffu : (1u << part);
+        if (s->pending_done[i] & bits) throw qb_error(-1, "run_steps: a step would run twice on the same amplitudes");
+        s->pending_done[i] |= bits;
+        s->pending_parts_of.resize(plan->steps.size(), 1);
+        s->pending_parts_of[i] = nparts;
+    }
+    engine_run_steps(s, plan, s->pending_jit, (size_t)from, (size_t)to, part, nparts, sms > 0 && sms < s->sms ? sms : s->sms);
+}
+
+void qb_engine_finish_pending(qb_state* s) {
+    std::lock_guard<std::mutex> lk(g_engine_mu);
+    CachedPlan* plan = (CachedPlan*)s->pending_plan;
+    if (!plan) return;
+    s->pending_plan = nullptr;
+    for (size_t i = 0; i < plan->steps.size(); i++) {
+        const int np = i < s->pending_parts_of.size() ? s->pending_parts_of[i] : 1;
+        const uint32_t want = np == 1 ? 0xffffu : ((1u << np) - 1u);
+        if (i >= s->pending_done.size() || (s->pending_done[i] & want) != want) {
+            s->pending_done.clear(); s->pending_parts_of.clear();
+            throw qb_error(-1, "finish_queue: not every step of the plan has run on every part of the state");
+        }
+    }
+    s->pending_done.clear();
+    s->pending_parts_of.clear();
 }

@@ -25,12 +25,20 @@ class OpReturnVal:
         self.halt = halt
 
 
+_token_cache = {}
+
+
 def processLineIntoTokens(line: str):
-    line = line.strip()
-    if not line:
+    cached = _token_cache.get(line)
+    if cached is not None:
+        return list(cached)          # loops and re-runs meet the same source lines again
+    text = line.strip()
+    if not text:
         return []
-    tokens = [line[:4].lower()]
-    tokens += [s.strip() for s in line[4:].split(';') if s.strip()]
+    tokens = [text[:4].lower()]
+    tokens += [s.strip() for s in text[4:].split(';') if s.strip()]
+    if len(_token_cache) < 65536:
+        _token_cache[line] = tuple(tokens)
     return tokens
 
 

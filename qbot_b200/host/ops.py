@@ -418,6 +418,27 @@ def make_ops(host: Host) -> dict:
             assertProbValType(lines, lineNum, cond, bool)
         if not isinstance(cond, ProbVal) and not cond:
             return
+        # the plain case -- one matrix, one int target, int controls, a certain condition, a register the ops own --
+        # straight to the device; anything else (ProbVal arguments, a check that fails) takes the general path
+        # below, which validates in the reference's order and raises its messages
+        if cond is True and type(firstTarget) is int and type(g) is np.ndarray and g.ndim == 2 and type(controls) is list:
+            st = ns['state']
+            dim = g.shape[0]
+            if (getattr(st, '_qb_device_state', False) and not getattr(st, '_shared', True) and dim == g.shape[1] and dim > 1
+                    and not dim & (dim - 1) and not _program_names_state(ns, lines)):
+                last = firstTarget + dim.bit_length() - 2
+                ok = 0 <= firstTarget and last <= numQubits - 1
+                for c in controls:
+                    if type(c) is not int or c < 0 or c > numQubits - 1 or firstTarget <= c <= last:
+                        ok = False
+                if ok:
+                    try:
+                        st.apply_gate(g, firstTarget, controls)
+                    except ValueError as e:
+                        err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+                    ns['__is_q_state'] = True
+                    ns['__updated_state'] = True
+                    return
         try:
             desc = funcWrapper(_gate, lines, lineNum, numQubits, controls, firstTarget, g)
         except Exception as e:

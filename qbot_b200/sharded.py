@@ -33,6 +33,12 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 INF = 1 << 60
+
+
+def _trace(msg: str):
+    if os.environ.get('QBOT_B200_TRACE'):
+        import sys
+        print(f"[qbot_b200 rank {os.environ.get('RANK', '?')}] {msg}", file=sys.stderr, flush=True)
 LOW_KEEP = 5          # local positions 0..4 stay in place during a pack (512-byte runs)
 
 
@@ -104,6 +110,7 @@ class Exchange:
     src_bit_of_dst_bit: List[int]
     rank_bits: List[int]
     hbits: Tuple[int, ...] = ()     # logical bits parked at the top local positions: the sub-blocks of a pipelined exchange
+    send_side: bool = False         # the parked bits were on top before the exchange too: its pieces may leave between the sub-block runs of the pass's last sweeps
 
     @property
     def k(self) -> int:
@@ -133,15 +140,22 @@ class QubitMap:
                 m |= 1 << b
         return m
 
-    def plan_exchange(self, rem: Sequence[LGate], split: int = 0, min_first_phase: int = 40) -> Exchange:
-        """Choose the new rank bits (farthest next non-diagonal use) and update the map.
+    def plan_exchange(self, rem: Sequence[LGate], split: int = 0, min_first_phase: int = 40,
+                      prev: Optional[Sequence[LGate]] = None, phase_cap: int = 96) -> Exchange:
+        """Choose the new rank bits (farthest next non-diagonal use) and update the map.  `prev`: the gates of the
+        pass that runs right before this exchange, not applied yet (for the sending-side overlap, see below; the
+        caller localises them with the map as it is BEFORE this call).
 
-        split = v > 0 asks for a PIPELINED exchange: v further local bits -- the ones written last among the
-        gates that follow -- are parked at the top v local positions, so that the shard is 2^v contiguous
-        sub-blocks that (i) can be exchanged one after the other and (ii) can each run the gates that do not
-        write those v bits (for which they are predicates / scalars, like rank bits) as soon as their piece has
-        arrived, while the later pieces are still on the wire.  Declined (hbits = ()) when fewer than
-        min_first_phase gates could run that way."""
+        split = v > 0 asks for a PIPELINED exchange: v local bits are parked at the top v local positions, so that
+        the shard is 2^v contiguous sub-blocks that are exchanged one after the other while the sweeps next to the
+        exchange run sub-block by sub-block -- the last sweeps of the pass before it (each piece leaves as soon as
+        its sub-block is done) and the first sweeps of the pass after it (each sub-block starts as soon as its piece
+        has arrived).  A sweep can run that way when the parked bits are not tile bits of it, i.e. when none of its
+        gates writes them, so the parked bits are either (A) the ones already on top, if few of the gates around the
+        exchange write them (both sides overlap), or (B) the bits written last among the gates that follow (only the
+        receiving side overlaps: the sub-blocks do not exist before this exchange).  The count of gates that could
+        run in the overlapped phases (capped at phase_cap each) decides; below min_first_phase the exchange is
+        done in one go (hbits = ())."""
         n, nl, g = self.n, self.nl, self.g
         nxt = [INF] * n
         for i, gt in enumerate(rem):
@@ -152,8 +166,11 @@ class QubitMap:
                     nxt[b] = i
                 w &= w - 1
         # a local bit in the low LOW_KEEP positions is a last resort (keeps the pack coalesced)
+        # (ties: stay global > ordinary local positions, highest first > the top `split` local positions, where the
+        # bits parked by a pipelined exchange sit: they are worth more as the sub-block bits of the next one)
         order = sorted(range(n), key=lambda b: (0 if not (self.pos[b] < min(LOW_KEEP, max(nl - g, 0))) else 1,
-                                                -nxt[b], 0 if self.pos[b] >= nl else 1, -self.pos[b]))
+                                                -nxt[b], 0 if self.pos[b] >= nl else 2 if self.pos[b] >= nl - split else 1,
+                                                -self.pos[b]))
         head_w = rem[0].wmask if rem else 0
         new_global = []
         for b in order:
@@ -170,22 +187,43 @@ class QubitMap:
         k = len(victims)
         assert k == len(rank_bits)
         hbits: List[int] = []
+        tail: List[int] = []
         if split > 0 and k and nl - k - split >= max(LOW_KEEP, 8):
+            def first_phase(hb):
+                allowed = 0
+                for b in range(n):
+                    if b not in new_global and b not in hb:
+                        allowed |= 1 << b
+                return min(len(select_pass(rem, allowed)), phase_cap)
+
+            # (B) park the bits that are written last among the gates that follow: overlap on the receiving side
+            cand_b: List[int] = []
             for b in order:                     # farthest next write first
                 if b in new_global or self.pos[b] >= nl or self.pos[b] < LOW_KEEP or (head_w >> b) & 1:
                     continue
-                hbits.append(b)
-                if len(hbits) == split:
+                cand_b.append(b)
+                if len(cand_b) == split:
                     break
-            if len(hbits) == split:
-                allowed = 0
-                for b in range(n):
-                    if b not in new_global and b not in hbits:
-                        allowed |= 1 << b
-                if len(select_pass(rem, allowed)) < min_first_phase:
-                    hbits = []
-            else:
-                hbits = []
+            score_b = first_phase(cand_b) if len(cand_b) == split else -1
+            # (A) keep the bits that sit at the top local positions now: the sub-blocks exist on the SENDING side too,
+            # so the tail of the pass before the exchange (the gates of `prev` that can run last and leave those bits
+            # alone) runs sub-block by sub-block, each followed at once by its piece of the exchange
+            cand_a = [self.at[nl - split + i] for i in range(split)]
+            score_a, tail_a = -1, []
+            if prev and not any(b in new_global or (head_w >> b) & 1 for b in cand_a):
+                hm = 0
+                for b in cand_a:
+                    hm |= 1 << b
+                lm = self.local_mask()
+                rev = select_pass(list(reversed(prev)), lm & ~hm)          # gates that commute to the END of the pass
+                # (only as many gates as it takes to cover the exchange: sub-block sweeps share the SMs with the
+                # scatter kernels; any suffix of the deferrable set is itself deferrable)
+                tail_a = sorted(len(prev) - 1 - i for i in rev)[-phase_cap:]
+                score_a = len(tail_a) + first_phase(cand_a)
+            if score_a >= score_b and score_a >= min_first_phase:
+                hbits, tail = cand_a, tail_a
+            elif score_b >= min_first_phase:
+                hbits = cand_b
         v = len(hbits)
         perm = list(range(nl))
         if k:
@@ -208,7 +246,7 @@ class QubitMap:
             self.at = new_at
             for p, b in enumerate(self.at):
                 self.pos[b] = p
-        return Exchange(perm, rank_bits, tuple(hbits))
+        return Exchange(perm, rank_bits, tuple(hbits), bool(tail))
 
     def localise(self, g: LGate, rank: int, nl: Optional[int] = None):
         """The gate as this rank sees it: (matrix, local target positions, local control mask),
@@ -322,7 +360,12 @@ class CudaShard:
         self.split_exchanges = 0
         self.exchange_seconds = 0.0           # pack + transfer: between the two barriers, or (pipelined) first piece start -> last piece done on the exchange stream
         self._pending_times = []              # (start event, end event) of pipelined exchanges not yet read
-        self._subs = {}                       # (buffer index, v, j) -> DeviceState of sub-block j
+        self._incoming = None                 # pieces of a pipelined exchange the next sweeps have to wait for
+        self._sms = None
+        self.overlapped_steps = 0             # sweeps run sub-block by sub-block beside an exchange
+        # sweeps on either side of a pipelined exchange that run sub-block by sub-block (about what covers the exchange)
+        self.overlap_steps = int(os.environ.get('QBOT_B200_EXCHANGE_OVERLAP_STEPS', '4'))
+        self._subs = {}                       # (unused since the sweeps take tile ranges; kept for stats aggregation)
         self._jit = None
         self._xseq = 0                        # pieces signalled so far (same on every rank)
         self._streams = None
@@ -405,27 +448,59 @@ class CudaShard:
             self._streams = (cs, xs, tok)
         return self._streams
 
-    def _sub(self, buf_index: int, v: int, j: int):
-        key = (buf_index, v, j)
-        sub = self._subs.get(key)
-        if sub is None:
-            from .state import DeviceState, KET
-            h = C.c_void_p()
-            ptr = C.c_void_p(self.buf[buf_index].value + j * (self.bytes >> v))
-            self._lib.call('qb_create_external', C.byref(h), KET, self.nl - v, 1, self.device, ptr, None)
-            sub = DeviceState(h, KET, self.nl - v, 1)
-            if self._jit is not None:
-                sub.set_jit(self._jit)
+    def _plan_queue(self, v: int):
+        n, hd, tl = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._lib.call('qb_plan_queue', self.state._h, v, C.byref(n), C.byref(hd), C.byref(tl))
+        return n.value, hd.value, tl.value
+
+    def _run_queued(self, send_v: int = 0, on_part_done=None):
+        """Run the queued pass.  Its first sweeps wait, sub-block by sub-block, for the pieces of a pipelined
+        exchange that is still arriving (self._incoming); its last sweeps run sub-block by sub-block when the
+        pieces of the NEXT exchange are to leave behind them (send_v > 0; on_part_done(j) is called after sub-block
+        j's last sweep has been queued).  Everything else runs over the whole shard."""
+        lib, inc = self._lib, self._incoming
+        v = inc['v'] if inc is not None else send_v
+        if inc is not None and send_v and send_v != inc['v']:
+            send_v = 0                           # (different sub-block sizes on the two sides: keep the receiving one)
+        n, head, tail = self._plan_queue(v) if v else self._plan_queue(0)
+        cs = self._stream_pair()[0] if (inc is not None or send_v) else None
+        h = min(head, self.overlap_steps) if inc is not None else 0
+        t = min(tail, self.overlap_steps, n - h) if send_v else 0
+        Q = 1 << v
+        sm = self._sm_limit()
+        if inc is not None:
+            for j in range(Q):
+                ev, seq = inc['arrived'][j]
+                cs.wait_event(ev)                 # my own piece j has left ...
+                lib.call('qb_wait_flags', self.device, None, inc['wait'], inc['nwait'], seq)       # ... and every source's piece j is in
+                if h:
+                    lib.call('qb_run_steps', self.state._h, 0, h, j, Q, sm)
+            self._incoming = None
+            self.overlapped_steps += h
+        if n - h - t > 0:
+            lib.call('qb_run_steps', self.state._h, h, n - t, 0, 1, 0)
+        if send_v:
+            for j in range(Q):
+                if t:
+                    lib.call('qb_run_steps', self.state._h, n - t, n, j, Q, sm)
+                on_part_done(j)
+            self.overlapped_steps += t
+        if n:
+            lib.call('qb_finish_queue', self.state._h)
+
+    def _sm_limit(self) -> int:
+        if self._sms is None:
             sms = C.c_int(0)
             self._lib.call('qb_device_info', self.device, None, 0, C.byref(sms), None, None, None)
-            self._lib.call('qb_set_sm_limit', sub._h, max(sms.value - (self.exchange_ctas + 1) // 2, 8))
-            self._subs[key] = sub
-        return sub
+            self._sms = sms.value
+        return max(self._sms - (self.exchange_ctas + 1) // 2, 8)
 
-    def do_exchange_split(self, ex: "Exchange", per_sub):
-        """The exchange in 2^v pieces on a stream of its own, each piece followed on the compute stream by the
-        sweeps of the gates `per_sub[j]` (localised for sub-block j) on that piece.  No host synchronisation:
-        pieces are ordered by events (local) and by flag counters in the receivers' memory (between GPUs)."""
+    def do_exchange_split(self, ex: "Exchange"):
+        """The exchange in 2^v pieces on a stream of its own.  Sending side (ex.send_side): the last sweeps of the
+        queued pass run sub-block by sub-block and piece j leaves right behind sub-block j.  Receiving side: the
+        first sweeps of the NEXT pass run on sub-block j as soon as piece j has arrived from every source (see
+        _run_queued).  No host synchronisation: pieces are ordered by events (local) and by flag counters in the
+        receivers' memory (between GPUs)."""
         import torch
         lib, comm = self._lib, self.comm
         k, v, nl = ex.k, ex.split, self.nl
@@ -451,20 +526,25 @@ class CudaShard:
         fixed_mask = 0
         for i in range(v):
             fixed_mask |= 1 << perm[sub_bits + i]
-        self.state.flush()
-        ready = torch.cuda.Event()
-        ready.record(cs)                       # the sweeps of the pass before the exchange
-        xs.wait_event(ready)
-        with torch.cuda.stream(xs):
-            # every rank is past everything that read or wrote the buffers about to be overwritten remotely
-            comm.dist.all_reduce(tok, group=comm.group)
-        t0 = torch.cuda.Event(enable_timing=True)
-        t0.record(xs)
         dst = (C.c_void_p * (1 << k))()
         sig = (C.c_void_p * max(len(group), 1))(*[self.peer_flags[p] + 8 * rank for p in group])
         wait = (C.c_void_p * max(len(group), 1))(*[self.flags.value + 8 * p for p in group])
         arrived = []
-        for j in range(Q):
+        started = []
+        with torch.cuda.stream(xs):
+            # Every rank is past the scatters of the previous exchange (they read the buffers that are about to be
+            # overwritten remotely; those buffers have not been touched since): one tiny all-reduce on the exchange
+            # streams, queued before the tail sweeps so that it is long done when the first piece is ready to leave
+            comm.dist.all_reduce(tok, group=comm.group)
+
+        def piece(j):
+            done = torch.cuda.Event()
+            done.record(cs)                        # sub-block j of the pass before the exchange is finished
+            xs.wait_event(done)
+            if not started:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(xs)
+                started.append(t0)
             fixed_val = 0
             for i in range(v):
                 fixed_val |= ((j >> i) & 1) << perm[sub_bits + i]
@@ -474,24 +554,20 @@ class CudaShard:
                      C.c_void_p(xs.cuda_stream), self.exchange_ctas)
             self._xseq += 1
             lib.call('qb_signal_flags', self.device, C.c_void_p(xs.cuda_stream), sig, len(group), self._xseq)
-            # my own piece is complete when my kernel is (event) and the sources' counters say so (flags)
             ev = torch.cuda.Event()
             ev.record(xs)
             arrived.append((ev, self._xseq))
+
+        self._run_queued(send_v=v if ex.send_side else 0, on_part_done=piece if ex.send_side else None)
+        if not ex.send_side:
+            for j in range(Q):
+                piece(j)
         t1 = torch.cuda.Event(enable_timing=True)
         t1.record(xs)
-        self._pending_times.append((t0, t1))
+        self._pending_times.append((started[0], t1))
         lib.call('qb_rebind', self.state._h, self.buf[other])
         self.cur = other
-        for j in range(Q):
-            ev, seq = arrived[j]
-            cs.wait_event(ev)
-            lib.call('qb_wait_flags', self.device, None, wait, len(group), seq)
-            sub = self._sub(other, v, j)
-            for loc in per_sub[j]:
-                if loc is not None:
-                    sub.apply_gate_bits(loc[0], list(loc[1]), loc[2])
-            sub.flush()
+        self._incoming = dict(v=v, arrived=arrived, wait=wait, nwait=len(group))
         self.exchanged_bytes += (self.bytes >> k) * ((1 << k) - 1)
         self.exchanges += 1
         self.split_exchanges += 1
@@ -504,6 +580,7 @@ class CudaShard:
 
     def init_basis(self, has_one: bool, local_index: int = 0):
         import torch
+        self.flush()
         if has_one:
             self._lib.call('qb_init_basis', self.state._h, local_index)
         else:
@@ -514,6 +591,7 @@ class CudaShard:
 
     def init_product(self, local_factors: Sequence[np.ndarray], coeff: complex):
         """coeff * kron(local_factors) (first factor = highest local position) built on the device."""
+        self.flush()
         v = np.ascontiguousarray(np.stack([np.asarray(f, dtype=np.complex128).reshape(2) for f in local_factors]))
         v[0] = v[0] * coeff
         self._lib.call('qb_init_product', self.state._h, v.ctypes.data_as(C.c_void_p), 0)
@@ -523,15 +601,20 @@ class CudaShard:
     def rdm_local(self, positions: Sequence[int]) -> np.ndarray:
         """sum over the other local bits of psi psi^dagger on the listed local positions (first = MSB)."""
         nl = self.nl
+        self.flush()
         return np.asarray(self.state.ptrace_keep([nl - 1 - p for p in positions]))
 
     def apply(self, m: np.ndarray, target_positions: Sequence[int], cmask: int):
         self.state.apply_gate_bits(m, list(target_positions), cmask)
 
     def flush(self):
-        self.state.flush()
+        if self._incoming is not None:
+            self._run_queued()
+        else:
+            self.state.flush()
 
     def sync(self):
+        self.flush()
         self.state.sync()
         if self._pending_times:
             self._collect_times()
@@ -597,15 +680,18 @@ class CudaShard:
         self.exchanges += 1
 
     def probs_local(self, positions: Sequence[int]) -> np.ndarray:
+        self.flush()
         out = np.empty(1 << len(positions), dtype=np.float64)
         self._lib.call('qb_probs', self.state._h, self._lib.int_array(positions), len(positions),
                        out.ctypes.data_as(C.c_void_p))
         return out
 
     def download_range(self, first: int, count: int) -> np.ndarray:
+        self.flush()
         return self.state.download_range(first, count)
 
     def download(self) -> np.ndarray:
+        self.flush()
         out = np.empty(1 << self.nl, dtype=np.complex128)
         self._lib.call('qb_download', self.state._h, out.ctypes.data_as(C.c_void_p), out.nbytes)
         return out
@@ -616,19 +702,24 @@ class CudaShard:
 
     def close(self):
         lib = self._lib
-        self.state.sync()
+        _trace("close: sync")
+        self.sync()
         self._subs = {}
         if self.peer:
             import torch
             torch.cuda.synchronize(self.device)
+            _trace("close: barrier 1")
             self.comm.barrier()
+            _trace("close: unmapping the peers")
             for r, ptrs in enumerate(self.peer):
                 if r != self.comm.rank:
                     for p in ptrs + [self.peer_flags[r]]:
                         lib.call('qb_ipc_close', self.device, C.c_void_p(p))
             self.peer = None
             self.peer_flags = None
+            _trace("close: barrier 2")
             self.comm.barrier()
+        _trace("close: freeing")
         if self.flags.value:
             lib.call('qb_buffer_free', self.device, self.flags)
             self.flags.value = None
@@ -651,7 +742,10 @@ class ShardedKet:
         world = comm.world
         # pieces (2^split) of a pipelined exchange; QBOT_B200_EXCHANGE_SPLIT=0 exchanges in one go
         self.split = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT', '2')) if split is None else int(split)
-        self.min_first_phase = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT_MIN_GATES', '40'))   # fewer gates in the overlapped phase: not worth a split
+        self.min_first_phase = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT_MIN_GATES', '40'))   # fewer gates in the overlapped phases: not worth a split
+        # gates per overlapped phase (before / after the exchange): about what it takes to cover the exchange (30 gates per
+        # sweep, exchange = 2-3 sweeps); more would only keep more sweeps on the reduced grid
+        self.phase_cap = int(os.environ.get('QBOT_B200_EXCHANGE_PHASE_GATES', '96'))
         g = world.bit_length() - 1
         if 1 << g != world:
             raise ValueError("the number of ranks must be a power of two")
@@ -717,37 +811,26 @@ class ShardedKet:
         rem = self.queue
         self.queue = []
         mp = self.map
+        split = self.split if getattr(self.shard, 'supports_split', False) else 0
         while rem:
             picked = select_pass(rem, mp.local_mask())
-            if picked:
-                ps = set(picked)
-                for i in picked:
-                    loc = mp.localise(rem[i], self.rank)
-                    if loc is not None:
-                        self.shard.apply(*loc)
-                self.gates_applied += len(picked)
-                rem = [g for i, g in enumerate(rem) if i not in ps]
-                if not rem:
-                    break
-            ex = mp.plan_exchange(rem, self.split if getattr(self.shard, 'supports_split', False) else 0, self.min_first_phase)
+            ps = set(picked)
+            pass_gates = [rem[i] for i in picked]
+            rem = [g for i, g in enumerate(rem) if i not in ps]
+            for g in pass_gates:
+                loc = mp.localise(g, self.rank)
+                if loc is not None:
+                    self.shard.apply(*loc)
+            self.gates_applied += len(pass_gates)
+            if not rem:
+                break
+            ex = mp.plan_exchange(rem, split, self.min_first_phase, prev=pass_gates if split else None, phase_cap=self.phase_cap)
             if ex.k == 0 and not picked:
                 raise RuntimeError("sharded planner made no progress")
-            self.shard.flush()
             if ex.split:
-                # pipelined exchange: the gates that leave the parked bits alone run sub-block by sub-block,
-                # each as soon as its piece of the exchange has arrived (the parked bits and the rank bits
-                # are predicates / scalars there); the others follow on the whole shard
-                v = ex.split
-                hmask = 0
-                for b in ex.hbits:
-                    hmask |= 1 << b
-                first = select_pass(rem, mp.local_mask() & ~hmask)
-                fs = set(first)
-                per_sub = [[mp.localise(rem[i], (self.rank << v) | j, mp.nl - v) for i in first] for j in range(1 << v)]
-                self.shard.do_exchange_split(ex, per_sub)
-                self.gates_applied += len(first)
-                rem = [g for i, g in enumerate(rem) if i not in fs]
+                self.shard.do_exchange_split(ex)       # runs the queued pass; its last sweeps and the next pass's first ones overlap the pieces
             else:
+                self.shard.flush()
                 self.shard.do_exchange(ex)
         self.shard.flush()
 

@@ -20,6 +20,17 @@ KET, DM = 0, 1
 HOST_MATERIALIZE_LIMIT = 1 << 31      # bytes; larger states refuse implicit np.asarray()
 
 
+_ONE_BIT = [(C.c_int * 1)(b) for b in range(64)]
+_fn_cache = {}
+
+
+def _apply_gate_fn():
+    f = _fn_cache.get('qb_apply_gate')
+    if f is None:
+        f = _fn_cache['qb_apply_gate'] = _lib.load().qb_apply_gate
+    return f
+
+
 def _cptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -237,18 +248,24 @@ class DeviceState:
         return self.nq - 1 - int(qubit)
 
     def apply_gate(self, matrix, first_target: int = 0, controls: Iterable[int] = ()) -> "DeviceState":
-        m = _cmat(matrix)
-        k = int(m.shape[0]).bit_length() - 1
-        if m.shape != (1 << k, 1 << k):
+        m = matrix if type(matrix) is np.ndarray and matrix.dtype == np.complex128 else _cmat(matrix)
+        dim = m.shape[0]
+        k = dim.bit_length() - 1
+        if m.ndim != 2 or m.shape[1] != dim or dim != 1 << k:
             raise Exception("gate size must be power of 2")
-        if first_target < 0 or first_target + k - 1 >= self.nq:
-            raise IndexError(f"{k} qubit gate does not fit the {self.nq} qubit hilbertspace when started on qubit {first_target}")
-        bits = _lib.int_array([self._bit(first_target + j) for j in range(k)])
+        nq = self.nq
+        if first_target < 0 or first_target + k - 1 >= nq:
+            raise IndexError(f"{k} qubit gate does not fit the {nq} qubit hilbertspace when started on qubit {first_target}")
+        # (this is the per-line cost of a `gate` op: the matrix travels as a bytes object -- the library copies it
+        # while queueing -- and one-target bit lists are shared constants; ndarray.ctypes alone costs 2-4 us)
+        bits = _ONE_BIT[nq - 1 - first_target] if k == 1 else _lib.int_array([nq - 1 - first_target - j for j in range(k)])
         cmask = 0
         for c in controls:
-            cmask |= 1 << self._bit(c)
-        _lib.call('qb_apply_gate', self._h, _cptr(m), k, bits, cmask)
-        self._dirty()
+            cmask |= 1 << (nq - 1 - int(c))
+        rc = _apply_gate_fn()(self._h, m.tobytes(), k, bits, cmask)
+        if rc:
+            _lib.check(rc)
+        self._host_cache = None
         return self
 
     def apply_gate_bits(self, matrix, target_bits: Sequence[int], control_mask: int = 0) -> "DeviceState":

@@ -151,20 +151,12 @@ class NumpyShard:
 
     supports_split = True      # (tests switch it off to compare with the plain exchange)
 
-    def do_exchange_split(self, ex, per_sub):
-        """The data movement of a pipelined exchange in one go, then the first-phase gates sub-block by
-        sub-block (what CudaShard overlaps with the later pieces)."""
+    def do_exchange_split(self, ex):
+        """The data movement of a pipelined exchange (packed layout [parked bits][chunk bits][rest]) in one go; what
+        CudaShard overlaps with it -- sweeps on tile ranges -- does not exist on the numpy shard."""
         self.do_exchange(ex)
-        v = ex.split
-        sub = 1 << (self.nl - v)
-        for j, gates in enumerate(per_sub):
-            blk = self.psi[j * sub:(j + 1) * sub]
-            for loc in gates:
-                if loc is not None:
-                    blk = np_apply_bits(blk, self.nl - v, np.asarray(loc[0]), list(loc[1]), loc[2])
-                    self.applied += 1
-            self.psi[j * sub:(j + 1) * sub] = blk
         self.split_exchanges = getattr(self, 'split_exchanges', 0) + 1
+        self.send_side_exchanges = getattr(self, 'send_side_exchanges', 0) + (1 if ex.send_side else 0)
 
     def probs_local(self, positions):
         m = len(positions)

@@ -65,6 +65,9 @@ ops = circuit_ops(n, 6, 11)
 split = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 sk = ShardedKet(n, TorchComm(), device=dev, exchange=mode, split=split)
 sk.min_first_phase = 6
+if split:
+    sk.shard.set_jit(2)              # only specialised sweeps take tile ranges (run sub-block by sub-block beside the exchange)
+    sk.shard.overlap_steps = 2
 for m, t, cs in ops:
     sk.apply_gate(m, t, cs)
 ket = sk.gather()
@@ -74,8 +77,9 @@ err = float(np.max(np.abs(ket - want)))
 perr = float(np.max(np.abs(pr - orc.ket_probs(want, n, [1, n - 1, 0]))))
 amp = sk.amplitudes([3, (1 << n) - 2])
 aerr = float(np.max(np.abs(amp - want[[3, (1 << n) - 2]])))
-print(json.dumps(dict(rank=rank, err=err, perr=perr, aerr=aerr, exchanges=sk.shard.exchanges, split_exchanges=sk.shard.split_exchanges,
-                      launches=sk.shard.state.stats()['kernel_launches'])))
+sys.stdout.write(json.dumps(dict(rank=rank, err=err, perr=perr, aerr=aerr, exchanges=sk.shard.exchanges, split_exchanges=sk.shard.split_exchanges, overlapped=sk.shard.overlapped_steps,
+                            launches=sk.shard.state.stats()['kernel_launches'])) + '\n')
+sys.stdout.flush()
 sk.close()
 dist.barrier()
 dist.destroy_process_group()
@@ -111,8 +115,10 @@ def test_pipelined_exchange_processes_sharing_one_gpu(tmp_path, nproc, n, split)
     sub-ket handles with a reduced grid: same ket as the oracle, and the pipelined path was taken."""
     import json
     out = _run_ranks(nproc, 'p2p', 'gloo', n, tmp_path, split)
-    recs = [json.loads(ln) for ln in out.splitlines() if ln.startswith('{')]
+    import re
+    recs = [json.loads(x) for x in re.findall(r'\{[^{}]*\}', out)]       # (two ranks may print on one line)
     assert len(recs) == nproc and all(r['split_exchanges'] >= 1 for r in recs), recs
+    assert any(r['overlapped'] >= 1 for r in recs), recs        # some sweeps did run on tile ranges
 
 
 @pytest.mark.parametrize('mode', ['p2p', 'nccl'])
@@ -134,7 +140,8 @@ def test_pipelined_exchange_one_rank_per_gpu(tmp_path):
         pytest.skip("needs >= 2 GPUs")
     nproc = 1 << (ng.bit_length() - 1)
     out = _run_ranks(nproc, 'p2p', 'nccl', 20, tmp_path, 2)
-    recs = [json.loads(ln) for ln in out.splitlines() if ln.startswith('{')]
+    import re
+    recs = [json.loads(x) for x in re.findall(r'\{[^{}]*\}', out)]       # (two ranks may print on one line)
     assert len(recs) == nproc and all(r['split_exchanges'] >= 1 for r in recs), recs
 
 
@@ -222,7 +229,8 @@ keep = [0, 5, n - 1]
 mm = np.ascontiguousarray(t.transpose(keep + [a for a in range(n) if a not in keep])).reshape(8, -1)
 errs['rho_a'] = float(np.max(np.abs(np.asarray(ns['rho_a']) - mm @ mm.conj().T)))
 st = reg.stats()
-print(json.dumps(dict(rank=rank, kind=type(reg).__name__, errs=errs, exchanges=st['exchanges'], launches=st['kernel_launches'])))
+sys.stdout.write(json.dumps(dict(rank=rank, kind=type(reg).__name__, errs=errs, exchanges=st['exchanges'], launches=st['kernel_launches'])) + '\n')
+sys.stdout.flush()
 del ns, reg
 sr.disable()
 dist.barrier()

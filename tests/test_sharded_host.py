@@ -106,9 +106,9 @@ def test_virtual_ranks_match_oracle(n, world):
 
 @pytest.mark.parametrize('n,world,split', [(15, 2, 2), (16, 4, 2), (16, 8, 1), (16, 4, 3)])
 def test_pipelined_exchange_plan_matches_oracle(n, world, split):
-    """Exchanges planned in 2^split pieces: parked bits on top of the shard, the first-phase gates localised
-    per sub-block (parked bits as predicates / scalars), the rest on the whole shard -- same ket as the oracle,
-    same ket as the plain exchange, and the pipelined path is actually taken."""
+    """Exchanges planned in 2^split pieces: parked bits on top of the shard (kept there from one exchange to the next
+    when the gates around the exchange leave them alone, re-chosen otherwise), packed layout [parked][chunk][rest] --
+    same ket as the oracle, and the pipelined path is actually taken."""
     ops = circuit_ops(n, 8, 300 + n)
     want = expected_ket(n, ops)
     shared = VirtualComm.Shared(world)
@@ -119,13 +119,14 @@ def test_pipelined_exchange_plan_matches_oracle(n, world, split):
         try:
             sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard, split=split)
             sk.min_first_phase = 6
-            for rep in range(2):                 # the second pass starts from a permuted qubit map
+            for rep in range(3):                 # later passes start from a permuted qubit map with parked bits on top
                 for m, t, cs in ops:
                     sk.apply_gate(m, t, cs)
                 sk.flush()
                 if rep == 0:
                     first = sk.gather()
             out[rank] = dict(first=first, second=sk.gather(), split_exchanges=getattr(sk.shard, 'split_exchanges', 0),
+                             send_side=getattr(sk.shard, 'send_side_exchanges', 0),
                              exchanges=sk.shard.exchanges, probs=sk.probs([0, n - 1]))
         except Exception as e:     # pragma: no cover
             errors.append(e)
@@ -137,8 +138,9 @@ def test_pipelined_exchange_plan_matches_oracle(n, world, split):
     if errors:
         raise errors[0]
     want2 = want
-    for m, t, cs in ops:
-        want2 = orc.ket_apply(want2, n, t, m, cs)
+    for rep in range(2):
+        for m, t, cs in ops:
+            want2 = orc.ket_apply(want2, n, t, m, cs)
     for r in range(world):
         assert np.max(np.abs(out[r]['first'] - want)) < 1e-12
         assert np.max(np.abs(out[r]['second'] - want2)) < 1e-12
