@@ -230,11 +230,14 @@ int qb_set_sm_limit(qb_state* s, int nsms);
 /* Stream-ordered signals between the GPUs of a box.  `flags` are 8-byte counters in device memory, local or
  * peer-mapped (qb_buffer_alloc + qb_ipc_export / qb_ipc_open; zero them once).  qb_signal_flags stores `value`
  * into each of them after everything queued earlier on `cuda_stream` (NULL = the compute stream) has completed;
- * qb_wait_flags holds `cuda_stream` until every listed counter is >= value (bounded: after ~10 s the wait gives
+ * qb_wait_flags holds `cuda_stream` until every listed counter is >= value (bounded: after ~60 s the wait gives
  * up and qb_flag_timeouts counts it -- a lost peer must not hang the GPU). */
 int qb_signal_flags(int device, void* cuda_stream, void* const* flags, int n, uint64_t value);
 int qb_wait_flags(int device, void* cuda_stream, void* const* flags, int n, uint64_t value);
 int qb_flag_timeouts(int device, uint64_t* count);
+/* Asynchronous device-to-device copy on `cuda_stream` (NULL = the compute stream); dst / src may be peer mappings
+ * (qb_ipc_open): the copy engines carry it over NVLink while the SMs keep running sweeps. */
+int qb_copy_async(int device, void* dst, const void* src, size_t bytes, void* cuda_stream);
 /* The CUDA stream every handle of `device` works on unless it was given one of its own
  * (qb_create_external / qb_set_stream): for event-ordering foreign streams against the library's work. */
 int qb_compute_stream(int device, void** cuda_stream_out);

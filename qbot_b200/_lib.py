@@ -86,6 +86,7 @@ PROTOTYPES = {
     'qb_wait_flags': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint64]),
     'qb_flag_timeouts': (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
     'qb_compute_stream': (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    'qb_copy_async': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'qb_get_stats': (C.c_int, [c_state_p, C.POINTER(QbStats)]),
     'qb_reset_stats': (C.c_int, [c_state_p]),
     'qb_timer_start': (C.c_int, [c_state_p]),

@@ -1257,6 +1257,15 @@ int qb_flag_timeouts(int device, uint64_t* count) {
     QB_API_END
 }
 
+int qb_copy_async(int device, void* dst, const void* src, size_t bytes, void* cuda_stream) {
+    QB_API_BEGIN
+    QB_REQUIRE(dst && src, "NULL argument");
+    DevGuard g(device);
+    // device-to-device (local or a peer mapping): the copy engines move it, no SM is involved
+    QB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, cuda_stream ? (cudaStream_t)cuda_stream : default_stream(device)));
+    QB_API_END
+}
+
 int qb_compute_stream(int device, void** cuda_stream_out) {
     QB_API_BEGIN
     QB_REQUIRE(cuda_stream_out, "NULL argument");

@@ -814,7 +814,7 @@ __global__ void k_wait_flags(FlagPtrs f, unsigned long long value, unsigned long
         volatile unsigned long long* p = (volatile unsigned long long*)f.p[i];
         bool ok = false;
         while (!(ok = *p >= value)) {
-            if (clock64() - t0 > 20000000000ll) break;        // ~10 s: a peer died; fail (counted) instead of hanging the GPU
+            if (clock64() - t0 > 120000000000ll) break;       // ~60 s (ranks may be seconds apart while one compiles): a peer died; fail (counted) instead of hanging the GPU
             __nanosleep(500);
         }
         __threadfence_system();

