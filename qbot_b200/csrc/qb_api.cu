@@ -357,15 +357,32 @@ void qb_state::enqueue(QGate&& g) {
     if (!fusion || queue.size() >= 4096) flush();
 }
 
+void qb_state::materialize() {
+    if (!virt) return;
+    virt = false;
+    DevGuard gd(device);
+    qb_launch_fill_basis(ctx(), d, per_branch(), nbranch, virt_index);
+    stats.bytes_moved += bytes();
+}
+
+// true when an initial basis state may stay virtual (see qb_state::virt): large single-branch kets only -- small
+// registers and density matrices are written at once (their first steps are not specialised sweeps anyway)
+static bool lazy_basis_ok(const qb_state* s) {
+    static const bool on = [] { const char* e = getenv("QBOT_B200_LAZY_INIT"); return !e || atoi(e) != 0; }();
+    return on && s->kind == QB_KET && s->nbranch == 1 && s->nbits >= 22 && s->fusion && qb_engine_available();
+}
+
 void qb_state::flush() {
-    if (queue.empty()) return;
+    if (queue.empty()) { materialize(); return; }
     if (pending_plan) throw qb_error(-4, "gates were queued while a planned queue is being run step by step (qb_finish_queue first)");
     DevGuard gd(device);
     std::vector<QGate> q;
     q.swap(queue);
     if (fusion && qb_engine_available()) {
         qb_engine_run(this, q);
+        materialize();               // (a plan without steps)
     } else {
+        materialize();
         for (const QGate& g : q) run_gate_unfused(g);
     }
 }
@@ -476,6 +493,8 @@ int qb_init_basis(qb_state* s, uint64_t index) {
         QB_REQUIRE(index < (1ull << s->nq), "basis index out of range");
         flat = (index << s->nq) | index;
     } else QB_REQUIRE(index < per, "basis index out of range");
+    if (lazy_basis_ok(s)) { s->virt = true; s->virt_index = flat; return QB_OK; }      // written by whoever needs it first
+    s->virt = false;
     qb_launch_fill_basis(s->ctx(), s->d, per, s->nbranch, flat);
     s->stats.bytes_moved += s->bytes();
     QB_API_END
@@ -485,6 +504,19 @@ int qb_init_product(qb_state* s, const double* vecs, int per_branch) {
     QB_API_BEGIN
     QB_REQUIRE(s && vecs, "NULL argument");
     s->queue.clear();
+    s->virt = false;
+    if (!per_branch && lazy_basis_ok(s)) {
+        // a product of computational basis kets (tensorExp(comp.kets[0], n), ...) is a basis state
+        uint64_t index = 0;
+        bool basis = true;
+        for (int q = 0; q < s->nq && basis; q++) {
+            const double* f = vecs + 4 * q;          // (re0, im0, re1, im1)
+            if (f[0] == 1.0 && f[1] == 0.0 && f[2] == 0.0 && f[3] == 0.0) { }
+            else if (f[0] == 0.0 && f[1] == 0.0 && f[2] == 1.0 && f[3] == 0.0) index |= 1ull << (s->nq - 1 - q);
+            else basis = false;
+        }
+        if (basis) { s->virt = true; s->virt_index = index; return QB_OK; }
+    }
     DevGuard g(s->device);
     size_t per = (s->kind == QB_KET ? 2 : 4) * (size_t)s->nq;
     size_t count = per * (per_branch ? (size_t)s->nbranch : 1);
@@ -502,6 +534,7 @@ int qb_init_diag(qb_state* s, const double* values) {
     QB_REQUIRE(s && values, "NULL argument");
     QB_REQUIRE(s->kind == QB_DM && s->nbranch == 1, "init_diag: needs a single-branch density matrix");
     s->queue.clear();
+    s->virt = false;
     DevGuard g(s->device);
     const size_t vb = sizeof(double) << s->nq;
     double* dv = (double*)work_alloc(s->device, vb, s->stream);
@@ -517,6 +550,7 @@ int qb_upload(qb_state* s, const void* host, size_t bytes) {
     QB_REQUIRE(s && host, "NULL argument");
     QB_REQUIRE(bytes == s->bytes(), "upload: byte count does not match the state size");
     s->queue.clear();
+    s->virt = false;
     DevGuard g(s->device);
     QB_CUDA(cudaMemcpyAsync(s->d, host, bytes, cudaMemcpyHostToDevice, s->stream));
     QB_CUDA(cudaStreamSynchronize(s->stream));
@@ -757,7 +791,9 @@ int qb_jit_check(int nbits, int ngates, const int* ks, const int* target_bits, c
     }
     for (const QtPlanStep& st : steps) {
         if (!st.fused) continue;
-        const std::string src = qb_jit_full_source(st.program.data(), nullptr, nullptr);
+        // (QBOT_B200_JIT_CHECK_VIRTUAL=1: the first sweep as its virtual-basis variant -- what runs right after qb_init_basis)
+        const bool virt = n == 0 && getenv("QBOT_B200_JIT_CHECK_VIRTUAL") != nullptr;
+        const std::string src = qb_jit_full_source(st.program.data(), nullptr, nullptr, virt);
         const std::vector<char> cubin = qb_jit_compile(src, nullptr);
         if (cubin_dir) {
             const std::string base = std::string(cubin_dir) + "/sweep_" + std::to_string(n);

@@ -26,6 +26,12 @@ struct qb_state {
     size_t stage_off = 0;
     // fused engine state (plan cache, device copies of the sweep programs)
     void* engine = nullptr;
+    // The register IS the basis state |virt_index> and nothing has been written yet (qb_init_basis / a product of basis
+    // kets on a large single-branch ket): the first fused sweep starts from the known state instead of loading it
+    // (qj_kernel's virtual-basis variant); anything else that touches the amplitudes writes them first (materialize).
+    bool virt = false;
+    uint64_t virt_index = 0;
+    void materialize();
     // a planned gate list whose steps the caller runs range by range (qb_plan_queue / qb_run_steps / qb_finish_queue)
     void* pending_plan = nullptr;
     int pending_jit = 0;

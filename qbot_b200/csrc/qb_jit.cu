@@ -149,6 +149,36 @@ qj_kernel(double2* __restrict__ psi, const unsigned long long tile0, const unsig
 }
 )QJ";
 
+// Variant of a sweep for a register that still IS a computational basis state |vindex> (qb_init_basis, or a product of
+// basis kets, followed directly by gates): the tile is not loaded -- every amplitude is 0 except the one at vindex -- so
+// the pass that would write the initial state and the read of it by the first sweep never happen (2 x 16 * 2^n bytes).
+// Same stage functions; only the load / prefetch macros and the kernel skeleton differ, appended AFTER the common
+// prelude so that the ordinary kernels' sources (and hashes) are untouched.
+const char* kVirtualPatch = R"QJ(
+#undef QJ_LD
+#define QJ_LD(p) (((unsigned long long)((p) - psi)) == nbase ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0))
+#undef QJ_ISSUE_EARLY
+#define QJ_ISSUE_EARLY(tid, nbase, psi, buf) do { } while (0)
+#undef QJ_ISSUE_NEXT
+#define QJ_ISSUE_NEXT(tid, nbase, psi, buf) __syncthreads()
+#undef QJ_PREFETCH
+#define QJ_PREFETCH(psi, nbase, tid) do { } while (0)
+)QJ";
+const char* kVirtualPostlude = R"QJ(
+extern "C" __global__ void __launch_bounds__(QJ_T, QJ_CTAS)
+qj_kernel(double2* __restrict__ psi, const unsigned long long tile0, const unsigned long long ntiles, const int prefetch, QJ_POOL_KPARAM,
+          const unsigned long long vindex) {
+    extern __shared__ __align__(16) double2 buf[];
+    const unsigned tid = threadIdx.x;
+    (void)prefetch;
+    for (unsigned long long tile = tile0 + blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned long long tbase = qj_tile_base(tile);
+        // `nbase` carries the index of the one non-zero amplitude; pre = 0: every tile takes the "load" path of stage 0
+        QJ_RUN_STAGES(tid, tbase, vindex, ~0ull, 0u, psi, buf, P)
+    }
+}
+)QJ";
+
 // ---- dynamically bound NVRTC + driver API ---------------------------------------------------------
 struct Nvrtc {
     void* so = nullptr;
@@ -258,7 +288,7 @@ constexpr int kMaxParamPoolDoubles = 480;     // 3840 bytes of coefficients + 24
 
 }  // namespace
 
-std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool* pool_global) {
+std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool* pool_global, bool virtual_basis) {
     QjSourceInfo li;
     std::string body = qj_generate(program, &li);
     const bool pg = li.npool > kMaxParamPoolDoubles;
@@ -272,8 +302,9 @@ std::string qb_jit_full_source(const uint8_t* program, QjSourceInfo* info, bool*
     if (getenv("QBOT_B200_DEBUG_NOWAIT")) src += "#define QJ_DEBUG_NOWAIT 1\n";
     if (const int c = jit_ctas_override(li.M)) src += "#define QJ_CTAS " + std::to_string(c) + "\n";
     src += kPrelude;
+    if (virtual_basis) src += kVirtualPatch;
     src += body;
-    src += kPostlude;
+    src += virtual_basis ? kVirtualPostlude : kPostlude;
     return src;
 }
 
@@ -375,10 +406,10 @@ void qb_jit_precompile(const std::vector<const uint8_t*>& programs) {
 }
 
 // compile one program into the cache without loading it on any device (host work only)
-void qb_jit_compile_cached(const uint8_t* program) {
+void qb_jit_compile_cached(const uint8_t* program, bool virtual_basis) {
     QjSourceInfo info;
     bool pg = false;
-    const std::string src = qb_jit_full_source(program, &info, &pg);
+    const std::string src = qb_jit_full_source(program, &info, &pg, virtual_basis);
     const uint64_t key = qj_hash(src);
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -399,10 +430,10 @@ void qb_jit_compile_cached(const uint8_t* program) {
 }
 
 // the compiled kernel of `program` on `device` (compiling / loading it on first use)
-QbJitKernel qb_jit_get(const uint8_t* program, int device) {
+QbJitKernel qb_jit_get(const uint8_t* program, int device, bool virtual_basis) {
     QjSourceInfo info;
     bool pg = false;
-    const std::string src = qb_jit_full_source(program, &info, &pg);
+    const std::string src = qb_jit_full_source(program, &info, &pg, virtual_basis);
     const uint64_t key = qj_hash(src);
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_cache.find(key);
@@ -452,13 +483,13 @@ QbJitKernel qb_jit_get(const uint8_t* program, int device) {
 
 // launch: `pool` = qj_pool(program) on the host (parameter variant) or its device copy
 void qb_jit_launch(const QbJitKernel& k, cudaStream_t stream, int sms, cplx* psi, uint64_t tile_begin, uint64_t tile_end, int prefetch,
-                   const double* pool_host, const double* pool_dev) {
+                   const double* pool_host, const double* pool_dev, uint64_t virtual_index) {
     Driver& d = driver();
-    unsigned long long t0 = tile_begin, nt = tile_end;
+    unsigned long long t0 = tile_begin, nt = tile_end, vi = virtual_index;
     int pf = prefetch;
     void* psi_arg = (void*)psi;
     const void* pool_ptr = pool_dev;
-    void* args[5] = {&psi_arg, &t0, &nt, &pf, k.pool_global ? (void*)&pool_ptr : (void*)pool_host};
+    void* args[6] = {&psi_arg, &t0, &nt, &pf, k.pool_global ? (void*)&pool_ptr : (void*)pool_host, &vi};     // (vi: the virtual-basis variant only)
     const unsigned grid = (unsigned)std::min<uint64_t>(tile_end - tile_begin, (uint64_t)sms * k.ctas_per_sm);
     CUresult e = d.LaunchKernel((CUfunction)k.fn, grid, 1, 1, (unsigned)k.threads, 1, 1, (unsigned)k.smem_bytes, (CUstream)stream, args, nullptr);
     if (e != CUDA_SUCCESS) throw qb_error(-2, "cuLaunchKernel(sweep): " + cu_err(e));

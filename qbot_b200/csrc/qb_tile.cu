@@ -185,6 +185,8 @@ struct CachedPlan {
     // seen before (in this plan, an earlier plan or another state)
     struct StepJit {
         uint64_t key = 0;              // hash of the specialised source (0: not generated yet)
+        QbJitKernel kv;                // the virtual-basis variant (first sweep after qb_init_basis), compiled on first use
+        bool kv_ready = false, kv_failed = false;
         bool ready = false, failed = false;
         QbJitKernel k;
         std::vector<double> pool;      // run-time coefficients (host copy, passed as kernel parameters)
@@ -388,7 +390,7 @@ void wait_for_warm(uint64_t plan_hash) {
     if (t.joinable()) t.join();
 }
 
-void warm_in_background(const std::vector<QGate>& gates, int nbits, int total_bits, int M, uint64_t plan_hash) {
+void warm_in_background(const std::vector<QGate>& gates, int nbits, int total_bits, int M, uint64_t plan_hash, bool virtual_first) {
     if (!qb_jit_available(nullptr)) return;
     std::lock_guard<std::mutex> lk(g_warmers.mu);
     if (g_warmers.running >= 2) return;
@@ -396,7 +398,7 @@ void warm_in_background(const std::vector<QGate>& gates, int nbits, int total_bi
     g_warmers.started.push_back(plan_hash);
     g_warmers.running++;
     const int trials = env_int("QBOT_B200_PLAN_TRIALS", total_bits >= 29 ? 128 : total_bits >= 27 ? 32 : total_bits >= 23 ? 8 : 1);   // as get_plan
-    g_warmers.threads.emplace_back([gates, nbits, M, trials]() {
+    g_warmers.threads.emplace_back([gates, nbits, M, trials, virtual_first]() {
         try {
             QtPlanOptions opt;
             opt.M = M;
@@ -408,6 +410,9 @@ void warm_in_background(const std::vector<QGate>& gates, int nbits, int total_bi
             for (const QtPlanStep& st : steps) if (st.fused) progs.push_back(st.program.data());
             if (progs.size() == 1) qb_jit_compile_cached(progs[0]);
             else if (!progs.empty()) qb_jit_precompile(progs);
+            // the gate list came right behind a basis-state initialisation: a run on a fresh register will start its
+            // first sweep from the known state (virtual-basis variant of that sweep)
+            if (virtual_first && !steps.empty() && steps[0].fused) qb_jit_compile_cached(steps[0].program.data(), true);
         } catch (...) {
         }
         std::lock_guard<std::mutex> lk2(g_warmers.mu);
@@ -451,7 +456,7 @@ static CachedPlan* engine_prepare(qb_state* s, const std::vector<QGate>& gates, 
         plan->uses++;
         if (tiled && jit_mode == 1 && big && engine_jit_R() == QT_MAXR && plan->uses == 1 && env_int("QBOT_B200_JIT_BACKGROUND", 1))
             warm_in_background(gates, s->nbits, s->nbits + (s->nbranch > 1 ? 63 - __builtin_clzll((unsigned long long)s->nbranch) : 0), M,
-                               plan->hash);     // a second run will find its kernels compiled
+                               plan->hash, s->virt);     // a second run will find its kernels compiled
         if (tiled && jit_mode == 1 && big && engine_jit_R() == QT_MAXR && plan->uses >= 2 && !plan->upgrade_failed) {
             CachedPlan* base = plan;
             try {
@@ -483,6 +488,32 @@ static void engine_run_steps(qb_state* s, CachedPlan* plan, int jit_mode, size_t
     const bool counts = part == nparts - 1;          // a pass over the state is complete with its last part
     for (size_t i = from; i < to && i < plan->steps.size(); i++) {
         const QtPlanStep& st = plan->steps[i];
+        if (s->virt) {
+            // the register is still the untouched basis state: a specialised sweep over the whole state starts from the
+            // known amplitudes (no load); every other kind of step needs them in memory first
+            bool done = false;
+            if (st.fused && nparts == 1 && jit_mode != 0 && step_jit(s, plan, i, jit_mode)) {
+                CachedPlan::StepJit& j = plan->jit[i];
+                if (!j.kv_ready && !j.kv_failed) {
+                    try { j.kv = qb_jit_get(st.program.data(), s->device, true); j.kv_ready = true; }
+                    catch (const qb_error&) { j.kv_failed = true; }
+                }
+                if (j.kv_ready) {
+                    qb_jit_launch(j.kv, s->stream, sms, s->d, t0, t1, 0, j.pool.data(), j.pool_dev, s->virt_index);
+                    s->virt = false;
+                    s->stats.jit_passes++;
+                    s->stats.kernel_launches++;
+                    s->stats.fused_passes++;
+                    s->stats.state_passes++;
+                    s->stats.fused_gates += st.ngates;
+                    s->stats.gates_applied += st.ngates;
+                    s->stats.bytes_moved += (uint64_t)s->bytes();          // written once, never read
+                    done = true;
+                }
+            }
+            if (done) continue;
+            s->materialize();
+        }
         if (!st.fused) {
             if (nparts != 1) throw qb_error(-1, "a one-gate step cannot run on a sub-block");
             s->run_gate_unfused(plan->gates[st.gate_index]);
@@ -527,6 +558,7 @@ void qb_engine_run(qb_state* s, const std::vector<QGate>& gates) {
 int qb_engine_plan_pending(qb_state* s, const std::vector<QGate>& gates, int park_bits, int* head, int* tail) {
     std::lock_guard<std::mutex> lk(g_engine_mu);
     int jit_mode = 0;
+    s->materialize();
     CachedPlan* plan = engine_prepare(s, gates, &jit_mode);
     s->pending_plan = plan;
     s->pending_jit = jit_mode;

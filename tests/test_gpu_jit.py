@@ -155,3 +155,67 @@ def test_jit_large_coefficient_pool(DS, jit_R):
     for m, tb, cm in gl:
         ref = oracle_apply_bits(ref, n, m, tb, cm)
     assert close(got, ref, 1e-12)
+
+
+def test_lazy_basis_state_initialisation():
+    """A large single-branch ket initialised to a basis state (qb_init_basis, or a product of basis kets) is not
+    written until something needs it: the first specialised sweep starts from the known amplitudes (qj_kernel's
+    virtual-basis variant), every other consumer makes the library write the state first.  All routes against the
+    oracle / the definition."""
+    import numpy as np
+    from oracle import qbot_oracle as orc
+    from qbot_b200 import DeviceState, circuits
+    n = 22
+    # (1) read before any gate: probabilities, a range, a clone
+    st = DeviceState.zero_state(n)
+    assert st.probs([0, n - 1]).tolist() == [1.0, 0.0, 0.0, 0.0]
+    st = DeviceState.zero_state(n)
+    assert st.download_range(0, 2).tolist() == [1.0, 0.0]
+    st = DeviceState.zero_state(n)
+    c = st.clone()
+    assert c.download_range(0, 1)[0] == 1.0 and float(c.norm2()[0]) == 1.0
+    # (2) product of basis kets with some |1> factors, specialised sweeps at first sight
+    ones = [1, 7, n - 1]
+    factors = [np.array([0, 1], dtype=complex) if q in ones else np.array([1, 0], dtype=complex) for q in range(n)]
+    index = sum(1 << (n - 1 - q) for q in ones)
+    gates = circuits.rc(n, 3, 77)
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[index] = 1
+    for g in gates:
+        orc.ket_apply_inplace(psi, n, g.target, g.matrix(), g.controls)
+    for jit, fusion in ((2, True), (0, True), (2, False)):
+        st = DeviceState.product(factors)
+        st.set_jit(jit)
+        st.set_fusion(fusion)
+        for g in gates:
+            st.apply_gate(g.matrix(), g.target, g.controls)
+        got = np.asarray(st)
+        assert np.max(np.abs(got - psi)) < 1e-12 * np.max(np.abs(psi)), (jit, fusion)
+        if jit == 2 and fusion:
+            s = st.stats()
+            assert s['jit_passes'] == s['fused_passes'] > 0
+    # (3) a one-gate kernel first (dense 3-qubit block: not fused), then sweeps
+    u = np.linalg.qr(np.random.default_rng(3).normal(size=(8, 8)) + 1j * np.random.default_rng(4).normal(size=(8, 8)))[0]
+    st = DeviceState.zero_state(n)
+    st.set_jit(2)
+    st.apply_gate(u, 4)
+    ref = np.zeros(1 << n, dtype=complex)
+    ref[0] = 1
+    ref = orc.ket_apply(ref, n, 4, u, [])
+    for g in gates[:20]:
+        st.apply_gate(g.matrix(), g.target, g.controls)
+        orc.ket_apply_inplace(ref, n, g.target, g.matrix(), g.controls)
+    assert np.max(np.abs(np.asarray(st) - ref)) < 1e-12 * np.max(np.abs(ref))
+    # (4) the same state object initialised again after use
+    st = DeviceState.zero_state(n)
+    st.set_jit(2)
+    for rep in range(2):
+        for g in gates:
+            st.apply_gate(g.matrix(), g.target, g.controls)
+        st.flush()
+    from qbot_b200 import _lib
+    _lib.call('qb_init_basis', st._h, index)
+    st._dirty()
+    for g in gates:
+        st.apply_gate(g.matrix(), g.target, g.controls)
+    assert np.max(np.abs(np.asarray(st) - psi)) < 1e-12 * np.max(np.abs(psi))
