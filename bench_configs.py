@@ -148,6 +148,25 @@ def _peak():
     return measured_peaks()
 
 
+def _warm_until_steady(torch, call, max_calls: int = 16, min_calls: int = 6):
+    """Untimed calls of `call` until the specialiser is done with it: gate lists are planned in the specialised shape and
+    NVRTC-compiled over their first few sightings, partly by background threads (two at a time).  Steady = nothing compiled
+    for three calls in a row and a call takes about as long as the fastest one seen."""
+    from qbot_b200 import _lib as _l
+    quiet, best = 0, float('inf')
+    for i in range(max_calls):
+        c0 = _l.jit_info()['kernels_compiled']
+        torch.cuda.synchronize()
+        tw = time.perf_counter()
+        call()
+        torch.cuda.synchronize()
+        tw = time.perf_counter() - tw
+        best = min(best, tw)
+        quiet = quiet + 1 if (_l.jit_info()['kernels_compiled'] == c0 and tw < 1.5 * best) else 0
+        if i + 1 >= min_calls and quiet >= 3:
+            break
+
+
 def _flush_l2(torch, buf):
     buf.add_(1)          # 256 MiB read + write on torch's stream: evicts the 126 MB L2
 
@@ -187,8 +206,7 @@ def run_c2(steps: int, warmup: int, cpu: bool = True):
     import qbot_b200
     qs = [0, 7, 13, 19]
     script = "\n".join([f"qset tensorExp(comp.kets[0], {n})"] + [g.dsl() for g in gates] + [f"peek r ; comp ; {qs}"])
-    for _ in range(3):
-        ns = qbot_b200.executeTxt(script)
+    _warm_until_steady(torch, lambda: qbot_b200.executeTxt(script), min_calls=3)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -313,12 +331,13 @@ def run_c3(steps: int, warmup: int, cpu: bool = True, cpu_budget_s: float = 20.0
     # product descriptor built on the device (host -> device: the per-qubit factors and every gate matrix); the
     # final 8-qubit register and every measurement's weights / rho_A come back to the host.
     from qbot_b200 import _lib as _l
-    for i in range(8):          # warm-up: the program's sweeps are specialised (NVRTC) when it is seen again; none of that is timed
-        c0 = _l.jit_info()['kernels_compiled']
+    # warm-up (scripts/c3_e2e_probe.py: 8.2-8.5 ms per call in the steady state, single calls of 14-360 ms while kernels arrive)
+    def _one():
+        nonlocal ns, final
         ns = qbot_b200.executeTxt(program)
         final = np.asarray(ns['state'])
-        if i >= 2 and _l.jit_info()['kernels_compiled'] == c0:
-            break
+    ns = final = None
+    _warm_until_steady(torch, _one)
     torch.cuda.synchronize()
     e2e_s = 0.0
     for _ in range(steps):
@@ -419,12 +438,7 @@ def run_c4(steps: int, warmup: int, cpu: bool = True):
         s2 = DeviceState.product_batch(factors)
         return body(s2)
 
-    from qbot_b200 import _lib as _l
-    for i in range(8):          # specialised sweeps of the fresh-register variant are compiled here, not in the timed calls
-        c0 = _l.jit_info()['kernels_compiled']
-        e2e_step()
-        if i >= 1 and _l.jit_info()['kernels_compiled'] == c0:
-            break
+    _warm_until_steady(torch, e2e_step, min_calls=4)      # specialised sweeps of the fresh-register variant are compiled here, not in the timed calls
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
