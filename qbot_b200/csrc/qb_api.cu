@@ -124,8 +124,19 @@ void work_free(int device, size_t bytes, void* p, cudaStream_t user) {
     const size_t c = work_class(bytes);
     pool_leave(device, user);
     if (c <= (256u << 20)) {
-        std::lock_guard<std::mutex> lk(g_bufs.mu);
-        if (g_bufs.small_list.size() < 64) { g_bufs.small_list.emplace_back(device, c, p); return; }
+        void* old = nullptr;
+        int old_dev = device;
+        {
+            std::lock_guard<std::mutex> lk(g_bufs.mu);
+            g_bufs.small_list.emplace_back(device, c, p);
+            if (g_bufs.small_list.size() > 96) {
+                old_dev = std::get<0>(g_bufs.small_list.front());
+                old = std::get<2>(g_bufs.small_list.front());
+                g_bufs.small_list.erase(g_bufs.small_list.begin());
+            }
+        }
+        if (old) { cudaStreamSynchronize(default_stream(old_dev)); cudaFree(old); }      // (the oldest one makes room)
+        return;
     }
     cudaStreamSynchronize(default_stream(device));
     cudaFree(p);
@@ -180,13 +191,31 @@ void cached_free(int device, size_t bytes, void* p, cudaStream_t stream) {
         const size_t total_b = device_total_mem(device);
         if (bytes <= total_b / 3) {
             pool_leave(device, stream);            // nothing on a foreign stream may still be writing into it
-            std::lock_guard<std::mutex> lk(g_bufs.mu);
-            int mine = 0;
-            size_t held = 0;
-            for (auto& b : g_bufs.free_list) if (std::get<0>(b) == device) { mine++; held += std::get<1>(b); }
-            // a few registers (density-matrix ops create a new one per partial trace / scatter / mix),
-            // never more than a third of the device memory in total
-            if (mine < 8 && held + bytes <= total_b / 3) { g_bufs.free_list.emplace_back(device, bytes, p); return; }
+            // A few registers are kept (density-matrix ops create a new one per partial trace / scatter / mix), never more
+            // than a third of the device memory in total.  The buffer just freed is the likeliest to be asked for again,
+            // so it always goes in and the OLDEST ones make room: a program that moves on to another register size (the
+            // bench's configs after its 16 GiB headline) is not left allocating and freeing through the driver.
+            std::vector<void*> evict;
+            {
+                std::lock_guard<std::mutex> lk(g_bufs.mu);
+                g_bufs.free_list.emplace_back(device, bytes, p);
+                for (;;) {
+                    int mine = 0;
+                    size_t held = 0;
+                    for (auto& b : g_bufs.free_list) if (std::get<0>(b) == device) { mine++; held += std::get<1>(b); }
+                    if (mine <= 12 && held <= total_b / 3) break;
+                    auto it = std::find_if(g_bufs.free_list.begin(), g_bufs.free_list.end(),
+                                           [&](const std::tuple<int, size_t, void*>& b) { return std::get<0>(b) == device; });
+                    evict.push_back(std::get<2>(*it));
+                    g_bufs.free_list.erase(it);
+                }
+            }
+            if (!evict.empty()) {
+                if (stream) cudaStreamSynchronize(stream);
+                cudaStreamSynchronize(default_stream(device));
+                for (void* q : evict) cudaFree(q);
+            }
+            return;
         }
     }
     if (stream) cudaStreamSynchronize(stream);

@@ -207,7 +207,7 @@ struct EngineState {
     std::list<CachedPlan> cache;       // most recent first
     bool attr_set[16] = {false};
 };
-constexpr size_t kMaxCachedPlans = 32;
+constexpr size_t kMaxCachedPlans = 256;     // (32 thrashed once one process ran all the configs: a 28-bit plan takes ~0.1 s to search again)
 std::mutex g_engine_mu;                // guards the caches and the lazily resolved StepJit records
 std::map<int, EngineState> g_engines;
 
