@@ -87,13 +87,16 @@ assert err < 1e-12 and perr < 1e-12 and aerr < 1e-12 and sk.shard.exchanges >= 1
 '''
 
 
-def _run_ranks(nproc, mode, backend, n, tmp_path, split=0):
+def _run_ranks(nproc, mode, backend, n, tmp_path, split=0, pieces=None):
     script = tmp_path / 'worker.py'
     script.write_text(WORKER.format(root=ROOT))
     port = 29600 + (os.getpid() % 300)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={nproc}',
            '--master-addr', '127.0.0.1', '--master-port', str(port), str(script), mode, backend, str(n), str(split)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if pieces:
+        env['QBOT_B200_EXCHANGE_PIECES'] = pieces        # who carries the pieces of a pipelined exchange: 'sm' or 'ce'
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
 
@@ -108,13 +111,15 @@ def test_p2p_exchange_four_processes_one_gpu(tmp_path):
     assert out.count('"err"') == 4
 
 
-@pytest.mark.parametrize('nproc,n,split', [(2, 17, 2), (4, 18, 1)])
-def test_pipelined_exchange_processes_sharing_one_gpu(tmp_path, nproc, n, split):
-    """The exchange in 2^split pieces on its own stream (qb_permute_scatter_sub), pieces announced by flag
-    counters in the receivers' memory (qb_signal_flags / qb_wait_flags), first-phase sweeps per sub-block on
-    sub-ket handles with a reduced grid: same ket as the oracle, and the pipelined path was taken."""
+@pytest.mark.parametrize('nproc,n,split,pieces', [(2, 17, 2, 'sm'), (4, 18, 1, 'ce'), (2, 18, 2, 'ce')])
+def test_pipelined_exchange_processes_sharing_one_gpu(tmp_path, nproc, n, split, pieces):
+    """The exchange in 2^split pieces on its own stream -- peer stores by a scatter kernel ('sm': qb_permute_scatter_sub
+    on a capped grid) or a local pack + device-to-device copies by the copy engines ('ce': qb_copy_async) -- pieces
+    announced by flag counters in the receivers' memory (qb_signal_flags / qb_wait_flags), the sweeps next to the
+    exchange run sub-block by sub-block where their tiles allow (qb_plan_queue / qb_run_steps): same ket as the oracle,
+    and the pipelined path was taken."""
     import json
-    out = _run_ranks(nproc, 'p2p', 'gloo', n, tmp_path, split)
+    out = _run_ranks(nproc, 'p2p', 'gloo', n, tmp_path, split, pieces)
     import re
     recs = [json.loads(x) for x in re.findall(r'\{[^{}]*\}', out)]       # (two ranks may print on one line)
     assert len(recs) == nproc and all(r['split_exchanges'] >= 1 for r in recs), recs
