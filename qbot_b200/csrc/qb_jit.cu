@@ -43,6 +43,16 @@ const char* kPrelude = R"QJ(
 #define QJ_XSIGN(a, s) do { (a).x = __hiloint2double(__double2hiint((a).x) ^ (int)(s), __double2loint((a).x)); \
                             (a).y = __hiloint2double(__double2hiint((a).y) ^ (int)(s), __double2loint((a).y)); } while (0)
 #define QJ_SYNC() __syncthreads()
+// warp number as a value ptxas knows to be warp-uniform (shuffle broadcast), and one elected lane of a converged warp:
+// what the bulk copies of the next tile are issued from (uniform-datapath addresses, no per-lane serialisation)
+#define QJ_WARP_ID(tid) __shfl_sync(0xffffffffu, (tid) >> 5, 0)
+__device__ __forceinline__ bool qj_elect_one() {
+    unsigned p_;
+    asm volatile("{ .reg .pred P; elect.sync _|P, 0xffffffff; selp.u32 %0, 1, 0, P; }" : "=r"(p_));
+    return p_ != 0u;
+}
+#define QJ_ELECT(tid) qj_elect_one()
+#define QJ_L2_PREFETCH(gsrc) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(512) : "memory")
 // two mbarriers per CTA count the bytes of the next tile's bulk copies: [0] the early half (landing
 // buffer behind the transposition buffer), [1] the late half (transposition buffer)
 __device__ __forceinline__ unsigned qj_mbar(const int which) {
@@ -78,12 +88,18 @@ __device__ __forceinline__ unsigned qj_mbar(const int which) {
     } while (0)
 #define QJ_EXPECT(which)                                                                           \
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qj_mbar(which)), "r"(QJ_HALF_RUNS * 512) : "memory")
+// The expect_tx of a half is posted by thread 0 BEFORE the barrier that releases the copies (its previous phase has
+// been waited for by every thread in stage 0, and the new phase cannot complete before its bytes have arrived), so
+// that every warp may issue its share of the copies right behind the barrier without racing the expectation.
 // early half: issued right after the first barrier of a tile (everybody has read the landing buffer)
+#define QJ_EXPECT_EARLY(tid, nbase)                                                                \
+    do {                                                                                           \
+        if (nbase != ~0ull && tid == 0) QJ_EXPECT(0);                                              \
+    } while (0)
 #define QJ_ISSUE_EARLY(tid, nbase, psi, buf)                                                       \
     do {                                                                                           \
         if (nbase != ~0ull) {                                                                      \
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                           \
-            if (tid == 0) QJ_EXPECT(0);                                                            \
             qj_issue_early(tid, nbase, psi, buf + QJ_TILE_UNITS);                                  \
         }                                                                                          \
     } while (0)
@@ -92,15 +108,15 @@ __device__ __forceinline__ unsigned qj_mbar(const int which) {
 // has no earlier barrier, so its early half goes out here too.
 #define QJ_ISSUE_NEXT(tid, nbase, psi, buf)                                                        \
     do {                                                                                           \
+        if (nbase != ~0ull && tid == 0) {                                                          \
+            QJ_EXPECT(1);                                                                          \
+            if (!QJ_NSTAGES_GT1) QJ_EXPECT(0);                                                     \
+        }                                                                                          \
         __syncthreads();                                                                           \
         if (nbase != ~0ull) {                                                                      \
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                           \
-            if (tid == 0) QJ_EXPECT(1);                                                            \
             qj_issue_next(tid, nbase, psi, buf);                                                   \
-            if (!QJ_NSTAGES_GT1) {                                                                 \
-                if (tid == 0) QJ_EXPECT(0);                                                        \
-                qj_issue_early(tid, nbase, psi, buf + QJ_TILE_UNITS);                              \
-            }                                                                                      \
+            if (!QJ_NSTAGES_GT1) qj_issue_early(tid, nbase, psi, buf + QJ_TILE_UNITS);             \
         }                                                                                          \
     } while (0)
 #ifdef QJ_POOL_GLOBAL
@@ -159,6 +175,8 @@ const char* kVirtualPatch = R"QJ(
 #define QJ_LD(p) (((unsigned long long)((p) - psi)) == nbase ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0))
 #undef QJ_ISSUE_EARLY
 #define QJ_ISSUE_EARLY(tid, nbase, psi, buf) do { } while (0)
+#undef QJ_EXPECT_EARLY
+#define QJ_EXPECT_EARLY(tid, nbase) do { } while (0)
 #undef QJ_ISSUE_NEXT
 #define QJ_ISSUE_NEXT(tid, nbase, psi, buf) __syncthreads()
 #undef QJ_PREFETCH

@@ -103,6 +103,8 @@ struct Gen {
         return false;
     }
     bool bank_aware = false;
+    bool l2_late = false;
+    bool uniform_issue = true; // bulk copies of the next tile issued per warp from warp-uniform addresses (emit_issue_next)
     // would the store offsets chosen by pending flip p put two lanes of an 8-lane wavefront on one bank?
     bool store_conflicts(const QtStage& st, const Pend& p) const {
         uint32_t phase = 0;
@@ -729,17 +731,58 @@ struct Gen {
     void emit_issue_next() {
         const int eb = early_bit();
         o.f("#define QJ_RUNS %d\n#define QJ_HALF_RUNS %d\n", 1 << NH, 1 << (NH - 1));
-        // k' enumerates the runs of one half; the full run index gets a 0 (early) / 1 (late) at bit eb
-        o.f("QJ_DEV void qj_issue_early(const unsigned tid, const unsigned long long nbase, QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT inb) {\n");
-        o.f("    if (nbase == ~0ull) return;\n");
-        o.f("    for (unsigned kp = tid; kp < QJ_HALF_RUNS; kp += QJ_T) {\n");
-        o.f("        const unsigned k = (kp & 0x%xu) | ((kp >> %d) << %d);\n", (1u << eb) - 1u, eb, eb + 1);
-        o.f("        QJ_BULK_COPY_EARLY(inb + 32u * kp, psi + (nbase + qj_run_offset(k)));\n    }\n}\n\n");
-        o.f("QJ_DEV void qj_issue_next(const unsigned tid, const unsigned long long nbase, QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT buf) {\n");
-        o.f("    if (nbase == ~0ull) return;\n");
-        o.f("    for (unsigned kp = tid; kp < QJ_HALF_RUNS; kp += QJ_T) {\n");
-        o.f("        const unsigned k = (kp & 0x%xu) | ((kp >> %d) << %d) | 0x%xu;\n", (1u << eb) - 1u, eb, eb + 1, 1u << eb);
-        o.f("        QJ_BULK_COPY(buf + (32u * k + k + (k >> 3) + (k >> 6)), psi + (nbase + qj_run_offset(k)));\n    }\n}\n\n");
+        // k' enumerates the runs of one half; the full run index gets a 0 (early) / 1 (late) at bit eb.
+        // A bulk copy is a warp-level instruction of the UNIFORM datapath (UBLKCP takes its addresses from
+        // uniform registers).  With one copy per lane (kp = tid) ptxas has to serialise the lanes in a
+        // "waterfall" loop -- ELECT / 3 x R2UR.BROADCAST / UBLKCP / BRA.U.ANY, a dependent chain of ~50 clk per
+        // copy -- and with 64 copies per half only warps 0 and 1 of the CTA ran it while the others waited
+        // at the next barrier (ncu source view of the heaviest benchmark sweep: 10 % of all warp samples in
+        // those two loops, 21 % of the time of warps 0-1).  Now every warp issues its 2^(R-1) copies from
+        // one elected lane with addresses derived from warp-uniform values only (the warp number through a
+        // shuffle broadcast, the tile base, compile-time run numbers): straight-line UBLKCPs, no waterfall.
+        // The run number is k = spread(w * per) | spread(j) (| the late bit): disjoint bits, and both the padded
+        // buffer position and the HBM offset of a run are sums over the bits of k, so the part of warp w is computed
+        // once (uniform registers) and the part of copy j is an immediate.
+        const int per = 1 << (R - 1);       // HALF_RUNS / warps of the CTA
+        auto spread = [&](unsigned kp) { return (kp & ((1u << eb) - 1u)) | ((kp >> eb) << (eb + 1)); };
+        auto pad = [](unsigned k) { return 32u * k + k + (k >> 3) + (k >> 6); };
+        auto run_off = [&](unsigned k) {
+            unsigned long long off = 0;
+            for (int i = 0; i < NH; i++) if ((k >> i) & 1u) off |= 1ull << h->hb[i];
+            return off;
+        };
+        for (int late = 0; late < 2; late++) {
+            o.f("QJ_DEV void %s(const unsigned tid, const unsigned long long nbase, QJ_C* QJ_RESTRICT psi, QJ_C* QJ_RESTRICT %s) {\n",
+                late ? "qj_issue_next" : "qj_issue_early", late ? "buf" : "inb");
+            o.f("    if (nbase == ~0ull) return;\n");
+            if (uniform_issue) {
+                o.f("    const unsigned wp = QJ_WARP_ID(tid) * %du;\n", per);
+                o.f("    const unsigned kw = (wp & 0x%xu) | ((wp >> %d) << %d);\n", (1u << eb) - 1u, eb, eb + 1);
+                if (late) o.f("    QJ_C* const sb = buf + (32u * kw + kw + (kw >> 3) + (kw >> 6));\n");
+                else o.f("    QJ_C* const sb = inb + 32u * wp;\n");
+                o.f("    const QJ_C* const gb = psi + (nbase + qj_run_offset(kw));\n");
+                o.f("    if (QJ_ELECT(tid)) {\n");
+                for (int j = 0; j < per; j++) {
+                    const unsigned kj = spread((unsigned)j) | (late ? 1u << eb : 0u);
+                    o.f("        %s(sb + %uu, gb + 0x%llxull);\n", late ? "QJ_BULK_COPY" : "QJ_BULK_COPY_EARLY", late ? pad(kj) : 32u * (unsigned)j,
+                        run_off(kj));
+                }
+                // experiment (QBOT_B200_JIT_L2_LATE=1): the late half cannot land before the last stage has emptied the
+                // transposition buffer; pull it into L2 together with the early half so that its copies find it there
+                if (!late && l2_late)
+                    for (int j = 0; j < per; j++) o.f("        QJ_L2_PREFETCH(gb + 0x%llxull);\n", run_off(spread((unsigned)j) | (1u << eb)));
+                o.f("    }\n}\n\n");
+                continue;
+            }
+            o.f("    for (unsigned kp = tid; kp < QJ_HALF_RUNS; kp += QJ_T) {\n");
+            if (late) {
+                o.f("        const unsigned k = (kp & 0x%xu) | ((kp >> %d) << %d) | 0x%xu;\n", (1u << eb) - 1u, eb, eb + 1, 1u << eb);
+                o.f("        QJ_BULK_COPY(buf + (32u * k + k + (k >> 3) + (k >> 6)), psi + (nbase + qj_run_offset(k)));\n    }\n}\n\n");
+            } else {
+                o.f("        const unsigned k = (kp & 0x%xu) | ((kp >> %d) << %d);\n", (1u << eb) - 1u, eb, eb + 1);
+                o.f("        QJ_BULK_COPY_EARLY(inb + 32u * kp, psi + (nbase + qj_run_offset(k)));\n    }\n}\n\n");
+            }
+        }
     }
 
     void emit_stage(int s) {
@@ -893,6 +936,8 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     g.npool_prog = (int)((g.h->total_bytes - g.h->pool_off) / sizeof(double));
     g.lazy_x = getenv("QBOT_B200_EAGER_X") == nullptr;
     g.xor_signs = getenv("QBOT_B200_BRANCHY_SIGNS") == nullptr;        // A/B switch: conditional sign flips as branches + FP64 negations
+    g.l2_late = getenv("QBOT_B200_JIT_L2_LATE") != nullptr && atoi(getenv("QBOT_B200_JIT_L2_LATE")) != 0;
+    g.uniform_issue = getenv("QBOT_B200_LANE_ISSUE") == nullptr;        // A/B switch: one bulk copy per lane (ptxas waterfall loop)
     g.bank_aware = getenv("QBOT_B200_FLIP_BANK_AWARE") != nullptr;      // measured neutral (5 016 vs 5 023 gates/s): off by default
     const int npool = g.npool_prog + 1;      // + header scale
     Out& o = g.o;
@@ -920,6 +965,7 @@ std::string qj_generate(const uint8_t* program, QjSourceInfo* info) {
     // the NEXT tile starts to arrive while stages 1.. of this tile run
     o.f("#define QJ_RUN_STAGES(tid, tbase, nbase, pfbase, pre, psi, buf, P) \\\n");
     for (int s = 0; s < g.h->nstages; s++) {
+        if (s == 1) o.f("    QJ_EXPECT_EARLY(tid, nbase); \\\n");
         if (s) o.f("    QJ_SYNC(); \\\n");
         if (s == 1) o.f("    QJ_ISSUE_EARLY(tid, nbase, psi, buf); \\\n");
         o.f("    qj_stage%d(tid, tbase, nbase, pfbase, pre, psi, buf, P); \\\n", s);

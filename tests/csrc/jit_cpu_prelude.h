@@ -16,10 +16,14 @@ struct QjC { double x, y; };
 static inline double qj_xsign1(double v, unsigned s) { unsigned long long b; memcpy(&b, &v, 8); b ^= (unsigned long long)s << 32; memcpy(&v, &b, 8); return v; }
 #define QJ_XSIGN(a, s) do { (a).x = qj_xsign1((a).x, (s)); (a).y = qj_xsign1((a).y, (s)); } while (0)
 #define QJ_SYNC()
+#define QJ_WARP_ID(tid) ((tid) >> 5)
+#define QJ_ELECT(tid) (((tid) & 31u) == 0u)
 #define QJ_BULK_COPY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
 #define QJ_BULK_COPY_EARLY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
 #define QJ_ISSUE_EARLY(tid, nbase, psi, buf)     /* the harness runs qj_issue_early at the end of the tile */
 #define QJ_ASYNC_WAIT(parity)
+#define QJ_EXPECT_EARLY(tid, nbase)
+#define QJ_L2_PREFETCH(gsrc)
 #define QJ_ISSUE_NEXT(tid, nbase, psi, buf)      /* the harness runs qj_issue_next after the last stage (the kernel's barrier) */
 #define QJ_PREFETCH(psi, nbase, tid)
 #define QJ_PRELUDE
