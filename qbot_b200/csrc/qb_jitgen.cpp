@@ -810,18 +810,18 @@ struct Gen {
             // registers whose top register bit is 0 belong to the early half (landing buffer, runs stored
             // back to back in squeezed run order), the others to the late half (transposition buffer)
             const int eb = early_bit();
-            o.f("    if (pre) {\n        QJ_ASYNC_WAIT(pre - 1u);\n");
+            // the early half has been in its landing buffer for most of a tile: read it before waiting for the late one
+            o.f("    if (pre) {\n        QJ_MBAR_WAIT(0, pre - 1u);\n");
             o.f("        const unsigned kb = lb >> %d;\n", QT_L);
             o.f("        const QJ_C* const ip = buf + QJ_TILE_UNITS + 32u * ((kb & 0x%xu) | ((kb >> %d) << %d)) + (lb & 31u);\n",
                 (1u << eb) - 1u, eb + 1, eb);
-            for (int i = 0; i < NR; i++) {
-                if ((i >> (R - 1)) & 1) o.f("        a%d = sp[%u];\n", i, smem_reg_offset(st, i));
-                else {
-                    unsigned rr = 0;
-                    for (int q = 0; q < R; q++) if ((i >> q) & 1) rr |= 1u << (st.rb[q] - QT_L);
-                    o.f("        a%d = ip[%u];\n", i, 32u * squeeze(rr, eb));
-                }
+            for (int i = 0; i < NR / 2; i++) {
+                unsigned rr = 0;
+                for (int q = 0; q < R; q++) if ((i >> q) & 1) rr |= 1u << (st.rb[q] - QT_L);
+                o.f("        a%d = ip[%u];\n", i, 32u * squeeze(rr, eb));
             }
+            o.f("        QJ_MBAR_WAIT(1, pre - 1u);\n");
+            for (int i = NR / 2; i < NR; i++) o.f("        a%d = sp[%u];\n", i, smem_reg_offset(st, i));
             o.f("    } else {\n");
             for (int i = 0; i < NR; i++) o.f("        a%d = QJ_LD(gp + 0x%llxull);\n", i, (unsigned long long)hbm_reg_offset(st, i));
             o.f("    }\n    QJ_PREFETCH(psi, pfbase, tid);\n");

@@ -5,7 +5,7 @@
 #                            profiles/r02_qj_head_ncu_summary.txt)
 #   QBOT_B200_JIT_L2_LATE=1  default + L2 prefetch of the late half together with the early half
 # interleaved so that box-to-box and thermal differences cancel; then the specialised-sweep GPU tests, then the ncu
-# passes of the new kernel set (per-launch DRAM bytes + durations of all 11 sweeps, --set full of the first two).
+# passes of the new kernel set (per-launch DRAM bytes + durations of all 11 sweeps, --set full + source view of the heaviest).
 set -u
 mkdir -p gpurun_out
 B="python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-configs"
@@ -14,7 +14,6 @@ QBOT_B200_LANE_ISSUE=1 timeout 90 $B --no-parity > gpurun_out/ab_issue_lanes_1.j
 QBOT_B200_JIT_L2_LATE=1 timeout 90 $B --no-parity > gpurun_out/ab_issue_l2late_1.json 2> gpurun_out/ab_issue_l2late_1.err
 timeout 90 $B --no-parity > gpurun_out/ab_issue_uniform_2.json 2> gpurun_out/ab_issue_uniform_2.err
 QBOT_B200_LANE_ISSUE=1 timeout 90 $B --no-parity > gpurun_out/ab_issue_lanes_2.json 2> gpurun_out/ab_issue_lanes_2.err
-QBOT_B200_JIT_L2_LATE=1 timeout 90 $B --no-parity > gpurun_out/ab_issue_l2late_2.json 2> gpurun_out/ab_issue_l2late_2.err
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob('gpurun_out/ab_issue_*.json')):
@@ -29,9 +28,9 @@ timeout 150 python -m pytest tests/test_gpu_jit.py -x -q > gpurun_out/ab_issue_p
 tail -3 gpurun_out/ab_issue_pytest.log
 timeout 120 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:qj_kernel -c 22 --csv \
     --log-file gpurun_out/r02_qj_uniform_launches.csv python scripts/traffic_capture.py run > gpurun_out/ab_issue_ncu1.log 2>&1
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:qj_kernel -s 11 -c 2 -f -o gpurun_out/r02_qj_uniform \
+timeout 150 ncu --set full --clock-control none --import-source on -k regex:qj_kernel -s 11 -c 1 -f -o gpurun_out/r02_qj_uniform \
     python scripts/traffic_capture.py run > gpurun_out/ab_issue_ncu2.log 2>&1
 ncu -i gpurun_out/r02_qj_uniform.ncu-rep --page raw --csv > gpurun_out/r02_qj_uniform_raw.csv 2>/dev/null
-ncu -i gpurun_out/r02_qj_uniform.ncu-rep --page source --csv --kernel-id :::1 > gpurun_out/r02_qj_uniform_sweep0_source.csv 2>/dev/null
+ncu -i gpurun_out/r02_qj_uniform.ncu-rep --page source --csv > gpurun_out/r02_qj_uniform_sweep0_source.csv 2>/dev/null
 rm -f gpurun_out/r02_qj_uniform.ncu-rep
 tail -2 gpurun_out/ab_issue_ncu1.log gpurun_out/ab_issue_ncu2.log

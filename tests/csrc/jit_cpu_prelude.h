@@ -22,6 +22,7 @@ static inline double qj_xsign1(double v, unsigned s) { unsigned long long b; mem
 #define QJ_BULK_COPY_EARLY(sdst, gsrc) memcpy((sdst), (gsrc), 512)
 #define QJ_ISSUE_EARLY(tid, nbase, psi, buf)     /* the harness runs qj_issue_early at the end of the tile */
 #define QJ_ASYNC_WAIT(parity)
+#define QJ_MBAR_WAIT(which, parity)
 #define QJ_EXPECT_EARLY(tid, nbase)
 #define QJ_L2_PREFETCH(gsrc)
 #define QJ_ISSUE_NEXT(tid, nbase, psi, buf)      /* the harness runs qj_issue_next after the last stage (the kernel's barrier) */
