@@ -27,22 +27,42 @@ def run(n):
 
 
 def record(rep, kernel_set, n):
-    # REP: an .ncu-rep, or the `ncu -i REP --page raw --csv` text of one (the report itself can exceed what travels back)
+    # REP: an .ncu-rep, or the `ncu -i REP --page raw --csv` text of one (the report itself can exceed what travels back),
+    # or the --csv --log-file of a --metrics pass
     text = open(rep).read() if rep.endswith('.csv') else subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(text.splitlines()))
-    hdr = rows[0]
-    ir, iw, it = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
+    rows = [r for r in csv.reader(text.splitlines()) if r]
     unit = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
-    ur, uw = unit[rows[1][ir]], unit[rows[1][iw]]
-    per = [float(r[ir]) * ur + float(r[iw]) * uw for r in rows[2:]]
+    tunit = {'ns': 1e-6, 'us': 1e-3, 'usecond': 1e-3, 'ms': 1.0, 'msecond': 1.0, 'nsecond': 1e-6}
+    hdr = next(r for r in rows if r[0] == 'ID')
+    how = "ncu --set full --clock-control none"
+    if 'Metric Name' in hdr:
+        # the log of an `ncu --metrics a,b,c --csv --log-file` pass: one row per launch and metric
+        how = "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none"
+        im, iu, iv = hdr.index('Metric Name'), hdr.index('Metric Unit'), hdr.index('Metric Value')
+        by = {}
+        for r in rows:
+            if r[0].isdigit():
+                by.setdefault(int(r[0]), {})[r[im]] = (r[iu], float(r[iv].replace(',', '')))
+        per, ms = [], []
+        for k in sorted(by):
+            (u1, v1), (u2, v2), (u3, v3) = by[k]['dram__bytes_read.sum'], by[k]['dram__bytes_write.sum'], by[k]['gpu__time_duration.sum']
+            per.append(v1 * unit[u1] + v2 * unit[u2])
+            ms.append(round(v3 * tunit[u3], 3))
+    else:
+        ir, iw, it = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
+        body = rows[rows.index(hdr) + 1:]
+        ur, uw = unit[body[0][ir]], unit[body[0][iw]]
+        per = [float(r[ir]) * ur + float(r[iw]) * uw for r in body[1:]]
+        ms = [round(float(r[it]), 3) for r in body[1:]]
     path = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     tj = json.load(open(path)) if os.path.exists(path) else {"qj_kernel": {}}
     tj['qj_kernel'][kernel_set] = {
         "qubits": n, "dram_bytes_per_launch": int(sum(per) / len(per)), "launches_captured": len(per),
         "min": int(min(per)), "max": int(max(per)), "algorithmic_bytes_per_launch": 32 << n,
-        "ms_per_launch_under_ncu": [round(float(r[it]), 3) for r in rows[2:]],
-        "source": f"profiles/{os.path.basename(rep).replace('.ncu-rep', '').replace('_raw.csv', '')}_ncu_summary.txt (ncu --set full --clock-control none, "
-                  f"{len(per)} launches of qj_kernel, kernel set {kernel_set})"}
+        "ms_per_launch_under_ncu": ms,
+        "source": (f"profiles/{os.path.basename(rep)}" if 'Metric Name' in hdr else
+                   f"profiles/{os.path.basename(rep).replace('.ncu-rep', '').replace('_raw.csv', '')}_ncu_summary.txt") +
+                  f" ({how}, {len(per)} launches of qj_kernel, kernel set {kernel_set})"}
     json.dump(tj, open(path, 'w'), indent=1)
     print(json.dumps(tj['qj_kernel'][kernel_set]))
 
