@@ -84,3 +84,38 @@ print("OURS", [[float(x) for x in r] if isinstance(r, list) else r for r in ours
 assert stock == ours == again, (stock, ours, again)
 ''' % (REF, ROOT, text, text, text))
     assert ("OURS " + want) in out, out
+
+
+@pytest.mark.skipif(not have_ref, reason="baseline/_ref (reference install) not present")
+def test_large_ket_program_through_the_installed_reference():
+    """rows f1 + b on the device: the UNMODIFIED reference's executeTxt drives a 22-qubit register (a 2^44-entry
+    density matrix in its own representation): qset of a lazy product ket, `gate` lines fused into sweeps, `peek`;
+    probabilities against the oracle's ket path"""
+    out = _run(r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path[:0] = [%r, %r]
+import numpy as np
+import qbot, qbot_b200
+from qbot_b200 import DeviceState, circuits
+from qbot_b200.state import KET
+from oracle import qbot_oracle as orc
+qbot_b200.install()
+n = 22
+gates = circuits.rc(n, 4, 22)
+qs = [0, 7, 14, 21]
+script = "\n".join(["qset tensorExp(comp.kets[0], %%d)" %% n] + [g.dsl() for g in gates] + ["peek r ; comp ; %%s" %% qs])
+ns = qbot.executeTxt(script)
+st = ns['state']
+assert isinstance(st, DeviceState) and st.nq == n and st.kind == KET, (type(st), st.nq)
+psi = np.zeros(1 << n, dtype=complex)
+psi[0] = 1
+for g in gates:
+    psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+err = float(np.max(np.abs(np.array(ns['r'].probs) - orc.ket_probs(psi, n, qs))))
+amp = float(np.max(np.abs(np.asarray(st) - psi)))
+print("ERR", err, amp, st.stats()['fused_passes'])
+assert err < 1e-12 and amp < 1e-12, (err, amp)
+assert st.stats()['fused_passes'] >= 1
+''' % (REF, ROOT))
+    assert 'ERR' in out, out[-2000:]

@@ -71,3 +71,41 @@ print("OK", dt)
 ''' % (REF, ROOT, os.path.join(ROOT, 'tests'))
     p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_large_ket_program_through_the_real_reference():
+    """rows f1 + b: with the ops installed, the UNMODIFIED reference's executeTxt runs a register it cannot
+    represent itself -- `qset tensorExp(comp.kets[0], 16)` stays a product descriptor (install() swaps the
+    namespace's tensorExp / tensorProd for the lazy ones), the register is a ket, `gate` lines and `peek` drive it;
+    probabilities against the oracle's ket path"""
+    code = r'''
+import sys
+sys.dont_write_bytecode = True
+sys.path[:0] = [%r, %r, %r]
+import numpy as np
+from fake_backend import FakeState, KET
+import qbot_b200.integration as integ
+integ.install(state_cls=FakeState)
+import qbot
+from qbot_b200 import circuits
+from oracle import qbot_oracle as orc
+n = 16
+gates = circuits.rc(n, 3, 5)
+qs = [0, 5, 9, 15]
+script = "\n".join(["qset tensorExp(comp.kets[0], %%d)" %% n] + [g.dsl() for g in gates] + ["peek r ; comp ; %%s" %% qs])
+ns = qbot.executeTxt(script)
+assert isinstance(ns['state'], FakeState) and ns['state'].kind == KET and ns['state'].nq == n, type(ns['state'])
+psi = np.zeros(1 << n, dtype=complex)
+psi[0] = 1
+for g in gates:
+    psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+err = float(np.max(np.abs(np.array(ns['r'].probs) - orc.ket_probs(psi, n, qs))))
+assert err < 1e-12, err
+integ.uninstall()
+small = qbot.executeTxt("cdef x ; tensorExp(comp.kets[0], 2)\n")['x']
+assert isinstance(small, np.ndarray) and small.shape == (4,)      # the stock constructor is back
+print("OK", err)
+''' % (REF, ROOT, os.path.join(ROOT, 'tests'))
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
