@@ -446,6 +446,10 @@ class DeviceState:
                         b_positions: Sequence[int] = (), scale: complex = None) -> "DeviceState":
         """rho_A (x) rho_B with A's qubit i at final qubit a_positions[i], B's at b_positions[i]."""
         n = a.nq + (b.nq if b is not None else 0)
+        # the C entry point takes no lengths: it reads a.nq + b.nq positions
+        if len(a_positions) != a.nq or len(b_positions) != (b.nq if b is not None else 0):
+            raise ValueError(f"scatter_product: {len(a_positions)} + {len(b_positions)} positions for a {a.nq} + "
+                             f"{b.nq if b is not None else 0} qubit product")
         abits = _lib.int_array([n - 1 - p for p in a_positions])
         bbits = _lib.int_array([n - 1 - p for p in b_positions])
         h = C.c_void_p()
