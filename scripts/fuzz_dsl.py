@@ -1,7 +1,8 @@
 """Differential fuzzer of the host side (build container only, no GPU): random `.qb` programs
 run through the REAL reference (`/root/reference`, executeTxt) and through this repo's interpreter
 mirror + ops (`qbot_b200.executeTxt`) over the numpy test double; stdout, exit behaviour, the final
-register and every named result must agree (state 1e-12, probabilities and ProbVal ordering exact).
+register and every named result must agree (state 1e-12, ProbVal ordering exact, outcome weights exact up to the 15th decimal place --
+see probs_agree).
 
     PYTHONDONTWRITEBYTECODE=1 python scripts/fuzz_dsl.py --seeds 0:500 [--emit tests/golden/scripts_fuzz_src.json]
 
@@ -189,6 +190,24 @@ def run(execute, text, **kw):
     return ns, buf.getvalue(), exited
 
 
+LAST_DIGIT = []      # results whose outcome weights differ from the reference's in the 15th decimal place only
+
+
+def probs_agree(a, b):
+    """Outcome weights are rounded to 15 decimal places by MeasurementResult (qbot/measurement.py:18-29); the
+    reference gets them from abs(trace(rho_A P_i)), the backend from the diagonal of the rotated rho_A -- two
+    summation orders, so about one result in a thousand lands on the other side of a rounding boundary (1e-15).
+    Bit-identical lists pass silently; a difference <= 2e-15 passes and is counted; anything else is a difference
+    (the contract is 1e-12 relative, north_star)."""
+    a, b = [float(x) for x in a], [float(x) for x in b]
+    if a == b:
+        return True
+    if len(a) != len(b) or max(abs(x - y) for x, y in zip(a, b)) > 2e-15:
+        return False
+    LAST_DIGIT.append((a, b))
+    return True
+
+
 def compare(seed, ref_exec, our_exec, FakeState, extra=False):
     text, names = program(seed, extra)
     rns, rout, rexit = run(ref_exec, text)
@@ -203,7 +222,7 @@ def compare(seed, ref_exec, our_exec, FakeState, extra=False):
     for v in names:
         x, y = rns.get(v), ons.get(v)
         if hasattr(x, 'unMeasuredDensity'):
-            if list(x.probs) != list(y.probs) or list(x.basisSymbols) != list(y.basisSymbols):
+            if list(x.basisSymbols) != list(y.basisSymbols) or not probs_agree(x.probs, y.probs):
                 return text, '%s: probs / symbols differ: %s vs %s' % (v, x.probs, y.probs)
             if not np.allclose(np.asarray(x.unMeasuredDensity), np.asarray(y.unMeasuredDensity), rtol=0, atol=1e-12):
                 return text, '%s: unmeasured density differs' % v
@@ -215,7 +234,7 @@ def compare(seed, ref_exec, our_exec, FakeState, extra=False):
                 return text, '%s: ProbVal differs' % v
             for p, q in zip(x.values, y.values):
                 if hasattr(p, 'probs') and hasattr(p, 'basisSymbols'):
-                    if list(p.probs) != list(q.probs):
+                    if not probs_agree(p.probs, q.probs):
                         return text, '%s: branch probs differ %s vs %s' % (v, p.probs, q.probs)
                 elif not np.allclose(np.asarray(p, dtype=complex), np.asarray(q, dtype=complex), rtol=0, atol=1e-12):
                     return text, '%s: ProbVal value differs' % v
@@ -252,7 +271,7 @@ def main():
             print('seed %d:\n%s\n=> %s\n' % (seed, text, why), flush=True)
         else:
             emitted.append(dict(name='fuzz_%d' % seed, text=text, vars=program(seed, a.extra)[1]))
-    print('seeds %d:%d: %d differences' % (lo, hi, bad))
+    print('seeds %d:%d: %d differences (%d results differ in the 15th decimal place of a weight only)' % (lo, hi, bad, len(LAST_DIGIT)))
     if a.emit:
         with open(a.emit, 'w') as f:
             json.dump(emitted, f, indent=0)
