@@ -1,0 +1,91 @@
+"""CPU fuzzer of the sharded ket's host logic (no GPU): random circuits (rc + dense / diagonal / swap-like 2-qubit
+blocks with controls) on P virtual ranks over numpy shards -- qubit map, exchange planning (plain and pipelined),
+gate localisation, probability gather -- compared with the oracle's strided update on the full register.
+
+    python scripts/fuzz_sharded.py --seeds 0:300
+
+TEST INFRASTRUCTURE: uses oracle/ as the checker (through tests/test_sharded_host.py's harness)."""
+import argparse
+import os
+import sys
+import threading
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+
+def case(seed):
+    from oracle import qbot_oracle as orc
+    from qbot_b200.sharded import ShardedKet
+    from np_shard import NumpyShard, VirtualComm
+    from test_sharded_host import circuit_ops, expected_ket
+    rng = np.random.default_rng(77_000 + seed)
+    world = int(rng.choice([2, 4, 8]))
+    g = world.bit_length() - 1
+    pipelined = rng.random() < 0.4
+    split = int(rng.integers(1, 4)) if pipelined else 0
+    lo = max(g + 2, 4) if not pipelined else max(g + 2 + split, 12)       # pipelined plans need room for parked + tile bits
+    n = int(rng.integers(lo, lo + 4))
+    depth = int(rng.integers(1, 9))
+    ops = circuit_ops(n, depth, seed)
+    cuts = sorted(int(c) for c in rng.integers(0, len(ops) + 1, size=int(rng.integers(0, 3))))
+    probe = [int(q) for q in rng.choice(n, size=int(rng.integers(1, min(n, 4) + 1)), replace=False)]
+    reps = int(rng.integers(1, 3))
+    desc = dict(seed=seed, world=world, n=n, depth=depth, split=split, cuts=cuts, probe=probe, reps=reps, gates=len(ops))
+    want = expected_ket(n, ops)
+    for _ in range(reps - 1):
+        for m, t, cs in ops:
+            want = orc.ket_apply(want, n, t, m, cs)
+    shared = VirtualComm.Shared(world)
+    out = [None] * world
+    errors = []
+
+    def work(rank):
+        try:
+            kw = dict(split=split) if split else {}
+            sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard, **kw)
+            if split:
+                sk.min_first_phase = int(rng.integers(2, 8)) if rank < 0 else 6
+            for _ in range(reps):
+                for i, (m, t, cs) in enumerate(ops):
+                    if i in cuts:
+                        sk.flush()
+                    sk.apply_gate(m, t, cs)
+                sk.flush()
+            out[rank] = dict(ket=sk.gather(), probs=sk.probs(probe), norm=sk.norm2())
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+            shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    if errors:
+        return 'error', desc, repr(errors[0])
+    err = max(float(np.max(np.abs(o['ket'] - want))) for o in out)
+    perr = max(float(np.max(np.abs(o['probs'] - orc.ket_probs(want, n, probe)))) for o in out)
+    nerr = max(abs(float(o['norm']) - 1.0) for o in out)
+    worst = max(err, perr, nerr)
+    return ('ok' if worst < 1e-12 else 'MISMATCH'), desc, worst
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--seeds', default='0:100')
+    a = ap.parse_args()
+    lo, hi = (int(x) for x in a.seeds.split(':'))
+    bad = 0
+    for seed in range(lo, hi):
+        status, desc, info = case(seed)
+        if status != 'ok':
+            bad += 1
+            print(status, desc, info, flush=True)
+    print(f"seeds {lo}:{hi}: {bad} failures")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == '__main__':
+    main()
