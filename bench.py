@@ -336,7 +336,11 @@ def run_single_gpu(args):
                      "kernel": dom_kernel, "per_launch": dom_unit, "launches": dom_launches,
                      "avg_launch_ms": 1e3 * avg_launch_s, "peak_source": peak_src,
                      "unfused_equivalent_gbs": unfused_equiv, "unfused_equivalent_frac": unfused_equiv / peak,
-                     "sweeps_per_step": passes / args.steps, "gates_per_sweep": ngates * args.steps / max(passes, 1)},
+                     "sweeps_per_step": passes / args.steps, "gates_per_sweep": ngates * args.steps / max(passes, 1),
+                     # north_star's "DRAM bytes per gate": measured traffic of a step's sweeps over its gates, next to the
+                     # one-gate-per-pass definition (32 * 2^(n - controls) B summed over the circuit)
+                     "dram_bytes_per_gate": None if traffic is None else traffic * (passes / args.steps) / ngates,
+                     "unfused_bytes_per_gate": alg_bytes / ngates},
         "amp_updates_per_s": value * (1 << n),
         "norm_check": norm,
     }
