@@ -268,20 +268,33 @@ def main():
     ap.add_argument('--emit')
     ap.add_argument('--show', type=int)
     ap.add_argument('--extra', action='store_true', help='also result-dependent conditions, cout of results, ProbVal arithmetic')
+    ap.add_argument('--installed', action='store_true',
+                    help="second arm = the REAL reference's executeTxt with the ops installed into it (qbot_b200.install) "
+                         "instead of this repo's interpreter mirror")
     a = ap.parse_args()
     from qbot.interpreter import executeTxt as ref_exec
     import qbot_b200
     from fake_backend import FakeState
+    our_exec = qbot_b200.executeTxt
+    if a.installed:
+        import qbot_b200.integration as integ
+
+        def our_exec(text, state_cls=None):
+            integ.install(state_cls=state_cls)
+            try:
+                return ref_exec(text)
+            finally:
+                integ.uninstall()
     if a.show is not None:
         print(program(a.show, a.extra)[0])
-        print(compare(a.show, ref_exec, qbot_b200.executeTxt, FakeState, a.extra)[1])
+        print(compare(a.show, ref_exec, our_exec, FakeState, a.extra)[1])
         return
     lo, hi = (int(x) for x in a.seeds.split(':'))
     bad = 0
     emitted = []
     for seed in range(lo, hi):
         try:
-            text, why = compare(seed, ref_exec, qbot_b200.executeTxt, FakeState, a.extra)
+            text, why = compare(seed, ref_exec, our_exec, FakeState, a.extra)
         except Exception as e:  # noqa: BLE001
             text, why = program(seed, a.extra)[0], 'exception: %r' % e
         if why:
