@@ -34,3 +34,31 @@ def test_reference_arm_line():
 
 def test_reference_arm_other_ranks_are_silent():
     assert run_ref({'RANK': '1', 'WORLD_SIZE': '2', 'LOCAL_RANK': '1'}) == ''
+
+
+def test_traffic_capture_is_of_heads_kernel_set(tmp_path):
+    """bench.py prints roofline.traffic only when profiles/r02_traffic.json holds an ncu capture of the
+    kernel set it ran (looked up by qb_stats.jit_kernel_hash = the sum of the FNV-1a hashes of the
+    generated sweep sources of one step).  The sources come out of the planner + specialiser, which need
+    no GPU: regenerate the headline's sweeps here and check that their hash is one of the captured sets,
+    i.e. that nobody changed the generator after the last capture without re-measuring."""
+    sys.path.insert(0, ROOT)
+    import plan_emu
+    from qbot_b200 import _lib
+    from qbot_b200.circuits import rc
+    n = 30
+    nk = _lib.jit_check(n, plan_emu.circuit_to_bits(n, rc(n, 20, 30)), str(tmp_path))
+    total = 0
+    srcs = sorted(f for f in os.listdir(tmp_path) if f.endswith('.cu'))
+    assert len(srcs) == nk and nk > 0
+    for f in srcs:
+        h = 1469598103934665603
+        for c in open(os.path.join(tmp_path, f), 'rb').read():
+            h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        total = (total + h) & 0xFFFFFFFFFFFFFFFF
+    captured = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))['qj_kernel']
+    key = f"{total:016x}"
+    assert key in captured, f"HEAD's kernel set {key} has no ncu capture (captured: {sorted(captured)})"
+    assert captured[key]['qubits'] == n and captured[key]['launches_captured'] == nk
+    # no wasted re-reads: measured DRAM traffic per launch within 1 % of the algorithmic 32 * 2^n bytes
+    assert abs(captured[key]['dram_bytes_per_launch'] / (32 * 2 ** n) - 1) < 0.01
