@@ -172,6 +172,8 @@ namespace {
 
 struct CachedPlan {
     uint64_t hash = 0;
+    uint64_t hash2 = 0;                // second, independent fingerprint of the same gate list (a hit needs both)
+    int pins = 0;                      // handles that run this plan step by step right now (qb_plan_queue): not evictable
     size_t ngates = 0;
     int nbits = 0;
     int R = QT_R;                      // register bits per stage the plan was built for (5: specialised kernels only)
@@ -217,8 +219,8 @@ uint64_t fnv(uint64_t h, const void* p, size_t n) {
     return h;
 }
 
-uint64_t hash_gates(const std::vector<QGate>& gates, int nbits, int M) {
-    uint64_t h = 1469598103934665603ull;
+uint64_t hash_gates(const std::vector<QGate>& gates, int nbits, int M, uint64_t seed = 1469598103934665603ull) {
+    uint64_t h = seed;
     h = fnv(h, &nbits, sizeof(nbits));
     h = fnv(h, &M, sizeof(M));
     for (const QGate& g : gates) {
@@ -322,14 +324,15 @@ bool qb_engine_available_impl() { return getenv("QBOT_B200_NO_FUSION") == nullpt
 CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gates, int M, int R) {
     uint64_t hsh = hash_gates(gates, s->nbits, M);
     hsh = fnv(hsh, &R, sizeof(R));
+    const uint64_t hsh2 = hash_gates(gates, s->nbits, M, 0x9e3779b97f4a7c15ull);
     for (auto it = es->cache.begin(); it != es->cache.end(); ++it) {
-        if (it->hash == hsh && it->ngates == gates.size() && it->nbits == s->nbits && it->R == R) {
+        if (it->hash == hsh && it->hash2 == hsh2 && it->ngates == gates.size() && it->nbits == s->nbits && it->R == R) {
             es->cache.splice(es->cache.begin(), es->cache, it);
             return &es->cache.front();
         }
     }
     CachedPlan cp;
-    cp.hash = hsh; cp.ngates = gates.size(); cp.nbits = s->nbits; cp.R = R;
+    cp.hash = hsh; cp.hash2 = hsh2; cp.ngates = gates.size(); cp.nbits = s->nbits; cp.R = R;
     QtPlanOptions opt;
     opt.M = M;
     opt.R = R;
@@ -355,9 +358,17 @@ CachedPlan* get_plan(qb_state* s, EngineState* es, const std::vector<QGate>& gat
         QB_CUDA(cudaStreamSynchronize(s->stream));     // hostbuf dies here
     }
     if (es->cache.size() >= kMaxCachedPlans) {
-        QB_CUDA(cudaStreamSynchronize(s->stream));
-        es->cache.back().release();
-        es->cache.pop_back();
+        // the least recently used plan that no handle is in the middle of running (qb_plan_queue pins its plan)
+        auto victim = es->cache.end();
+        for (auto it = es->cache.end(); it != es->cache.begin();) {
+            --it;
+            if (it->pins == 0) { victim = it; break; }
+        }
+        if (victim != es->cache.end()) {
+            QB_CUDA(cudaStreamSynchronize(s->stream));
+            victim->release();
+            es->cache.erase(victim);
+        }
     }
     cp.jit.assign(cp.steps.size(), CachedPlan::StepJit());
     es->cache.push_front(std::move(cp));
@@ -432,7 +443,14 @@ void precompile_plan(CachedPlan* plan) {
 
 bool qb_engine_available() { return qb_engine_available_impl(); }
 
-void qb_engine_free(qb_state* s) { s->engine = nullptr; }      // plans belong to the device, not to the handle
+void qb_engine_free(qb_state* s) {          // plans belong to the device, not to the handle
+    if (s->pending_plan) {              // destroyed in the middle of a planned queue: its plan may be evicted again
+        std::lock_guard<std::mutex> lk(g_engine_mu);
+        ((CachedPlan*)s->pending_plan)->pins--;
+        s->pending_plan = nullptr;
+    }
+    s->engine = nullptr;
+}
 
 // plan (or find the cached plan of) `gates` and decide which executor runs it
 static CachedPlan* engine_prepare(qb_state* s, const std::vector<QGate>& gates, int* jit_mode_out) {
@@ -561,6 +579,7 @@ int qb_engine_plan_pending(qb_state* s, const std::vector<QGate>& gates, int par
     s->materialize();
     CachedPlan* plan = engine_prepare(s, gates, &jit_mode);
     s->pending_plan = plan;
+    plan->pins++;
     s->pending_jit = jit_mode;
     const size_t n = plan->steps.size();
     s->pending_done.assign(n, 0u);
@@ -605,6 +624,7 @@ void qb_engine_finish_pending(qb_state* s) {
     CachedPlan* plan = (CachedPlan*)s->pending_plan;
     if (!plan) return;
     s->pending_plan = nullptr;
+    plan->pins--;
     for (size_t i = 0; i < plan->steps.size(); i++) {
         const int np = i < s->pending_parts_of.size() ? s->pending_parts_of[i] : 1;
         const uint32_t want = np == 1 ? 0xffffu : ((1u << np) - 1u);
