@@ -909,6 +909,14 @@ int qb_probs_basis(qb_state* s, const int* bits, int m, const double* basis, int
     QB_REQUIRE(s && out && bits, "NULL argument");
     QB_REQUIRE(b >= 1 && b <= 5 && m >= b && m % b == 0, "probs_basis: the basis size must divide the number of bits");
     QB_REQUIRE(m <= s->nq && m <= 26, "probs_basis: too many outcome bits");
+    {   // the bits become gate targets below: check them before anything is queued (run_bins checks again, too late for that)
+        uint64_t seen = 0;
+        for (int t = 0; t < m; t++) {
+            QB_REQUIRE(bits[t] >= 0 && bits[t] < s->nq, "probs_basis: bit out of range");
+            QB_REQUIRE(!((seen >> bits[t]) & 1ull), "probs_basis: duplicate bit");
+            seen |= 1ull << bits[t];
+        }
+    }
     s->flush();
     DevGuard g(s->device);
     // rotate a scratch copy so that basis ket j of every group sits at group index j, then read the
