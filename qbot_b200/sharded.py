@@ -145,6 +145,31 @@ class QubitMap:
                 m |= 1 << b
         return m
 
+    def choose_initial(self, rem: Sequence[LGate]):
+        """A register that is still a PRODUCT state can start with any qubits on the rank bits (a relabelling, no data
+        moves): take the logical bits whose first non-diagonal use among the queued gates `rem` is farthest away (never
+        written first; ties keep the current rank bits), the same rule plan_exchange applies later.  With the identity
+        map the first exchange of rc(34, 10) on 8 ranks comes after 141 gates and a second one is needed for the
+        last gate; chosen this way it comes after 215 and is the only one."""
+        n, nl, g = self.n, self.nl, self.g
+        nxt = [INF] * n
+        for i, gt in enumerate(rem):
+            w = gt.wmask
+            while w:
+                b = (w & -w).bit_length() - 1
+                if nxt[b] == INF:
+                    nxt[b] = i
+                w &= w - 1
+        order = sorted(range(n), key=lambda b: (-nxt[b], 0 if self.pos[b] >= nl else 1, -self.pos[b]))
+        new_global = order[:g]
+        cur_global = [self.at[nl + r] for r in range(g)]
+        incoming = [b for b in new_global if b not in cur_global]
+        outgoing = [b for b in cur_global if b not in new_global]
+        for bi, bo in zip(incoming, outgoing):
+            pi, po = self.pos[bi], self.pos[bo]
+            self.at[pi], self.at[po] = bo, bi
+            self.pos[bi], self.pos[bo] = po, pi
+
     def plan_exchange(self, rem: Sequence[LGate], split: int = 0, min_first_phase: int = 40,
                       prev: Optional[Sequence[LGate]] = None, phase_cap: int = 96) -> Exchange:
         """Choose the new rank bits (farthest next non-diagonal use) and update the map.  `prev`: the gates of the
@@ -846,6 +871,8 @@ class ShardedKet:
         self.queue: List[LGate] = []
         self.gates_applied = 0
         self.label = list(range(nq))     # qubit of the caller -> qubit of the stored ket (`swap` only relabels)
+        self._fresh: Optional[List[np.ndarray]] = None       # factors of a product ket that has not been written yet (init_product)
+        self.lazy_map = os.environ.get('QBOT_B200_LAZY_MAP', '1') != '0'
         self.shard.init_basis(self.rank == 0, 0)
 
     def init_product(self, factors: Sequence[np.ndarray]):
@@ -855,16 +882,32 @@ class ShardedKet:
         entries selected by its rank bits."""
         if len(factors) != self.nq:
             raise ValueError("one factor per qubit")
-        g = self.map.g
         self.queue = []
+        self.map = QubitMap(self.nq, self.map.g)
+        self.label = list(range(self.nq))
+        # Nothing is written yet: the first flush picks the qubits that start on the rank bits from the gates queued
+        # by then (QubitMap.choose_initial) and builds the shards for that map.
+        self._fresh = [np.array(f, dtype=np.complex128).reshape(2) for f in factors]
+        if not self.lazy_map:
+            self._realise()
+
+    def _realise(self):
+        """Write the product ket of a pending init_product into the shards (called by every rank at the same point)."""
+        factors = self._fresh
+        if factors is None:
+            return
+        self._fresh = None
         self.shard.sync()
         self.comm.barrier()
-        self.map = QubitMap(self.nq, g)
-        self.label = list(range(self.nq))
+        mp = self.map
+        if self.lazy_map:
+            mp.choose_initial(self.queue)
+        n, nl, g = self.nq, mp.nl, mp.g
+        of_bit = lambda b: factors[n - 1 - b]               # noqa: E731  logical index bit b <-> qubit n-1-b of the stored ket
         coeff = 1.0 + 0.0j
-        for q in range(g):
-            coeff *= complex(np.asarray(factors[q]).reshape(2)[(self.rank >> (g - 1 - q)) & 1])
-        self.shard.init_product([np.asarray(f, dtype=np.complex128).reshape(2) for f in factors[g:]], coeff)
+        for r in range(g):                                   # rank bit r = physical position nl + r
+            coeff *= complex(of_bit(mp.at[nl + r])[(self.rank >> r) & 1])
+        self.shard.init_product([of_bit(mp.at[p]) for p in range(nl - 1, -1, -1)], coeff)
 
     # -- gates ---------------------------------------------------------------------------------
     def _bit(self, q: int) -> int:
@@ -893,6 +936,7 @@ class ShardedKet:
         return self
 
     def flush(self):
+        self._realise()
         rem = self.queue
         self.queue = []
         mp = self.map
@@ -930,6 +974,7 @@ class ShardedKet:
     def reset_zero(self):
         """|0...0> again, identity qubit map (a fresh register without re-allocating the shards)."""
         self.queue = []
+        self._fresh = None
         self.shard.sync()
         self.comm.barrier()
         self.map = QubitMap(self.nq, self.map.g)

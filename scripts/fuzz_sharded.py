@@ -34,8 +34,31 @@ def case(seed):
     cuts = sorted(int(c) for c in rng.integers(0, len(ops) + 1, size=int(rng.integers(0, 3))))
     probe = [int(q) for q in rng.choice(n, size=int(rng.integers(1, min(n, 4) + 1)), replace=False)]
     reps = int(rng.integers(1, 3))
-    desc = dict(seed=seed, world=world, n=n, depth=depth, split=split, cuts=cuts, probe=probe, reps=reps, gates=len(ops))
-    want = expected_ket(n, ops)
+    # half of the cases start from a random PRODUCT ket set through init_product (what `qset tensorExp(..)` does): the first
+    # flush chooses which qubits start on the rank bits (QubitMap.choose_initial), or keeps the identity map (lazy off)
+    product = rng.random() < 0.5
+    lazy = bool(rng.random() < 0.75)
+    swaps = [tuple(int(x) for x in rng.choice(n, size=2, replace=False)) for _ in range(int(rng.integers(0, 3)))] if product else []
+    desc = dict(seed=seed, world=world, n=n, depth=depth, split=split, cuts=cuts, probe=probe, reps=reps, gates=len(ops),
+                product=product, lazy=lazy, swaps=swaps)
+    if product:
+        factors = rng.normal(size=(n, 2)) + 1j * rng.normal(size=(n, 2))
+        factors /= np.linalg.norm(factors, axis=1, keepdims=True)
+        want = np.array([1.0 + 0j])
+        for q in range(n):
+            want = np.kron(want, factors[q])
+        # `swap` before the gates only relabels: the caller's qubit q is the stored ket's qubit perm[q]; the check below
+        # un-relabels the gathered ket, so the expected ket is simply the circuit on the relabelled qubits
+        perm = list(range(n))
+        for a, b in swaps:
+            perm[a], perm[b] = perm[b], perm[a]
+        inv = [perm.index(q) for q in range(n)]
+        want = np.ascontiguousarray(want.reshape([2] * n).transpose(perm)).reshape(-1)     # the ket as the caller numbers it
+        for m, t, cs in ops:
+            want = orc.ket_apply(want, n, t, m, cs)
+        del inv
+    else:
+        want = expected_ket(n, ops)
     for _ in range(reps - 1):
         for m, t, cs in ops:
             want = orc.ket_apply(want, n, t, m, cs)
@@ -49,6 +72,11 @@ def case(seed):
             sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard, **kw)
             if split:
                 sk.min_first_phase = int(rng.integers(2, 8)) if rank < 0 else 6
+            if product:
+                sk.lazy_map = lazy
+                sk.init_product(list(factors))
+                for a, b in swaps:
+                    sk.swap_qubits(a, b)
             for _ in range(reps):
                 for i, (m, t, cs) in enumerate(ops):
                     if i in cuts:

@@ -376,3 +376,160 @@ def test_sharded_register_behind_the_dsl_ops_gloo():
         assert np.max(np.abs(out['rho_a'] - want_r['rho_a'])) < 1e-12
         assert out['p2'] == [0.5, 0.0, 0.0, 0.5]
         assert out['err'] == 'exit'          # a ProbVal condition leaves a mixed state: refused on a sharded ket, formatted error
+
+
+# ---------------------------------------------------------------------------------------------
+# a fresh product ket starts with the qubits of its choice on the rank bits (QubitMap.choose_initial)
+# ---------------------------------------------------------------------------------------------
+def _product_case(n, world, seed, lazy, two_programs=False):
+    rng = np.random.default_rng(seed)
+    factors = rng.normal(size=(n, 2)) + 1j * rng.normal(size=(n, 2))
+    factors /= np.linalg.norm(factors, axis=1, keepdims=True)
+    ops = circuit_ops(n, 5, seed)
+    psi = np.array([1.0 + 0j])
+    for q in range(n):
+        psi = np.kron(psi, factors[q])
+    want = psi
+    for m, t, cs in ops:
+        want = orc.ket_apply(want, n, t, m, cs)
+    shared = VirtualComm.Shared(world)
+    out, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard)
+            sk.lazy_map = lazy
+            for rep in range(2 if two_programs else 1):
+                sk.init_product(list(factors))
+                for m, t, cs in ops:
+                    sk.apply_gate(m, t, cs)
+                ket = sk.gather()
+            out[rank] = dict(ket=ket, at=list(sk.map.at), exchanges=sk.shard.exchanges, norm=sk.norm2())
+        except Exception as e:     # pragma: no cover
+            errors.append(e)
+            shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out, want
+
+
+@pytest.mark.parametrize('n,world', [(6, 2), (8, 4), (9, 8)])
+@pytest.mark.parametrize('lazy', [True, False])
+def test_product_ket_with_chosen_initial_map_matches_oracle(n, world, lazy):
+    out, want = _product_case(n, world, 500 + n, lazy)
+    for r in out:
+        assert np.max(np.abs(r['ket'] - want)) < 1e-12
+        assert abs(r['norm'] - 1) < 1e-12
+        assert r['at'] == out[0]['at']
+    # a second program on the same (pooled) ket starts from a fresh map again
+    out2, want2 = _product_case(n, world, 500 + n, lazy, two_programs=True)
+    for r in out2:
+        assert np.max(np.abs(r['ket'] - want2)) < 1e-12
+
+
+def test_product_ket_initial_map_with_relabelled_qubits():
+    """`swap` before the first flush only relabels the caller's qubits: the factors stay with the stored ket's qubits"""
+    n, world = 8, 4
+    # single-qubit circuits only, so that relabelled multi-qubit blocks stay contiguous in the check above
+    rng = np.random.default_rng(9)
+    factors = rng.normal(size=(n, 2)) + 1j * rng.normal(size=(n, 2))
+    factors /= np.linalg.norm(factors, axis=1, keepdims=True)
+    gates = [g for g in circuits.rc(n, 6, 77)]
+    swaps = [(0, 5), (2, 7), (5, 1)]
+    perm = list(range(n))
+    for a, b in swaps:
+        perm[a], perm[b] = perm[b], perm[a]
+    psi = np.array([1.0 + 0j])
+    for q in range(n):
+        psi = np.kron(psi, factors[q])
+    for g in gates:
+        psi = orc.ket_apply(psi, n, perm[g.target], g.matrix(), [perm[c] for c in g.controls])
+    want = np.ascontiguousarray(psi.reshape([2] * n).transpose(perm)).reshape(-1)
+    shared = VirtualComm.Shared(world)
+    out, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard)
+            sk.init_product(list(factors))
+            for a, b in swaps:
+                sk.swap_qubits(a, b)
+            for g in gates:
+                sk.apply_gate(g.matrix(), g.target, g.controls)
+            out[rank] = sk.gather()
+        except Exception as e:     # pragma: no cover
+            errors.append(e)
+            shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise errors[0]
+    for k in out:
+        assert np.max(np.abs(k - want)) < 1e-12
+
+
+class _PlanOnlyShard:
+    """records what a shard would be asked to do (no amplitudes): the exchange plan of a 34-qubit circuit"""
+    supports_split = False
+
+    def __init__(self, nl, comm):
+        self.nl, self.exchanges, self.segments, self._n = nl, 0, [], 0
+
+    def init_basis(self, has_one, local_index=0):
+        pass
+
+    def init_product(self, local_factors, coeff):
+        assert len(local_factors) == self.nl
+
+    def apply(self, m, tpos, cmask):
+        assert all(0 <= p < self.nl for p in tpos) and cmask >> self.nl == 0
+        self._n += 1
+
+    def flush(self):
+        if self._n:
+            self.segments.append(self._n)
+        self._n = 0
+
+    def do_exchange(self, ex):
+        self.exchanges += 1
+
+    def sync(self):
+        pass
+
+
+class _OneRank:
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def barrier(self):
+        pass
+
+
+def test_fresh_register_of_the_benchmark_needs_one_exchange():
+    """BASELINE config 5 as a .qb program (what the multi-GPU e2e leg runs): rc(34, 10, 34) on a fresh product ket on
+    8 ranks.  From the identity map the planner needs two exchanges (the second one for the last gate alone); with
+    the initial map chosen from the queued gates it needs one."""
+    n, world = 34, 8
+    gates = circuits.rc(n, 10, n)
+    zero = [np.array([1, 0], dtype=complex)] * n
+    counts = {}
+    for lazy in (False, True):
+        sk = ShardedKet(n, _OneRank(3, world), shard_factory=_PlanOnlyShard)
+        sk.lazy_map = lazy
+        sk.init_product(zero)
+        for g in gates:
+            sk.apply_gate(g.matrix(), g.target, g.controls)
+        sk.flush()
+        counts[lazy] = (sk.shard.exchanges, list(sk.shard.segments))
+    assert counts[False][0] == 2 and counts[True][0] == 1, counts
+    assert sum(counts[True][1]) <= len(gates)
