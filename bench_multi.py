@@ -149,11 +149,27 @@ def run_multi_gpu(args):
         tt = torch.tensor([_t.perf_counter() - t0], dtype=torch.float64, device=f'cuda:{local}')
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
+        # in-run check of the register's start-up choice (QubitMap.choose_initial picks the rank bits of a fresh product
+        # register from the queued gates): the same program once more from the IDENTITY map -- the start the cross-rank
+        # parity check above covers -- must give the same weights
+        lazy_check = None
+        try:
+            pooled = ctx._idle.get(n) or []
+            if pooled and getattr(pooled[-1], 'lazy_map', False):
+                pooled[-1].lazy_map = False
+                pr_ident, _ = e2e_step()
+                for p_ in ctx._idle.get(n) or []:
+                    p_.lazy_map = True
+                lazy_check = {"max_abs_err_vs_identity_start": float(np.max(np.abs(pr - pr_ident))), "tolerance": 1e-12,
+                              "status": "pass" if float(np.max(np.abs(pr - pr_ident))) < 1e-12 else "FAIL"}
+        except Exception as e:      # noqa: BLE001
+            lazy_check = {"error": f"{type(e).__name__}: {e}"[:200]}
         sk = ctx.acquire(n)     # (closed below with everything else)
         e2e = {"value": ngates * args.steps / e2e_s * 2.0 ** (n - 30), "unit": "gates/s",
                "h2d_bytes_per_step": int(sum(m.nbytes for m in mats)), "d2h_bytes_per_step": int(pr.nbytes),
                "ms_per_step": 1e3 * e2e_s / args.steps, "probs_sum": float(pr.sum()), "program_bytes": len(program),
-               "register": reg_kind,
+               "register": reg_kind, "start_map": "chosen from the queued gates (QubitMap.choose_initial)" if lazy_check else "identity",
+               "start_map_check": lazy_check,
                "what": "qbot_b200.executeTxt(program) on every rank: qset tensorExp(comp.kets[0], n) -> sharded register "
                        "(device-side constructor per shard), one `gate` line per gate (expression evaluation, validation, host "
                        "matrices -> C ABI), fused sweeps + NVLink exchanges, peek of 4 qubits (local reduce + all-reduce -> "

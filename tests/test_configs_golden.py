@@ -4,6 +4,8 @@ REAL reference (tests/golden/make_golden_configs.py -> configs.npz / configs.jso
     rc(10, 200, 20) density matrix     (config 2's parity run)
     config 3 at n = 6 and 8            (mid-circuit meas with the reference's collapse, ProbVal-target gate, disc)
     config 4 at B = 64, n = 6          (per-branch circuit + per-branch RZ + measurement weights)
+    config 3 at its FULL size, n = 12  (tests/golden/make_golden_c3_full.py -> c3_12.npz / c3_12.json: the program
+                                        bench.py's configs.c3 sub-line and --impl reference run)
 
 CPU: the oracle against the fixtures (pins the oracle at these sizes).  GPU (-m gpu): the CUDA path,
 through the DSL / the C ABI, against the same fixtures directly."""
@@ -53,6 +55,32 @@ def test_oracle_config3(cfg, n, depth):
         assert np.allclose(probs[name], p, rtol=0, atol=1e-12), name
 
 
+@pytest.fixture(scope='module')
+def c3_full():
+    return json.load(open(os.path.join(GOLDEN, 'c3_12.json')))['c3_12'], np.load(os.path.join(GOLDEN, 'c3_12.npz'))
+
+
+# 1e-12 relative to the largest entry as everywhere; the register ends close to I / 256 (purity 2.5e-4 before the disc), so
+# the informative part, rho - I / 256 (at most 9.4e-6), is checked on its own scale as well (oracle vs reference: 2.3e-13)
+C3_FULL_RTOL = 1e-12
+C3_FULL_DEV_RTOL = 1e-11
+
+
+def _close_on_deviation(got, want):
+    dim = want.shape[0]
+    dev = want - np.eye(dim) / dim
+    return float(np.max(np.abs(got - want))) <= C3_FULL_DEV_RTOL * float(np.max(np.abs(dev)))
+
+
+@pytest.mark.skipif(os.environ.get('QBOT_B200_SLOW') != '1', reason="3 minutes of numpy: QBOT_B200_SLOW=1 (result recorded in DESIGN.md)")
+def test_oracle_config3_full_size(c3_full):
+    meta, arr = c3_full
+    rho, probs = orc.run_config3(circuits.c3_ops(12, 50, 12), 12)
+    assert close(rho, arr['c3_12_state'], C3_FULL_RTOL) and _close_on_deviation(rho, arr['c3_12_state'])
+    for name, p in meta['probs'].items():
+        assert np.allclose(probs[name], p, rtol=0, atol=1e-12), name
+
+
 def test_oracle_config4(cfg):
     meta, arr = cfg
     B, n = 64, 6
@@ -99,6 +127,30 @@ def test_device_config3(cfg, n, depth):
     assert close(np.asarray(ns['state']), arr[f'c3_{n}_state'], 1e-12)
     for name, p in meta[f'c3_{n}']['probs'].items():
         assert np.allclose(ns[name].probs, p, rtol=0, atol=1e-12), name
+
+
+@pytest.mark.gpu
+def test_device_config3_full_size(c3_full):
+    """config 3 as benchmarked (12 qubits, 256 MiB density matrix, 447 ops) against the REAL reference's output:
+    every measurement's weights, the final 8-qubit register, and the 12-qubit register before the `disc`
+    (diagonal, sampled rows, trace, purity)"""
+    import qbot_b200
+    meta, arr = c3_full
+    prog = circuits.c3_program(12, 50, 12)
+    ns = qbot_b200.executeTxt(prog)
+    assert close(np.asarray(ns['state']), arr['c3_12_state'], C3_FULL_RTOL)
+    assert _close_on_deviation(np.asarray(ns['state']), arr['c3_12_state'])
+    for name, p in meta['probs'].items():
+        assert np.allclose(ns[name].probs, p, rtol=0, atol=1e-12), name
+    lines = prog.split("\n")
+    assert lines[-1].startswith('disc')
+    ns = qbot_b200.executeTxt("\n".join(lines[:-1]))
+    rho = np.asarray(ns['state'])
+    assert rho.shape == (4096, 4096)
+    assert close(np.diag(rho), arr['c3_12_before_disc_diag'], C3_FULL_RTOL)
+    assert close(rho[meta['rows']], arr['c3_12_before_disc_rows'], C3_FULL_RTOL)
+    assert abs(np.trace(rho) - complex(*meta['before_disc_trace'])) < 1e-11
+    assert abs(np.vdot(rho.conj().T, rho).real - meta['before_disc_purity']) < 1e-11
 
 
 @pytest.mark.gpu
