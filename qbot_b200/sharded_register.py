@@ -23,6 +23,7 @@ Nothing here touches a device directly; the shards go through ``include/qbot_b20
 from __future__ import annotations
 
 import os
+import sys
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -98,6 +99,10 @@ def context() -> Optional[ShardingContext]:
     global _ctx, _auto_failed
     if _ctx is not None or _auto_failed:
         return _ctx
+    # one process, no launcher: nothing to shard over -- and no reason to import torch (seconds on a cold start;
+    # the single-GPU path never needs it)
+    if int(os.environ.get('WORLD_SIZE', '1') or 1) < 2 and 'torch.distributed' not in sys.modules:
+        return None
     try:
         import torch.distributed as dist
         if not dist.is_available():
