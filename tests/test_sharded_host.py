@@ -533,3 +533,85 @@ def test_fresh_register_of_the_benchmark_needs_one_exchange():
         counts[lazy] = (sk.shard.exchanges, list(sk.shard.segments))
     assert counts[False][0] == 2 and counts[True][0] == 1, counts
     assert sum(counts[True][1]) <= len(gates)
+
+
+# ---------------------------------------------------------------------------------------------
+# the whole host-visible chain on the CPU: product start with a chosen map -> local gate lists -> fusion planner ->
+# the specialiser's generated kernel text (compiled with g++, tests/jit_emu.py) -> exchange -> ...
+# ---------------------------------------------------------------------------------------------
+class _GeneratedCodeShard(NumpyShard):
+    """a numpy shard whose queued gates run as the fused sweeps the CUDA shard would launch: the same plan, the same
+    generated source (CPU definitions of its macros), instead of one numpy update per gate"""
+
+    def __init__(self, nl, comm):
+        super().__init__(nl, comm)
+        self.pending, self.sweeps = [], 0
+
+    def apply(self, m, tpos, cmask):
+        self.pending.append((np.array(m, dtype=complex), [int(p) for p in tpos], int(cmask)))
+        self.applied += 1
+
+    def flush(self):
+        if self.pending:
+            import jit_emu
+            with _GeneratedCodeShard.lock:                       # one g++ at a time; the ranks are threads
+                self.psi, st = jit_emu.run(self.nl, self.pending, self.psi)
+            self.sweeps += st['sweeps']
+            self.pending = []
+
+    def do_exchange(self, ex):
+        self.flush()
+        super().do_exchange(ex)
+
+    def download(self):
+        self.flush()
+        return super().download()
+
+    def probs_local(self, positions):
+        self.flush()
+        return super().probs_local(positions)
+
+
+_GeneratedCodeShard.lock = threading.Lock()
+
+
+@pytest.mark.parametrize('n,world,depth,seed,lazy', [(16, 4, 8, 15, True), (15, 2, 12, 3, True), (16, 4, 8, 15, False)])
+def test_fresh_product_register_through_planner_and_generated_kernels(n, world, depth, seed, lazy):
+    # (14 / 13 local bits: free tile bits above the 12-bit tile)
+    rng = np.random.default_rng(41)
+    factors = rng.normal(size=(n, 2)) + 1j * rng.normal(size=(n, 2))
+    factors /= np.linalg.norm(factors, axis=1, keepdims=True)
+    gates = circuits.rc(n, depth, seed)
+    want = np.array([1.0 + 0j])
+    for q in range(n):
+        want = np.kron(want, factors[q])
+    for g in gates:
+        want = orc.ket_apply(want, n, g.target, g.matrix(), g.controls)
+    shared = VirtualComm.Shared(world)
+    out, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=_GeneratedCodeShard)
+            sk.lazy_map = lazy
+            sk.init_product(list(factors))
+            for g in gates:
+                sk.apply_gate(g.matrix(), g.target, g.controls)
+            out[rank] = dict(ket=sk.gather(), probs=sk.probs([0, 7, n - 1]), sweeps=sk.shard.sweeps, exchanges=sk.shard.exchanges,
+                             at=list(sk.map.at))
+        except Exception as e:     # pragma: no cover
+            errors.append(e)
+            shared.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errors:
+        raise errors[0]
+    for r in out:
+        assert np.max(np.abs(r['ket'] - want)) < 1e-12
+        assert np.max(np.abs(r['probs'] - orc.ket_probs(want, n, [0, 7, n - 1]))) < 1e-12
+        assert r['sweeps'] >= 1 and r['exchanges'] >= 1
+    assert all(r['at'] == out[0]['at'] for r in out)
