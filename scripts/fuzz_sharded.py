@@ -17,6 +17,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
+GENERATED = False          # --generated: the shards run their gate lists as planned sweeps of generated kernel text (g++)
+
+
 def case(seed):
     from oracle import qbot_oracle as orc
     from qbot_b200.sharded import ShardedKet
@@ -29,6 +32,9 @@ def case(seed):
     split = int(rng.integers(1, 4)) if pipelined else 0
     lo = max(g + 2, 4) if not pipelined else max(g + 2 + split, 12)       # pipelined plans need room for parked + tile bits
     n = int(rng.integers(lo, lo + 4))
+    if GENERATED:
+        pipelined, split = False, 0          # (sub-block sweeps are a CUDA-shard feature)
+        n = g + int(rng.integers(12, 15))    # every flush must be plannable as fused sweeps: >= one 12-bit tile per shard
     depth = int(rng.integers(1, 9))
     ops = circuit_ops(n, depth, seed)
     cuts = sorted(int(c) for c in rng.integers(0, len(ops) + 1, size=int(rng.integers(0, 3))))
@@ -69,7 +75,10 @@ def case(seed):
     def work(rank):
         try:
             kw = dict(split=split) if split else {}
-            sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=NumpyShard, **kw)
+            factory = NumpyShard
+            if GENERATED:
+                from test_sharded_host import _GeneratedCodeShard as factory
+            sk = ShardedKet(n, VirtualComm(shared, rank), shard_factory=factory, **kw)
             if split:
                 sk.min_first_phase = int(rng.integers(2, 8)) if rank < 0 else 6
             if product:
@@ -103,7 +112,13 @@ def case(seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--seeds', default='0:100')
+    ap.add_argument('--generated', action='store_true',
+                    help="shards execute their local gate lists through the fusion planner and the specialiser's generated source "
+                         "compiled with g++ (tests/jit_emu.py) instead of one numpy update per gate: host logic + planner + code "
+                         "generator in one chain; seconds per case")
     a = ap.parse_args()
+    global GENERATED
+    GENERATED = a.generated
     lo, hi = (int(x) for x in a.seeds.split(':'))
     bad = 0
     for seed in range(lo, hi):
