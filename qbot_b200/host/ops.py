@@ -535,8 +535,22 @@ def make_ops(host: Host) -> dict:
         for target in targets:
             if target < 0 or target > numQubits - 1:
                 err.raiseFormattedError(err.customIndexError(lines, lineNum, 'target', target, numQubits - 1))
-        st = current_dm(ns)
         drop = set(int(t) for t in targets)
+        st = current(ns)
+        if is_state(st) and st.kind == 0 and getattr(st, 'nbranch', 1) == 1 and (st.nq > KET_AS_DENSITY_MAX or getattr(st, '_qb_sharded', False)):
+            # a large ket-mode register (the new representation) never becomes 4^n entries: what is left after
+            # the discard is Tr_rest psi psi^dagger, computed straight from the amplitudes (qb_ptrace on a ket; on a sharded
+            # register the kept qubits are made local, every rank sums over its shard, one all-reduce).  The result is an
+            # ordinary density-matrix register; too many kept qubits are refused with the formatted error.
+            if len(st.shape) == 1 and st.nq - len(drop) > KET_AS_DENSITY_MAX:
+                err.raiseFormattedError(err.pythonError(lines, lineNum, ValueError(
+                    f"disc on a {st.nq}-qubit ket-mode register leaves a mixed state of {st.nq - len(drop)} qubits; a ket-mode "
+                    f"register can be cut down to at most {KET_AS_DENSITY_MAX} qubits")))
+            try:
+                return st.ptrace_keep([q for q in range(st.nq) if q not in drop])
+            except (ValueError, RuntimeError) as e:
+                err.raiseFormattedError(err.pythonError(lines, lineNum, e))
+        st = current_dm(ns)
         return st.ptrace_keep([q for q in range(st.nq) if q not in drop])
 
     def disc(ns, lines, lineNum, tokens):

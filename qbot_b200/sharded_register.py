@@ -14,6 +14,8 @@ functions as on any other register:
     gate   queued on the sharded ket; fused sweeps per shard, NVLink exchange when a target is a rank bit
     swap   a relabelling of two qubits (no data moves)
     peek   outcome weights: local binning + one all-reduce; every rank gets the same ProbVal / result
+    disc   what is left, Tr_rest psi psi^dagger of at most 10 kept qubits (made local, per-rank partial sums, one
+           all-reduce), becomes an ordinary single-GPU density-matrix register on every rank
     meas   refused like on any ket-mode register above 13 qubits: the reference's collapse is a mixed
            product state (measurement.py:160-165) that only a 4^n density matrix can hold
     ProbVal-valued gates / conditions: refused for the same reason (they leave a mixed state)

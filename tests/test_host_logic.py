@@ -266,3 +266,42 @@ def test_probval_measurement_targets_behind_the_flag(monkeypatch):
     assert np.allclose(ns['m'].probs, want_p, atol=1e-15)
     assert close(np.asarray(ns['state']), .25 * r0['newState'] + .75 * r1['newState'])
     assert close(np.asarray(ns['m'].unMeasuredDensity), .25 * r0['unMeasuredDensity'] + .75 * r1['unMeasuredDensity'])
+
+
+def _disc_ket_case(n, drop):
+    from qbot_b200.circuits import rc
+    from oracle import qbot_oracle as orc
+    gates = rc(n, 3, 5)
+    prog = "\n".join([f"qset tensorExp(comp.kets[0], {n})"] + [g.dsl() for g in gates] + [f"disc {drop}", "peek p ; comp ; [0, 3]"])
+    psi = np.zeros(1 << n, dtype=complex)
+    psi[0] = 1
+    for g in gates:
+        psi = orc.ket_apply(psi, n, g.target, g.matrix(), g.controls)
+    keep = [q for q in range(n) if q not in drop]
+    m = np.ascontiguousarray(psi.reshape([2] * n).transpose(keep + list(drop))).reshape(1 << len(keep), -1)
+    rho = m @ m.conj().T
+    d = np.real(np.diag(rho)).reshape([2] * len(keep))
+    peek = d.sum(axis=tuple(a for a in range(len(keep)) if a not in (0, 3))).reshape(-1)
+    return prog, rho, peek
+
+
+def test_disc_on_a_large_ket_register():
+    """`disc` on a ket-mode register of more than 13 qubits (the new representation): what is left is
+    Tr_rest psi psi^dagger of the kept qubits, computed from the amplitudes -- an ordinary density-matrix register (the
+    reference's disc, operators.py:169-188 -> density.partialTraceArbitrary, on a state it could never hold); a discard
+    that would leave more than 13 qubits is refused with the formatted error."""
+    n, drop = 16, [0, 2, 3, 5, 8, 9, 12, 15]
+    prog, rho, peek = _disc_ket_case(n, drop)
+    ns = qbot_b200.executeTxt(prog, state_cls=FakeState)
+    st = ns['state']
+    assert st.kind == 1 and st.nq == n - len(drop)
+    assert np.max(np.abs(np.asarray(st) - rho)) < 1e-12
+    assert np.max(np.abs(np.array(ns['p'].probs) - peek)) < 1e-12
+    buf = io.StringIO()
+    with pytest.raises(SystemExit), redirect_stdout(buf):
+        qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\ndisc [0, 1]\n", state_cls=FakeState)
+    assert "ket-mode register can be cut down to at most 13 qubits" in buf.getvalue()
+    # small ket-mode registers keep going through psi psi^dagger (unchanged path)
+    ns = qbot_b200.executeTxt("qset tensorExp(comp.kets[0], 14)\ngate hadamardGate ; 0\ngate pauliXGate ; 13 ; [0]\ndisc [13]\npeek p ; comp ; [0]\n",
+                              state_cls=FakeState)
+    assert ns['state'].nq == 13 and list(ns['p'].probs) == [0.5, 0.5]

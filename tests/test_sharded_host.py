@@ -300,6 +300,9 @@ def expected_sharded_program(n, ops):
     return psi
 
 
+DISC_DROP = [0, 2, 3, 5, 8, 9, 12, 15]
+
+
 def _register_worker(rank, world, n, port, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
@@ -329,6 +332,21 @@ def _register_worker(rank, world, n, port, q):
             qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\ngate hadamardGate ; 0 ; [] ; ProbVal([.5, .5], [True, False])\n", state_cls=FakeState)
         except SystemExit:
             out['err'] = 'exit'
+        # `disc` on the sharded ket: Tr_rest psi psi^dagger of the kept qubits (made local, per-rank partial, one all-reduce)
+        # becomes an ordinary density-matrix register; too many kept qubits are refused with the formatted error
+        gl = "\n".join(g.dsl() for g in circuits.rc(n, 3, 5))
+        ns3 = qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\n{gl}\ndisc {DISC_DROP}\npeek d ; comp ; [0, 3]\n", state_cls=FakeState)
+        out['disc_rho'] = np.asarray(ns3['state'])
+        out['disc_kind'] = type(ns3['state']).__name__
+        out['disc_peek'] = list(ns3['d'].probs)
+        out['disc_err'] = None
+        try:
+            import io
+            from contextlib import redirect_stdout
+            with redirect_stdout(io.StringIO()):
+                qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\ndisc [0]\n", state_cls=FakeState)
+        except SystemExit:
+            out['disc_err'] = 'exit'
         q.put((rank, out))
     except BaseException as e:      # noqa: BLE001  (a formatted DSL error ends in sys.exit(): report it instead of hanging the parent)
         q.put((rank, dict(failed=f"{type(e).__name__}: {e}")))
@@ -367,6 +385,15 @@ def test_sharded_register_behind_the_dsl_ops_gloo():
     keep = [0, 5, n - 1]
     mm = np.ascontiguousarray(t.transpose(keep + [a for a in range(n) if a not in keep])).reshape(8, -1)
     want_r['rho_a'] = mm @ mm.conj().T
+    psi3 = np.zeros(1 << n, dtype=complex)
+    psi3[0] = 1
+    for g in circuits.rc(n, 3, 5):
+        psi3 = orc.ket_apply(psi3, n, g.target, g.matrix(), g.controls)
+    keep3 = [a for a in range(n) if a not in DISC_DROP]
+    m3 = np.ascontiguousarray(psi3.reshape([2] * n).transpose(keep3 + DISC_DROP)).reshape(1 << len(keep3), -1)
+    want_disc = m3 @ m3.conj().T
+    d3 = np.real(np.diag(want_disc)).reshape([2] * len(keep3))
+    want_disc_peek = d3.sum(axis=tuple(a for a in range(len(keep3)) if a not in (0, 3))).reshape(-1)
     for rank, out in got:
         assert 'failed' not in out, out
         assert out['kind'] == 'ShardedRegister'
@@ -376,6 +403,9 @@ def test_sharded_register_behind_the_dsl_ops_gloo():
         assert np.max(np.abs(out['rho_a'] - want_r['rho_a'])) < 1e-12
         assert out['p2'] == [0.5, 0.0, 0.0, 0.5]
         assert out['err'] == 'exit'          # a ProbVal condition leaves a mixed state: refused on a sharded ket, formatted error
+        assert out['disc_kind'] != 'ShardedRegister' and out['disc_err'] == 'exit'
+        assert np.max(np.abs(out['disc_rho'] - want_disc)) < 1e-12
+        assert np.max(np.abs(np.array(out['disc_peek']) - want_disc_peek)) < 1e-12
 
 
 # ---------------------------------------------------------------------------------------------
