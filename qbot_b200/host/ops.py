@@ -322,7 +322,11 @@ def make_ops(host: Host) -> dict:
         return ns['state']
 
     def current_dm(ns):
-        return current(ns).as_density()
+        st = current(ns)
+        if is_state(st) and st.kind == 0 and st.nq > KET_AS_DENSITY_MAX and not getattr(st, '_qb_sharded', False):
+            # (a 16-qubit psi psi^dagger is 64 GiB, a 20-qubit one 16 TiB; the sharded register refuses by itself)
+            raise ValueError(f"the {st.nq}-qubit ket-mode register cannot become a density matrix (limit {KET_AS_DENSITY_MAX} qubits)")
+        return st.as_density()
 
     def ensemble_base(ns):
         """The register as something an ensemble sum may be taken of.  A ProbVal-valued gate /

@@ -83,6 +83,9 @@ class FakeState:
         return self
 
     def apply_swap(self, a, b):
+        if self.kind == KET:                  # (no 2^n x 2^n permutation matrix for the large ket-mode registers)
+            self.data = orc.ket_swap(self.data, self.nq, a, b)
+            return self
         u = orc.swap_unitary(self.nq, a, b)
         self.data = orc.conjugate(u, self.data) if self.kind == DM else u @ self.data
         return self
@@ -154,6 +157,11 @@ class FakeState:
         dens = [np.outer(k, k) for k in kets]
         b = orc.ilog2(kets[0].shape[0])
         qubits = list(qubits)
+        if self.kind == KET and self.nq > 12:
+            # psi psi^dagger of a large ket does not fit: the rotated-amplitude form (equal for real bases, and what the
+            # device computes for a ket-mode register)
+            assert qubits == sorted(qubits)
+            return orc.basis_weights(self.data, self.nq, qubits, kets)
         rho = self.data if self.kind == DM else np.outer(self.data, self.data.conj())
         if qubits != list(range(self.nq)):
             assert qubits == sorted(qubits)

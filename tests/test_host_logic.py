@@ -305,3 +305,42 @@ def test_disc_on_a_large_ket_register():
     ns = qbot_b200.executeTxt("qset tensorExp(comp.kets[0], 14)\ngate hadamardGate ; 0\ngate pauliXGate ; 13 ; [0]\ndisc [13]\npeek p ; comp ; [0]\n",
                               state_cls=FakeState)
     assert ns['state'].nq == 13 and list(ns['p'].probs) == [0.5, 0.5]
+
+
+def test_every_op_on_a_large_ket_register_answers_or_refuses_with_a_formatted_error():
+    """A ket-mode register above 13 qubits has no 4^n form: every op either works on the amplitudes or ends like any
+    other DSL error (formatted window + sys.exit, qbot/errors.py) -- never with a raw exception or a 64 GiB allocation."""
+    n = 16
+    head = f"qset tensorExp(comp.kets[0], {n})\ngate hadamardGate ; 0\n"
+    works = {
+        'peek_all': ("peek p ; comp\n", None),
+        'peek_hada': ("peek p ; hadamard ; [0, 1]\n", [0.5, 0.5, 0.0, 0.0]),
+        'peek_bell': ("peek p ; bell ; [0, 1]\n", [0.25, 0.25, 0.25, 0.25]),
+        'swap': ("swap 0 ; 3\npeek p ; comp ; [3]\n", [0.5, 0.5]),
+        'qset_again': (f"qset tensorExp(hadamard.kets[0], {n})\npeek p ; comp ; [0]\n", [0.5, 0.5]),
+        'names_state': ("cdef x ; state\ngate hadamardGate ; 1\npeek p ; comp ; [1]\n", [0.5, 0.5]),
+        'dense_block': ("gate qftGate(3) ; 2\npeek p ; comp ; [2]\n", [0.5, 0.5]),
+        'disc_to_13': ("disc [0, 1, 2]\npeek p ; comp ; [0]\n", [1.0, 0.0]),
+        'disc_all': (f"disc {list(range(n))}\n", None),
+        'disc_probval': ("disc ProbVal([.5,.5],[[0,1,2],[3,4,5]])\n", None),
+    }
+    for name, (tail, probs) in works.items():
+        ns = qbot_b200.executeTxt(head + tail, state_cls=FakeState)
+        if probs is not None:
+            assert np.allclose(ns['p'].probs, probs, atol=1e-12), name
+    refused = {
+        'meas': ("meas m ; comp ; [0]\n", "meas on a 16-qubit ket-mode register"),
+        'disc_too_many_left': ("disc [0]\n", "at most 13 qubits"),
+        'qset_sub_register': ("qset comp.kets[1] ; [0]\n", "cannot become a density matrix"),
+        'probval_gate': ("gate ProbVal([.5,.5],[hadamardGate, pauliXGate]) ; 1\n", "leaves a mixed state"),
+        'probval_target': ("gate hadamardGate ; ProbVal([.5,.5],[1,2])\n", "leaves a mixed state"),
+        'probval_condition': ("gate hadamardGate ; 1 ; [] ; ProbVal([.5,.5],[True, False])\n", "leaves a mixed state"),
+        'probval_swap': ("swap ProbVal([.5,.5],[0,1]) ; 3\n", "leaves a mixed state"),
+        'range': (f"peek p ; comp ; [{n}]\n", "outside of valid range"),
+        'bell_odd': ("peek p ; bell ; [0]\n", "must be divisable"),
+    }
+    for name, (tail, text) in refused.items():
+        buf = io.StringIO()
+        with pytest.raises(SystemExit), redirect_stdout(buf):
+            qbot_b200.executeTxt(head + tail, state_cls=FakeState)
+        assert text in buf.getvalue(), (name, buf.getvalue()[:300])
