@@ -81,6 +81,19 @@ def test_oracle_config3_full_size(c3_full):
         assert np.allclose(probs[name], p, rtol=0, atol=1e-12), name
 
 
+@pytest.mark.skipif(os.environ.get('QBOT_B200_SLOW') != '1', reason="4 minutes of numpy: QBOT_B200_SLOW=1 (result recorded in DESIGN.md)")
+def test_host_ops_config3_full_size(c3_full):
+    """the six DSL ops (host/ops.py) over the numpy double, through executeTxt, on the full-size program"""
+    import qbot_b200
+    from fake_backend import FakeState
+    meta, arr = c3_full
+    ns = qbot_b200.executeTxt(circuits.c3_program(12, 50, 12), state_cls=FakeState)
+    got = np.asarray(ns['state'])
+    assert close(got, arr['c3_12_state'], C3_FULL_RTOL) and _close_on_deviation(got, arr['c3_12_state'])
+    for name, p in meta['probs'].items():
+        assert np.allclose(ns[name].probs, p, rtol=0, atol=1e-12), name
+
+
 def test_oracle_config4(cfg):
     meta, arr = cfg
     B, n = 64, 6
