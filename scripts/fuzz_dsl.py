@@ -153,13 +153,43 @@ def line(rng, n, names, extra=False):
     return 'cdef %s ; %s' % (name, rng.choice(['np_trace(state)', 'np_real(state[0][0])', 'state.shape[0]']))
 
 
+BIG = False        # --big: 5-6 qubit registers; `swap` and off-slot controls stay out (the reference builds wrong unitaries for them at
+                   # n >= 5), everything else (gates, slot-aligned controls, ProbVal arguments, qset / disc / meas /
+                   # peek, error lines) as below
+
+
+def _valid_for_big(n, ln):
+    if isinstance(ln, tuple):
+        return True
+    if ln.startswith('swap'):
+        return False
+    if ln.startswith('gate '):
+        parts = [x.strip() for x in ln.split(';')]
+        if len(parts) >= 3:
+            if 'ProbVal' in parts[2]:
+                return False                     # ProbVal control lists: off-slot in general
+            try:
+                cs = list(eval(parts[2]))
+            except Exception:                    # noqa: BLE001
+                return False
+            if cs:
+                if 'ProbVal' in parts[1]:
+                    return False
+                t = int(parts[1])
+                if not slot_aligned(n, t, cs):
+                    return False
+    return True
+
+
 def program(seed, extra=False):
     rng = np.random.default_rng(50_000 + seed)
-    n = int(rng.integers(1, 5))
+    n = int(rng.integers(5, 7)) if BIG else int(rng.integers(1, 5))
     names = []
     lines = [initial(rng, n)]
     for _ in range(int(rng.integers(2, 12))):
         ln = line(rng, n, names, extra)
+        while BIG and n >= 5 and not _valid_for_big(n, ln):
+            ln = line(rng, n, names, extra)
         if isinstance(ln, tuple):
             _, m, ln = ln
             n -= m
@@ -175,7 +205,11 @@ def program(seed, extra=False):
                'gate hadamardGate ; 0 ; [] ; []', 'gate hadamardGate ; 0.5', 'swap 0 ; 0']
         if extra:
             bad.append('disc %s' % list(range(n)))      # a 0-qubit register: legal in the reference, kept out of the fixtures
-        lines.insert(int(rng.integers(1, len(lines) + 1)), bad[int(rng.integers(len(bad)))])
+        if BIG:
+            bad = [b for b in bad if not b.startswith('swap')]
+        # (--big: at the end only -- the templates use the FINAL register size; earlier in the program, before a `disc`, some of
+        # them are valid lines with an off-slot control)
+        lines.insert(len(lines) if BIG else int(rng.integers(1, len(lines) + 1)), bad[int(rng.integers(len(bad)))])
     return '\n'.join(lines), names
 
 
@@ -268,10 +302,13 @@ def main():
     ap.add_argument('--emit')
     ap.add_argument('--show', type=int)
     ap.add_argument('--extra', action='store_true', help='also result-dependent conditions, cout of results, ProbVal arithmetic')
+    ap.add_argument('--big', action='store_true', help='5-6 qubit registers inside the validity domain of the reference at that size (no swap, slot-aligned controls only)')
     ap.add_argument('--installed', action='store_true',
                     help="second arm = the REAL reference's executeTxt with the ops installed into it (qbot_b200.install) "
                          "instead of this repo's interpreter mirror")
     a = ap.parse_args()
+    global BIG
+    BIG = a.big
     from qbot.interpreter import executeTxt as ref_exec
     import qbot_b200
     from fake_backend import FakeState
