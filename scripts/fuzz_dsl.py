@@ -153,6 +153,7 @@ def line(rng, n, names, extra=False):
     return 'cdef %s ; %s' % (name, rng.choice(['np_trace(state)', 'np_real(state[0][0])', 'state.shape[0]']))
 
 
+BIG_MAX = 6
 BIG = False        # --big: 5-6 qubit registers; `swap` and off-slot controls stay out (the reference builds wrong unitaries for them at
                    # n >= 5), everything else (gates, slot-aligned controls, ProbVal arguments, qset / disc / meas /
                    # peek, error lines) as below
@@ -183,7 +184,7 @@ def _valid_for_big(n, ln):
 
 def program(seed, extra=False):
     rng = np.random.default_rng(50_000 + seed)
-    n = int(rng.integers(5, 7)) if BIG else int(rng.integers(1, 5))
+    n = int(rng.integers(5, BIG_MAX + 1)) if BIG else int(rng.integers(1, 5))
     names = []
     lines = [initial(rng, n)]
     for _ in range(int(rng.integers(2, 12))):
@@ -302,13 +303,15 @@ def main():
     ap.add_argument('--emit')
     ap.add_argument('--show', type=int)
     ap.add_argument('--extra', action='store_true', help='also result-dependent conditions, cout of results, ProbVal arithmetic')
+    ap.add_argument('--big-max', type=int, default=6, help='largest register of --big (default 6)')
     ap.add_argument('--big', action='store_true', help='5-6 qubit registers inside the validity domain of the reference at that size (no swap, slot-aligned controls only)')
     ap.add_argument('--installed', action='store_true',
                     help="second arm = the REAL reference's executeTxt with the ops installed into it (qbot_b200.install) "
                          "instead of this repo's interpreter mirror")
     a = ap.parse_args()
-    global BIG
+    global BIG, BIG_MAX
     BIG = a.big
+    BIG_MAX = a.big_max
     from qbot.interpreter import executeTxt as ref_exec
     import qbot_b200
     from fake_backend import FakeState
