@@ -40,6 +40,8 @@ class Golden:
         self.scripts_arr = np.load(os.path.join(GOLDEN, 'scripts.npz'))
         self.scripts_fuzz = json.load(open(os.path.join(GOLDEN, 'scripts_fuzz.json')))
         self.scripts_fuzz_arr = np.load(os.path.join(GOLDEN, 'scripts_fuzz.npz'))
+        self.scripts_fuzz_big = json.load(open(os.path.join(GOLDEN, 'scripts_fuzz_big.json')))
+        self.scripts_fuzz_big_arr = np.load(os.path.join(GOLDEN, 'scripts_fuzz_big.npz'))
         self.probval = json.load(open(os.path.join(GOLDEN, 'probval.json')))
         self.rc = np.load(os.path.join(GOLDEN, 'rc_small.npz'))
 

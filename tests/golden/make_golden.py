@@ -10,6 +10,7 @@ Outputs (small, committed):
     l1_cases.npz / l1_cases.json   -- qgates / density / measurement functions on seeded inputs
     scripts.json + scripts.npz     -- DSL programs run through the reference's executeTxt
     scripts_fuzz.json + .npz       -- random DSL programs (scripts/fuzz_dsl.py --emit ...scripts_fuzz_src.json), same recording
+    scripts_fuzz_big.json + .npz   -- the same on 5-6 qubit registers (scripts/fuzz_dsl.py --big --emit ...scripts_fuzz_big_src.json)
     probval.json                   -- ProbVal normalise / funcWrapper ordering cases
     rc_small.npz                   -- rc(n, D, seed) circuits pushed through the reference's applyGate
 
@@ -278,6 +279,8 @@ def main():
     sout = record_scripts('scripts_src.json', 'scripts')
     # ---- random DSL programs (scripts/fuzz_dsl.py --emit), recorded the same way ----------
     fout = record_scripts('scripts_fuzz_src.json', 'scripts_fuzz')
+    # ---- the same on 5-6 qubit registers (scripts/fuzz_dsl.py --big --emit: no swap, slot-aligned controls only, F5 / F6) ----
+    bout = record_scripts('scripts_fuzz_big_src.json', 'scripts_fuzz_big')
 
     # ---- rc circuits through the reference's applyGate --------------------------------
     rarr = {}
@@ -299,7 +302,7 @@ def main():
         rarr[f'rc_{n}_{depth}_{seed}'] = rho
         rarr[f'rc_{n}_{depth}_{seed}_info'] = np.array([len(gates), ref_built])
     np.savez_compressed(os.path.join(HERE, 'rc_small.npz'), **rarr)
-    print('golden fixtures written:', len(meta), 'L1 cases,', len(sout), 'scripts,', len(fout), 'fuzz scripts')
+    print('golden fixtures written:', len(meta), 'L1 cases,', len(sout), 'scripts,', len(fout), 'fuzz scripts,', len(bout), 'fuzz scripts on 5-6 qubits')
 
 
 if __name__ == '__main__':

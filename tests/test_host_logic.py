@@ -67,6 +67,14 @@ def test_fuzzed_scripts(golden):
         check_script(rec, golden.scripts_fuzz_arr, FakeState)
 
 
+def test_fuzzed_scripts_on_5_and_6_qubits(golden):
+    """the same generator on 5-6 qubit registers, inside what the reference still gets right at that size (no swap,
+    slot-aligned controls only: SURVEY.md F5 / F6), recorded from the real reference"""
+    assert len(golden.scripts_fuzz_big) >= 60
+    for rec in golden.scripts_fuzz_big:
+        check_script(rec, golden.scripts_fuzz_big_arr, FakeState)
+
+
 def test_probval_rules(golden):
     for c in golden.probval:
         if c['kind'] == 'normalize':
