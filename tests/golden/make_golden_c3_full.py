@@ -10,6 +10,9 @@
       make_golden_configs.py, at the size `bench.py`'s `configs.c3` sub-line and `--impl reference` run.
       Stored: the final 8-qubit register (256 x 256), every measurement's probabilities, and of the
       12-qubit register just before the `disc`: its diagonal, 2 sampled rows, trace and purity.
+(Reproducibility: the 4096-cubed zgemms run on all BLAS threads, so a re-run on another machine / thread count reproduces the
+arrays to rounding (~1e-15 of the largest entry), not bit for bit; the recorded probabilities are rounded to 15 decimals by the
+reference itself.  Recorded here with numpy 2.3 / OpenBLAS on 8 threads.)
 Unitaries come from the reference's builders inside their validity domain and from the definitional
 unitary outside it, exactly as in make_golden_configs.py.
 """
