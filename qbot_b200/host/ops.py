@@ -782,6 +782,9 @@ class _LazyReducedDensity:
     def __init__(self, ket_state, keep):
         big = ket_state.nq > 24 or getattr(ket_state, '_qb_sharded', False)
         self._snapshot = ket_state if big else ket_state.clone()                  # large / sharded kets: a view of the live register
+        # ... which is only good until the register is updated in place: reading it later must not hand out rho_A of
+        # another state (a copy of a 16 GiB shard per peek is not an option; computing rho_A eagerly costs 2^(n+k+1) loads)
+        self._version = getattr(ket_state, '_version', None) if big else None
         self._keep = list(keep)
         self._val = None
         d = 1 << len(self._keep)
@@ -789,6 +792,10 @@ class _LazyReducedDensity:
 
     def __array__(self, dtype=None, copy=None):
         if self._val is None:
+            if self._version is not None and getattr(self._snapshot, '_version', self._version) != self._version:
+                raise ValueError("unMeasuredDensity of a peek on a large ket-mode register is computed when it is first read, and the "
+                                 "register has been updated since the peek: read it (e.g. `cdef rhoA ; np_array(r.unMeasuredDensity)`) "
+                                 "before the next gate")
             self._val = np.asarray(self._snapshot.ptrace_keep(self._keep))
             self._snapshot = None
         return self._val if dtype is None else self._val.astype(dtype)

@@ -132,6 +132,7 @@ class ShardedRegister:
     kind = 0                     # KET
     nbranch = 1
     GATHER_MAX_QUBITS = 26       # user expressions may read `state` as an ndarray up to this size
+    _version = 0                 # bumped by every update: a peek result's lazily computed rho_A checks it when it is read
 
     def __init__(self, sk: ShardedKet, ctx: ShardingContext):
         self._sk, self._ctx = sk, ctx
@@ -181,10 +182,12 @@ class ShardedRegister:
     # ---- what gate / swap / peek call --------------------------------------------------------------
     def apply_gate(self, matrix, first_target: int = 0, controls: Iterable[int] = ()):
         self._sk.apply_gate(matrix, first_target, controls)
+        self._version += 1
         return self
 
     def apply_swap(self, qubit_a: int, qubit_b: int):
         self._sk.swap_qubits(qubit_a, qubit_b)
+        self._version += 1
         return self
 
     def probs(self, qubits: Sequence[int]) -> np.ndarray:

@@ -87,6 +87,7 @@ class DeviceState:
     _qb_device_state = True
     __array_priority__ = 1000
     _shared = True        # ownership flag of the DSL ops (host/ops.py _exclusively_owned): conservative default
+    _version = 0          # bumped by every in-place update: lazily computed views of the register (host/ops.py _LazyReducedDensity) check it
 
     def __init__(self, handle, kind: int, nq: int, nbranch: int = 1):
         self._h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
@@ -199,6 +200,7 @@ class DeviceState:
 
     def _dirty(self):
         self._host_cache = None
+        self._version += 1
 
     def to_host(self) -> np.ndarray:
         if self._host_cache is None:
@@ -266,6 +268,7 @@ class DeviceState:
         if rc:
             _lib.check(rc)
         self._host_cache = None
+        self._version += 1
         return self
 
     def apply_gate_bits(self, matrix, target_bits: Sequence[int], control_mask: int = 0) -> "DeviceState":

@@ -347,6 +347,20 @@ def _register_worker(rank, world, n, port, q):
                 qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\ndisc [0]\n", state_cls=FakeState)
         except SystemExit:
             out['disc_err'] = 'exit'
+        # rho_A of a peek on a sharded ket is computed when it is first read: after an update of the register that read is
+        # refused (formatted error) instead of handing out rho_A of another state; read at once, it is the peeked state's
+        import io as _io
+        from contextlib import redirect_stdout as _redirect
+        head = f"qset tensorExp(hadamard.kets[0], {n})\npeek s ; comp ; [1, 2]\n"
+        ns4 = qbot_b200.executeTxt(head + "cdef a ; np_array(s.unMeasuredDensity)\ngate pauliZGate ; 1\n", state_cls=FakeState)
+        out['rho_at_once'] = np.asarray(ns4['a'])
+        buf = _io.StringIO()
+        out['stale'] = None
+        try:
+            with _redirect(buf):
+                qbot_b200.executeTxt(head + "gate pauliZGate ; 1\ncdef a ; np_array(s.unMeasuredDensity)\n", state_cls=FakeState)
+        except SystemExit:
+            out['stale'] = buf.getvalue()
         q.put((rank, out))
     except BaseException as e:      # noqa: BLE001  (a formatted DSL error ends in sys.exit(): report it instead of hanging the parent)
         q.put((rank, dict(failed=f"{type(e).__name__}: {e}")))
@@ -403,6 +417,8 @@ def test_sharded_register_behind_the_dsl_ops_gloo():
         assert np.max(np.abs(out['rho_a'] - want_r['rho_a'])) < 1e-12
         assert out['p2'] == [0.5, 0.0, 0.0, 0.5]
         assert out['err'] == 'exit'          # a ProbVal condition leaves a mixed state: refused on a sharded ket, formatted error
+        assert np.max(np.abs(out['rho_at_once'] - np.full((4, 4), 0.25))) < 1e-12
+        assert out['stale'] is not None and 'has been updated since the peek' in out['stale']
         assert out['disc_kind'] != 'ShardedRegister' and out['disc_err'] == 'exit'
         assert np.max(np.abs(out['disc_rho'] - want_disc)) < 1e-12
         assert np.max(np.abs(np.array(out['disc_peek']) - want_disc_peek)) < 1e-12
