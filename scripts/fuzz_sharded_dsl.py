@@ -3,7 +3,11 @@ ket -- gates (plain, controlled, dense 2-qubit, conditions), `swap`, `peek` in t
 
   (a) by two gloo ranks through qbot_b200.executeTxt with sharding enabled (ShardedRegister over numpy shards,
       qbot_b200/sharded_register.py: the chosen start map, exchanges, relabelling swaps, all-reduced weights), and
-  (b) by one process on the ordinary ket-mode register of the numpy double;
+  (b) by one process on the ordinary ket-mode register of the numpy double, and
+  (c) op by op by the ORACLE on the full ket (oracle/qbot_oracle.py: ket_apply, ket_swap, basis_weights, partial traces by
+      reshaping), with the gate matrices from the reference's own namespace when /root/reference is there -- independent of
+      host/ops.py, so the large-ket code paths that (a) and (b) share (measure_ket, the lazy rho_A, `disc` on a ket) are
+      checked as well;
 
 registers (gathered), outcome weights, reduced densities and the register left by `disc` must agree to 1e-12 on every rank.
 
@@ -33,6 +37,7 @@ def program(seed):
     # (a run of equal factors as tensorExp, the rest listed: both constructors of the DSL)
     lines = ["qset tensorProd(%s)" % ", ".join(parts)] if rng.random() < 0.7 else [f"qset tensorExp({ONE_Q[int(rng.integers(4))]}, {n})"]
     names = []
+    ops = [('init', lines[0][5:])]           # structured copy of the program for the oracle arm
     for _ in range(int(rng.integers(8, 40))):
         r = rng.random()
         if r < 0.62:
@@ -45,12 +50,18 @@ def program(seed):
             free = [q for q in range(n) if not t <= q < t + k]
             cs = [int(x) for x in rng.choice(free, size=int(rng.choice([0, 0, 1, 1, 2])), replace=False)]
             ln = f"gate {g} ; {t} ; {cs}"
+            on = True
             if rng.random() < 0.08:
-                ln += " ; %d > 1" % rng.integers(0, 4)
+                c = int(rng.integers(0, 4))
+                ln += " ; %d > 1" % c
+                on = c > 1
             lines.append(ln)
+            if on:
+                ops.append(('gate', g, t, cs))
         elif r < 0.72:
             a, b = rng.choice(n, 2, replace=False)
             lines.append(f"swap {a} ; {b}")
+            ops.append(('swap', int(a), int(b)))
         else:
             basis = str(rng.choice(['comp', 'comp', 'hadamard', 'bell']))
             m = 2 if basis == 'bell' else int(rng.integers(1, 4))
@@ -58,15 +69,62 @@ def program(seed):
             name = f"m{len(names)}"
             names.append(name)
             lines.append(f"peek {name} ; {basis} ; {tg}")
+            ops.append(('peek', name, basis, tg))
             if rng.random() < 0.3:
                 lines.append(f"cdef rho_{name} ; np_array({name}.unMeasuredDensity)")
                 names.append(f"rho_{name}")
+                ops.append(('rho', f"rho_{name}", tg))
     disc = None
     if rng.random() < 0.4:
         keep = int(rng.integers(1, 9))
         disc = sorted(int(x) for x in rng.choice(n, n - keep, replace=False))
         lines.append(f"disc {disc}")
-    return n, "\n".join(lines) + "\n", names
+        ops.append(('disc', disc))
+    return n, "\n".join(lines) + "\n", names, ops
+
+
+def oracle_run(n, ops):
+    """the program op by op on the full ket, by the oracle"""
+    from oracle import qbot_oracle as orc
+    if os.path.isdir('/root/reference'):
+        sys.dont_write_bytecode = True
+        if '/root/reference' not in sys.path:
+            sys.path.insert(0, '/root/reference')
+        import qbot.evaluation as ev              # the reference's own constants / constructors
+        env = dict(ev.globalNameSpace) if hasattr(ev, 'globalNameSpace') else None
+    else:
+        env = None
+    if env is None:
+        from qbot_b200.host import namespace as nsm
+        env = dict(nsm.build_namespace()) if hasattr(nsm, 'build_namespace') else {}
+    def ev_(expr):
+        return eval(expr, {'__builtins__': {}}, env)
+    out = {}
+    psi = None
+    rho = None
+    for op in ops:
+        if op[0] == 'init':
+            psi = np.asarray(ev_(op[1]), dtype=complex).reshape(-1)
+        elif op[0] == 'gate':
+            psi = orc.ket_apply(psi, n, op[2], np.asarray(ev_(op[1]), dtype=complex), op[3])
+        elif op[0] == 'swap':
+            psi = orc.ket_swap(psi, n, op[1], op[2])
+        elif op[0] == 'peek':
+            kets = ev_(op[2]).kets
+            tg = sorted(set(op[3]))
+            w = orc.basis_weights(psi, n, tg, kets)
+            out[op[1]] = np.array([round(float(x), 15) for x in (w / w.sum())])
+        elif op[0] == 'rho':
+            keep = sorted(set(op[2]))
+            rest = [q for q in range(n) if q not in keep]
+            m = np.ascontiguousarray(psi.reshape([2] * n).transpose(keep + rest)).reshape(1 << len(keep), -1)
+            out[op[1]] = m @ m.conj().T
+        elif op[0] == 'disc':
+            keep = [q for q in range(n) if q not in op[1]]
+            m = np.ascontiguousarray(psi.reshape([2] * n).transpose(keep + list(op[1]))).reshape(1 << len(keep), -1)
+            rho = m @ m.conj().T
+    out['state'] = rho if rho is not None else psi
+    return out
 
 
 def collect(ns, names):
@@ -92,7 +150,7 @@ def worker(rank, world, port, lo, hi, q):
     sr.enable(TorchComm(), shard_factory=NumpyShard, min_qubits=14)
     res = {}
     for seed in range(lo, hi):
-        n, text, names = program(seed)
+        n, text, names, _ = program(seed)
         try:
             with redirect_stdout(io.StringIO()):
                 ns = qbot_b200.executeTxt(text, state_cls=FakeState)
@@ -124,13 +182,26 @@ def main():
     from fake_backend import FakeState
     want = {}
     for seed in range(lo, hi):
-        n, text, names = program(seed)
+        n, text, names, _ = program(seed)
         try:
             with redirect_stdout(io.StringIO()):
                 ns = qbot_b200.executeTxt(text, state_cls=FakeState)
             want[seed] = ('ok', collect(ns, names))
         except BaseException as e:      # noqa: BLE001
             want[seed] = ('error', f"{type(e).__name__}: {e}"[:300])
+    # (c) the oracle, op by op
+    bad_oracle = 0
+    for seed in range(lo, hi):
+        n, text, names, ops = program(seed)
+        if want[seed][0] != 'ok':
+            continue
+        exp = oracle_run(n, ops)
+        for k, y in want[seed][1].items():
+            x = exp[k]
+            if x.shape != y.shape or np.max(np.abs(x - y)) > 1e-12:
+                bad_oracle += 1
+                print(f"seed {seed}: single register vs ORACLE: {k} differs ({x.shape} vs {y.shape}, max {np.max(np.abs(x - y)) if x.shape == y.shape else -1})\n{text}", flush=True)
+                break
     got = [q.get(timeout=3600) for _ in range(a.world)]
     for p in procs:
         p.join(timeout=120)
@@ -153,8 +224,9 @@ def main():
                 print(f"seed {seed}: {why}\n{program(seed)[1]}", flush=True)
                 break
         sharded += got[0][1][seed][2] == 'ShardedRegister'
-    print(f"seeds {lo}:{hi}: {bad} differences ({sharded} programs ended on a ShardedRegister, the others on the register `disc` left)")
-    sys.exit(1 if bad else 0)
+    print(f"seeds {lo}:{hi}: {bad} differences between the sharded and the single register, {bad_oracle} between the single register and the "
+          f"oracle ({sharded} programs ended on a ShardedRegister, the others on the register `disc` left)")
+    sys.exit(1 if bad or bad_oracle else 0)
 
 
 if __name__ == '__main__':
