@@ -18,6 +18,7 @@ The module is written against a *binding* (``Host``) so that the same functions 
 from __future__ import annotations
 
 import re
+import weakref
 from typing import List, Sequence
 
 import numpy as np
@@ -304,6 +305,14 @@ def make_ops(host: Host) -> dict:
         it.  A host array / product descriptor is uploaded into a new device object, fresh by
         construction; a device object that came out of a user expression stays shared."""
         val = convertToDensity(lines, lineNum, value)
+        old = ns.get('state')
+        if hm.is_lazy(val) and is_state(old) and not getattr(old, '_shared', True) and not _program_names_state(ns, lines):
+            # The register is about to be replaced by one that is built on the device from a product descriptor, and
+            # nothing but the namespace holds the old one: let go of it first, so that its buffers (register pool /
+            # pooled shards) carry the new register instead of a second allocation next to them -- a loop that
+            # re-initialises a 34-qubit sharded register would otherwise alternate between two sets of shards.
+            ns['state'] = np.array([], dtype=complex)
+            del old
         dev = to_device(val)
         if is_state(dev):
             try:
@@ -781,7 +790,10 @@ class _LazyReducedDensity:
 
     def __init__(self, ket_state, keep):
         big = ket_state.nq > 24 or getattr(ket_state, '_qb_sharded', False)
-        self._snapshot = ket_state if big else ket_state.clone()                  # large / sharded kets: a view of the live register
+        # large / sharded kets: a view of the live register (held weakly: a peek result must not keep 16-64 GiB of a
+        # register alive that the program has replaced); smaller ones: a snapshot
+        self._snapshot = None if big else ket_state.clone()
+        self._live = weakref.ref(ket_state) if big else None
         # ... which is only good until the register is updated in place: reading it later must not hand out rho_A of
         # another state (a copy of a 16 GiB shard per peek is not an option; computing rho_A eagerly costs 2^(n+k+1) loads)
         self._version = getattr(ket_state, '_version', None) if big else None
@@ -792,12 +804,13 @@ class _LazyReducedDensity:
 
     def __array__(self, dtype=None, copy=None):
         if self._val is None:
-            if self._version is not None and getattr(self._snapshot, '_version', self._version) != self._version:
+            src = self._snapshot if self._live is None else self._live()
+            if src is None or (self._version is not None and getattr(src, '_version', self._version) != self._version):
                 raise ValueError("unMeasuredDensity of a peek on a large ket-mode register is computed when it is first read, and the "
                                  "register has been updated since the peek: read it (e.g. `cdef rhoA ; np_array(r.unMeasuredDensity)`) "
                                  "before the next gate")
-            self._val = np.asarray(self._snapshot.ptrace_keep(self._keep))
-            self._snapshot = None
+            self._val = np.asarray(src.ptrace_keep(self._keep))
+            self._snapshot = self._live = None
         return self._val if dtype is None else self._val.astype(dtype)
 
 

@@ -661,3 +661,31 @@ def test_fresh_product_register_through_planner_and_generated_kernels(n, world, 
         assert np.max(np.abs(r['probs'] - orc.ket_probs(want, n, [0, 7, n - 1]))) < 1e-12
         assert r['sweeps'] >= 1 and r['exchanges'] >= 1
     assert all(r['at'] == out[0]['at'] for r in out)
+
+
+def test_requalified_register_reuses_the_shards():
+    """a program that sets the (sharded) register again -- a loop that re-initialises it -- lets go of the old register before
+    the new one is built, so the pooled shards carry it: one ShardedKet for the whole program, not two"""
+    import qbot_b200
+    from qbot_b200 import sharded_register as sr
+    from fake_backend import FakeState
+    made = []
+
+    class CountingShard(NumpyShard):
+        def __init__(self, nl, comm):
+            super().__init__(nl, comm)
+            made.append(self)
+
+    n = 14
+    sr.enable(VirtualComm(VirtualComm.Shared(1), 0), shard_factory=CountingShard, min_qubits=n)
+    try:
+        prog = "\n".join(["cdef i ; 0", "mark loop", f"qset tensorExp(hadamard.kets[0], {n})", "gate pauliZGate ; i",
+                          "peek p ; hadamard ; [0, 1, 2]", "cdef i ; i + 1", "cjmp loop ; i < 3"]) + "\n"
+        ns = qbot_b200.executeTxt(prog, state_cls=FakeState)
+        assert type(ns['state']).__name__ == 'ShardedRegister'
+        # the last iteration flipped qubit 2 from |+> to |->: outcome (0, 0, 1) in the hadamard basis
+        assert np.allclose(ns['p'].probs, [0, 1, 0, 0, 0, 0, 0, 0], atol=1e-12)
+        assert len(made) == 1, len(made)
+        del ns
+    finally:
+        sr.disable()
