@@ -73,11 +73,17 @@ def make_lgate(matrix, target_bits: Sequence[int], control_bits: Iterable[int] =
     if set(controls) & set(target_bits):
         raise ValueError("control overlaps target")
     w = r = 0
-    for ax, b in enumerate(target_bits):
-        if _axis_is_diagonal(m, k, ax):
-            r |= 1 << b
+    if k == 1:            # (the common case, without numpy index arithmetic: 4 us instead of 20 per gate of a queued circuit)
+        if m[0, 1] == 0 and m[1, 0] == 0:
+            r = 1 << target_bits[0]
         else:
-            w |= 1 << b
+            w = 1 << target_bits[0]
+    else:
+        for ax, b in enumerate(target_bits):
+            if _axis_is_diagonal(m, k, ax):
+                r |= 1 << b
+            else:
+                w |= 1 << b
     for c in controls:
         r |= 1 << c
     return LGate(m, tuple(int(b) for b in target_bits), controls, w, r)
