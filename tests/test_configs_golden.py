@@ -143,30 +143,6 @@ def test_device_config3(cfg, n, depth):
 
 
 @pytest.mark.gpu
-def test_device_config3_full_size(c3_full):
-    """config 3 as benchmarked (12 qubits, 256 MiB density matrix, 447 ops) against the REAL reference's output:
-    every measurement's weights, the final 8-qubit register, and the 12-qubit register before the `disc`
-    (diagonal, sampled rows, trace, purity)"""
-    import qbot_b200
-    meta, arr = c3_full
-    prog = circuits.c3_program(12, 50, 12)
-    ns = qbot_b200.executeTxt(prog)
-    assert close(np.asarray(ns['state']), arr['c3_12_state'], C3_FULL_RTOL)
-    assert _close_on_deviation(np.asarray(ns['state']), arr['c3_12_state'])
-    for name, p in meta['probs'].items():
-        assert np.allclose(ns[name].probs, p, rtol=0, atol=1e-12), name
-    lines = prog.split("\n")
-    assert lines[-1].startswith('disc')
-    ns = qbot_b200.executeTxt("\n".join(lines[:-1]))
-    rho = np.asarray(ns['state'])
-    assert rho.shape == (4096, 4096)
-    assert close(np.diag(rho), arr['c3_12_before_disc_diag'], C3_FULL_RTOL)
-    assert close(rho[meta['rows']], arr['c3_12_before_disc_rows'], C3_FULL_RTOL)
-    assert abs(np.trace(rho) - complex(*meta['before_disc_trace'])) < 1e-11
-    assert abs(np.vdot(rho.conj().T, rho).real - meta['before_disc_purity']) < 1e-11
-
-
-@pytest.mark.gpu
 def test_device_config4(cfg):
     from qbot_b200 import DeviceState
     meta, arr = cfg

@@ -57,22 +57,3 @@ def test_large_ket_register_through_the_dsl():
     got = np.array([st.download_range(int(i), 1)[0] for i in idx])
     assert np.max(np.abs(got - psi[idx])) < 1e-12
 
-
-def test_disc_on_a_large_ket_register():
-    """`disc` on a ket-mode register above 13 qubits: Tr_rest psi psi^dagger of the kept qubits straight from the
-    amplitudes (qb_ptrace on a ket), then an ordinary density-matrix register -- against the oracle's ket path."""
-    import io
-    from contextlib import redirect_stdout
-    import qbot_b200
-    from test_host_logic import _disc_ket_case
-    n, drop = 20, [0, 1, 2, 4, 5, 7, 8, 10, 11, 13, 14, 16, 17, 19]
-    prog, rho, peek = _disc_ket_case(n, drop)
-    ns = qbot_b200.executeTxt(prog)
-    st = ns['state']
-    assert st.kind == 1 and st.nq == n - len(drop)
-    assert np.max(np.abs(np.asarray(st) - rho)) < 1e-12
-    assert np.max(np.abs(np.array(ns['p'].probs) - peek)) < 1e-12
-    buf = io.StringIO()
-    with pytest.raises(SystemExit), redirect_stdout(buf):
-        qbot_b200.executeTxt(f"qset tensorExp(comp.kets[0], {n})\ndisc [0, 1]\n")
-    assert "at most 13 qubits" in buf.getvalue()

@@ -14,8 +14,3 @@ def test_fuzzed_scripts_on_device(golden):
     for rec in golden.scripts_fuzz:
         check_script(rec, golden.scripts_fuzz_arr, DeviceState, prob_tol=1e-12)
 
-
-def test_fuzzed_scripts_on_5_and_6_qubits_on_device(golden):
-    from qbot_b200 import DeviceState
-    for rec in golden.scripts_fuzz_big:
-        check_script(rec, golden.scripts_fuzz_big_arr, DeviceState, prob_tol=1e-12)
