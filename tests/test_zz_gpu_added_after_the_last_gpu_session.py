@@ -4,7 +4,9 @@ and against the oracle / the reference fixtures on the CPU, but not yet on a B20
 
   - config 3 at its full size (12 qubits, 447 ops) against the fixture recorded from the stock reference (tests/golden/c3_12.*)
   - `disc` on a ket-mode register above 13 qubits (Tr_rest psi psi^dagger straight from the amplitudes)
-  - the 70 random DSL programs on 5-6 qubit registers recorded from the reference (tests/golden/scripts_fuzz_big.*)"""
+  - the 70 random DSL programs on 5-6 qubit registers recorded from the reference (tests/golden/scripts_fuzz_big.*)
+  - the sharded register behind the DSL ops with the start map a fresh product register chooses for itself (the default;
+    tests/test_gpu_sharded.py keeps running the same program from the identity map, as it last did on hardware)"""
 import json
 import os
 
@@ -71,3 +73,8 @@ def test_fuzzed_scripts_on_5_and_6_qubits_on_device(golden):
     from qbot_b200 import DeviceState
     for rec in golden.scripts_fuzz_big:
         check_script(rec, golden.scripts_fuzz_big_arr, DeviceState, prob_tol=1e-12)
+
+
+def test_sharded_register_through_the_dsl_with_the_chosen_start_map(tmp_path):
+    from test_gpu_sharded import run_register_worker
+    run_register_worker(tmp_path, '1')
