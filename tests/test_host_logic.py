@@ -352,3 +352,21 @@ def test_every_op_on_a_large_ket_register_answers_or_refuses_with_a_formatted_er
         with pytest.raises(SystemExit), redirect_stdout(buf):
             qbot_b200.executeTxt(head + tail, state_cls=FakeState)
         assert text in buf.getvalue(), (name, buf.getvalue()[:300])
+
+
+def test_single_process_programs_do_not_import_torch():
+    """the sharded-register hook is consulted by every `qset` of a large product ket; without a launcher (WORLD_SIZE < 2,
+    torch.distributed not loaded) it must answer without importing torch -- seconds on a cold start, and the single-GPU
+    path needs nothing from it"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path[:0] = [%r, %r]\n"
+            "import qbot_b200\nfrom fake_backend import FakeState\n"
+            "ns = qbot_b200.executeTxt('qset tensorExp(comp.kets[0], 16)\\ngate hadamardGate ; 0\\npeek p ; comp ; [0]\\n', state_cls=FakeState)\n"
+            "assert list(ns['p'].probs) == [0.5, 0.5]\n"
+            "assert 'torch' not in sys.modules, 'torch was imported'\n") % (root, os.path.join(root, 'tests'))
+    env = {k: v for k, v in os.environ.items() if k not in ('WORLD_SIZE', 'RANK', 'LOCAL_RANK', 'QBOT_B200_SHARD')}
+    p = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
